@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — exact-KNN queries/s + achieved HBM GB/s (BASELINE.json metric).
+
+Workload at every N: BASELINE.json configs[1] — vec0 float[768], 10 M vectors,
+exact cosine k=10, single-query scans.  The corpus is fixed (strong scaling) and
+sharded by rowid range across the N ranks; one step = BATCH independent
+single-query scans (each streams the whole shard from HBM: no reuse across
+queries), followed for N>1 by ONE all-gather of the local top-k and a merge.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement).
+`--impl reference` times the CPU oracle port of the reference path
+(oracle/, "port": the Rust+simsimd reference cannot be built here) on a bounded
+prefix of the same corpus, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS = int(os.environ.get("VECGPU_BENCH_ROWS", 10_000_000))
+DIMS = int(os.environ.get("VECGPU_BENCH_DIMS", 768))
+K = 10
+BATCH = 16  # single-query scans per step
+SEED, QSEED = 3, 33
+F32, COSINE, GAUSS4 = 0, 2, 1
+METRIC_NAME = "exact-KNN queries/sec, 10Mx768 f32 cosine k=10 single-query"
+CPU_PREFIX_ROWS = int(os.environ.get("VECGPU_BENCH_CPU_ROWS", 400_000))
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(s[1]) for s in self.samples if len(s) >= 8 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) >= 8 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) >= 8:
+                for nm, v in zip(names, s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(seconds_budget=12.0):
+    """The oracle port of the reference path on the host cores, bounded prefix of the same corpus."""
+    import oracle
+
+    oracle.build()
+    n = CPU_PREFIX_ROWS
+    cores = oracle.num_threads()
+    vec = oracle.synth_rows(F32, SEED, 1, n, DIMS, GAUSS4)
+    q = oracle.synth_rows(F32, QSEED, 1, 64, DIMS, GAUSS4)
+    oracle.knn(F32, DIMS, vec, q[:1], K, COSINE)  # warm
+    t0, done = time.perf_counter(), 0
+    while True:
+        oracle.knn(F32, DIMS, vec, q[done % 64: done % 64 + 1], K, COSINE)
+        done += 1
+        el = time.perf_counter() - t0
+        if el > seconds_budget or done >= 64:
+            break
+    qps_prefix = done / el
+    return {
+        "value": qps_prefix * n / N_ROWS, "unit": "queries/s", "cores": cores, "kind": "port",
+        "sample": f"{done} single queries over the first {n} rows of the {N_ROWS}x{DIMS} corpus "
+                  f"({qps_prefix:.2f} q/s on the prefix, {n * DIMS * 4 * qps_prefix / 1e9:.1f} GB/s), scaled by {n}/{N_ROWS}; "
+                  "vectors contiguous in RAM (no SQLite per-row lookups, which flatters the reference)",
+    }, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    import oracle
+
+    oracle.build()
+    n = CPU_PREFIX_ROWS
+    vec = oracle.synth_rows(F32, SEED, 1, n, DIMS, GAUSS4)
+    q = oracle.synth_rows(F32, QSEED, 1, BATCH, DIMS, GAUSS4)
+    per_step = max(1, min(BATCH, 4))  # bounded sample: a few single queries per step
+    for _ in range(args.warmup):
+        oracle.knn(F32, DIMS, vec, q[:1], K, COSINE)
+    t1 = time.perf_counter()
+    for s in range(args.steps):
+        for j in range(per_step):
+            oracle.knn(F32, DIMS, vec, q[(s * per_step + j) % BATCH][None, :], K, COSINE)
+    el = time.perf_counter() - t1
+    qps_prefix = args.steps * per_step / el
+    value = qps_prefix * n / N_ROWS
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"vec0 float[{DIMS}], {N_ROWS} vectors, exact cosine k={K}, single-query (BASELINE.json configs[1])",
+                   "cpu_sample_rows": n},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": oracle.num_threads(), "kind": "port",
+                         "sample": f"{per_step} single queries per step over the first {n} rows "
+                                   f"({qps_prefix:.2f} q/s on the prefix), scaled by {n}/{N_ROWS}; distance for every "
+                                   "row + full sort + truncate as src/vtab.rs:2594-2620, OpenMP over rows"},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import sqlite_vec_hnsw_b200 as vg
+    from sqlite_vec_hnsw_b200 import dist as vdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    vg.load_library()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sh = vdist.ShardedSlab(vg, F32, DIMS, N_ROWS, rank, world, local_rank)
+    sh.fill_synthetic(SEED, GAUSS4)
+    rows_local = sh.hi - sh.lo
+    bytes_local = rows_local * DIMS * 4
+
+    # queries: generated on the host by the same counter-based generator (rowids 1..BATCH of seed QSEED)
+    import oracle  # only to regenerate inputs + cpu_baseline; never on the measured GPU path
+
+    q_host = torch.from_numpy(oracle.synth_rows(F32, QSEED, 1, BATCH, DIMS, GAUSS4).copy()).pin_memory()
+    q_dev = q_host.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        """BATCH single-query scans on resident inputs, then one exchange + merge."""
+        outs_r, outs_d = [], []
+        for j in range(BATCH):
+            r, d = sh.slab.knn_device(q_dev[j], K, COSINE, stream=stream.cuda_stream)
+            outs_r.append(r)
+            outs_d.append(d)
+        r = torch.cat(outs_r)
+        d = torch.cat(outs_d)
+        if world > 1:
+            gr, gd = vdist.all_gather_topk(r, d)
+            r, d = vg.merge_device(gr, gd, stream=stream.cuda_stream)
+        return r, d
+
+    def step_e2e():
+        """Public API, host buffers: per query H2D of the query, scan, (exchange+merge), D2H of the result."""
+        res = None
+        for j in range(BATCH):
+            if world == 1:
+                res = sh.slab.knn(q_host[j].numpy(), K, COSINE)  # vecgpu_knn: pinned H2D + scan + merge + D2H + sync
+            else:
+                res = sh.knn(q_host[j], K, COSINE)
+        return res
+
+    # ---- warm-up + correctness guard (top-1 of query j must be reproducible and sorted)
+    for _ in range(max(args.warmup, 3)):
+        r0, d0 = step_device()
+    torch.cuda.synchronize()
+    assert bool((d0[:, 1:] >= d0[:, :-1]).all()), "results not sorted"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed: device-resident
+    launches0 = vg.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    scan_ev = []
+    barrier()
+    ev[0].record(stream)
+    for s in range(args.steps):
+        r, d = step_device()
+    ev[1].record(stream)
+    barrier()
+    launches = vg.launch_count() - launches0
+    t_dev = ev[0].elapsed_time(ev[1]) / 1e3
+
+    # ---- per-launch duration of the dominant kernel (scan), CUDA events on the launch stream
+    for j in range(BATCH):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sh.slab.knn_device(q_dev[j], K, COSINE, stream=stream.cuda_stream)
+        b.record(stream)
+        scan_ev.append((a, b))
+    torch.cuda.synchronize()
+    scan_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev]))
+
+    # ---- timed: end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    t_e2e = time.perf_counter() - t0  # host-synchronous API: wall clock brackets device work + copies
+
+    clocks = sampler.summary() if rank == 0 else None
+
+    # max over ranks
+    tt = torch.tensor([t_dev, t_e2e, scan_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, scan_ms = [float(x) for x in tt.tolist()]
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        qps = args.steps * BATCH / t_dev
+        achieved = bytes_local / (scan_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"vec0 float[{DIMS}], {N_ROWS} vectors, exact cosine k={K}, single-query (BASELINE.json configs[1])",
+                "queries_per_step": BATCH, "rows_per_gpu": rows_local, "sharding": f"rowid-range x{world}",
+                "l2_policy": f"inputs larger than L2 ({bytes_local / 1e9:.2f} GB streamed per query per GPU vs 126 MB L2)",
+                "synthetic": "counter-based generator seed 3, Irwin-Hall(4) bell values, not normalised",
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "scan_kernel<F32Cos<1>,1,false> (+ merge_kernel, <1% of the pair)",
+                "algorithmic_bytes_per_launch": bytes_local, "avg_launch_ms": scan_ms,
+                "hbm_aggregate_gbs": achieved * world,
+            },
+            "e2e": {"value": args.steps * BATCH / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": BATCH * DIMS * 4,
+                    "d2h_bytes_per_step": BATCH * (K * 12 + 4),
+                    "api": "vecgpu_knn (host query in, host top-k out)" if world == 1 else "ShardedSlab.knn (pinned host query in, host top-k out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cb, _ = cpu_baseline()
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

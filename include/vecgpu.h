@@ -1,0 +1,165 @@
+/*
+ * vecgpu.h — C ABI of libvecgpu.so, the B200 (sm_100a) replacement for the
+ * distance-scoring hot path of sqlite-vec-hnsw.
+ *
+ * Every entry point below states the reference interface (file:line under the
+ * reference tree) it replaces.  Signatures are plain C: pointers + sizes, no
+ * torch / C++ types.  All calls are synchronous unless a `stream` is passed
+ * (the *_device variants), return 0 on success or a vecgpu_status code, and
+ * never throw / unwind across the boundary (cf. catch_unwind, src/lib.rs:149).
+ * The message for the last failing call on the calling thread is available
+ * from vecgpu_last_error().
+ *
+ * There is NO CPU fallback behind this ABI: if no CUDA device is usable every
+ * compute entry point fails with VECGPU_ERR_CUDA.
+ */
+#ifndef VECGPU_H
+#define VECGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == VectorType order, src/vector.rs:9-16 */
+enum vecgpu_elem { VECGPU_F32 = 0, VECGPU_I8 = 1, VECGPU_BIT = 2 };
+
+/* == DistanceMetric order, src/distance/mod.rs:12-21 */
+enum vecgpu_metric { VECGPU_L2 = 0, VECGPU_L1 = 1, VECGPU_COSINE = 2, VECGPU_HAMMING = 3 };
+
+/* Error codes; the mapping to src/error.rs:5-36 is in INTEGRATION.md. */
+enum vecgpu_status {
+    VECGPU_OK = 0,
+    VECGPU_ERR_INVALID_PARAM = 1, /* Error::InvalidParameter                       */
+    VECGPU_ERR_DIM_MISMATCH = 2,  /* Error::DimensionMismatch (distance/mod.rs:57)  */
+    VECGPU_ERR_UNSUPPORTED = 3,   /* Error::InvalidDistanceMetric / InvalidVectorType (distance/mod.rs:64-82) */
+    VECGPU_ERR_CUDA = 4           /* Error::InvalidState: no device, OOM, launch failure */
+};
+
+/* Synthetic value distributions for vecgpu_slab_fill_synthetic. */
+enum vecgpu_synth {
+    VECGPU_SYNTH_UNIFORM = 0, /* f32: U[-1,1) on a 2^-23 grid; i8: quantize_int8(U[-1,1)); bit: Bernoulli(1/2) */
+    VECGPU_SYNTH_GAUSS4 = 1   /* f32 only: Irwin-Hall(4) bell curve, exact integer arithmetic, std ~1.155   */
+};
+
+/* One slab = the HBM-resident, rowid-indexed copy of one vector column of one
+ * vec0 table ({table}_data.vecNN, src/shadow.rs:111-129).  Opaque. */
+typedef struct vecgpu_slab vecgpu_slab;
+
+/* ---- library ---------------------------------------------------------- */
+
+/* Thread-local message of the last failing call ("" if none). */
+const char* vecgpu_last_error(void);
+/* "vecgpu x.y.z sm_100a"; mirrors vec_version(), src/sql_functions.rs:13-48. */
+const char* vecgpu_version(void);
+/* Number of visible CUDA devices (0 when none; never fails). */
+int vecgpu_device_count(void);
+/* Bytes one stored row occupies in a blob: dims*4 | dims | ceil(dims/8)
+ * (src/vector.rs:223-242, 592-600).  0 on bad elem type. */
+uint32_t vecgpu_row_bytes(int elem_type, uint32_t dims);
+/* 1 if (elem_type, metric) is one of the seven pairs distance() dispatches
+ * (src/distance/mod.rs:70-83), else 0. */
+int vecgpu_metric_supported(int elem_type, int metric);
+
+/* ---- slab lifecycle: replaces per-row shadow::read_vector (src/shadow.rs:721-740)
+ *      + get_all_rowids (src/shadow.rs:853-868) as the scan's data source ---- */
+
+int vecgpu_slab_create(int elem_type, uint32_t dims, uint64_t capacity_hint, int device, vecgpu_slab** out);
+void vecgpu_slab_destroy(vecgpu_slab* slab);
+
+/* Bulk (re)load: replaces the slab contents with n rows.  `rowids` must be
+ * strictly ascending (the order of "SELECT rowid FROM _data ORDER BY rowid",
+ * src/shadow.rs:856) or NULL for dense 1..n.  `vectors` is row-major with
+ * vecgpu_row_bytes() bytes per row, host memory. */
+int vecgpu_slab_load(vecgpu_slab* slab, const int64_t* rowids, const void* vectors, uint64_t n);
+
+/* Append n more rows whose rowids are all greater than every rowid already in
+ * the slab (bulk staging in pieces).  rowids NULL => continue densely. */
+int vecgpu_slab_append(vecgpu_slab* slab, const int64_t* rowids, const void* vectors, uint64_t n);
+
+/* Hooks for Vec0Tab::insert / update / delete (src/vtab.rs:1409, 1684, 1326).
+ * nbytes != vecgpu_row_bytes() marks the row as "skipped by scans", which is
+ * what brute_force_search does with empty / wrong-length blobs
+ * (src/vtab.rs:2596-2613).  Deleting an absent rowid is not an error. */
+int vecgpu_slab_upsert(vecgpu_slab* slab, int64_t rowid, const void* vec, uint32_t nbytes);
+int vecgpu_slab_delete(vecgpu_slab* slab, int64_t rowid);
+
+/* rows = stored rows including skipped/tombstoned; live = rows scans visit. */
+int vecgpu_slab_count(vecgpu_slab* slab, uint64_t* rows, uint64_t* live);
+/* Copy one row back (debug / tests).  *found = 0 if absent or skipped. */
+int vecgpu_slab_get(vecgpu_slab* slab, int64_t rowid, void* out_vec, int* found);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* Exact KNN: replaces the body of brute_force_search (src/vtab.rs:2586-2622)
+ * for nq queries at once.  Order of results per query is (distance_f32, rowid)
+ * ascending == the reference's stable sort over ascending rowids
+ * (src/vtab.rs:2619-2620).  out_counts[q] = min(k, live rows); result slots
+ * past out_counts[q] are filled with rowid -1 / distance +inf.
+ * `queries`: nq rows of vecgpu_row_bytes() bytes, host memory.
+ * Errors: unsupported (type, metric) pair -> VECGPU_ERR_UNSUPPORTED exactly
+ * like src/distance/mod.rs:78-82. */
+int vecgpu_knn(vecgpu_slab* slab, const void* queries, uint32_t nq, uint32_t k, int metric,
+               int64_t* out_rowids, float* out_dists, uint32_t* out_counts);
+
+/* Candidate scoring: replaces the neighbour loop of search_layer
+ * (src/hnsw/search.rs:501-513, and the entry-point distance :385-389) for nq
+ * queries with CSR candidate lists: candidates of query q are
+ * cand_rowids[cand_offsets[q] .. cand_offsets[q+1]).  out_dists has
+ * cand_offsets[nq] entries; a rowid that is absent or skipped yields NaN. */
+int vecgpu_score(vecgpu_slab* slab, const void* queries, uint32_t nq, const int64_t* cand_rowids,
+                 const uint32_t* cand_offsets, int metric, float* out_dists);
+
+/* n independent pairs a[i] vs b[i] (host memory, row-major): replaces
+ * distance::distance (src/distance/mod.rs:52-84) for the vec_distance_* SQL
+ * functions (src/sql_functions.rs:153-215).  dims_a != dims_b ->
+ * VECGPU_ERR_DIM_MISMATCH, type mismatch is inexpressible here by design. */
+int vecgpu_distance_pairs(int elem_type, uint32_t dims_a, uint32_t dims_b, const void* a, const void* b, uint64_t n,
+                          int metric, int device, float* out_dists);
+
+/* ---- producers (src/vector.rs:444-608), on device, host in / host out ---- */
+
+/* normalize: out = v / sqrtf(sum v^2) per row; a zero row -> VECGPU_ERR_INVALID_PARAM
+ * (src/vector.rs:444-466). */
+int vecgpu_normalize_f32(const float* in, uint64_t n, uint32_t dims, int device, float* out);
+/* quantize_int8: per-vector min/max -> [-128,127] (src/vector.rs:514-545). */
+int vecgpu_quantize_int8(const float* in, uint64_t n, uint32_t dims, int device, int8_t* out);
+/* quantize_int8_for_index: clamp(v,-1,1)*127 rounded (src/vector.rs:554-575). */
+int vecgpu_quantize_int8_for_index(const float* in, uint64_t n, uint32_t dims, int device, int8_t* out);
+/* quantize_binary: bit = v >= mean, LSB-first (src/vector.rs:579-608). */
+int vecgpu_quantize_binary(const float* in, uint64_t n, uint32_t dims, int device, uint8_t* out);
+
+/* ---- device-resident variants (bench `value`, multi-GPU shards) ---------
+ * Pointers prefixed d_ are device pointers on the slab's device; `stream` is a
+ * cudaStream_t passed as void* (NULL = the slab's own stream).  These calls
+ * only enqueue work; the caller synchronises. */
+
+/* Make the slab hold n rows with dense rowids first_rowid.. generated on the
+ * device by the counter-based generator value(seed, rowid, j) that
+ * oracle/vecgpu_oracle.c restates, so the CPU can regenerate any row. */
+int vecgpu_slab_fill_synthetic(vecgpu_slab* slab, uint64_t seed, int64_t first_rowid, uint64_t n, int kind);
+/* Device addresses of the slab arrays (vectors: rows * row_stride bytes). */
+int vecgpu_slab_device_view(vecgpu_slab* slab, void** d_vectors, uint32_t* row_stride, uint64_t* rows);
+
+/* Same computation as vecgpu_knn, queries and results in device memory.
+ * d_out_rowids / d_out_dists: nq*k, padded with INT64_MAX / +inf. */
+int vecgpu_knn_device(vecgpu_slab* slab, const void* d_queries, uint32_t nq, uint32_t k, int metric,
+                      int64_t* d_out_rowids, float* d_out_dists, void* stream);
+
+/* k-way merge of `nlists` per-shard result lists (as produced by
+ * vecgpu_knn_device and gathered from the other GPUs): for each of nq queries
+ * the inputs are d_rowids/d_dists[list][q][k]; output is the global top-k in
+ * (distance, rowid) order.  Replaces nothing in the reference (it is single
+ * process); it is the exchange step of SURVEY §8e. */
+int vecgpu_merge_device(int device, const int64_t* d_rowids, const float* d_dists, uint32_t nlists, uint32_t nq,
+                        uint32_t k, int64_t* d_out_rowids, float* d_out_dists, void* stream);
+
+/* Number of kernels this library has launched in this process (bench's
+ * gpu_launches claim). */
+uint64_t vecgpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VECGPU_H */

@@ -1,0 +1,69 @@
+"""ctypes binding of libvecgpu.so (include/vecgpu.h).  Loading fails loudly:
+there is no Python / CPU fallback for any compute entry point."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvecgpu.so")
+
+F32, I8, BIT = 0, 1, 2
+L2, L1, COSINE, HAMMING = 0, 1, 2, 3
+OK, ERR_INVALID_PARAM, ERR_DIM_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3, 4
+SYNTH_UNIFORM, SYNTH_GAUSS4 = 0, 1
+
+_c_slab = C.c_void_p
+_p = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/vecgpu.h declares
+SIGNATURES = {
+    "vecgpu_last_error": (C.c_char_p, []),
+    "vecgpu_version": (C.c_char_p, []),
+    "vecgpu_device_count": (C.c_int, []),
+    "vecgpu_row_bytes": (C.c_uint32, [C.c_int, C.c_uint32]),
+    "vecgpu_metric_supported": (C.c_int, [C.c_int, C.c_int]),
+    "vecgpu_slab_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_c_slab)]),
+    "vecgpu_slab_destroy": (None, [_c_slab]),
+    "vecgpu_slab_load": (C.c_int, [_c_slab, _p, _p, C.c_uint64]),
+    "vecgpu_slab_append": (C.c_int, [_c_slab, _p, _p, C.c_uint64]),
+    "vecgpu_slab_upsert": (C.c_int, [_c_slab, C.c_int64, _p, C.c_uint32]),
+    "vecgpu_slab_delete": (C.c_int, [_c_slab, C.c_int64]),
+    "vecgpu_slab_count": (C.c_int, [_c_slab, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vecgpu_slab_get": (C.c_int, [_c_slab, C.c_int64, _p, C.POINTER(C.c_int)]),
+    "vecgpu_knn": (C.c_int, [_c_slab, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
+    "vecgpu_score": (C.c_int, [_c_slab, _p, C.c_uint32, _p, _p, C.c_int, _p]),
+    "vecgpu_distance_pairs": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _p, _p, C.c_uint64, C.c_int, C.c_int, _p]),
+    "vecgpu_normalize_f32": (C.c_int, [_p, C.c_uint64, C.c_uint32, C.c_int, _p]),
+    "vecgpu_quantize_int8": (C.c_int, [_p, C.c_uint64, C.c_uint32, C.c_int, _p]),
+    "vecgpu_quantize_int8_for_index": (C.c_int, [_p, C.c_uint64, C.c_uint32, C.c_int, _p]),
+    "vecgpu_quantize_binary": (C.c_int, [_p, C.c_uint64, C.c_uint32, C.c_int, _p]),
+    "vecgpu_slab_fill_synthetic": (C.c_int, [_c_slab, C.c_uint64, C.c_int64, C.c_uint64, C.c_int]),
+    "vecgpu_slab_device_view": (C.c_int, [_c_slab, C.POINTER(_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "vecgpu_knn_device": (C.c_int, [_c_slab, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
+    "vecgpu_merge_device": (C.c_int, [C.c_int, _p, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _p, _p]),
+    "vecgpu_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load libvecgpu.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C sqlite-vec-hnsw_b200/csrc).  There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().vecgpu_last_error().decode("utf-8", "replace")

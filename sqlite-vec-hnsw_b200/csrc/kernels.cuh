@@ -1,0 +1,1031 @@
+// kernels.cuh — sm_100a device code of libvecgpu.so.
+//
+// Replaces, on the GPU, the arithmetic of src/distance/scalar.rs:12-112 (7
+// distance functions), the scan + sort + truncate of brute_force_search
+// (src/vtab.rs:2594-2620) and the neighbour-scoring loop of search_layer
+// (src/hnsw/search.rs:501-513) of the reference.  Not a translation: the
+// reference scores one pair per call through simsimd behind one SQLite lookup
+// per row; here a persistent grid streams the HBM-resident slab through shared
+// memory with bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on
+// mbarriers, scores QB queries per pass in a fixed ("canonical") accumulation
+// order and keeps a fused per-warp top-k, so no distance array is written.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vg {
+
+// ---------------------------------------------------------------------------
+// ranking keys: (order_bits(d_f32) << 32) | row position.  u64 '<' on keys ==
+// (distance_f32, rowid) ascending because slab rows are stored in ascending
+// rowid order (src/shadow.rs:856 order; stable sort of src/vtab.rs:2619).
+// NaN ranks after +inf.
+// ---------------------------------------------------------------------------
+static constexpr uint64_t KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
+
+__host__ __device__ __forceinline__ uint32_t order_bits(float d) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(d);
+#else
+    uint32_t u;
+    memcpy(&u, &d, 4);
+#endif
+    if (d != d) return 0xFFFFFFFFu;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float order_bits_inv(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    if (k == 0xFFFFFFFFu) u = 0x7FC00000u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t pos) {
+    return ((uint64_t)order_bits(d) << 32) | (uint64_t)pos;
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, no tensor map).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// metric traits.  A "unit" is 16 bytes of a row.  LPR lanes cooperate on one
+// row; lane g of the group handles units g, g+LPR, g+2*LPR, ... in increasing
+// order.  For f32 L2/cosine LPR=4 and the lane's 4 accumulators are canonical
+// lanes 4g..4g+3 of SURVEY §A.4 (element i -> lane i%16), reduced with the
+// i<->i+8, i<->i+4, i<->i+2, i<->i+1 tree; for f32 L1 LPR=1 (strict order,
+// src/distance/scalar.rs:31-35); integer metrics are order-free.
+// QC = per-query constant computed once (|q|^2).
+// ---------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum_f(float v);
+template <>
+__device__ __forceinline__ float group_sum_f<4>(float v) {  // unused generic helper
+    v = v + __shfl_xor_sync(0xffffffffu, v, 2);
+    v = v + __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// canonical tree over the 16 lanes held as 4 lanes x 4 accumulators
+__device__ __forceinline__ float canon_tree(float a0, float a1, float a2, float a3) {
+    a0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, 2));  // l[i] + l[i+8]
+    a1 = __fadd_rn(a1, __shfl_xor_sync(0xffffffffu, a1, 2));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, 2));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(0xffffffffu, a3, 2));
+    a0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, 1));  // + l[i+4]
+    a1 = __fadd_rn(a1, __shfl_xor_sync(0xffffffffu, a1, 1));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, 1));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(0xffffffffu, a3, 1));
+    return __fadd_rn(__fadd_rn(a0, a2), __fadd_rn(a1, a3));    // (l0+l2)+(l1+l3)
+}
+__device__ __forceinline__ int group4_sum_i(int v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// cosine finish in f64 with IEEE sqrt/div
+__device__ __forceinline__ float cos_finish(double ab, double a2, double b2) {
+    if (a2 == 0.0 && b2 == 0.0) return 0.0f;
+    if (ab == 0.0) return 1.0f;
+    double r = __dsub_rn(1.0, __ddiv_rn(ab, __dmul_rn(__dsqrt_rn(a2), __dsqrt_rn(b2))));
+    return __double2float_rn(r > 0.0 ? r : 0.0);
+}
+
+struct QCNone {};
+
+template <int QB>
+struct F32L2 {
+    static constexpr int LPR = 4;
+    using QC = QCNone;
+    struct Acc {
+        float s[QB][4];
+    };
+    __device__ static void init(Acc& a) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.s[q][e] = 0.0f;
+    }
+    __device__ static void qc_unit(float (&qa)[4], uint4) {}
+    __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
+        const float xf[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const float qf[4] = {__uint_as_float(q[i].x), __uint_as_float(q[i].y), __uint_as_float(q[i].z),
+                                 __uint_as_float(q[i].w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t = __fsub_rn(qf[e], xf[e]);
+                a.s[i][e] = __fmaf_rn(t, t, a.s[i][e]);
+            }
+        }
+    }
+    // returns the distance of query i; all lanes of the group get the same value
+    __device__ static float finish(const Acc& a, int i, const float*) {
+        float s = canon_tree(a.s[i][0], a.s[i][1], a.s[i][2], a.s[i][3]);
+        return __fsqrt_rn(s);  // src/distance/scalar.rs:20: (s as f32).sqrt()
+    }
+    static constexpr bool HAS_QC = false;
+};
+
+template <int QB>
+struct F32Cos {
+    static constexpr int LPR = 4;
+    struct Acc {
+        float b2[4];
+        float ab[QB][4];
+    };
+    __device__ static void init(Acc& a) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a.b2[e] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < QB; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.ab[q][e] = 0.0f;
+    }
+    __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
+        const float xf[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a.b2[e] = __fmaf_rn(xf[e], xf[e], a.b2[e]);
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const float qf[4] = {__uint_as_float(q[i].x), __uint_as_float(q[i].y), __uint_as_float(q[i].z),
+                                 __uint_as_float(q[i].w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.ab[i][e] = __fmaf_rn(qf[e], xf[e], a.ab[i][e]);
+        }
+    }
+    __device__ static float finish(const Acc& a, int i, const float* qc) {
+        float b2 = canon_tree(a.b2[0], a.b2[1], a.b2[2], a.b2[3]);
+        float ab = canon_tree(a.ab[i][0], a.ab[i][1], a.ab[i][2], a.ab[i][3]);
+        return cos_finish((double)ab, (double)qc[i], (double)b2);
+    }
+    static constexpr bool HAS_QC = true;
+};
+
+template <int QB>
+struct F32L1 {
+    static constexpr int LPR = 1;
+    struct Acc {
+        float s[QB];
+    };
+    __device__ static void init(Acc& a) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) a.s[q] = 0.0f;
+    }
+    __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
+        const float xf[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const float qf[4] = {__uint_as_float(q[i].x), __uint_as_float(q[i].y), __uint_as_float(q[i].z),
+                                 __uint_as_float(q[i].w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.s[i] = __fadd_rn(a.s[i], fabsf(__fsub_rn(qf[e], xf[e])));
+        }
+    }
+    __device__ static float finish(const Acc& a, int i, const float*) { return a.s[i]; }
+    static constexpr bool HAS_QC = false;
+};
+
+// int8: exact int32 partial sums by dp4a; |q|^2 arrives as a float-encoded pair in qc (hi/lo split not
+// needed: we pass it as int via __float_as_int).
+template <int QB, bool COS>
+struct I8Dot {
+    static constexpr int LPR = 4;
+    struct Acc {
+        int bb;
+        int ab[QB];
+    };
+    __device__ static void init(Acc& a) {
+        a.bb = 0;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) a.ab[q] = 0;
+    }
+    __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
+        const int xw[4] = {(int)x.x, (int)x.y, (int)x.z, (int)x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a.bb = __dp4a(xw[e], xw[e], a.bb);
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const int qw[4] = {(int)q[i].x, (int)q[i].y, (int)q[i].z, (int)q[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.ab[i] = __dp4a(qw[e], xw[e], a.ab[i]);
+        }
+    }
+    __device__ static float finish(const Acc& a, int i, const float* qc) {
+        long long bb = group4_sum_i(a.bb);
+        long long ab = group4_sum_i(a.ab[i]);
+        long long a2 = (long long)__float_as_int(qc[i]);
+        if (COS) return cos_finish((double)ab, (double)a2, (double)bb);
+        long long s = a2 + bb - 2 * ab;  // == sum (a-b)^2 exactly
+        // src/distance/scalar.rs:65: distance.sqrt() as f32  (f64 sqrt, then cast)
+        return __double2float_rn(__dsqrt_rn((double)s));
+    }
+    static constexpr bool HAS_QC = true;
+};
+
+__device__ __forceinline__ unsigned absdiff_s8x4(unsigned a, unsigned b) {
+    // per-byte |a-b| for signed bytes, as unsigned bytes 0..255
+    unsigned mx = __vmaxs4(a, b), mn = __vmins4(a, b);
+    return __vsub4(mx, mn);
+}
+
+template <int QB>
+struct I8L1 {
+    static constexpr int LPR = 4;
+    struct Acc {
+        int s[QB];
+    };
+    __device__ static void init(Acc& a) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) a.s[q] = 0;
+    }
+    __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
+        const unsigned xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const unsigned qw[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.s[i] = (int)__dp4a(absdiff_s8x4(qw[e], xw[e]), 0x01010101u, (unsigned)a.s[i]);
+        }
+    }
+    __device__ static float finish(const Acc& a, int i, const float*) { return (float)group4_sum_i(a.s[i]); }
+    static constexpr bool HAS_QC = false;
+};
+
+template <int QB>
+struct BitHamming {
+    static constexpr int LPR = 4;
+    struct Acc {
+        int s[QB];
+    };
+    __device__ static void init(Acc& a) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) a.s[q] = 0;
+    }
+    __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
+#pragma unroll
+        for (int i = 0; i < QB; ++i)
+            a.s[i] += __popc(x.x ^ q[i].x) + __popc(x.y ^ q[i].y) + __popc(x.z ^ q[i].z) + __popc(x.w ^ q[i].w);
+    }
+    __device__ static float finish(const Acc& a, int i, const float*) { return (float)group4_sum_i(a.s[i]); }
+    static constexpr bool HAS_QC = false;
+};
+
+// |q|^2 of one query in the representation finish() expects; executed by one
+// 4-lane group (lanes 0..3 of a warp) over a zero-padded query in shared or
+// global memory.  kind: 0 = f32 canonical sum of squares, 1 = int8 exact.
+__device__ __forceinline__ float query_const(const uint4* q, uint32_t units, int g, int kind) {
+    if (kind == 0) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (uint32_t u = g; u < units; u += 4) {
+            uint4 v = q[u];
+            const float f[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a[e] = __fmaf_rn(f[e], f[e], a[e]);
+        }
+        return canon_tree(a[0], a[1], a[2], a[3]);
+    } else {
+        int s = 0;
+        for (uint32_t u = g; u < units; u += 4) {
+            uint4 v = q[u];
+            s = __dp4a((int)v.x, (int)v.x, s);
+            s = __dp4a((int)v.y, (int)v.y, s);
+            s = __dp4a((int)v.z, (int)v.z, s);
+            s = __dp4a((int)v.w, (int)v.w, s);
+        }
+        return __int_as_float(group4_sum_i(s));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per-warp top-k list in shared memory: unsorted buffer of K keys + tracked
+// maximum.  All lanes call with warp-uniform arguments.
+// ---------------------------------------------------------------------------
+struct ListHdr {
+    uint64_t tau;     // current admission bound: max key in list when full, else KEY_NONE
+    uint32_t maxpos;  // position of tau in list when full
+    uint32_t cnt;
+};
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void list_refresh_max(uint64_t* list, ListHdr* hdr, uint32_t K, int lane) {
+    uint64_t best = 0;
+    uint32_t bpos = 0;
+    for (uint32_t i = lane; i < K; i += 32) {
+        uint64_t v = list[i];
+        if (v >= best) {
+            best = v;
+            bpos = i;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        uint64_t ob = shfl_xor_u64(best, m);
+        uint32_t op = __shfl_xor_sync(0xffffffffu, bpos, m);
+        if (ob > best || (ob == best && op > bpos)) {
+            best = ob;
+            bpos = op;
+        }
+    }
+    if (lane == 0) {
+        hdr->tau = best;
+        hdr->maxpos = bpos;
+    }
+    __syncwarp();
+}
+
+// insert a key known to be < hdr->tau (or list not yet full)
+__device__ __forceinline__ void list_insert(uint64_t* list, ListHdr* hdr, uint32_t K, uint64_t key, int lane) {
+    uint32_t cnt = hdr->cnt;
+    __syncwarp();
+    if (cnt < K) {
+        if (lane == 0) {
+            list[cnt] = key;
+            hdr->cnt = cnt + 1;
+        }
+        __syncwarp();
+        if (cnt + 1 == K) list_refresh_max(list, hdr, K, lane);
+    } else {
+        if (lane == 0) list[hdr->maxpos] = key;
+        __syncwarp();
+        list_refresh_max(list, hdr, K, lane);
+    }
+}
+
+// offer the keys held by the lanes in `mask` (one key per lane) to the list
+__device__ __forceinline__ void list_offer(uint64_t* list, ListHdr* hdr, uint32_t K, uint64_t key, bool want, int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, want && key < hdr->tau);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        uint64_t kq = shfl_u64(key, src);
+        if (kq < hdr->tau) list_insert(list, hdr, K, kq, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1/K3/K4 (+K2a when QB>1): the streaming scan.
+// ---------------------------------------------------------------------------
+struct ScanParams {
+    const uint8_t* vectors;  // slab rows, row_stride bytes apart, zero padded
+    const uint8_t* skip;     // per-row flags (non-zero = skipped by scans) or nullptr
+    const uint8_t* queries;  // nq_total rows of row_stride bytes, zero padded (device)
+    uint64_t* out_keys;      // TOPK: [nq_total][gridDim.x][k] ; EMIT: [nq_total][n_rows]
+    uint64_t n_rows;
+    uint32_t nq_total;
+    uint32_t k;
+    uint32_t row_stride;       // bytes, multiple of 16
+    uint32_t chunk_bytes;      // multiple of 64 (or == row_stride)
+    uint32_t n_chunks;
+    uint32_t smem_row_stride;  // bytes between rows of a stage in shared memory
+    uint32_t rows_per_stage;   // R = RPW * C * m   (m == 1 when n_chunks > 1)
+    uint32_t n_stages;
+    uint32_t contig;           // 1: a stage is one contiguous bulk copy (smem_row_stride == row_stride)
+    uint32_t n_consumers;      // C consumer warps; warp C is the producer
+    uint32_t qc_kind;          // 0 f32 sum of squares, 1 int8
+};
+
+template <class T, int QB, bool EMIT>
+__global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
+    constexpr int LPR = T::LPR;
+    constexpr int RPW = 32 / LPR;  // rows a warp scores at once
+    extern __shared__ __align__(128) uint8_t smem[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t C = p.n_consumers, S = p.n_stages, R = p.rows_per_stage;
+    const uint32_t stage_bytes = R * p.smem_row_stride;
+    // layout: [stages][queries QB*row_stride][qc QB floats, padded to 64][hdr C*QB][lists C*QB*k][barriers 2*S]
+    uint8_t* s_stage = smem;
+    uint8_t* s_query = s_stage + (size_t)S * stage_bytes;
+    float* s_qc = (float*)(s_query + (size_t)QB * p.row_stride);
+    ListHdr* s_hdr = (ListHdr*)((uint8_t*)s_qc + 64);
+    uint64_t* s_list = (uint64_t*)(s_hdr + C * QB);
+    uint64_t* s_bar = s_list + (EMIT ? 0 : (size_t)C * QB * p.k);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + S);
+
+    const uint32_t q0 = blockIdx.y * QB;  // first query of this pass
+    const uint32_t nq_here = min((uint32_t)QB, p.nq_total - q0);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, C);
+        }
+        mbar_fence_init();
+    }
+    // stage queries (zero-fill the slots past nq_here so the arithmetic stays finite)
+    {
+        const uint32_t qunits = p.row_stride / 16;
+        const uint4* gq = (const uint4*)(p.queries + (size_t)q0 * p.row_stride);
+        uint4* sq = (uint4*)s_query;
+        for (uint32_t i = threadIdx.x; i < QB * qunits; i += blockDim.x)
+            sq[i] = (i / qunits) < nq_here ? gq[i] : make_uint4(0, 0, 0, 0);
+        if (!EMIT)
+            for (uint32_t i = threadIdx.x; i < C * QB; i += blockDim.x) {
+                s_hdr[i].tau = KEY_NONE;
+                s_hdr[i].maxpos = 0;
+                s_hdr[i].cnt = 0;
+            }
+    }
+    __syncthreads();
+    if (T::HAS_QC) {
+        // warp w computes |q|^2 for queries w, w+nwarps, ... with its lanes 0..3
+        const uint32_t qunits = p.row_stride / 16;
+        for (uint32_t i = warp; i < QB; i += (blockDim.x >> 5)) {
+            float v = query_const((const uint4*)(s_query + (size_t)i * p.row_stride), qunits, lane & 3, p.qc_kind);
+            if (lane == 0) s_qc[i] = v;
+        }
+        __syncthreads();
+    }
+
+    const uint64_t n_tiles = (p.n_rows + R - 1) / R;
+
+    if ((uint32_t)warp == C) {
+        // ================= producer warp: bulk copies global -> shared =================
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint64_t row0 = tile * R;
+            const uint32_t valid = (uint32_t)min((uint64_t)R, p.n_rows - row0);
+            for (uint32_t c = 0; c < p.n_chunks; ++c, ++it) {
+                const uint32_t s = it % S, ph = (it / S) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                const uint32_t dst0 = smem_u32(s_stage + (size_t)s * stage_bytes);
+                if (p.contig) {
+                    if (lane == 0) {
+                        // a stage is at most ~200 KB, so `bytes` fits both the tx-count and the copy size
+                        const uint32_t bytes = valid * p.row_stride;
+                        mbar_expect_tx(bar_full + 8 * s, bytes);
+                        bulk_g2s(dst0, p.vectors + row0 * p.row_stride, bytes, bar_full + 8 * s);
+                    }
+                } else {
+                    const uint32_t off = c * p.chunk_bytes;
+                    const uint32_t len = min(p.chunk_bytes, p.row_stride - off);
+                    if (lane == 0) mbar_expect_tx(bar_full + 8 * s, valid * len);
+                    __syncwarp();
+                    for (uint32_t r = lane; r < valid; r += 32)
+                        bulk_g2s(dst0 + r * p.smem_row_stride, p.vectors + (row0 + r) * p.row_stride + off, len,
+                                 bar_full + 8 * s);
+                }
+            }
+        }
+    } else if ((uint32_t)warp < C) {
+        // ================= consumer warps =================
+        const int g = lane % LPR;
+        const int rl = lane / LPR;
+        const uint32_t m_steps = R / (RPW * C);
+        uint64_t* my_list = EMIT ? nullptr : s_list + (size_t)warp * QB * p.k;
+        ListHdr* my_hdr = s_hdr + warp * QB;
+        const uint32_t q_base = smem_u32(s_query);
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint64_t row0 = tile * R;
+            const uint32_t it0 = it;
+            for (uint32_t ms = 0; ms < m_steps; ++ms) {
+                const uint32_t r_in_stage = (ms * C + warp) * RPW + rl;
+                typename T::Acc acc;
+                T::init(acc);
+                it = it0;
+                for (uint32_t c = 0; c < p.n_chunks; ++c, ++it) {
+                    const uint32_t s = it % S, ph = (it / S) & 1;
+                    if (ms == 0) mbar_wait(bar_full + 8 * s, ph);
+                    const uint32_t off = p.contig ? 0 : c * p.chunk_bytes;
+                    const uint32_t len = p.contig ? p.row_stride : min(p.chunk_bytes, p.row_stride - off);
+                    const uint32_t units = len / 16;
+                    const uint32_t xb =
+                        smem_u32(s_stage + (size_t)s * stage_bytes) + r_in_stage * p.smem_row_stride + g * 16;
+                    const uint32_t qb = q_base + off + g * 16;
+                    uint32_t u = g;
+                    // 4 units in flight per lane
+                    for (; u + 3 * LPR < units; u += 4 * LPR) {
+                        const uint32_t o = (u - g) * 16;
+                        uint4 x0 = lds128(xb + o), x1 = lds128(xb + o + LPR * 16), x2 = lds128(xb + o + 2 * LPR * 16),
+                              x3 = lds128(xb + o + 3 * LPR * 16);
+                        uint4 qv[QB];
+#pragma unroll
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o);
+                        T::step(acc, x0, qv);
+#pragma unroll
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o + LPR * 16);
+                        T::step(acc, x1, qv);
+#pragma unroll
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o + 2 * LPR * 16);
+                        T::step(acc, x2, qv);
+#pragma unroll
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o + 3 * LPR * 16);
+                        T::step(acc, x3, qv);
+                    }
+                    for (; u < units; u += LPR) {
+                        const uint32_t o = (u - g) * 16;
+                        uint4 x0 = lds128(xb + o);
+                        uint4 qv[QB];
+#pragma unroll
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o);
+                        T::step(acc, x0, qv);
+                    }
+                    if (ms == m_steps - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+                    }
+                }
+                // ---- distance -> key -> fused top-k (or emit) ----
+                const uint64_t row = row0 + r_in_stage;
+                bool live = row < p.n_rows;
+                if (live && p.skip != nullptr && g == 0) live = p.skip[row] == 0;
+#pragma unroll
+                for (int i = 0; i < QB; ++i) {
+                    float d = T::finish(acc, i, s_qc);
+                    if (EMIT) {
+                        if (g == 0 && row < p.n_rows && (uint32_t)i < nq_here)
+                            p.out_keys[(size_t)(q0 + i) * p.n_rows + row] = live ? make_key(d, (uint32_t)row) : KEY_NONE;
+                    } else {
+                        uint64_t key = make_key(d, (uint32_t)row);
+                        list_offer(my_list + (size_t)i * p.k, my_hdr + i, p.k, key, live && g == 0, lane);
+                    }
+                }
+            }
+        }
+    }
+    if (EMIT) return;
+    __syncthreads();
+    // ---- CTA merge: warp w folds the C lists of query i = w, w+C, ... into consumer 0's list ----
+    if ((uint32_t)warp < C) {
+        for (uint32_t i = warp; i < nq_here; i += C) {
+            uint64_t* dst = s_list + (size_t)i * p.k;  // consumer 0, query i
+            ListHdr* dh = s_hdr + i;
+            for (uint32_t w = 1; w < C; ++w) {
+                const uint64_t* src = s_list + ((size_t)w * QB + i) * p.k;
+                const uint32_t cnt = s_hdr[w * QB + i].cnt;
+                for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    uint64_t key = j < cnt ? src[j] : KEY_NONE;
+                    list_offer(dst, dh, p.k, key, j < cnt, lane);
+                }
+            }
+            __syncwarp();
+            uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
+            const uint32_t cnt = dh->cnt;
+            for (uint32_t j = lane; j < p.k; j += 32) out[j] = j < cnt ? dst[j] : KEY_NONE;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6: final selection + sort + decode.  One CTA per query reads `n_cand` keys
+// (per-CTA partial lists of the scan), keeps the k smallest, sorts them
+// ascending == (distance_f32, rowid) order, translates positions to rowids.
+// ---------------------------------------------------------------------------
+struct MergeParams {
+    const uint64_t* keys;  // [nq][n_cand]
+    uint64_t n_cand;
+    uint32_t k;
+    uint32_t kp2;             // next power of two >= k
+    const int64_t* rowids;    // position -> rowid, or nullptr when dense
+    int64_t first_rowid;      // dense: rowid = first_rowid + position
+    int64_t* out_rowids;      // [nq][k]
+    float* out_dists;         // [nq][k]
+    uint32_t* out_counts;     // [nq] or nullptr
+    int64_t pad_rowid;        // value for unused slots (-1 host API, INT64_MAX device API)
+};
+
+__global__ void __launch_bounds__(256) merge_kernel(const MergeParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = 8;
+    ListHdr* hdr = (ListHdr*)smem;
+    uint64_t* lists = (uint64_t*)(hdr + NW);  // NW * k
+    uint64_t* sorted = lists + (size_t)NW * p.k;  // kp2
+    const uint64_t* keys = p.keys + (size_t)blockIdx.x * p.n_cand;
+    if (threadIdx.x < NW) {
+        hdr[threadIdx.x].tau = KEY_NONE;
+        hdr[threadIdx.x].maxpos = 0;
+        hdr[threadIdx.x].cnt = 0;
+    }
+    __syncthreads();
+    uint64_t* my = lists + (size_t)warp * p.k;
+    for (uint64_t j0 = (uint64_t)warp * 32; j0 < p.n_cand; j0 += NW * 32) {
+        const uint64_t j = j0 + lane;
+        uint64_t key = j < p.n_cand ? keys[j] : KEY_NONE;
+        list_offer(my, hdr + warp, p.k, key, key != KEY_NONE, lane);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < NW; ++w) {
+            const uint64_t* src = lists + (size_t)w * p.k;
+            const uint32_t cnt = hdr[w].cnt;
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                uint64_t key = j < cnt ? src[j] : KEY_NONE;
+                list_offer(my, hdr, p.k, key, j < cnt, lane);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = hdr[0].cnt;
+    for (uint32_t j = threadIdx.x; j < p.kp2; j += blockDim.x) sorted[j] = j < cnt ? lists[j] : KEY_NONE;
+    __syncthreads();
+    // bitonic sort ascending over kp2 keys
+    for (uint32_t size = 2; size <= p.kp2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < p.kp2 / 2; t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t a = sorted[lo], b = sorted[hi];
+                if ((a > b) == up) {
+                    sorted[lo] = b;
+                    sorted[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
+        const uint64_t key = sorted[j];
+        const size_t o = (size_t)blockIdx.x * p.k + j;
+        if (key == KEY_NONE) {
+            p.out_rowids[o] = p.pad_rowid;
+            p.out_dists[o] = __int_as_float(0x7F800000);
+        } else {
+            const uint32_t pos = (uint32_t)key;
+            p.out_rowids[o] = p.rowids ? p.rowids[pos] : p.first_rowid + (int64_t)pos;
+            p.out_dists[o] = order_bits_inv((uint32_t)(key >> 32));
+        }
+    }
+    if (threadIdx.x == 0 && p.out_counts) p.out_counts[blockIdx.x] = cnt;
+}
+
+// large-k path (k > fused limit): after a full radix sort of the emitted keys
+// the first k keys of each query are decoded.
+__global__ void decode_sorted_kernel(const uint64_t* keys, uint64_t n_rows, uint32_t k, const int64_t* rowids,
+                                     int64_t first_rowid, int64_t pad_rowid, int64_t* out_rowids, float* out_dists,
+                                     uint32_t* out_count) {
+    uint32_t cnt = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += gridDim.x * blockDim.x) {
+        const uint64_t key = j < n_rows ? keys[j] : KEY_NONE;
+        if (key == KEY_NONE) {
+            out_rowids[j] = pad_rowid;
+            out_dists[j] = __int_as_float(0x7F800000);
+        } else {
+            const uint32_t pos = (uint32_t)key;
+            out_rowids[j] = rowids ? rowids[pos] : first_rowid + (int64_t)pos;
+            out_dists[j] = order_bits_inv((uint32_t)(key >> 32));
+            ++cnt;
+        }
+    }
+    if (out_count) atomicAdd(out_count, cnt);
+}
+
+// cross-shard merge input: (dist, rowid) records from G lists -> keys are not
+// usable (positions are shard-local), so rank on (order_bits(dist), rowid).
+struct XMergeParams {
+    const int64_t* rowids;  // [nlists][nq][k]
+    const float* dists;     // [nlists][nq][k]
+    uint32_t nlists, nq, k, kp2;
+    int64_t* out_rowids;  // [nq][k]
+    float* out_dists;
+};
+__global__ void __launch_bounds__(256) xmerge_kernel(const XMergeParams p) {
+    // candidates per query: nlists*k (small: G<=8 shards).  Sort all of them
+    // with a bitonic network on (order_bits, rowid) and keep the first k.
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* kb = (uint32_t*)smem;          // [np2]
+    int64_t* rid = (int64_t*)(kb + p.kp2);   // [np2]  (kp2 here = pow2 >= nlists*k, 8-byte aligned by construction)
+    const uint32_t q = blockIdx.x, n = p.nlists * p.k, np2 = p.kp2;
+    for (uint32_t j = threadIdx.x; j < np2; j += blockDim.x) {
+        if (j < n) {
+            const uint32_t l = j / p.k, i = j % p.k;
+            const size_t o = ((size_t)l * p.nq + q) * p.k + i;
+            int64_t r = p.rowids[o];
+            kb[j] = (r == INT64_MAX) ? 0xFFFFFFFFu : order_bits(p.dists[o]);
+            rid[j] = r;
+        } else {
+            kb[j] = 0xFFFFFFFFu;
+            rid[j] = INT64_MAX;
+        }
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint32_t ka = kb[lo], kc = kb[hi];
+                int64_t ra = rid[lo], rc = rid[hi];
+                bool gt = ka > kc || (ka == kc && ra > rc);
+                if (gt == up) {
+                    kb[lo] = kc;
+                    kb[hi] = ka;
+                    rid[lo] = rc;
+                    rid[hi] = ra;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
+        const size_t o = (size_t)q * p.k + j;
+        p.out_rowids[o] = rid[j];
+        p.out_dists[o] = rid[j] == INT64_MAX ? __int_as_float(0x7F800000) : order_bits_inv(kb[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: gathered pair scoring.  One LPR-lane group per (a, b) pair, operands read
+// straight from global memory with 128-bit loads.  Used by vecgpu_score (a =
+// query of the candidate, b = slab row found by rowid) and
+// vecgpu_distance_pairs (a[i], b[i]).
+// ---------------------------------------------------------------------------
+struct PairParams {
+    const uint8_t* a_base;
+    const uint8_t* b_base;
+    uint32_t a_stride, b_stride;  // bytes between rows (multiples of 16, zero padded)
+    uint32_t units;               // 16-byte units per row
+    const uint32_t* a_index;      // pair -> row of a (nullptr: pair index)
+    const int64_t* b_index;       // pair -> row of b, -1 = missing (nullptr: pair index)
+    uint64_t n_pairs;
+    float* out;
+    uint32_t qc_kind;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
+    constexpr int LPR = T::LPR;
+    constexpr int GPB = 256 / LPR;  // groups per block
+    const int lane = threadIdx.x & 31;
+    const int g = lane % LPR;
+    const uint64_t n_iter = (p.n_pairs + GPB - 1) / GPB;
+    for (uint64_t itn = blockIdx.x; itn < n_iter; itn += gridDim.x) {
+        const uint64_t pair = itn * GPB + threadIdx.x / LPR;
+        const bool in = pair < p.n_pairs;
+        int64_t bi = in ? (p.b_index ? p.b_index[pair] : (int64_t)pair) : -1;
+        const uint64_t ai = in ? (p.a_index ? p.a_index[pair] : pair) : 0;
+        const uint4* a = (const uint4*)(p.a_base + ai * p.a_stride);
+        const uint4* b = (const uint4*)(p.b_base + (bi < 0 ? 0 : bi) * (uint64_t)p.b_stride);
+        typename T::Acc acc;
+        T::init(acc);
+        float qc = 0.f;
+        if (T::HAS_QC) {
+            // all 32 lanes participate in the shuffles; groups of 4 stay aligned because LPR==4 here
+            qc = query_const(a, in ? p.units : 0, g, p.qc_kind);
+        }
+        if (in && bi >= 0) {
+            for (uint32_t u = g; u < p.units; u += LPR) {
+                uint4 x = __ldg(b + u);
+                uint4 qv[1] = {__ldg(a + u)};
+                T::step(acc, x, qv);
+            }
+        }
+        float d = T::finish(acc, 0, &qc);
+        if (in && g == 0) p.out[pair] = bi >= 0 ? d : __int_as_float(0x7FC00000);
+    }
+}
+
+// rowid -> position (binary search over the ascending rowid array, or dense
+// arithmetic) and pair -> query index from the CSR offsets; skipped rows -> -1.
+__global__ void resolve_kernel(const int64_t* cand_rowids, uint64_t n_pairs, const uint32_t* offsets, uint32_t nq,
+                               const int64_t* rowids, uint64_t n_rows, int64_t first_rowid, const uint8_t* skip,
+                               uint32_t* out_q, int64_t* out_pos) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        // query of pair i: last q with offsets[q] <= i
+        uint32_t lo = 0, hi = nq;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (offsets[mid] <= i) lo = mid; else hi = mid;
+        }
+        out_q[i] = lo;
+        const int64_t r = cand_rowids[i];
+        int64_t pos = -1;
+        if (rowids == nullptr) {
+            // dense: guard the subtraction against overflow
+            if (r >= first_rowid && (uint64_t)(r - first_rowid) < n_rows) pos = r - first_rowid;
+        } else {
+            uint64_t a = 0, b = n_rows;
+            while (a < b) {
+                uint64_t mid = (a + b) >> 1;
+                if (rowids[mid] < r) a = mid + 1; else b = mid;
+            }
+            if (a < n_rows && rowids[a] == r) pos = (int64_t)a;
+        }
+        if (pos >= 0 && skip && skip[pos]) pos = -1;
+        out_pos[i] = pos;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K7 producers — src/vector.rs:444-608, bit-for-bit (IEEE ops, no contraction)
+// ---------------------------------------------------------------------------
+// normalize (vector.rs:444-466): strict left-to-right f32 sum of x*x.  One thread per row.
+__global__ void normalize_kernel(const float* in, uint64_t n, uint32_t d, float* out, int* zero_flag) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const float* v = in + r * d;
+        float s = 0.f;
+        for (uint32_t i = 0; i < d; ++i) s = __fadd_rn(s, __fmul_rn(v[i], v[i]));
+        float m = __fsqrt_rn(s);
+        if (m == 0.f) {
+            atomicExch(zero_flag, 1);
+            for (uint32_t i = 0; i < d; ++i) out[r * d + i] = v[i];
+        } else {
+            for (uint32_t i = 0; i < d; ++i) out[r * d + i] = __fdiv_rn(v[i], m);
+        }
+    }
+}
+
+__device__ __forceinline__ int8_t quant_i8(float v, float mn, float range) {
+    float normalized = __fdiv_rn(__fsub_rn(v, mn), range);
+    float scaled = __fsub_rn(__fmul_rn(normalized, 255.0f), 128.0f);
+    float r = roundf(scaled);  // half away from zero == Rust f32::round
+    r = r < -128.0f ? -128.0f : (r > 127.0f ? 127.0f : r);
+    return (int8_t)r;
+}
+
+// quantize_int8 (vector.rs:514-545): one warp per row
+__global__ void quantize_int8_kernel(const float* in, uint64_t n, uint32_t d, int8_t* out, uint32_t out_stride) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = w0; r < n; r += nw) {
+        const float* v = in + r * d;
+        float mn = __int_as_float(0x7F800000), mx = __int_as_float(0xFF800000);
+        for (uint32_t i = lane; i < d; i += 32) {
+            mn = fminf(mn, v[i]);
+            mx = fmaxf(mx, v[i]);
+        }
+        for (int m = 16; m >= 1; m >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        }
+        int8_t* o = out + r * out_stride;
+        if (mn == mx) {
+            for (uint32_t i = lane; i < d; i += 32) o[i] = 0;
+        } else {
+            const float range = __fsub_rn(mx, mn);
+            for (uint32_t i = lane; i < d; i += 32) o[i] = quant_i8(v[i], mn, range);
+        }
+    }
+}
+
+// quantize_int8_for_index (vector.rs:554-575)
+__global__ void quantize_index_kernel(const float* in, uint64_t total, int8_t* out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        float v = in[i];
+        float c = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);
+        out[i] = (int8_t)roundf(__fmul_rn(c, 127.0f));
+    }
+}
+
+// quantize_binary (vector.rs:579-608): strict-order mean, one thread per row
+__global__ void quantize_binary_kernel(const float* in, uint64_t n, uint32_t d, uint8_t* out) {
+    const uint32_t nb = (d + 7) / 8;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const float* v = in + r * d;
+        float s = 0.f;
+        for (uint32_t i = 0; i < d; ++i) s = __fadd_rn(s, v[i]);
+        const float mean = __fdiv_rn(s, (float)d);
+        for (uint32_t b = 0; b < nb; ++b) {
+            uint32_t byte = 0;
+            for (uint32_t j = 0; j < 8 && b * 8 + j < d; ++j)
+                if (v[b * 8 + j] >= mean) byte |= 1u << j;
+            out[r * nb + b] = (uint8_t)byte;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// synthetic corpus generator value(seed, rowid, word) of SURVEY §8d (the CPU checker restates it)
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t synth_word(uint64_t seed, int64_t rowid, uint32_t w) {
+    uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)rowid);
+    return mix64(h + 0xD1B54A32D192ED03ull * (uint64_t)(w + 1));
+}
+__device__ __forceinline__ float synth_f32(uint64_t seed, int64_t rowid, uint32_t j, int kind) {
+    if (kind == 1) {
+        uint64_t h = synth_word(seed, rowid, j);
+        int s = (int)(h & 0xFFFF) + (int)((h >> 16) & 0xFFFF) + (int)((h >> 32) & 0xFFFF) + (int)((h >> 48) & 0xFFFF) -
+                131070;
+        return __fmul_rn((float)s, 0x1p-15f);
+    }
+    uint64_t h = synth_word(seed, rowid, j >> 1);
+    uint32_t u = (j & 1) ? (uint32_t)(h >> 32) : (uint32_t)h;
+    return __fsub_rn(__fmul_rn((float)(u >> 8), 0x1p-23f), 1.0f);
+}
+
+// f32 rows: one thread per element, row_stride/4 floats per stored row (padding written as 0)
+__global__ void synth_f32_kernel(float* out, uint32_t stride_f, uint32_t d, uint64_t n, uint64_t seed,
+                                 int64_t first_rowid, int kind) {
+    const uint64_t total = n * stride_f;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / stride_f;
+        const uint32_t j = (uint32_t)(i - r * stride_f);
+        out[i] = j < d ? synth_f32(seed, first_rowid + (int64_t)r, j, kind) : 0.f;
+    }
+}
+
+// i8 rows: quantize_int8(uniform f32 row); one warp per row
+__global__ void synth_i8_kernel(int8_t* out, uint32_t stride, uint32_t d, uint64_t n, uint64_t seed, int64_t first_rowid) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = w0; r < n; r += nw) {
+        const int64_t rowid = first_rowid + (int64_t)r;
+        float mn = __int_as_float(0x7F800000), mx = __int_as_float(0xFF800000);
+        for (uint32_t i = lane; i < d; i += 32) {
+            float v = synth_f32(seed, rowid, i, 0);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+        for (int m = 16; m >= 1; m >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        }
+        int8_t* o = out + r * stride;
+        const float range = __fsub_rn(mx, mn);
+        for (uint32_t i = lane; i < stride; i += 32) {
+            int8_t q = 0;
+            if (i < d && mn != mx) q = quant_i8(synth_f32(seed, rowid, i, 0), mn, range);
+            o[i] = q;
+        }
+    }
+}
+
+// bit rows: one thread per 8-byte word of the stored row
+__global__ void synth_bit_kernel(uint8_t* out, uint32_t stride, uint32_t d, uint64_t n, uint64_t seed, int64_t first_rowid) {
+    const uint32_t wpr = stride / 8;  // stride is a multiple of 16
+    const uint64_t total = n * wpr;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / wpr;
+        const uint32_t w = (uint32_t)(i - r * wpr);
+        uint64_t h = synth_word(seed, first_rowid + (int64_t)r, w);
+        const uint64_t bit0 = (uint64_t)w * 64;
+        if (bit0 >= d) h = 0;
+        else if (d - bit0 < 64) h &= (1ull << (d - bit0)) - 1ull;
+        ((uint64_t*)out)[i] = h;
+    }
+}
+
+// pad-copy: host-layout rows (src_bytes each) -> slab rows (row_stride each, zero padded)
+__global__ void pad_rows_kernel(const uint8_t* src, uint32_t src_bytes, uint8_t* dst, uint32_t dst_stride, uint64_t n) {
+    const uint64_t total = n * dst_stride;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / dst_stride;
+        const uint32_t b = (uint32_t)(i - r * dst_stride);
+        dst[i] = b < src_bytes ? src[r * src_bytes + b] : 0;
+    }
+}
+
+}  // namespace vg

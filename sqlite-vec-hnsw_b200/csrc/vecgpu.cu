@@ -1,0 +1,1055 @@
+// vecgpu.cu — C ABI (include/vecgpu.h) + slab management + launch planning.
+// Host side of libvecgpu.so.  See kernels.cuh for the device code.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/vecgpu.h"
+#include "kernels.cuh"
+
+using namespace vg;
+
+// ---------------------------------------------------------------------------
+// errors: Result<T, Error> of src/error.rs:5-36 becomes (code, thread-local text)
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(VECGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                         \
+    } while (0)
+
+#define LAUNCHED()                                                                                               \
+    do {                                                                                                         \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                                      \
+        cudaError_t e_ = cudaGetLastError();                                                                     \
+        if (e_ != cudaSuccess)                                                                                   \
+            return fail(VECGPU_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                               \
+    } while (0)
+
+static constexpr uint32_t K_FUSED_MAX = 1024;     // above this knn uses emit + radix sort
+static constexpr uint32_t DIMS_MAX = 65536;       // keeps int8 partial sums inside int32
+static constexpr size_t SMEM_MAX = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+// ---------------------------------------------------------------------------
+// slab
+// ---------------------------------------------------------------------------
+struct vecgpu_slab {
+    int elem = 0, device = 0, num_sms = 148;
+    uint32_t dims = 0, row_bytes = 0, row_stride = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // rows, ascending rowid order
+    uint8_t* d_vec = nullptr;
+    uint64_t cap = 0, rows = 0;
+    // rowids: dense (first_rowid + position) until a gap appears, then explicit arrays
+    bool dense = true;
+    int64_t first_rowid = 1;
+    std::vector<int64_t> h_rowids;
+    int64_t* d_rowids = nullptr;
+    uint64_t cap_rowids = 0;
+    // skip flags (tombstones / wrong-length blobs), allocated on first use
+    std::vector<uint8_t> h_skip;
+    uint8_t* d_skip = nullptr;
+    uint64_t cap_skip = 0, n_skip = 0;
+    // workspaces
+    void* d_ws[8] = {nullptr};
+    size_t ws_cap[8] = {0};
+    void* h_pin[2] = {nullptr};
+    size_t pin_cap[2] = {0};
+};
+
+enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7 };
+
+static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
+    if (bytes <= s->ws_cap[i]) return 0;
+    if (s->d_ws[i]) CU(cudaFree(s->d_ws[i]));
+    s->d_ws[i] = nullptr;
+    s->ws_cap[i] = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CU(cudaMalloc(&s->d_ws[i], want));
+    s->ws_cap[i] = want;
+    return 0;
+}
+static int pin_reserve(vecgpu_slab* s, int i, size_t bytes) {
+    if (bytes <= s->pin_cap[i]) return 0;
+    if (s->h_pin[i]) CU(cudaFreeHost(s->h_pin[i]));
+    s->h_pin[i] = nullptr;
+    s->pin_cap[i] = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    CU(cudaMallocHost(&s->h_pin[i], want));
+    s->pin_cap[i] = want;
+    return 0;
+}
+
+static int grow_dev(void** p, uint64_t* cap_items, uint64_t used_items, uint64_t want_items, size_t item_bytes,
+                    cudaStream_t st) {
+    if (want_items <= *cap_items) return 0;
+    void* np = nullptr;
+    CU(cudaMalloc(&np, (size_t)want_items * item_bytes));
+    if (*p && used_items) CU(cudaMemcpyAsync(np, *p, (size_t)used_items * item_bytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    if (*p) CU(cudaFree(*p));
+    *p = np;
+    *cap_items = want_items;
+    return 0;
+}
+
+static int slab_reserve_rows(vecgpu_slab* s, uint64_t want) {
+    if (want <= s->cap) return 0;
+    if (want >= 0xFFFFFFFFull) return fail(VECGPU_ERR_INVALID_PARAM, "a slab holds at most 2^32-2 rows");
+    uint64_t ncap = std::max<uint64_t>(want, s->cap + s->cap / 2);
+    if (s->cap == 0) ncap = want;
+    int rc = grow_dev((void**)&s->d_vec, &s->cap, s->rows, ncap, s->row_stride, s->stream);
+    if (rc) return rc;
+    return 0;
+}
+
+static int slab_sync_rowids(vecgpu_slab* s) {  // upload host rowid mirror (non-dense mode)
+    if (s->dense) return 0;
+    if (s->h_rowids.size() > s->cap_rowids) {
+        if (s->d_rowids) CU(cudaFree(s->d_rowids));
+        s->d_rowids = nullptr;
+        s->cap_rowids = std::max<uint64_t>(s->h_rowids.size(), s->cap);
+        CU(cudaMalloc((void**)&s->d_rowids, s->cap_rowids * sizeof(int64_t)));
+    }
+    if (!s->h_rowids.empty())
+        CU(cudaMemcpy(s->d_rowids, s->h_rowids.data(), s->h_rowids.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int slab_sync_skip(vecgpu_slab* s) {  // upload the whole skip mirror
+    if (s->h_skip.empty()) return 0;
+    if (s->h_skip.size() > s->cap_skip) {
+        if (s->d_skip) CU(cudaFree(s->d_skip));
+        s->d_skip = nullptr;
+        s->cap_skip = std::max<uint64_t>(s->h_skip.size(), s->cap);
+        CU(cudaMalloc((void**)&s->d_skip, s->cap_skip));
+    }
+    CU(cudaMemcpy(s->d_skip, s->h_skip.data(), s->h_skip.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static void slab_materialize_rowids(vecgpu_slab* s) {
+    if (!s->dense) return;
+    s->h_rowids.resize(s->rows);
+    for (uint64_t i = 0; i < s->rows; ++i) s->h_rowids[i] = s->first_rowid + (int64_t)i;
+    s->dense = false;
+}
+
+static int64_t slab_last_rowid(const vecgpu_slab* s) {
+    if (s->rows == 0) return INT64_MIN;
+    return s->dense ? s->first_rowid + (int64_t)s->rows - 1 : s->h_rowids.back();
+}
+
+// position of rowid, or -1; *ins = insertion point when absent
+static int64_t slab_find(const vecgpu_slab* s, int64_t rowid, uint64_t* ins) {
+    if (s->dense) {
+        if (s->rows && rowid >= s->first_rowid && (uint64_t)(rowid - s->first_rowid) < s->rows)
+            return rowid - s->first_rowid;
+        if (ins) *ins = (s->rows == 0 || rowid > slab_last_rowid(s)) ? s->rows : 0;
+        return -1;
+    }
+    auto it = std::lower_bound(s->h_rowids.begin(), s->h_rowids.end(), rowid);
+    if (ins) *ins = (uint64_t)(it - s->h_rowids.begin());
+    if (it != s->h_rowids.end() && *it == rowid) return (int64_t)(it - s->h_rowids.begin());
+    return -1;
+}
+
+static int slab_set_skip(vecgpu_slab* s, uint64_t pos, uint8_t v) {
+    if (s->h_skip.size() < s->rows) s->h_skip.resize(s->rows, 0);
+    if (s->h_skip[pos] == v) return 0;
+    s->h_skip[pos] = v;
+    if (v) ++s->n_skip; else --s->n_skip;
+    if (s->cap_skip < s->h_skip.size() || !s->d_skip) return slab_sync_skip(s);
+    CU(cudaMemcpy(s->d_skip + pos, &s->h_skip[pos], 1, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// copy n host rows (row_bytes each) into slab rows [pos, pos+n)
+static int slab_write_rows(vecgpu_slab* s, uint64_t pos, const void* vectors, uint64_t n) {
+    if (n == 0) return 0;
+    uint8_t* dst = s->d_vec + pos * s->row_stride;
+    if (s->row_bytes == s->row_stride) {
+        CU(cudaMemcpy(dst, vectors, (size_t)n * s->row_bytes, cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemsetAsync(dst, 0, (size_t)n * s->row_stride, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaMemcpy2D(dst, s->row_stride, vectors, s->row_bytes, s->row_bytes, (size_t)n, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* vecgpu_last_error(void) { return g_err; }
+const char* vecgpu_version(void) { return "vecgpu 0.1.0 sm_100a"; }
+uint64_t vecgpu_launch_count(void) { return g_launches.load(); }
+
+int vecgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint32_t vecgpu_row_bytes(int elem, uint32_t dims) {
+    switch (elem) {
+        case VECGPU_F32: return dims * 4u;
+        case VECGPU_I8: return dims;
+        case VECGPU_BIT: return (dims + 7u) / 8u;
+        default: return 0;
+    }
+}
+
+int vecgpu_metric_supported(int elem, int metric) {
+    if (elem == VECGPU_F32 || elem == VECGPU_I8)
+        return metric == VECGPU_L2 || metric == VECGPU_L1 || metric == VECGPU_COSINE;
+    if (elem == VECGPU_BIT) return metric == VECGPU_HAMMING;
+    return 0;
+}
+
+}  // extern "C"
+
+static int check_pair(int elem, int metric) {
+    if (elem < 0 || elem > 2) return fail(VECGPU_ERR_UNSUPPORTED, "invalid vector type %d", elem);
+    if (metric < 0 || metric > 3) return fail(VECGPU_ERR_INVALID_PARAM, "invalid distance metric %d", metric);
+    if (!vecgpu_metric_supported(elem, metric)) {
+        static const char* mn[] = {"L2", "L1", "Cosine", "Hamming"};
+        static const char* en[] = {"Float32", "Int8", "Bit"};
+        // wording follows src/distance/mod.rs:78-82
+        return fail(VECGPU_ERR_UNSUPPORTED, "Distance metric %s not supported for vector type %s", mn[metric], en[elem]);
+    }
+    return 0;
+}
+
+static int use_device(int device) {
+    int n = vecgpu_device_count();
+    if (n <= 0) return fail(VECGPU_ERR_CUDA, "no CUDA device is available (libvecgpu has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(VECGPU_ERR_INVALID_PARAM, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int vecgpu_slab_create(int elem, uint32_t dims, uint64_t capacity_hint, int device, vecgpu_slab** out) {
+    if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "out is NULL");
+    *out = nullptr;
+    if (elem < 0 || elem > 2) return fail(VECGPU_ERR_UNSUPPORTED, "invalid vector type %d", elem);
+    if (dims == 0 || dims > DIMS_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "dims must be in 1..%u", DIMS_MAX);
+    int rc = use_device(device);
+    if (rc) return rc;
+    vecgpu_slab* s = new (std::nothrow) vecgpu_slab();
+    if (!s) return fail(VECGPU_ERR_CUDA, "out of host memory");
+    s->elem = elem;
+    s->device = device;
+    s->dims = dims;
+    s->row_bytes = vecgpu_row_bytes(elem, dims);
+    s->row_stride = (s->row_bytes + 15u) & ~15u;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete s;
+        return fail(VECGPU_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (capacity_hint) {
+        rc = slab_reserve_rows(s, capacity_hint);
+        if (rc) {
+            cudaStreamDestroy(s->stream);
+            delete s;
+            return rc;
+        }
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" void vecgpu_slab_destroy(vecgpu_slab* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_vec);
+    cudaFree(s->d_rowids);
+    cudaFree(s->d_skip);
+    for (int i = 0; i < 8; ++i) cudaFree(s->d_ws[i]);
+    for (int i = 0; i < 2; ++i)
+        if (s->h_pin[i]) cudaFreeHost(s->h_pin[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+}
+
+static int slab_append_locked(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
+    if (n == 0) return 0;
+    if (!vectors) return fail(VECGPU_ERR_INVALID_PARAM, "vectors is NULL");
+    const int64_t last = slab_last_rowid(s);
+    if (rowids) {
+        if (s->rows && rowids[0] <= last)
+            return fail(VECGPU_ERR_INVALID_PARAM, "appended rowids must be greater than the slab's last rowid");
+        for (uint64_t i = 1; i < n; ++i)
+            if (rowids[i] <= rowids[i - 1]) return fail(VECGPU_ERR_INVALID_PARAM, "rowids must be strictly ascending");
+    } else if (s->rows && last == INT64_MAX) {
+        return fail(VECGPU_ERR_INVALID_PARAM, "rowid overflow");
+    }
+    int rc = slab_reserve_rows(s, s->rows + n);
+    if (rc) return rc;
+    // still dense?
+    bool stays_dense = s->dense;
+    if (s->dense && rowids) {
+        const int64_t expect0 = s->rows ? last + 1 : rowids[0];
+        for (uint64_t i = 0; i < n && stays_dense; ++i) stays_dense = rowids[i] == expect0 + (int64_t)i;
+    }
+    if (s->dense && !stays_dense) slab_materialize_rowids(s);
+    if (s->dense) {
+        if (s->rows == 0) s->first_rowid = rowids ? rowids[0] : 1;
+    } else {
+        const int64_t start = s->rows ? last + 1 : 1;
+        for (uint64_t i = 0; i < n; ++i) s->h_rowids.push_back(rowids ? rowids[i] : start + (int64_t)i);
+    }
+    rc = slab_write_rows(s, s->rows, vectors, n);
+    if (rc) return rc;
+    s->rows += n;
+    if (!s->h_skip.empty()) {
+        s->h_skip.resize(s->rows, 0);
+        rc = slab_sync_skip(s);
+        if (rc) return rc;
+    }
+    return slab_sync_rowids(s);
+}
+
+extern "C" int vecgpu_slab_append(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    return slab_append_locked(s, rowids, vectors, n);
+}
+
+extern "C" int vecgpu_slab_load(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    s->rows = 0;
+    s->dense = true;
+    s->first_rowid = 1;
+    s->h_rowids.clear();
+    s->h_skip.clear();
+    s->n_skip = 0;
+    return slab_append_locked(s, rowids, vectors, n);
+}
+
+extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec, uint32_t nbytes) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    const bool good = vec != nullptr && nbytes == s->row_bytes;
+    uint64_t ins = 0;
+    int64_t pos = slab_find(s, rowid, &ins);
+    if (pos >= 0) {
+        if (good) {
+            rc = slab_write_rows(s, (uint64_t)pos, vec, 1);
+            if (rc) return rc;
+            if (!s->h_skip.empty()) return slab_set_skip(s, (uint64_t)pos, 0);
+            return 0;
+        }
+        return slab_set_skip(s, (uint64_t)pos, 1);
+    }
+    std::vector<uint8_t> zero;
+    const void* src = vec;
+    if (!good) {
+        zero.assign(s->row_bytes, 0);
+        src = zero.data();
+    }
+    if (s->rows == 0 || rowid > slab_last_rowid(s)) {
+        rc = slab_append_locked(s, &rowid, src, 1);
+        if (rc) return rc;
+        if (!good) return slab_set_skip(s, s->rows - 1, 1);
+        return 0;
+    }
+    // out-of-order insert (rare: explicit rowid below MAX): shift the tail by one row
+    slab_materialize_rowids(s);
+    slab_find(s, rowid, &ins);
+    rc = slab_reserve_rows(s, s->rows + 1);
+    if (rc) return rc;
+    const uint64_t tail = s->rows - ins;
+    if (tail) {
+        rc = ws_reserve(s, WS_TMP, (size_t)tail * s->row_stride);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_vec + ins * s->row_stride, (size_t)tail * s->row_stride,
+                           cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_vec + (ins + 1) * s->row_stride, s->d_ws[WS_TMP], (size_t)tail * s->row_stride,
+                           cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    s->h_rowids.insert(s->h_rowids.begin() + (ptrdiff_t)ins, rowid);
+    if (!s->h_skip.empty()) {
+        s->h_skip.resize(s->rows, 0);
+        s->h_skip.insert(s->h_skip.begin() + (ptrdiff_t)ins, 0);
+    }
+    s->rows += 1;
+    rc = slab_write_rows(s, ins, src, 1);
+    if (rc) return rc;
+    rc = slab_sync_rowids(s);
+    if (rc) return rc;
+    rc = slab_sync_skip(s);
+    if (rc) return rc;
+    if (!good) return slab_set_skip(s, ins, 1);
+    return 0;
+}
+
+extern "C" int vecgpu_slab_delete(vecgpu_slab* s, int64_t rowid) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    int64_t pos = slab_find(s, rowid, nullptr);
+    if (pos < 0) return 0;
+    return slab_set_skip(s, (uint64_t)pos, 1);
+}
+
+extern "C" int vecgpu_slab_count(vecgpu_slab* s, uint64_t* rows, uint64_t* live) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (rows) *rows = s->rows;
+    if (live) *live = s->rows - s->n_skip;
+    return 0;
+}
+
+extern "C" int vecgpu_slab_get(vecgpu_slab* s, int64_t rowid, void* out_vec, int* found) {
+    if (!s || !found) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    *found = 0;
+    int64_t pos = slab_find(s, rowid, nullptr);
+    if (pos < 0 || (!s->h_skip.empty() && s->h_skip[(size_t)pos])) return 0;
+    if (out_vec) CU(cudaMemcpy(out_vec, s->d_vec + (uint64_t)pos * s->row_stride, s->row_bytes, cudaMemcpyDeviceToHost));
+    *found = 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// scan planning
+// ---------------------------------------------------------------------------
+struct ScanCfg {
+    uint32_t C, QB, R, CB, n_chunks, srs, S, contig;
+    size_t smem;
+};
+
+static size_t scan_fixed_smem(uint32_t C, uint32_t QB, uint32_t row_stride, uint32_t k, bool emit) {
+    return (size_t)QB * row_stride + 64 + (size_t)C * QB * sizeof(ListHdr) + (emit ? 0 : (size_t)C * QB * k * 8) +
+           2 * 16 * 8 + 128;
+}
+
+static int plan_scan(int lpr, uint32_t row_stride, uint32_t k, uint32_t nq, bool emit, ScanCfg& c) {
+    const uint32_t RPW = 32 / lpr;
+    c.C = std::min(8u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", 4)));
+    c.QB = emit ? 1 : (nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1);
+    const uint32_t qb_cap = env_u32("VECGPU_SCAN_QB", 8);
+    while (c.QB > 1 && c.QB > qb_cap) c.QB >>= 1;
+    // keep lists + queries under ~1/3 of shared memory
+    while (c.QB > 1 && scan_fixed_smem(c.C, c.QB, row_stride, k, emit) > SMEM_MAX / 3) c.QB >>= 1;
+    while (c.C > 1 && scan_fixed_smem(c.C, c.QB, row_stride, k, emit) > SMEM_MAX / 2) c.C >>= 1;
+    const size_t fixed = scan_fixed_smem(c.C, c.QB, row_stride, k, emit);
+    if (fixed + 2 * 16 * RPW > SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "row too wide for the scan kernel");
+    const size_t avail = SMEM_MAX - fixed;
+    const uint32_t rows_min = RPW * c.C;
+    const uint32_t stage_target = env_u32("VECGPU_SCAN_STAGE_KB", 32) * 1024;
+
+    const bool conflict_free_contig = lpr == 4 ? (row_stride % 128 == 64) : ((row_stride / 16) % 2 == 1);
+    if (row_stride <= 1024 && (conflict_free_contig || row_stride < 256) && (size_t)rows_min * row_stride * 2 <= avail) {
+        c.contig = 1;
+        c.CB = row_stride;
+        c.n_chunks = 1;
+        c.srs = row_stride;
+        uint32_t m = std::max(1u, stage_target / (rows_min * row_stride));
+        while (m > 1 && (size_t)m * rows_min * row_stride * 3 > avail) --m;
+        c.R = rows_min * m;
+    } else {
+        c.contig = 0;
+        // chunk limit so that >= 3 stages fit
+        uint32_t cb_limit = (uint32_t)(avail / 3 / rows_min);
+        cb_limit = cb_limit > 128 ? ((cb_limit - 64) / 64) * 64 : 64;
+        uint32_t cb_target = std::min(std::max(64u, (env_u32("VECGPU_SCAN_CB", 2048) / 64) * 64), cb_limit);
+        if (row_stride <= cb_target) {
+            c.n_chunks = 1;
+            c.CB = row_stride;
+        } else {
+            c.n_chunks = (row_stride + cb_target - 1) / cb_target;
+            c.CB = (((row_stride + c.n_chunks - 1) / c.n_chunks) + 63) / 64 * 64;
+            c.n_chunks = (row_stride + c.CB - 1) / c.CB;
+        }
+        uint32_t pad;
+        if (lpr == 4) pad = (64 + 128 - (c.CB % 128)) % 128;
+        else pad = ((c.CB / 16) % 2 == 0) ? 16 : 0;
+        c.srs = c.CB + pad;
+        uint32_t m = 1;
+        if (c.n_chunks == 1) {
+            m = std::max(1u, stage_target / (rows_min * c.srs));
+            while (m > 1 && (size_t)m * rows_min * c.srs * 3 > avail) --m;
+        }
+        c.R = rows_min * m;
+    }
+    const size_t stage = (size_t)c.R * c.srs;
+    c.S = (uint32_t)std::min<size_t>(16, avail / stage);
+    const uint32_t s_cap = env_u32("VECGPU_SCAN_STAGES", 16);
+    if (c.S > s_cap && s_cap >= 2) c.S = s_cap;
+    if (c.S < 2) return fail(VECGPU_ERR_INVALID_PARAM, "scan plan does not fit shared memory (row_stride=%u k=%u)", row_stride, k);
+    c.smem = (size_t)c.S * stage + fixed;
+    return 0;
+}
+
+template <class T, int QB, bool EMIT>
+static int launch_scan_inst(const ScanParams& p, const ScanCfg& c, dim3 grid, cudaStream_t st) {
+    static int configured_for_device = -1;  // per instantiation; attribute is per device
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (configured_for_device != dev) {
+        CU(cudaFuncSetAttribute(scan_kernel<T, QB, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        configured_for_device = dev;
+    }
+    scan_kernel<T, QB, EMIT><<<grid, 32 * (c.C + 1), c.smem, st>>>(p);
+    LAUNCHED();
+    return 0;
+}
+
+template <template <int> class TT>
+static int launch_scan_qb(const ScanParams& p, const ScanCfg& c, bool emit, dim3 grid, cudaStream_t st) {
+    if (emit) return launch_scan_inst<TT<1>, 1, true>(p, c, grid, st);
+    switch (c.QB) {
+        case 1: return launch_scan_inst<TT<1>, 1, false>(p, c, grid, st);
+        case 2: return launch_scan_inst<TT<2>, 2, false>(p, c, grid, st);
+        case 4: return launch_scan_inst<TT<4>, 4, false>(p, c, grid, st);
+        default: return launch_scan_inst<TT<8>, 8, false>(p, c, grid, st);
+    }
+}
+
+template <int QB> using I8L2T = I8Dot<QB, false>;
+template <int QB> using I8CosT = I8Dot<QB, true>;
+
+static int metric_lpr(int elem, int metric) { return (elem == VECGPU_F32 && metric == VECGPU_L1) ? 1 : 4; }
+static uint32_t metric_qc_kind(int elem) { return elem == VECGPU_I8 ? 1u : 0u; }
+
+static int launch_scan(int elem, int metric, const ScanParams& p, const ScanCfg& c, bool emit, dim3 grid, cudaStream_t st) {
+    if (elem == VECGPU_F32) {
+        if (metric == VECGPU_L2) return launch_scan_qb<F32L2>(p, c, emit, grid, st);
+        if (metric == VECGPU_L1) return launch_scan_qb<F32L1>(p, c, emit, grid, st);
+        return launch_scan_qb<F32Cos>(p, c, emit, grid, st);
+    }
+    if (elem == VECGPU_I8) {
+        if (metric == VECGPU_L2) return launch_scan_qb<I8L2T>(p, c, emit, grid, st);
+        if (metric == VECGPU_L1) return launch_scan_qb<I8L1>(p, c, emit, grid, st);
+        return launch_scan_qb<I8CosT>(p, c, emit, grid, st);
+    }
+    return launch_scan_qb<BitHamming>(p, c, emit, grid, st);
+}
+
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int launch_merge(const MergeParams& mp, uint32_t nq, cudaStream_t st) {
+    const size_t smem = 8 * sizeof(ListHdr) + (size_t)8 * mp.k * 8 + (size_t)mp.kp2 * 8;
+    static int configured_for_device = -1;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (configured_for_device != dev) {
+        CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured_for_device = dev;
+    }
+    merge_kernel<<<nq, 256, smem, st>>>(mp);
+    LAUNCHED();
+    return 0;
+}
+
+// queries already on the device, padded to row_stride.  Results to device arrays.
+static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
+                    float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
+    int rc;
+    if (k == 0 || nq == 0) return 0;
+    const uint8_t* d_skip = s->n_skip ? s->d_skip : nullptr;
+    const int64_t* d_rowids = s->dense ? nullptr : s->d_rowids;
+    if (s->rows == 0) {
+        // nothing to scan: all slots are padding
+        MergeParams mp{};
+        rc = ws_reserve(s, WS_PART, 8);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(s->d_ws[WS_PART], 0xFF, 8, st));
+        mp.keys = (const uint64_t*)s->d_ws[WS_PART];
+        mp.n_cand = 0;
+        mp.k = std::min(k, K_FUSED_MAX);
+        mp.kp2 = next_pow2(mp.k);
+        mp.rowids = nullptr;
+        mp.first_rowid = 0;
+        mp.pad_rowid = pad_rowid;
+        // k may exceed the fused limit: fill by chunks of query-major rows is overkill; do it with memset-like kernel
+        if (k <= K_FUSED_MAX) {
+            mp.out_rowids = d_out_rowids;
+            mp.out_dists = d_out_dists;
+            mp.out_counts = d_out_counts;
+            return launch_merge(mp, nq, st);
+        }
+        for (uint32_t q = 0; q < nq; ++q) {
+            decode_sorted_kernel<<<64, 256, 0, st>>>((const uint64_t*)s->d_ws[WS_PART], 0, k, nullptr, 0, pad_rowid,
+                                                     d_out_rowids + (size_t)q * k, d_out_dists + (size_t)q * k, nullptr);
+            LAUNCHED();
+        }
+        if (d_out_counts) CU(cudaMemsetAsync(d_out_counts, 0, nq * sizeof(uint32_t), st));
+        return 0;
+    }
+    const int lpr = metric_lpr(s->elem, metric);
+    ScanParams p{};
+    p.vectors = s->d_vec;
+    p.skip = d_skip;
+    p.queries = d_q;
+    p.n_rows = s->rows;
+    p.nq_total = nq;
+    p.row_stride = s->row_stride;
+    p.qc_kind = metric_qc_kind(s->elem);
+
+    if (k <= K_FUSED_MAX) {
+        ScanCfg c;
+        rc = plan_scan(lpr, s->row_stride, k, nq, false, c);
+        if (rc) return rc;
+        const uint64_t n_tiles = (s->rows + c.R - 1) / c.R;
+        const uint32_t gx = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)s->num_sms);
+        const uint32_t gy = (nq + c.QB - 1) / c.QB;
+        rc = ws_reserve(s, WS_PART, (size_t)nq * gx * k * 8);
+        if (rc) return rc;
+        p.out_keys = (uint64_t*)s->d_ws[WS_PART];
+        p.k = k;
+        p.chunk_bytes = c.CB;
+        p.n_chunks = c.n_chunks;
+        p.smem_row_stride = c.srs;
+        p.rows_per_stage = c.R;
+        p.n_stages = c.S;
+        p.contig = c.contig;
+        p.n_consumers = c.C;
+        rc = launch_scan(s->elem, metric, p, c, false, dim3(gx, gy), st);
+        if (rc) return rc;
+        MergeParams mp{};
+        mp.keys = p.out_keys;
+        mp.n_cand = (uint64_t)gx * k;
+        mp.k = k;
+        mp.kp2 = next_pow2(k);
+        mp.rowids = d_rowids;
+        mp.first_rowid = s->first_rowid;
+        mp.out_rowids = d_out_rowids;
+        mp.out_dists = d_out_dists;
+        mp.out_counts = d_out_counts;
+        mp.pad_rowid = pad_rowid;
+        return launch_merge(mp, nq, st);
+    }
+
+    // ---- large k: emit one key per row, radix sort, decode the first k ----
+    ScanCfg c;
+    rc = plan_scan(lpr, s->row_stride, 1, 1, true, c);
+    if (rc) return rc;
+    const uint64_t n_tiles = (s->rows + c.R - 1) / c.R;
+    const uint32_t gx = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)s->num_sms);
+    rc = ws_reserve(s, WS_TMP, (size_t)s->rows * 8);
+    if (rc) return rc;
+    rc = ws_reserve(s, WS_TMP2, (size_t)s->rows * 8);
+    if (rc) return rc;
+    size_t sort_bytes = 0;
+    cub::DoubleBuffer<uint64_t> db((uint64_t*)s->d_ws[WS_TMP], (uint64_t*)s->d_ws[WS_TMP2]);
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, db, (int)s->rows, 0, 64, st));
+    rc = ws_reserve(s, WS_TMP3, sort_bytes);
+    if (rc) return rc;
+    if (d_out_counts) CU(cudaMemsetAsync(d_out_counts, 0, nq * sizeof(uint32_t), st));
+    p.k = 1;
+    p.chunk_bytes = c.CB;
+    p.n_chunks = c.n_chunks;
+    p.smem_row_stride = c.srs;
+    p.rows_per_stage = c.R;
+    p.n_stages = c.S;
+    p.contig = c.contig;
+    p.n_consumers = c.C;
+    p.nq_total = 1;
+    for (uint32_t q = 0; q < nq; ++q) {
+        cub::DoubleBuffer<uint64_t> dbq((uint64_t*)s->d_ws[WS_TMP], (uint64_t*)s->d_ws[WS_TMP2]);
+        p.queries = d_q + (size_t)q * s->row_stride;
+        p.out_keys = dbq.Current();
+        rc = launch_scan(s->elem, metric, p, c, true, dim3(gx, 1), st);
+        if (rc) return rc;
+        CU(cub::DeviceRadixSort::SortKeys(s->d_ws[WS_TMP3], sort_bytes, dbq, (int)s->rows, 0, 64, st));
+        g_launches.fetch_add(8, std::memory_order_relaxed);
+        decode_sorted_kernel<<<256, 256, 0, st>>>(dbq.Current(), s->rows, k, d_rowids, s->first_rowid, pad_rowid,
+                                                  d_out_rowids + (size_t)q * k, d_out_dists + (size_t)q * k,
+                                                  d_out_counts ? d_out_counts + q : nullptr);
+        LAUNCHED();
+    }
+    return 0;
+}
+
+// stage nq host queries (row_bytes each) into the slab's padded device query buffer
+static int stage_queries(vecgpu_slab* s, const void* queries, uint32_t nq) {
+    const size_t bytes = (size_t)nq * s->row_stride;
+    int rc = pin_reserve(s, 0, bytes);
+    if (rc) return rc;
+    rc = ws_reserve(s, WS_QUERY, bytes);
+    if (rc) return rc;
+    uint8_t* h = (uint8_t*)s->h_pin[0];
+    if (s->row_bytes == s->row_stride) {
+        memcpy(h, queries, bytes);
+    } else {
+        memset(h, 0, bytes);
+        for (uint32_t q = 0; q < nq; ++q)
+            memcpy(h + (size_t)q * s->row_stride, (const uint8_t*)queries + (size_t)q * s->row_bytes, s->row_bytes);
+    }
+    CU(cudaMemcpyAsync(s->d_ws[WS_QUERY], h, bytes, cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+extern "C" int vecgpu_knn(vecgpu_slab* s, const void* queries, uint32_t nq, uint32_t k, int metric, int64_t* out_rowids,
+                          float* out_dists, uint32_t* out_counts) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    int rc = check_pair(s->elem, metric);
+    if (rc) return rc;
+    if (nq == 0 || k == 0) {
+        if (out_counts)
+            for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+        return 0;
+    }
+    if (!queries || !out_rowids || !out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    rc = use_device(s->device);
+    if (rc) return rc;
+    const size_t n_out = (size_t)nq * k;
+    rc = stage_queries(s, queries, nq);
+    if (rc) return rc;
+    if ((rc = ws_reserve(s, WS_OUT_ROWID, n_out * 8))) return rc;
+    if ((rc = ws_reserve(s, WS_OUT_DIST, n_out * 4))) return rc;
+    if ((rc = ws_reserve(s, WS_OUT_CNT, (size_t)nq * 4))) return rc;
+    rc = knn_core(s, (const uint8_t*)s->d_ws[WS_QUERY], nq, k, metric, (int64_t*)s->d_ws[WS_OUT_ROWID],
+                  (float*)s->d_ws[WS_OUT_DIST], (uint32_t*)s->d_ws[WS_OUT_CNT], -1, s->stream);
+    if (rc) return rc;
+    // results come back through pinned memory, then into the caller's buffers
+    const size_t pin_bytes = n_out * 12 + (size_t)nq * 4;
+    if ((rc = pin_reserve(s, 1, pin_bytes))) return rc;
+    uint8_t* h = (uint8_t*)s->h_pin[1];
+    CU(cudaMemcpyAsync(h, s->d_ws[WS_OUT_ROWID], n_out * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h + n_out * 8, s->d_ws[WS_OUT_DIST], n_out * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(h + n_out * 12, s->d_ws[WS_OUT_CNT], (size_t)nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(out_rowids, h, n_out * 8);
+    memcpy(out_dists, h + n_out * 8, n_out * 4);
+    if (out_counts) memcpy(out_counts, h + n_out * 12, (size_t)nq * 4);
+    return 0;
+}
+
+extern "C" int vecgpu_knn_device(vecgpu_slab* s, const void* d_queries, uint32_t nq, uint32_t k, int metric,
+                                 int64_t* d_out_rowids, float* d_out_dists, void* stream) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    int rc = check_pair(s->elem, metric);
+    if (rc) return rc;
+    if (nq == 0 || k == 0) return 0;
+    if (!d_queries || !d_out_rowids || !d_out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    rc = use_device(s->device);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const uint8_t* dq = (const uint8_t*)d_queries;
+    if (s->row_bytes != s->row_stride) {
+        rc = ws_reserve(s, WS_QUERY, (size_t)nq * s->row_stride);
+        if (rc) return rc;
+        pad_rows_kernel<<<std::min<uint32_t>(1024, (nq * s->row_stride + 255) / 256), 256, 0, st>>>(
+            dq, s->row_bytes, (uint8_t*)s->d_ws[WS_QUERY], s->row_stride, nq);
+        LAUNCHED();
+        dq = (const uint8_t*)s->d_ws[WS_QUERY];
+    }
+    return knn_core(s, dq, nq, k, metric, d_out_rowids, d_out_dists, nullptr, INT64_MAX, st);
+}
+
+extern "C" int vecgpu_merge_device(int device, const int64_t* d_rowids, const float* d_dists, uint32_t nlists, uint32_t nq,
+                                   uint32_t k, int64_t* d_out_rowids, float* d_out_dists, void* stream) {
+    if (!d_rowids || !d_dists || !d_out_rowids || !d_out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    if (nq == 0 || k == 0 || nlists == 0) return 0;
+    int rc = use_device(device);
+    if (rc) return rc;
+    XMergeParams p{};
+    p.rowids = d_rowids;
+    p.dists = d_dists;
+    p.nlists = nlists;
+    p.nq = nq;
+    p.k = k;
+    if ((uint64_t)nlists * k > 16384) return fail(VECGPU_ERR_INVALID_PARAM, "nlists*k must be <= 16384");
+    p.kp2 = std::max(2u, next_pow2(nlists * k));
+    p.out_rowids = d_out_rowids;
+    p.out_dists = d_out_dists;
+    const size_t smem = (size_t)p.kp2 * 12;
+    CU(cudaFuncSetAttribute(xmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    xmerge_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(p);
+    LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// pair scoring
+// ---------------------------------------------------------------------------
+template <class T>
+static int launch_pairs_t(const PairParams& p, int num_sms, cudaStream_t st) {
+    const uint64_t gpb = 256 / T::LPR;
+    const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((p.n_pairs + gpb - 1) / gpb, (uint64_t)num_sms * 8));
+    pair_kernel<T><<<(uint32_t)blocks, 256, 0, st>>>(p);
+    LAUNCHED();
+    return 0;
+}
+static int launch_pairs(int elem, int metric, const PairParams& p, int num_sms, cudaStream_t st) {
+    if (elem == VECGPU_F32) {
+        if (metric == VECGPU_L2) return launch_pairs_t<F32L2<1>>(p, num_sms, st);
+        if (metric == VECGPU_L1) return launch_pairs_t<F32L1<1>>(p, num_sms, st);
+        return launch_pairs_t<F32Cos<1>>(p, num_sms, st);
+    }
+    if (elem == VECGPU_I8) {
+        if (metric == VECGPU_L2) return launch_pairs_t<I8Dot<1, false>>(p, num_sms, st);
+        if (metric == VECGPU_L1) return launch_pairs_t<I8L1<1>>(p, num_sms, st);
+        return launch_pairs_t<I8Dot<1, true>>(p, num_sms, st);
+    }
+    return launch_pairs_t<BitHamming<1>>(p, num_sms, st);
+}
+
+extern "C" int vecgpu_score(vecgpu_slab* s, const void* queries, uint32_t nq, const int64_t* cand_rowids,
+                            const uint32_t* cand_offsets, int metric, float* out_dists) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    int rc = check_pair(s->elem, metric);
+    if (rc) return rc;
+    if (nq == 0) return 0;
+    if (!queries || !cand_offsets) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    for (uint32_t q = 0; q < nq; ++q)
+        if (cand_offsets[q + 1] < cand_offsets[q]) return fail(VECGPU_ERR_INVALID_PARAM, "cand_offsets must be non-decreasing");
+    if (cand_offsets[0] != 0) return fail(VECGPU_ERR_INVALID_PARAM, "cand_offsets[0] must be 0");
+    const uint64_t np = cand_offsets[nq];
+    if (np == 0) return 0;
+    if (!cand_rowids || !out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    rc = use_device(s->device);
+    if (rc) return rc;
+    rc = stage_queries(s, queries, nq);
+    if (rc) return rc;
+    // candidates + offsets in one pinned upload: [rowids np*8][offsets (nq+1)*4]
+    const size_t up_bytes = np * 8 + (size_t)(nq + 1) * 4;
+    if ((rc = pin_reserve(s, 1, std::max(up_bytes, (size_t)np * 4)))) return rc;
+    if ((rc = ws_reserve(s, WS_TMP, up_bytes))) return rc;
+    if ((rc = ws_reserve(s, WS_TMP2, np * 12))) return rc;   // [pos np*8][qidx np*4]
+    if ((rc = ws_reserve(s, WS_OUT_DIST, np * 4))) return rc;
+    uint8_t* h = (uint8_t*)s->h_pin[1];
+    memcpy(h, cand_rowids, np * 8);
+    memcpy(h + np * 8, cand_offsets, (size_t)(nq + 1) * 4);
+    CU(cudaMemcpyAsync(s->d_ws[WS_TMP], h, up_bytes, cudaMemcpyHostToDevice, s->stream));
+    int64_t* d_pos = (int64_t*)s->d_ws[WS_TMP2];
+    uint32_t* d_qidx = (uint32_t*)((uint8_t*)s->d_ws[WS_TMP2] + np * 8);
+    const uint32_t rb = (uint32_t)std::min<uint64_t>((np + 255) / 256, 1024);
+    resolve_kernel<<<rb, 256, 0, s->stream>>>((const int64_t*)s->d_ws[WS_TMP], np,
+                                              (const uint32_t*)((uint8_t*)s->d_ws[WS_TMP] + np * 8), nq,
+                                              s->dense ? nullptr : s->d_rowids, s->rows, s->first_rowid,
+                                              s->n_skip ? s->d_skip : nullptr, d_qidx, d_pos);
+    LAUNCHED();
+    PairParams p{};
+    p.a_base = (const uint8_t*)s->d_ws[WS_QUERY];
+    p.b_base = s->d_vec;
+    p.a_stride = p.b_stride = s->row_stride;
+    p.units = s->row_stride / 16;
+    p.a_index = d_qidx;
+    p.b_index = d_pos;
+    p.n_pairs = np;
+    p.out = (float*)s->d_ws[WS_OUT_DIST];
+    p.qc_kind = metric_qc_kind(s->elem);
+    rc = launch_pairs(s->elem, metric, p, s->num_sms, s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h, s->d_ws[WS_OUT_DIST], np * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(out_dists, h, np * 4);
+    return 0;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+extern "C" int vecgpu_distance_pairs(int elem, uint32_t dims_a, uint32_t dims_b, const void* a, const void* b, uint64_t n,
+                                     int metric, int device, float* out) {
+    if (elem < 0 || elem > 2) return fail(VECGPU_ERR_UNSUPPORTED, "invalid vector type %d", elem);
+    // order of checks follows src/distance/mod.rs:57-83: dimensions, (types), then the metric match
+    if (dims_a != dims_b) return fail(VECGPU_ERR_DIM_MISMATCH, "Dimension mismatch: expected %u, got %u", dims_a, dims_b);
+    int rc = check_pair(elem, metric);
+    if (rc) return rc;
+    if (dims_a == 0 || dims_a > DIMS_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "dims must be in 1..%u", DIMS_MAX);
+    if (n == 0) return 0;
+    if (!a || !b || !out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    rc = use_device(device);
+    if (rc) return rc;
+    const uint32_t rbytes = vecgpu_row_bytes(elem, dims_a), stride = (rbytes + 15u) & ~15u;
+    DevBuf da, db, dout;
+    CU(cudaMalloc(&da.p, n * stride));
+    CU(cudaMalloc(&db.p, n * stride));
+    CU(cudaMalloc(&dout.p, n * 4));
+    if (stride == rbytes) {
+        CU(cudaMemcpy(da.p, a, n * stride, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(db.p, b, n * stride, cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemset(da.p, 0, n * stride));
+        CU(cudaMemset(db.p, 0, n * stride));
+        CU(cudaMemcpy2D(da.p, stride, a, rbytes, rbytes, n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy2D(db.p, stride, b, rbytes, rbytes, n, cudaMemcpyHostToDevice));
+    }
+    PairParams p{};
+    p.a_base = (const uint8_t*)da.p;
+    p.b_base = (const uint8_t*)db.p;
+    p.a_stride = p.b_stride = stride;
+    p.units = stride / 16;
+    p.n_pairs = n;
+    p.out = (float*)dout.p;
+    p.qc_kind = metric_qc_kind(elem);
+    rc = launch_pairs(elem, metric, p, 148, 0);
+    if (rc) return rc;
+    CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// producers
+// ---------------------------------------------------------------------------
+static int producer_common(const float* in, uint64_t n, uint32_t dims, int device, DevBuf& din) {
+    if (!in) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    if (dims == 0 || dims > DIMS_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "dims must be in 1..%u", DIMS_MAX);
+    int rc = use_device(device);
+    if (rc) return rc;
+    CU(cudaMalloc(&din.p, n * dims * 4));
+    CU(cudaMemcpy(din.p, in, n * dims * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+static uint32_t blocks_for(uint64_t threads) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((threads + 255) / 256, 148 * 16)); }
+
+extern "C" int vecgpu_normalize_f32(const float* in, uint64_t n, uint32_t dims, int device, float* out) {
+    if (n == 0) return 0;
+    if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    DevBuf din, dout, dflag;
+    int rc = producer_common(in, n, dims, device, din);
+    if (rc) return rc;
+    CU(cudaMalloc(&dout.p, n * dims * 4));
+    CU(cudaMalloc(&dflag.p, 4));
+    CU(cudaMemset(dflag.p, 0, 4));
+    normalize_kernel<<<blocks_for(n), 256>>>((const float*)din.p, n, dims, (float*)dout.p, (int*)dflag.p);
+    LAUNCHED();
+    int flag = 0;
+    CU(cudaMemcpy(&flag, dflag.p, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, dout.p, n * dims * 4, cudaMemcpyDeviceToHost));
+    if (flag) return fail(VECGPU_ERR_INVALID_PARAM, "Cannot normalize zero vector");  // src/vector.rs:451-455
+    return 0;
+}
+
+extern "C" int vecgpu_quantize_int8(const float* in, uint64_t n, uint32_t dims, int device, int8_t* out) {
+    if (n == 0) return 0;
+    if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    DevBuf din, dout;
+    int rc = producer_common(in, n, dims, device, din);
+    if (rc) return rc;
+    CU(cudaMalloc(&dout.p, n * dims));
+    quantize_int8_kernel<<<blocks_for(n * 32), 256>>>((const float*)din.p, n, dims, (int8_t*)dout.p, dims);
+    LAUNCHED();
+    CU(cudaMemcpy(out, dout.p, n * dims, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vecgpu_quantize_int8_for_index(const float* in, uint64_t n, uint32_t dims, int device, int8_t* out) {
+    if (n == 0) return 0;
+    if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    DevBuf din, dout;
+    int rc = producer_common(in, n, dims, device, din);
+    if (rc) return rc;
+    CU(cudaMalloc(&dout.p, n * dims));
+    quantize_index_kernel<<<blocks_for(n * dims), 256>>>((const float*)din.p, n * dims, (int8_t*)dout.p);
+    LAUNCHED();
+    CU(cudaMemcpy(out, dout.p, n * dims, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vecgpu_quantize_binary(const float* in, uint64_t n, uint32_t dims, int device, uint8_t* out) {
+    if (n == 0) return 0;
+    if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    DevBuf din, dout;
+    int rc = producer_common(in, n, dims, device, din);
+    if (rc) return rc;
+    const uint32_t nb = (dims + 7) / 8;
+    CU(cudaMalloc(&dout.p, n * nb));
+    quantize_binary_kernel<<<blocks_for(n), 256>>>((const float*)din.p, n, dims, (uint8_t*)dout.p);
+    LAUNCHED();
+    CU(cudaMemcpy(out, dout.p, n * nb, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// synthetic fill + device view
+// ---------------------------------------------------------------------------
+extern "C" int vecgpu_slab_fill_synthetic(vecgpu_slab* s, uint64_t seed, int64_t first_rowid, uint64_t n, int kind) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    if (kind != VECGPU_SYNTH_UNIFORM && !(kind == VECGPU_SYNTH_GAUSS4 && s->elem == VECGPU_F32))
+        return fail(VECGPU_ERR_INVALID_PARAM, "unsupported synthetic kind %d for this element type", kind);
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    s->rows = 0;
+    s->dense = true;
+    s->h_rowids.clear();
+    s->h_skip.clear();
+    s->n_skip = 0;
+    rc = slab_reserve_rows(s, n);
+    if (rc) return rc;
+    s->first_rowid = first_rowid;
+    s->rows = n;
+    if (n == 0) return 0;
+    const uint32_t grid = (uint32_t)s->num_sms * 16;
+    if (s->elem == VECGPU_F32)
+        synth_f32_kernel<<<grid, 256, 0, s->stream>>>((float*)s->d_vec, s->row_stride / 4, s->dims, n, seed, first_rowid, kind);
+    else if (s->elem == VECGPU_I8)
+        synth_i8_kernel<<<grid, 256, 0, s->stream>>>((int8_t*)s->d_vec, s->row_stride, s->dims, n, seed, first_rowid);
+    else
+        synth_bit_kernel<<<grid, 256, 0, s->stream>>>(s->d_vec, s->row_stride, s->dims, n, seed, first_rowid);
+    LAUNCHED();
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int vecgpu_slab_device_view(vecgpu_slab* s, void** d_vectors, uint32_t* row_stride, uint64_t* rows) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (d_vectors) *d_vectors = s->d_vec;
+    if (row_stride) *row_stride = s->row_stride;
+    if (rows) *rows = s->rows;
+    return 0;
+}

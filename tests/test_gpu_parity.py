@@ -1,0 +1,407 @@
+"""GPU parity: libvecgpu.so (through the C ABI / host mirror) against the CPU
+oracle and the committed golden fixtures.
+
+Bar (BASELINE.json north_star): rowids bit-exact; int8-L2/L1 + Hamming distances
+bit-exact; float distances within 1e-5 relative (in fact bit-exact against the
+oracle because both follow the canonical accumulation order, asserted below).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import BIT, COSINE, F32, HAMMING, I8, L1, L2, NP, PAIR_IDS, PAIRS, random_rows, rel_close, same_bits
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-5  # north_star tolerance for floating-point distances
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype="<f4").view("<u4")
+
+
+def check_knn(vg, orc, elem, dims, vectors, queries, k, metric, rowids=None, skip=None, slab=None):
+    own = slab is None
+    if own:
+        slab = vg.Slab(elem, dims)
+        slab.load(vectors, rowids)
+        if skip is not None:
+            ids = np.arange(1, len(vectors) + 1) if rowids is None else rowids
+            for i in np.flatnonzero(skip):
+                slab.delete(int(ids[i]))
+    r, d, c = slab.knn(queries, k, metric)
+    er, ed, ec = orc.knn(elem, dims, vectors, queries, k, metric, rowids=rowids, skip=skip)
+    assert np.array_equal(c, ec)
+    assert np.array_equal(r, er), "rowids must be bit-exact"
+    assert rel_close(d, ed, REL_TOL)
+    assert same_bits(d, ed), "canonical order makes distances bit-exact vs the oracle"
+    if own:
+        slab.close()
+    return r, d, c
+
+
+# ------------------------------------------------------------------ reference tests, replayed on the GPU
+def test_ref_distance_known_answers(vg, gpu):
+    V, M = vg.Vector, vg.DistanceMetric
+    assert abs(vg.distance(V.from_f32([1, 2, 3]), V.from_f32([4, 5, 6]), M.L2) - 5.196) < 0.01  # scalar.rs:120-130
+    assert abs(vg.distance(V.from_f32([1, 2, 3]), V.from_f32([4, 5, 6]), M.L1) - 9.0) < 0.01  # scalar.rs:133-143
+    assert abs(vg.distance(V.from_f32([1, 0, 0]), V.from_f32([0, 1, 0]), M.Cosine) - 1.0) < 0.01  # scalar.rs:146-157
+    assert abs(vg.distance(V.from_f32([1, 2, 3]), V.from_f32([2, 4, 6]), M.Cosine)) < 0.01  # scalar.rs:160-171
+    assert abs(vg.distance(V.from_i8([1, 2, 3]), V.from_i8([4, 5, 6]), M.L2) - 5.196) < 0.01  # scalar.rs:174-184
+    assert abs(vg.distance(V.from_i8([1, 2, 3]), V.from_i8([4, 5, 6]), M.L1) - 9.0) < 0.01  # scalar.rs:187-197
+    a = V(vg.VectorType.Bit, 32, bytes([1, 0, 1, 0]))
+    b = V(vg.VectorType.Bit, 32, bytes([0, 1, 1, 0]))
+    assert vg.distance(a, b, M.Hamming) == 2.0  # scalar.rs:200-212
+    assert abs(vg.distance(V.from_f32([1, 0, 0]), V.from_f32([0, 1, 0]), M.L2) - 1.414) < 0.01  # integration_test.rs:437-456
+
+
+def test_ref_distance_errors(vg, gpu):
+    V, M = vg.Vector, vg.DistanceMetric
+    with pytest.raises(vg.DimensionMismatch):  # mod.rs:155-162
+        vg.distance(V.from_f32([1, 2, 3]), V.from_f32([1, 2]), M.L2)
+    with pytest.raises(vg.InvalidDistanceMetric):  # mod.rs:78-82
+        vg.distance(V.from_f32([1, 2]), V.from_f32([1, 2]), M.Hamming)
+    with pytest.raises(vg.InvalidDistanceMetric):
+        vg.distance(V(vg.VectorType.Bit, 8, b"\x01"), V(vg.VectorType.Bit, 8, b"\x03"), M.L2)
+    with vg.Slab(vg.VectorType.Bit, 64) as s:
+        s.load(np.zeros((2, 8), dtype="u1"))
+        with pytest.raises(vg.InvalidDistanceMetric):
+            s.knn(np.zeros(8, dtype="u1"), 1, M.Cosine)
+
+
+def test_ref_knn_simple(vg, gpu):
+    # tests/test_knn_simple.rs:34-53 (default metric cosine): 2 rows, first rowid 1, tie 2 vs 3 -> 2
+    with vg.Slab(vg.VectorType.Float32, 3) as s:
+        s.load(np.eye(3, dtype="<f4"))
+        res = vg.brute_force_search(s, np.array([1, 0, 0], dtype="<f4").tobytes(), 2, vg.DistanceMetric.Cosine)
+    assert [r for r, _ in res] == [1, 2] and res[0][1] == 0.0 and res[1][1] == 1.0
+
+
+def test_ref_knn_integration_rows(vg, gpu):
+    # tests/integration_test.rs:635-678
+    v = np.array([[i, i + 1, i + 2] for i in range(1, 6)], dtype="<f4")
+    with vg.Slab(vg.VectorType.Float32, 3) as s:
+        for i in range(5):  # row-at-a-time inserts like the SQL INSERTs of the test
+            s.upsert(i + 1, v[i].tobytes())
+        res = vg.brute_force_search(s, v[0].tobytes(), 3, vg.DistanceMetric.Cosine)
+        assert len(res) == 3 and res[0][0] == 1 and res[0][1] < 0.01
+        res = vg.brute_force_search(s, v[0].tobytes(), 3, vg.DistanceMetric.L2)
+        assert [r for r, _ in res] == [1, 2, 3]
+
+
+def test_brute_force_k_semantics(vg, gpu):
+    # `k as usize` (src/vtab.rs:2292): 0 -> empty; k > N -> N rows; negative -> all rows
+    v = random_rows(F32, 9, 4, seed=3)
+    with vg.Slab(F32, 4) as s:
+        s.load(v)
+        q = v[2].tobytes()
+        assert vg.brute_force_search(s, q, 0, L2) == []
+        assert len(vg.brute_force_search(s, q, 100, L2)) == 9
+        assert len(vg.brute_force_search(s, q, -1, L2)) == 9
+        assert vg.brute_force_search(s, q[:8], 3, L2) == []  # wrong-length query: every row errors and is skipped
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(GOLDEN, "cases.json"))), ids=lambda c: c["name"])
+def test_golden_fixtures(vg, gpu, case):
+    z = np.load(os.path.join(GOLDEN, case["file"]))
+    with vg.Slab(case["elem"], case["dims"]) as s:
+        s.load(z["vectors"], z["rowids"])
+        if "skip" in z:
+            for i in np.flatnonzero(z["skip"]):
+                s.delete(int(z["rowids"][i]))
+        r, d, c = s.knn(z["queries"], case["k"], case["metric"])
+    assert np.array_equal(r, z["out_rowids"])
+    assert np.array_equal(c, z["out_counts"])
+    assert rel_close(d, z["out_dists"], REL_TOL)
+    if case["elem"] != F32 and case["metric"] != COSINE:
+        assert np.array_equal(bits(d), bits(z["out_dists"]))  # integer classes: bit-exact
+
+
+# ------------------------------------------------------------------ seeded sweeps vs the oracle
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+@pytest.mark.parametrize("dims", [1, 3, 8, 16, 17, 64, 100, 384, 768, 1024, 2000])
+def test_knn_dims_sweep(vg, orc, gpu, elem, metric, dims):
+    n = 700
+    v = random_rows(elem, n, dims, seed=dims + 10 * elem + metric)
+    q = random_rows(elem, 3, dims, seed=999 + dims)
+    check_knn(vg, orc, elem, dims, v, q, 10, metric)
+
+
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+@pytest.mark.parametrize("nq", [1, 2, 3, 5, 8, 13])
+def test_knn_query_batches(vg, orc, gpu, elem, metric, nq):
+    dims = 96
+    v = random_rows(elem, 3000, dims, seed=42 + elem)
+    q = random_rows(elem, nq, dims, seed=43 + nq)
+    check_knn(vg, orc, elem, dims, v, q, 7, metric)
+
+
+@pytest.mark.parametrize("k", [1, 2, 10, 32, 33, 100, 128, 1000, 1024, 1025, 5000])
+def test_knn_k_sweep(vg, orc, gpu, k):
+    dims = 32
+    v = random_rows(F32, 6000, dims, seed=77)
+    q = random_rows(F32, 2, dims, seed=78)
+    check_knn(vg, orc, F32, dims, v, q, k, L2)
+    vi = random_rows(I8, 6000, dims, seed=79)
+    check_knn(vg, orc, I8, dims, vi, vi[:2], k, L2)
+
+
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+def test_knn_heavy_ties(vg, orc, gpu, elem, metric):
+    # tiny alphabet -> most distances collide; the rowid tie-break decides
+    dims = 24 if elem == BIT else 6
+    v = random_rows(elem, 5000, dims, seed=5, ties=True)
+    q = random_rows(elem, 4, dims, seed=6, ties=True)
+    check_knn(vg, orc, elem, dims, v, q, 50, metric)
+
+
+def test_knn_adversarial_descending(vg, orc, gpu):
+    # distances strictly decreasing with rowid: every row beats the running threshold
+    n, dims = 20000, 8
+    v = np.zeros((n, dims), dtype="<f4")
+    v[:, 0] = np.arange(n, 0, -1)
+    check_knn(vg, orc, F32, dims, v, np.zeros((1, dims), dtype="<f4"), 10, L2)
+    check_knn(vg, orc, F32, dims, v, np.zeros((1, dims), dtype="<f4"), 200, L1)
+
+
+def test_knn_all_equal_rows(vg, orc, gpu):
+    v = np.ones((4097, 16), dtype="<f4")
+    r, d, c = check_knn(vg, orc, F32, 16, v, v[:1], 10, L2)
+    assert list(r[0]) == list(range(1, 11)) and np.all(d == 0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 1000])
+def test_knn_small_tables(vg, orc, gpu, n):
+    dims = 40
+    v = random_rows(F32, max(n, 1), dims, seed=n)[:n]
+    q = random_rows(F32, 2, dims, seed=500)
+    with vg.Slab(F32, dims) as s:
+        if n:
+            s.load(v)
+        r, d, c = s.knn(q, 5, COSINE)
+        er, ed, ec = orc.knn(F32, dims, v, q, 5, COSINE)
+        assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(bits(d), bits(ed))
+
+
+def test_knn_sparse_rowids_and_negative(vg, orc, gpu):
+    dims = 20
+    v = random_rows(I8, 900, dims, seed=8)
+    rowids = np.sort(np.random.default_rng(9).choice(np.arange(-5000, 10**12, 7919), size=900, replace=False)).astype("<i8")
+    check_knn(vg, orc, I8, dims, v, v[:3], 15, L1, rowids=rowids)
+
+
+def test_knn_special_values(vg, orc, gpu):
+    # zero vectors (cosine zero rules), huge magnitudes (inf distance), NaN ranks last
+    dims = 12
+    v = random_rows(F32, 300, dims, seed=10)
+    v[5] = 0
+    v[6] = 3e38
+    v[7, 3] = np.nan
+    q = random_rows(F32, 2, dims, seed=11)
+    q[1] = 0
+    for metric in (L2, L1, COSINE):
+        check_knn(vg, orc, F32, dims, v, q, 300, metric)
+
+
+# ------------------------------------------------------------------ slab maintenance (vtab.rs:1409/1684/1326 hooks)
+def test_slab_upsert_delete_skip(vg, orc, gpu):
+    dims = 10
+    rng = np.random.default_rng(12)
+    v = random_rows(F32, 50, dims, seed=12)
+    rowids = np.arange(1, 51, dtype="<i8")
+    skip = np.zeros(50, dtype="u1")
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        # update in place
+        v[10] = rng.standard_normal(dims).astype("<f4")
+        s.upsert(11, v[10].tobytes())
+        # delete, delete absent, re-insert
+        s.delete(20)
+        s.delete(999)
+        skip[19] = 1
+        s.delete(30)
+        v[29] = rng.standard_normal(dims).astype("<f4")
+        s.upsert(30, v[29].tobytes())
+        # wrong-length / empty blob => row skipped by scans (src/vtab.rs:2596-2613)
+        s.upsert(40, b"\x00" * 7)
+        skip[39] = 1
+        s.upsert(41, b"")
+        skip[40] = 1
+        assert s.count() == (50, 47)
+        assert s.get(20) is None and s.get(11) == v[10].tobytes()
+        check_knn(vg, orc, F32, dims, v, v[:4], 50, L2, rowids=rowids, skip=skip, slab=s)
+        # append (rowid = MAX+1, src/shadow.rs:888-900) and an out-of-order explicit rowid
+        nv = rng.standard_normal((3, dims)).astype("<f4")
+        s.upsert(51, nv[0].tobytes())
+        s.upsert(1000, nv[1].tobytes())
+        s.upsert(500, nv[2].tobytes())
+        v2 = np.concatenate([v, nv[[0, 2, 1]]])
+        rowids2 = np.concatenate([rowids, [51, 500, 1000]]).astype("<i8")
+        skip2 = np.concatenate([skip, [0, 0, 0]]).astype("u1")
+        assert s.count() == (53, 50)
+        check_knn(vg, orc, F32, dims, v2, v2[-3:], 53, COSINE, rowids=rowids2, skip=skip2, slab=s)
+        # scoring sees the same table
+        out = s.score(v2[:1], np.array([51, 500, 1000, 20, 777], dtype="<i8"), np.array([0, 5], dtype="<u4"), L2)
+        want = orc.distances(F32, dims, v2[[50, 51, 52]], v2[0], L2)
+        assert np.array_equal(bits(out[:3]), bits(want)) and np.isnan(out[3]) and np.isnan(out[4])
+
+
+def test_slab_append_in_pieces(vg, orc, gpu):
+    dims = 16
+    v = random_rows(BIT, 1000, dims * 8, seed=13)
+    with vg.Slab(BIT, dims * 8) as s:
+        s.load(v[:400])
+        s.append(v[400:700])
+        s.append(v[700:], rowids=np.arange(701, 1001))
+        check_knn(vg, orc, BIT, dims * 8, v, v[:2], 10, HAMMING, slab=s)
+        with pytest.raises(vg.InvalidParameter):
+            s.append(v[:1], rowids=[5])  # not greater than the last rowid
+
+
+# ------------------------------------------------------------------ K5: candidate scoring (search.rs:501-513)
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+def test_score_matches_oracle(vg, orc, gpu, elem, metric):
+    dims = 384 if elem != BIT else 1024
+    n = 2000
+    v = random_rows(elem, n, dims, seed=21 + elem)
+    q = random_rows(elem, 5, dims, seed=22)
+    rng = np.random.default_rng(23)
+    sizes = [1, 4, 32, 0, 17]  # per-expansion batch sizes incl. the 1-4 common case and max_m0=32
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype("<u4")
+    cands = rng.integers(1, n + 1, size=offsets[-1]).astype("<i8")
+    with vg.Slab(elem, dims) as s:
+        s.load(v)
+        out = s.score(q, cands, offsets, metric)
+    for qi in range(5):
+        for j in range(offsets[qi], offsets[qi + 1]):
+            want = orc.distance(elem, q[qi], v[cands[j] - 1], metric)
+            assert np.float32(out[j]).view("<u4") == np.float32(want).view("<u4")
+
+
+def test_score_hnsw_cosine_contract(vg, orc, gpu):
+    # HNSW cosine = L2 on normalised vectors, output d^2/2 (src/hnsw/mod.rs:129-146, insert.rs:300-322)
+    dims = 64
+    v = random_rows(F32, 200, dims, seed=31)
+    vn = vg.normalize(v)
+    assert np.array_equal(bits(vn), bits(orc.normalize(v)))
+    qn = vg.Vector.from_f32(v[3]).normalize().as_f32()
+    with vg.Slab(F32, dims) as s:
+        s.load(vn)
+        metric = vg.internal_distance_metric(vg.DistanceMetric.Cosine, True)
+        d = s.score(qn, np.arange(1, 201, dtype="<i8"), np.array([0, 200], dtype="<u4"), metric)
+    out = np.array([vg.convert_distance_for_output(vg.DistanceMetric.Cosine, True, x) for x in d], dtype="<f4")
+    exact = np.array([orc.distance(F32, v[3], v[i], COSINE) for i in range(200)])
+    assert np.all(np.abs(out - exact) < 1e-5)
+    assert out[3] < 1e-6
+
+
+def test_distance_pairs_bulk(vg, orc, gpu):
+    for elem, metric in PAIRS:
+        dims = 130 if elem != BIT else 136
+        a = random_rows(elem, 300, dims, seed=41)
+        b = random_rows(elem, 300, dims, seed=42)
+        out = vg.distance_pairs(elem, a, b, metric)
+        want = np.array([orc.distance(elem, a[i], b[i], metric) for i in range(300)], dtype="<f4")
+        assert np.array_equal(bits(out), bits(want))
+
+
+def test_i8_l1_exhaustive_bytes(vg, orc, gpu):
+    # every (a, b) byte pair once: the SIMD abs-diff must be exact over the whole int8 range
+    a = np.repeat(np.arange(-128, 128, dtype="i1"), 256).reshape(256, 256)
+    b = np.tile(np.arange(-128, 128, dtype="i1"), 256).reshape(256, 256)
+    for metric in (L1, L2, COSINE):
+        out = vg.distance_pairs(I8, a, b, metric)
+        want = np.array([orc.distance(I8, a[i], b[i], metric) for i in range(256)], dtype="<f4")
+        assert np.array_equal(bits(out), bits(want))
+
+
+# ------------------------------------------------------------------ K7 producers (vector.rs:444-608)
+def test_producers_bit_exact(vg, orc, gpu):
+    rng = np.random.default_rng(51)
+    for dims in (1, 2, 7, 8, 9, 128, 384, 1000):
+        x = (rng.standard_normal((64, dims)) * rng.choice([0.01, 1.0, 50.0], size=(64, 1))).astype("<f4")
+        x[3] = 0.25  # all-equal row -> quantize_int8 gives zeros
+        assert np.array_equal(vg.quantize_int8(x), orc.quantize_int8(x))
+        assert np.array_equal(vg.quantize_int8_for_index(x), orc.quantize_int8_for_index(x))
+        assert np.array_equal(vg.quantize_binary(x), orc.quantize_binary(x))
+        assert np.array_equal(bits(vg.normalize(x)), bits(orc.normalize(x)))
+    # half-way cases of round(): *.5 must round away from zero
+    h = np.array([[0.5 / 127, 1.5 / 127, -0.5 / 127, 2.5 / 127, 1.0, -1.0, 3.0, -3.0]], dtype="<f4")
+    assert np.array_equal(vg.quantize_int8_for_index(h), orc.quantize_int8_for_index(h))
+    q = vg.Vector.from_f32([0.0, 0.5, 1.0]).quantize_int8().as_i8()  # src/vector.rs:777-789
+    assert q[0] == -128 and q[2] == 127 and q[0] < q[1] < q[2]
+    n = vg.Vector.from_f32([3.0, 4.0]).normalize().as_f32()  # src/vector.rs:746-759
+    assert abs(n[0] - 0.6) < 1e-4 and abs(n[1] - 0.8) < 1e-4
+    with pytest.raises(vg.InvalidParameter):
+        vg.Vector.from_f32([0.0, 0.0]).normalize()  # src/vector.rs:451-455
+    with pytest.raises(vg.InvalidVectorType):
+        vg.Vector.from_i8([1, 2]).normalize()
+
+
+# ------------------------------------------------------------------ synthetic generator: device == CPU restatement
+@pytest.mark.parametrize("elem,dims,kind", [(F32, 384, 0), (F32, 768, 1), (F32, 5, 1), (I8, 1024, 0), (I8, 33, 0), (BIT, 1024, 0), (BIT, 77, 0)])
+def test_synthetic_generator_matches_cpu(vg, orc, gpu, elem, dims, kind):
+    n, first = 3000, 17
+    with vg.Slab(elem, dims) as s:
+        s.fill_synthetic(seed=1234, n=n, first_rowid=first, kind=kind)
+        cpu = orc.synth_rows(elem, 1234, first, n, dims, kind)
+        for rid in (first, first + 1, first + 1234, first + n - 1):
+            assert s.get(rid) == cpu[rid - first].tobytes()
+        assert s.get(first + n) is None
+        metric = {F32: COSINE, I8: L2, BIT: HAMMING}[elem]
+        q = orc.synth_rows(elem, 99, 1, 2, dims, kind)
+        r, d, c = s.knn(q, 10, metric)
+        er, ed, ec = orc.knn(elem, dims, cpu, q, 10, metric, rowids=np.arange(first, first + n))
+        assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed))
+
+
+# ------------------------------------------------------------------ larger shapes: config 1 in full, configs 2-4 scaled down
+def test_config1_full(vg, orc, gpu):
+    # vec0 float[384], 10K random vectors, brute-force L2 k=10 (+ cosine, L1), 100 queries
+    n, dims = 10000, 384
+    v = orc.synth_rows(F32, 1, 1, n, dims, 0)
+    q = orc.synth_rows(F32, 2, 1, 100, dims, 0)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        for metric in (L2, COSINE, L1):
+            check_knn(vg, orc, F32, dims, v, q, 10, metric, slab=s)
+
+
+@pytest.mark.parametrize("elem,dims,metric,k,n", [(F32, 768, COSINE, 10, 200_000), (I8, 1024, L2, 100, 200_000), (BIT, 1024, HAMMING, 10, 1_000_000)])
+def test_configs_2_3_4_prefix(vg, orc, gpu, elem, dims, metric, k, n):
+    kind = 1 if elem == F32 else 0
+    with vg.Slab(elem, dims) as s:
+        s.fill_synthetic(seed=3 + elem, n=n, kind=kind)
+        cpu = orc.synth_rows(elem, 3 + elem, 1, n, dims, kind)
+        q = orc.synth_rows(elem, 77, 1, 9, dims, kind)
+        r, d, c = s.knn(q, k, metric)
+        er, ed, ec = orc.knn(elem, dims, cpu, q, k, metric)
+        assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed)) and np.array_equal(c, ec)
+        # single-query launches agree with the batched pass
+        r1, d1, _ = s.knn(q[:1], k, metric)
+        assert np.array_equal(r1[0], r[0]) and np.array_equal(bits(d1[0]), bits(d[0]))
+
+
+def test_full_size_properties(vg, orc, gpu):
+    """Size-independent properties at a size the CPU cannot check row by row:
+    sortedness, self-match at distance 0, idempotence, and k-prefix consistency."""
+    n, dims = 2_000_000, 768
+    with vg.Slab(F32, dims) as s:
+        s.fill_synthetic(seed=3, n=n, kind=1)
+        probe = [1, 777_777, n]
+        q = orc.synth_rows(F32, 3, 1, 1, dims, 1)
+        q = np.concatenate([orc.synth_rows(F32, 3, rid, 1, dims, 1) for rid in probe])
+        r, d, c = s.knn(q, 10, COSINE)
+        assert list(r[:, 0]) == probe and np.all(d[:, 0] <= 1e-6)  # each probe row is its own nearest neighbour
+        assert np.all(np.diff(d, axis=1) >= 0)  # sorted
+        r2, d2, _ = s.knn(q, 10, COSINE)
+        assert np.array_equal(r, r2) and np.array_equal(bits(d), bits(d2))  # deterministic
+        r5, d5, _ = s.knn(q, 5, COSINE)
+        assert np.array_equal(r5, r[:, :5])  # top-5 is a prefix of top-10
+        # the returned distances are the oracle's distances for those rows
+        for qi in range(3):
+            rows = np.concatenate([orc.synth_rows(F32, 3, int(x), 1, dims, 1) for x in r[qi]])
+            want = orc.distances(F32, dims, rows, q[qi], COSINE)
+            assert np.array_equal(bits(d[qi]), bits(want))

@@ -1,0 +1,315 @@
+"""Pins the CPU oracle (oracle/vecgpu_oracle.c):
+
+  1. every known answer the reference's own tests hold for this path
+     (file:line cited per case),
+  2. an independent float64 / big-integer numpy restatement of the formulas,
+  3. a bit-exact pure-Python model of the canonical accumulation order,
+  4. the committed golden fixtures (tests/golden/*.npz).
+
+No GPU needed.
+"""
+import json
+import math
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from helpers import BIT, COSINE, F32, HAMMING, I8, L1, L2, PAIR_IDS, PAIRS, random_rows, rel_close
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------ 1. reference known answers
+def test_ref_l2_f32_known_answer(orc):
+    # src/distance/mod.rs:165-175, src/distance/scalar.rs:120-130, src/sql_functions.rs:560-575
+    d = orc.distance(F32, [1, 2, 3], [4, 5, 6], L2)
+    assert abs(d - 5.196) < 0.01
+    assert d == np.float32(math.sqrt(27.0))
+
+
+def test_ref_l1_f32_known_answer(orc):
+    # src/distance/scalar.rs:133-143
+    assert abs(orc.distance(F32, [1, 2, 3], [4, 5, 6], L1) - 9.0) < 0.01
+
+
+def test_ref_cosine_orthogonal(orc):
+    # src/distance/mod.rs:178-188, src/distance/scalar.rs:146-157
+    assert abs(orc.distance(F32, [1, 0, 0], [0, 1, 0], COSINE) - 1.0) < 0.01
+
+
+def test_ref_cosine_parallel(orc):
+    # src/distance/scalar.rs:160-171
+    assert abs(orc.distance(F32, [1, 2, 3], [2, 4, 6], COSINE)) < 0.01
+
+
+def test_ref_l2_i8_known_answer(orc):
+    # src/distance/scalar.rs:174-184
+    assert abs(orc.distance(I8, [1, 2, 3], [4, 5, 6], L2) - 5.196) < 0.01
+
+
+def test_ref_l1_i8_known_answer(orc):
+    # src/distance/scalar.rs:187-197
+    assert abs(orc.distance(I8, [1, 2, 3], [4, 5, 6], L1) - 9.0) < 0.01
+
+
+def test_ref_hamming_bytes(orc):
+    # src/distance/scalar.rs:200-212 only asserts >= 0; the true value is 2 differing bits
+    d = orc.distance(BIT, np.array([1, 0, 1, 0], dtype="u1"), np.array([0, 1, 1, 0], dtype="u1"), HAMMING)
+    assert d >= 0.0 and d == 2.0
+
+
+def test_ref_l2_sql_unit_vectors(orc):
+    # tests/integration_test.rs:437-456
+    assert abs(orc.distance(F32, [1, 0, 0], [0, 1, 0], L2) - 1.414) < 0.01
+
+
+def test_ref_dimension_mismatch(orc):
+    # src/distance/mod.rs:155-162 -> Err(DimensionMismatch)
+    with pytest.raises(orc.OracleError) as e:
+        orc.distance(F32, [1, 2, 3], [1, 2], L2)
+    assert e.value.code == 2
+
+
+@pytest.mark.parametrize("elem,metric", [(F32, HAMMING), (I8, HAMMING), (BIT, L2), (BIT, L1), (BIT, COSINE)])
+def test_ref_unsupported_pairs(orc, elem, metric):
+    # src/distance/mod.rs:78-82 -> Err(InvalidDistanceMetric)
+    a = np.zeros(8, dtype=orc._NP[elem])
+    with pytest.raises(orc.OracleError) as e:
+        orc.distance(elem, a, a, metric)
+    assert e.value.code == 3
+
+
+def test_ref_knn_unit_vectors(orc):
+    # tests/test_knn_simple.rs:34-53: e1,e2,e3, query e1, k=2 (default metric = cosine):
+    # 2 rows, first rowid 1; the second is a tie between rowids 2 and 3 -> stable sort keeps 2.
+    v = np.eye(3, dtype="<f4")
+    r, d, c = orc.knn(F32, 3, v, v[0], 2, COSINE)
+    assert c[0] == 2 and list(r[0]) == [1, 2]
+    assert d[0, 0] == 0.0 and d[0, 1] == 1.0
+
+
+def test_ref_knn_integration_rows(orc):
+    # tests/integration_test.rs:635-678: rows [i,i+1,i+2] i=1..5, query [1,2,3], k=3 -> first rowid 1, distance < 0.01
+    v = np.array([[i, i + 1, i + 2] for i in range(1, 6)], dtype="<f4")
+    for metric in (COSINE, L2):
+        r, d, c = orc.knn(F32, 3, v, v[0], 3, metric)
+        assert c[0] == 3 and r[0, 0] == 1 and d[0, 0] < 0.01
+    r, d, _ = orc.knn(F32, 3, v, v[0], 3, L2)
+    assert list(r[0]) == [1, 2, 3]
+
+
+def test_ref_recall_generator_ground_truth(orc):
+    # tests/test_recall_accuracy.rs:28-44, 79-94: vectors (i*100+j)/1000, query all 0.5, k=10;
+    # the test's own ground truth ranks by squared L2 — same ranking as L2.
+    n, dims = 1000, 128
+    i = np.arange(n, dtype=np.int64)[:, None]
+    j = np.arange(dims, dtype=np.int64)[None, :]
+    v = ((i * 100 + j).astype("<f4") / np.float32(1000.0)).astype("<f4")
+    q = np.full(dims, 0.5, dtype="<f4")
+    r, d, _ = orc.knn(F32, dims, v, q, 10, L2)
+    gt = np.sum((q.astype(np.float64) - v.astype(np.float64)) ** 2, axis=1)
+    order = np.lexsort((np.arange(n), gt))[:10] + 1
+    assert list(r[0]) == list(order)
+
+
+def test_ref_quantize_int8_known(orc):
+    # src/vector.rs:777-789: quantize_int8([0, .5, 1]) -> first -128, last 127, monotone
+    q = orc.quantize_int8(np.array([[0.0, 0.5, 1.0]], dtype="<f4"))[0]
+    assert q[0] == -128 and q[2] == 127 and q[0] < q[1] < q[2]
+
+
+def test_ref_normalize_known(orc):
+    # src/vector.rs:746-759: normalize([3,4]) -> [.6,.8] +-1e-4
+    out = orc.normalize(np.array([[3.0, 4.0]], dtype="<f4"))[0]
+    assert abs(out[0] - 0.6) < 1e-4 and abs(out[1] - 0.8) < 1e-4
+
+
+def test_ref_normalize_zero_vector_errors(orc):
+    # src/vector.rs:451-455
+    with pytest.raises(orc.OracleError):
+        orc.normalize(np.zeros((1, 4), dtype="<f4"))
+
+
+def test_ref_cosine_output_conversion(orc):
+    # src/hnsw/mod.rs:139-146: d_out = d_L2^2 / 2
+    assert orc.convert_cosine_output(np.float32(1.0)) == np.float32(0.5)
+    assert orc.convert_cosine_output(np.float32(0.2)) == np.float32(np.float32(0.2) * np.float32(0.2)) / np.float32(2)
+
+
+# ------------------------------------------------------------------ 2. independent f64 / integer restatement
+def ref64(elem, metric, a, b):
+    if elem == BIT:
+        return float(np.unpackbits(np.bitwise_xor(a, b)).sum())
+    if elem == I8:
+        x, y = a.astype(np.int64), b.astype(np.int64)
+        if metric == L2:
+            return math.sqrt(float(np.sum((x - y) ** 2)))
+        if metric == L1:
+            return float(np.sum(np.abs(x - y)))
+        ab, a2, b2 = int(np.sum(x * y)), int(np.sum(x * x)), int(np.sum(y * y))
+    else:
+        x, y = a.astype(np.float64), b.astype(np.float64)
+        if metric == L2:
+            return math.sqrt(float(np.sum((x - y) ** 2)))
+        if metric == L1:
+            return float(np.sum(np.abs(x - y)))
+        ab, a2, b2 = float(np.sum(x * y)), float(np.sum(x * x)), float(np.sum(y * y))
+    if a2 == 0 and b2 == 0:
+        return 0.0
+    if ab == 0:
+        return 1.0
+    return max(0.0, 1.0 - ab / (math.sqrt(a2) * math.sqrt(b2)))
+
+
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+@pytest.mark.parametrize("dims", [1, 3, 16, 17, 100, 384, 768, 1024])
+def test_oracle_matches_f64_restatement(orc, elem, metric, dims):
+    rows = random_rows(elem, 6, dims, seed=dims * 7 + elem)
+    for i in range(1, 6):
+        got = float(orc.distance(elem, rows[0], rows[i], metric))
+        want = ref64(elem, metric, rows[0], rows[i])
+        if elem == BIT or (elem == I8 and metric in (L2, L1)):
+            assert got == float(np.float32(want))  # integer-exact classes: bit-exact
+        elif metric == COSINE:
+            # f32 accumulation error is absolute on the similarity; compare similarities
+            assert abs(got - want) <= 1e-5 * max(1.0, abs(want)) + 4e-6
+        else:
+            assert rel_close(got, want, 1e-5)
+
+
+# ------------------------------------------------------------------ 3. bit-exact model of the canonical order
+def _round_f32(fr):
+    """Correctly rounded (nearest-even) Fraction -> float32 for normal-range values."""
+    if fr == 0:
+        return np.float32(0.0)
+    sign = -1 if fr < 0 else 1
+    fr = abs(fr)
+    e = fr.numerator.bit_length() - fr.denominator.bit_length()
+    if Fraction(2) ** e > fr:
+        e -= 1
+    scaled = fr / Fraction(2) ** (e - 23)
+    n = scaled.numerator // scaled.denominator
+    rem = scaled - n
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and n % 2 == 1):
+        n += 1
+    return np.float32(sign * float(Fraction(n) * Fraction(2) ** (e - 23)))
+
+
+def _fma32(a, b, c):
+    return _round_f32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def _tree16(lanes):
+    l = [np.float32(x) for x in lanes]
+    for w in (8, 4, 2):
+        for i in range(w):
+            l[i] = np.float32(l[i] + l[i + w])
+    return np.float32(l[0] + l[1])
+
+
+def model_l2sq(a, b):
+    lanes = [np.float32(0)] * 16
+    for i in range(len(a)):
+        t = np.float32(a[i] - b[i])
+        lanes[i % 16] = _fma32(t, t, lanes[i % 16])
+    return _tree16(lanes)
+
+
+def model_dot3(a, b):
+    ab, a2, b2 = [np.float32(0)] * 16, [np.float32(0)] * 16, [np.float32(0)] * 16
+    for i in range(len(a)):
+        ab[i % 16] = _fma32(a[i], b[i], ab[i % 16])
+        a2[i % 16] = _fma32(a[i], a[i], a2[i % 16])
+        b2[i % 16] = _fma32(b[i], b[i], b2[i % 16])
+    return _tree16(ab), _tree16(a2), _tree16(b2)
+
+
+@pytest.mark.parametrize("dims", [1, 5, 16, 31, 48, 100])
+def test_oracle_canonical_order_bit_exact(orc, dims):
+    rows = random_rows(F32, 4, dims, seed=1234 + dims)
+    a = rows[0]
+    for b in rows[1:]:
+        want_l2 = np.sqrt(model_l2sq(a, b))  # float32 sqrt is correctly rounded
+        assert orc.distance(F32, a, b, L2) == want_l2
+        ab, a2, b2 = model_dot3(a, b)
+        r = 1.0 - float(ab) / (math.sqrt(float(a2)) * math.sqrt(float(b2)))
+        want_cos = np.float32(r if r > 0 else 0.0)
+        assert orc.distance(F32, a, b, COSINE) == want_cos
+        s = np.float32(0)
+        for i in range(dims):
+            s = np.float32(s + np.abs(np.float32(a[i] - b[i])))
+        assert orc.distance(F32, a, b, L1) == s  # strict left-to-right, src/distance/scalar.rs:31-35
+
+
+def test_oracle_cosine_zero_rules(orc):
+    z = np.zeros(8, dtype="<f4")
+    x = np.arange(8, dtype="<f4")
+    assert orc.distance(F32, z, z, COSINE) == 0.0
+    assert orc.distance(F32, z, x, COSINE) == 1.0
+    assert orc.distance(F32, x, x, COSINE) == 0.0  # clamp at 0
+    zi = np.zeros(8, dtype="i1")
+    assert orc.distance(I8, zi, zi, COSINE) == 0.0
+
+
+def test_oracle_i8_extremes(orc):
+    a = np.full(1024, -128, dtype="i1")
+    b = np.full(1024, 127, dtype="i1")
+    assert orc.distance(I8, a, b, L2) == np.float32(math.sqrt(1024 * 255 * 255))
+    assert orc.distance(I8, a, b, L1) == np.float32(1024 * 255)
+
+
+# ------------------------------------------------------------------ scan semantics (src/vtab.rs:2594-2620)
+def test_oracle_knn_tie_break_and_skip(orc):
+    v = random_rows(I8, 200, 16, seed=5, ties=True)
+    q = v[7]
+    skip = np.zeros(200, dtype="u1")
+    skip[[3, 7, 50]] = 1
+    rowids = np.arange(200, dtype="<i8") * 3 + 10
+    r, d, c = orc.knn(I8, 16, v, q, 20, L2, rowids=rowids, skip=skip)
+    dist = orc.distances(I8, 16, v, q, L2)
+    live = np.flatnonzero(skip == 0)
+    order = live[np.lexsort((live, dist[live]))][:20]
+    assert list(r[0]) == list(rowids[order])
+    assert np.array_equal(d[0], dist[order])
+    assert c[0] == 20
+    # k > live rows -> all live rows, padding after
+    r, d, c = orc.knn(I8, 16, v[:5], q, 8, L2, skip=np.array([0, 1, 0, 0, 0], dtype="u1"))
+    assert c[0] == 4 and list(r[0, 4:]) == [-1] * 4 and np.all(np.isinf(d[0, 4:]))
+
+
+def test_oracle_synth_generator_is_stable(orc):
+    # the generator is part of the bench/test contract: pin a few values
+    a = orc.synth_rows(F32, 3, 1, 2, 8, 0)
+    b = orc.synth_rows(F32, 3, 2, 1, 8, 0)
+    assert np.array_equal(a[1], b[0])  # rows are a pure function of (seed, rowid)
+    assert np.all((a >= -1) & (a < 1))
+    g = orc.synth_rows(F32, 3, 1, 2000, 16, 1)
+    assert abs(float(g.mean())) < 0.05 and 1.0 < float(g.std()) < 1.3
+    i8 = orc.synth_rows(I8, 4, 1, 4, 64, 0)
+    assert i8.min() == -128 and i8.max() == 127
+    bits = orc.synth_rows(BIT, 5, 1, 64, 1024, 0)
+    frac = np.unpackbits(bits).mean()
+    assert 0.48 < frac < 0.52
+    odd = orc.synth_rows(BIT, 5, 1, 4, 13, 0)
+    assert odd.shape == (4, 2) and np.all(odd[:, 1] < 32)  # padding bits are zero
+
+
+# ------------------------------------------------------------------ 4. committed golden fixtures
+def _golden_cases():
+    path = os.path.join(GOLDEN, "cases.json")
+    with open(path) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_oracle_reproduces_golden(orc, case):
+    z = np.load(os.path.join(GOLDEN, case["file"]))
+    r, d, c = orc.knn(
+        case["elem"], case["dims"], z["vectors"], z["queries"], case["k"], case["metric"], rowids=z["rowids"],
+        skip=z["skip"] if "skip" in z else None,
+    )
+    assert np.array_equal(r, z["out_rowids"])
+    assert np.array_equal(d.view("<u4"), z["out_dists"].view("<u4"))
+    assert np.array_equal(c, z["out_counts"])
