@@ -132,8 +132,10 @@ int vecgpu_quantize_binary(const float* in, uint64_t n, uint32_t dims, int devic
 
 /* ---- device-resident variants (bench `value`, multi-GPU shards) ---------
  * Pointers prefixed d_ are device pointers on the slab's device; `stream` is a
- * cudaStream_t passed as void* (NULL = the slab's own stream).  These calls
- * only enqueue work; the caller synchronises. */
+ * cudaStream_t passed as void* (NULL = the CUDA default stream).  These calls
+ * only enqueue work on that stream; the caller synchronises, and must not run
+ * them concurrently with other calls on the same slab (they share the slab's
+ * scratch buffers in stream order). */
 
 /* Make the slab hold n rows with dense rowids first_rowid.. generated on the
  * device by the counter-based generator value(seed, rowid, j) that

@@ -95,15 +95,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // src/distance/scalar.rs:31-35); integer metrics are order-free.
 // QC = per-query constant computed once (|q|^2).
 // ---------------------------------------------------------------------------
-template <int LPR>
-__device__ __forceinline__ float group_sum_f(float v);
-template <>
-__device__ __forceinline__ float group_sum_f<4>(float v) {  // unused generic helper
-    v = v + __shfl_xor_sync(0xffffffffu, v, 2);
-    v = v + __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
-}
-
 // canonical tree over the 16 lanes held as 4 lanes x 4 accumulators
 __device__ __forceinline__ float canon_tree(float a0, float a1, float a2, float a3) {
     a0 = __fadd_rn(a0, __shfl_xor_sync(0xffffffffu, a0, 2));  // l[i] + l[i+8]
@@ -130,12 +121,9 @@ __device__ __forceinline__ float cos_finish(double ab, double a2, double b2) {
     return __double2float_rn(r > 0.0 ? r : 0.0);
 }
 
-struct QCNone {};
-
 template <int QB>
 struct F32L2 {
     static constexpr int LPR = 4;
-    using QC = QCNone;
     struct Acc {
         float s[QB][4];
     };
@@ -145,7 +133,6 @@ struct F32L2 {
 #pragma unroll
             for (int e = 0; e < 4; ++e) a.s[q][e] = 0.0f;
     }
-    __device__ static void qc_unit(float (&qa)[4], uint4) {}
     __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
         const float xf[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
 #pragma unroll
@@ -165,6 +152,7 @@ struct F32L2 {
         return __fsqrt_rn(s);  // src/distance/scalar.rs:20: (s as f32).sqrt()
     }
     static constexpr bool HAS_QC = false;
+    static constexpr bool ORDER_FREE = false;
 };
 
 template <int QB>
@@ -200,6 +188,7 @@ struct F32Cos {
         return cos_finish((double)ab, (double)qc[i], (double)b2);
     }
     static constexpr bool HAS_QC = true;
+    static constexpr bool ORDER_FREE = false;
 };
 
 template <int QB>
@@ -224,6 +213,7 @@ struct F32L1 {
     }
     __device__ static float finish(const Acc& a, int i, const float*) { return a.s[i]; }
     static constexpr bool HAS_QC = false;
+    static constexpr bool ORDER_FREE = false;
 };
 
 // int8: exact int32 partial sums by dp4a; |q|^2 arrives as a float-encoded pair in qc (hi/lo split not
@@ -261,6 +251,7 @@ struct I8Dot {
         return __double2float_rn(__dsqrt_rn((double)s));
     }
     static constexpr bool HAS_QC = true;
+    static constexpr bool ORDER_FREE = true;
 };
 
 __device__ __forceinline__ unsigned absdiff_s8x4(unsigned a, unsigned b) {
@@ -290,11 +281,13 @@ struct I8L1 {
     }
     __device__ static float finish(const Acc& a, int i, const float*) { return (float)group4_sum_i(a.s[i]); }
     static constexpr bool HAS_QC = false;
+    static constexpr bool ORDER_FREE = true;
 };
 
+// Hamming: one thread per row (rows are short: bit[1024] = 128 B), exact popcount
 template <int QB>
 struct BitHamming {
-    static constexpr int LPR = 4;
+    static constexpr int LPR = 1;
     struct Acc {
         int s[QB];
     };
@@ -307,8 +300,9 @@ struct BitHamming {
         for (int i = 0; i < QB; ++i)
             a.s[i] += __popc(x.x ^ q[i].x) + __popc(x.y ^ q[i].y) + __popc(x.z ^ q[i].z) + __popc(x.w ^ q[i].w);
     }
-    __device__ static float finish(const Acc& a, int i, const float*) { return (float)group4_sum_i(a.s[i]); }
+    __device__ static float finish(const Acc& a, int i, const float*) { return (float)a.s[i]; }
     static constexpr bool HAS_QC = false;
+    static constexpr bool ORDER_FREE = true;
 };
 
 // |q|^2 of one query in the representation finish() expects; executed by one
@@ -415,6 +409,28 @@ __device__ __forceinline__ void list_offer(uint64_t* list, ListHdr* hdr, uint32_
 
 // ---------------------------------------------------------------------------
 // K1/K3/K4 (+K2a when QB>1): the streaming scan.
+//
+// Persistent CTAs (one per SM): warp C is the producer, warps 0..C-1 consume.
+// The slab is cut into tiles of RS rows; tile t belongs to CTA t % gridDim.x,
+// and the j-th tile of a CTA to consumer warp j % C.  Every tile travels
+// through a ring of S shared-memory stages:
+//   contig mode : ONE cp.async.bulk per stage (RS*row_stride contiguous bytes,
+//                 >= 16 KB, so the fixed per-copy cost of the copy engine — about
+//                 70 cycles, measured — is amortised).  Bank conflicts are
+//                 avoided without padding by rotating the order in which a lane
+//                 reads the 16-byte units of a 128-byte segment (legal for the
+//                 order-free integer metrics); the canonical-order f32 metrics
+//                 accept a 2-way conflict (shared memory has >2x headroom).
+//   per-row mode: one bulk copy per row chunk into a padded stage; used for
+//                 f32 L1 (strict order, thread-per-row needs odd unit strides)
+//                 and for rows too wide for RPW whole rows per stage.
+// Each consumer warp owns a private ring of D stages (S = C*D in total) that the
+// producer fills in tile order, so every full[]/empty[] barrier is waited on
+// strictly in phase order by one warp.  (With shared round-robin stages a warp
+// could observe the parity of an older, still incomplete phase when bulk copies
+// complete out of order — measured as sporadic launch failures.)
+// full[s] completes on the copy's transaction bytes, empty[s] on the single
+// arrival of the owning consumer warp.
 // ---------------------------------------------------------------------------
 struct ScanParams {
     const uint8_t* vectors;  // slab rows, row_stride bytes apart, zero padded
@@ -425,15 +441,23 @@ struct ScanParams {
     uint32_t nq_total;
     uint32_t k;
     uint32_t row_stride;       // bytes, multiple of 16
-    uint32_t chunk_bytes;      // multiple of 64 (or == row_stride)
+    uint32_t chunk_bytes;      // per-row mode: multiple of 64; contig: == row_stride
     uint32_t n_chunks;
     uint32_t smem_row_stride;  // bytes between rows of a stage in shared memory
-    uint32_t rows_per_stage;   // R = RPW * C * m   (m == 1 when n_chunks > 1)
-    uint32_t n_stages;
+    uint32_t rows_per_stage;   // RS = RPW * m   (m == 1 when n_chunks > 1); one consumer warp per stage
+    uint32_t n_stages;         // D: ring depth per consumer warp (C*D stages in total)
     uint32_t contig;           // 1: a stage is one contiguous bulk copy (smem_row_stride == row_stride)
     uint32_t n_consumers;      // C consumer warps; warp C is the producer
     uint32_t qc_kind;          // 0 f32 sum of squares, 1 int8
 };
+
+// physical unit read by a lane for logical unit u (see "rotating" above)
+template <class T>
+__device__ __forceinline__ uint32_t phys_unit(uint32_t u, uint32_t units8, uint32_t rot) {
+    if (!T::ORDER_FREE) return u;
+    if (T::LPR == 4) return u < units8 ? (u ^ rot) : u;
+    return u < units8 ? ((u & ~7u) | ((u + rot) & 7u)) : u;
+}
 
 template <class T, int QB, bool EMIT>
 __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
@@ -442,8 +466,8 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t C = p.n_consumers, S = p.n_stages, R = p.rows_per_stage;
-    const uint32_t stage_bytes = R * p.smem_row_stride;
+    const uint32_t C = p.n_consumers, D = p.n_stages, S = C * D, RS = p.rows_per_stage;
+    const uint32_t stage_bytes = RS * p.smem_row_stride;
     // layout: [stages][queries QB*row_stride][qc QB floats, padded to 64][hdr C*QB][lists C*QB*k][barriers 2*S]
     uint8_t* s_stage = smem;
     uint8_t* s_query = s_stage + (size_t)S * stage_bytes;
@@ -459,7 +483,7 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, C);
+            mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_fence_init();
     }
@@ -488,26 +512,38 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
         __syncthreads();
     }
 
-    const uint64_t n_tiles = (p.n_rows + R - 1) / R;
+    const uint64_t n_tiles = (p.n_rows + RS - 1) / RS;
 
     if ((uint32_t)warp == C) {
         // ================= producer warp: bulk copies global -> shared =================
-        uint32_t it = 0;
-        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint64_t row0 = tile * R;
-            const uint32_t valid = (uint32_t)min((uint64_t)R, p.n_rows - row0);
-            for (uint32_t c = 0; c < p.n_chunks; ++c, ++it) {
-                const uint32_t s = it % S, ph = (it / S) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint32_t dst0 = smem_u32(s_stage + (size_t)s * stage_bytes);
-                if (p.contig) {
-                    if (lane == 0) {
-                        // a stage is at most ~200 KB, so `bytes` fits both the tx-count and the copy size
-                        const uint32_t bytes = valid * p.row_stride;
-                        mbar_expect_tx(bar_full + 8 * s, bytes);
-                        bulk_g2s(dst0, p.vectors + row0 * p.row_stride, bytes, bar_full + 8 * s);
-                    }
-                } else {
+        // Parity waits alias every two phases, so every lane that waits must stay within one
+        // iteration of the lane that issues: contig mode runs on lane 0 alone, per-row mode
+        // re-converges the warp at the end of each iteration.
+        uint32_t j = 0;  // index of the tile in this CTA's tile sequence; tile j belongs to consumer j % C
+        if (p.contig) {
+            if (lane == 0) {
+                for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                    const uint64_t row0 = tile * RS;
+                    const uint32_t valid = (uint32_t)min((uint64_t)RS, p.n_rows - row0);
+                    const uint32_t lit = j / C;  // n_chunks == 1 in contig mode
+                    const uint32_t s = (j % C) * D + lit % D, ph = (lit / D) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t bytes = valid * p.row_stride;  // <= ~200 KB: fits tx-count and copy size
+                    mbar_expect_tx(bar_full + 8 * s, bytes);
+                    bulk_g2s(smem_u32(s_stage + (size_t)s * stage_bytes), p.vectors + row0 * p.row_stride, bytes,
+                             bar_full + 8 * s);
+                }
+            }
+            __syncwarp();  // lanes 1..31 wait here: the CTA barrier below must be reached by a converged warp
+        } else {
+            for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const uint64_t row0 = tile * RS;
+                const uint32_t valid = (uint32_t)min((uint64_t)RS, p.n_rows - row0);
+                for (uint32_t c = 0; c < p.n_chunks; ++c) {
+                    const uint32_t lit = (j / C) * p.n_chunks + c;
+                    const uint32_t s = (j % C) * D + lit % D, ph = (lit / D) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t dst0 = smem_u32(s_stage + (size_t)s * stage_bytes);
                     const uint32_t off = c * p.chunk_bytes;
                     const uint32_t len = min(p.chunk_bytes, p.row_stride - off);
                     if (lane == 0) mbar_expect_tx(bar_full + 8 * s, valid * len);
@@ -515,57 +551,60 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
                     for (uint32_t r = lane; r < valid; r += 32)
                         bulk_g2s(dst0 + r * p.smem_row_stride, p.vectors + (row0 + r) * p.row_stride + off, len,
                                  bar_full + 8 * s);
+                    __syncwarp();
                 }
             }
         }
     } else if ((uint32_t)warp < C) {
-        // ================= consumer warps =================
+        // ================= consumer warps: one warp per stage =================
         const int g = lane % LPR;
         const int rl = lane / LPR;
-        const uint32_t m_steps = R / (RPW * C);
+        const uint32_t m_steps = RS / RPW;
+        const uint32_t rot = !p.contig ? 0u : (LPR == 4 ? 4u * (rl & 1) : (uint32_t)(lane & 7));
         uint64_t* my_list = EMIT ? nullptr : s_list + (size_t)warp * QB * p.k;
         ListHdr* my_hdr = s_hdr + warp * QB;
         const uint32_t q_base = smem_u32(s_query);
-        uint32_t it = 0;
-        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint64_t row0 = tile * R;
-            const uint32_t it0 = it;
+        uint32_t jl = 0;  // how many tiles this warp has taken
+        for (uint64_t tile = blockIdx.x + (uint64_t)warp * gridDim.x; tile < n_tiles;
+             tile += (uint64_t)C * gridDim.x, ++jl) {
+            const uint64_t row0 = tile * RS;
+            const uint32_t it0 = jl * p.n_chunks;
             for (uint32_t ms = 0; ms < m_steps; ++ms) {
-                const uint32_t r_in_stage = (ms * C + warp) * RPW + rl;
+                const uint32_t r_in_stage = ms * RPW + rl;
                 typename T::Acc acc;
                 T::init(acc);
-                it = it0;
-                for (uint32_t c = 0; c < p.n_chunks; ++c, ++it) {
-                    const uint32_t s = it % S, ph = (it / S) & 1;
+                for (uint32_t c = 0; c < p.n_chunks; ++c) {
+                    const uint32_t lit = it0 + c;
+                    const uint32_t s = warp * D + lit % D, ph = (lit / D) & 1;
                     if (ms == 0) mbar_wait(bar_full + 8 * s, ph);
                     const uint32_t off = p.contig ? 0 : c * p.chunk_bytes;
                     const uint32_t len = p.contig ? p.row_stride : min(p.chunk_bytes, p.row_stride - off);
-                    const uint32_t units = len / 16;
-                    const uint32_t xb =
-                        smem_u32(s_stage + (size_t)s * stage_bytes) + r_in_stage * p.smem_row_stride + g * 16;
-                    const uint32_t qb = q_base + off + g * 16;
+                    const uint32_t units = len / 16, units8 = units & ~7u;
+                    const uint32_t xb = smem_u32(s_stage + (size_t)s * stage_bytes) + r_in_stage * p.smem_row_stride;
+                    const uint32_t qb = q_base + off;
                     uint32_t u = g;
                     // 4 units in flight per lane
                     for (; u + 3 * LPR < units; u += 4 * LPR) {
-                        const uint32_t o = (u - g) * 16;
-                        uint4 x0 = lds128(xb + o), x1 = lds128(xb + o + LPR * 16), x2 = lds128(xb + o + 2 * LPR * 16),
-                              x3 = lds128(xb + o + 3 * LPR * 16);
+                        const uint32_t o0 = phys_unit<T>(u, units8, rot) * 16, o1 = phys_unit<T>(u + LPR, units8, rot) * 16,
+                                       o2 = phys_unit<T>(u + 2 * LPR, units8, rot) * 16,
+                                       o3 = phys_unit<T>(u + 3 * LPR, units8, rot) * 16;
+                        uint4 x0 = lds128(xb + o0), x1 = lds128(xb + o1), x2 = lds128(xb + o2), x3 = lds128(xb + o3);
                         uint4 qv[QB];
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o);
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o0);
                         T::step(acc, x0, qv);
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o + LPR * 16);
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o1);
                         T::step(acc, x1, qv);
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o + 2 * LPR * 16);
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o2);
                         T::step(acc, x2, qv);
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o + 3 * LPR * 16);
+                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o3);
                         T::step(acc, x3, qv);
                     }
                     for (; u < units; u += LPR) {
-                        const uint32_t o = (u - g) * 16;
+                        const uint32_t o = phys_unit<T>(u, units8, rot) * 16;
                         uint4 x0 = lds128(xb + o);
                         uint4 qv[QB];
 #pragma unroll
@@ -606,15 +645,15 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
                 const uint64_t* src = s_list + ((size_t)w * QB + i) * p.k;
                 const uint32_t cnt = s_hdr[w * QB + i].cnt;
                 for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                    const uint32_t j = j0 + lane;
-                    uint64_t key = j < cnt ? src[j] : KEY_NONE;
-                    list_offer(dst, dh, p.k, key, j < cnt, lane);
+                    const uint32_t jj = j0 + lane;
+                    uint64_t key = jj < cnt ? src[jj] : KEY_NONE;
+                    list_offer(dst, dh, p.k, key, jj < cnt, lane);
                 }
             }
             __syncwarp();
             uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
             const uint32_t cnt = dh->cnt;
-            for (uint32_t j = lane; j < p.k; j += 32) out[j] = j < cnt ? dst[j] : KEY_NONE;
+            for (uint32_t jj = lane; jj < p.k; jj += 32) out[jj] = jj < cnt ? dst[jj] : KEY_NONE;
         }
     }
 }

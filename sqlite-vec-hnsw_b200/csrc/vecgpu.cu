@@ -463,18 +463,18 @@ extern "C" int vecgpu_slab_get(vecgpu_slab* s, int64_t rowid, void* out_vec, int
 // scan planning
 // ---------------------------------------------------------------------------
 struct ScanCfg {
-    uint32_t C, QB, R, CB, n_chunks, srs, S, contig;
+    uint32_t C, QB, R, CB, n_chunks, srs, S /* ring depth per consumer warp */, contig;
     size_t smem;
 };
 
 static size_t scan_fixed_smem(uint32_t C, uint32_t QB, uint32_t row_stride, uint32_t k, bool emit) {
     return (size_t)QB * row_stride + 64 + (size_t)C * QB * sizeof(ListHdr) + (emit ? 0 : (size_t)C * QB * k * 8) +
-           2 * 16 * 8 + 128;
+           2 * 32 * 8 + 128;
 }
 
-static int plan_scan(int lpr, uint32_t row_stride, uint32_t k, uint32_t nq, bool emit, ScanCfg& c) {
+static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint32_t nq, bool emit, ScanCfg& c) {
     const uint32_t RPW = 32 / lpr;
-    c.C = std::min(8u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", 4)));
+    c.C = std::min(8u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", strict ? 4 : 6)));
     c.QB = emit ? 1 : (nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1);
     const uint32_t qb_cap = env_u32("VECGPU_SCAN_QB", 8);
     while (c.QB > 1 && c.QB > qb_cap) c.QB >>= 1;
@@ -484,24 +484,24 @@ static int plan_scan(int lpr, uint32_t row_stride, uint32_t k, uint32_t nq, bool
     const size_t fixed = scan_fixed_smem(c.C, c.QB, row_stride, k, emit);
     if (fixed + 2 * 16 * RPW > SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "row too wide for the scan kernel");
     const size_t avail = SMEM_MAX - fixed;
-    const uint32_t rows_min = RPW * c.C;
-    const uint32_t stage_target = env_u32("VECGPU_SCAN_STAGE_KB", 32) * 1024;
+    const uint32_t stage_target = std::max(1u, env_u32("VECGPU_SCAN_STAGE_KB", 24)) * 1024;
+    const bool force_rows = env_u32("VECGPU_SCAN_PERROW", 0) != 0;
 
-    const bool conflict_free_contig = lpr == 4 ? (row_stride % 128 == 64) : ((row_stride / 16) % 2 == 1);
-    if (row_stride <= 1024 && (conflict_free_contig || row_stride < 256) && (size_t)rows_min * row_stride * 2 <= avail) {
+    if (!strict && !force_rows && (size_t)RPW * row_stride * 3 <= avail) {
+        // contig mode: a stage is RS whole rows, one bulk copy
         c.contig = 1;
         c.CB = row_stride;
         c.n_chunks = 1;
         c.srs = row_stride;
-        uint32_t m = std::max(1u, stage_target / (rows_min * row_stride));
-        while (m > 1 && (size_t)m * rows_min * row_stride * 3 > avail) --m;
-        c.R = rows_min * m;
+        uint32_t m = std::max(1u, stage_target / (RPW * row_stride));
+        while (m > 1 && (size_t)m * RPW * row_stride * 4 > avail) --m;
+        c.R = RPW * m;
     } else {
+        // per-row mode: padded stage, one bulk copy per row chunk
         c.contig = 0;
-        // chunk limit so that >= 3 stages fit
-        uint32_t cb_limit = (uint32_t)(avail / 3 / rows_min);
+        uint32_t cb_limit = (uint32_t)(avail / 3 / RPW);
         cb_limit = cb_limit > 128 ? ((cb_limit - 64) / 64) * 64 : 64;
-        uint32_t cb_target = std::min(std::max(64u, (env_u32("VECGPU_SCAN_CB", 2048) / 64) * 64), cb_limit);
+        uint32_t cb_target = std::min(std::max(64u, (env_u32("VECGPU_SCAN_CB", strict ? 1024 : 4096) / 64) * 64), cb_limit);
         if (row_stride <= cb_target) {
             c.n_chunks = 1;
             c.CB = row_stride;
@@ -511,22 +511,25 @@ static int plan_scan(int lpr, uint32_t row_stride, uint32_t k, uint32_t nq, bool
             c.n_chunks = (row_stride + c.CB - 1) / c.CB;
         }
         uint32_t pad;
-        if (lpr == 4) pad = (64 + 128 - (c.CB % 128)) % 128;
-        else pad = ((c.CB / 16) % 2 == 0) ? 16 : 0;
+        if (lpr == 4) pad = (64 + 128 - (c.CB % 128)) % 128;   // row pitch == 64 (mod 128): 4-lane groups never collide
+        else pad = ((c.CB / 16) % 2 == 0) ? 16 : 0;            // odd unit pitch: thread-per-row never collides
         c.srs = c.CB + pad;
         uint32_t m = 1;
         if (c.n_chunks == 1) {
-            m = std::max(1u, stage_target / (rows_min * c.srs));
-            while (m > 1 && (size_t)m * rows_min * c.srs * 3 > avail) --m;
+            m = std::max(1u, stage_target / (RPW * c.srs));
+            while (m > 1 && (size_t)m * RPW * c.srs * 4 > avail) --m;
         }
-        c.R = rows_min * m;
+        c.R = RPW * m;
     }
     const size_t stage = (size_t)c.R * c.srs;
-    c.S = (uint32_t)std::min<size_t>(16, avail / stage);
-    const uint32_t s_cap = env_u32("VECGPU_SCAN_STAGES", 16);
-    if (c.S > s_cap && s_cap >= 2) c.S = s_cap;
-    if (c.S < 2) return fail(VECGPU_ERR_INVALID_PARAM, "scan plan does not fit shared memory (row_stride=%u k=%u)", row_stride, k);
-    c.smem = (size_t)c.S * stage + fixed;
+    uint32_t s_max = (uint32_t)std::min<size_t>(32, avail / stage);
+    const uint32_t s_cap = env_u32("VECGPU_SCAN_STAGES", 32);
+    if (s_max > s_cap && s_cap >= 1) s_max = s_cap;
+    if (s_max < 2) return fail(VECGPU_ERR_INVALID_PARAM, "scan plan does not fit shared memory (row_stride=%u k=%u)", row_stride, k);
+    // private ring of D >= 2 stages per consumer warp (so a warp's next stage loads while it computes)
+    while (c.C > 1 && s_max / c.C < 2) --c.C;
+    c.S = std::max(1u, std::min(s_max / c.C, env_u32("VECGPU_SCAN_RING", 4)));   // D
+    c.smem = (size_t)c.S * c.C * stage + fixed;
     return 0;
 }
 
@@ -558,7 +561,8 @@ static int launch_scan_qb(const ScanParams& p, const ScanCfg& c, bool emit, dim3
 template <int QB> using I8L2T = I8Dot<QB, false>;
 template <int QB> using I8CosT = I8Dot<QB, true>;
 
-static int metric_lpr(int elem, int metric) { return (elem == VECGPU_F32 && metric == VECGPU_L1) ? 1 : 4; }
+static bool metric_strict(int elem, int metric) { return elem == VECGPU_F32 && metric == VECGPU_L1; }
+static int metric_lpr(int elem, int metric) { return (metric_strict(elem, metric) || elem == VECGPU_BIT) ? 1 : 4; }
 static uint32_t metric_qc_kind(int elem) { return elem == VECGPU_I8 ? 1u : 0u; }
 
 static int launch_scan(int elem, int metric, const ScanParams& p, const ScanCfg& c, bool emit, dim3 grid, cudaStream_t st) {
@@ -642,7 +646,7 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
 
     if (k <= K_FUSED_MAX) {
         ScanCfg c;
-        rc = plan_scan(lpr, s->row_stride, k, nq, false, c);
+        rc = plan_scan(lpr, metric_strict(s->elem, metric), s->row_stride, k, nq, false, c);
         if (rc) return rc;
         const uint64_t n_tiles = (s->rows + c.R - 1) / c.R;
         const uint32_t gx = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)s->num_sms);
@@ -676,7 +680,7 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
 
     // ---- large k: emit one key per row, radix sort, decode the first k ----
     ScanCfg c;
-    rc = plan_scan(lpr, s->row_stride, 1, 1, true, c);
+    rc = plan_scan(lpr, metric_strict(s->elem, metric), s->row_stride, 1, 1, true, c);
     if (rc) return rc;
     const uint64_t n_tiles = (s->rows + c.R - 1) / c.R;
     const uint32_t gx = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)s->num_sms);
@@ -781,7 +785,7 @@ extern "C" int vecgpu_knn_device(vecgpu_slab* s, const void* d_queries, uint32_t
     std::lock_guard<std::mutex> lk(s->mu);
     rc = use_device(s->device);
     if (rc) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA default stream, as everywhere in CUDA
     const uint8_t* dq = (const uint8_t*)d_queries;
     if (s->row_bytes != s->row_stride) {
         rc = ws_reserve(s, WS_QUERY, (size_t)nq * s->row_stride);
