@@ -474,7 +474,7 @@ static size_t scan_fixed_smem(uint32_t C, uint32_t QB, uint32_t row_stride, uint
 
 static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint32_t nq, bool emit, ScanCfg& c) {
     const uint32_t RPW = 32 / lpr;
-    c.C = std::min(8u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", strict ? 4 : 6)));
+    c.C = std::min(8u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", 8)));
     c.QB = emit ? 1 : (nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1);
     const uint32_t qb_cap = env_u32("VECGPU_SCAN_QB", 8);
     while (c.QB > 1 && c.QB > qb_cap) c.QB >>= 1;
@@ -484,7 +484,7 @@ static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint
     const size_t fixed = scan_fixed_smem(c.C, c.QB, row_stride, k, emit);
     if (fixed + 2 * 16 * RPW > SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "row too wide for the scan kernel");
     const size_t avail = SMEM_MAX - fixed;
-    const uint32_t stage_target = std::max(1u, env_u32("VECGPU_SCAN_STAGE_KB", 24)) * 1024;
+    const uint32_t stage_target = std::max(1u, env_u32("VECGPU_SCAN_STAGE_KB", 16)) * 1024;
     const bool force_rows = env_u32("VECGPU_SCAN_PERROW", 0) != 0;
 
     if (!strict && !force_rows && (size_t)RPW * row_stride * 3 <= avail) {

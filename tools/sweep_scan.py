@@ -41,9 +41,9 @@ def main():
         ("bit[1024] ham k=10", BIT, 1024, HAM, 10, 64_000_000, 0),
     ]
     knobs = {
-        "VECGPU_SCAN_WARPS": ["6"] if quick else ["4", "6", "8"],
+        "VECGPU_SCAN_WARPS": ["6"] if quick else ["2", "4", "6", "8"],
         "VECGPU_SCAN_CB": ["4096"] if quick else ["1024", "2048"],
-        "VECGPU_SCAN_STAGE_KB": ["24"] if quick else ["16", "32", "48"],
+        "VECGPU_SCAN_STAGE_KB": ["24"] if quick else ["8", "16", "24", "48"],
     }
     results = []
     for name, elem, dims, metric, k, n, kind in cfgs:
