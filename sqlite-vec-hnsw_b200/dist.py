@@ -43,9 +43,10 @@ def all_gather_topk(rowids, dists, group=None):
 
     world = dist.get_world_size(group)
     local = pack_local(rowids, dists)
-    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    # concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [world, nq, k, 2]
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local, group=group)
-    return unpack_gathered(out)
+    return unpack_gathered(out.view((world,) + tuple(local.shape)))
 
 
 class ShardedSlab:

@@ -405,3 +405,61 @@ def test_full_size_properties(vg, orc, gpu):
             rows = np.concatenate([orc.synth_rows(F32, 3, int(x), 1, dims, 1) for x in r[qi]])
             want = orc.distances(F32, dims, rows, q[qi], COSINE)
             assert np.array_equal(bits(d[qi]), bits(want))
+
+
+# ------------------------------------------------------------------ multi-GPU pieces on one GPU
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_cross_shard_merge_kernel(vg, orc, gpu, world):
+    """Shards emulated on one device: per-shard vecgpu_knn_device results -> vecgpu_merge_device == one big slab."""
+    import torch
+
+    from sqlite_vec_hnsw_b200.dist import pack_local, shard_range, unpack_gathered
+
+    dims, n, k = 16, 3001, 20
+    v = random_rows(I8, n, dims, seed=61, ties=True)
+    q = random_rows(I8, 5, dims, seed=62, ties=True)
+    dq = torch.from_numpy(q).cuda()
+    parts = []
+    for rank in range(world):
+        lo, hi = shard_range(n, rank, world)
+        s = vg.Slab(I8, dims)
+        s.load(v[lo:hi], np.arange(1 + lo, 1 + hi, dtype="<i8"))
+        r, d = s.knn_device(dq, k, L2)
+        torch.cuda.synchronize()
+        parts.append(pack_local(r, d))
+        s.close()
+    gr, gd = unpack_gathered(torch.stack(parts))
+    mr, md = vg.merge_device(gr, gd)
+    torch.cuda.synchronize()
+    er, ed, _ = orc.knn(I8, dims, v, q, k, L2)
+    assert np.array_equal(mr.cpu().numpy(), er) and np.array_equal(bits(md.cpu().numpy()), bits(ed))
+
+
+def test_knn_device_matches_host_api(vg, orc, gpu):
+    import torch
+
+    for elem, dims, metric in ((F32, 100, COSINE), (BIT, 1000, HAMMING), (F32, 6, L1)):
+        v = random_rows(elem, 5000, dims, seed=71)
+        q = random_rows(elem, 9, dims, seed=72)
+        with vg.Slab(elem, dims) as s:
+            s.load(v)
+            r, d, c = s.knn(q, 10, metric)
+            dr, dd = s.knn_device(torch.from_numpy(q).cuda(), 10, metric)
+            torch.cuda.synchronize()
+        assert np.array_equal(dr.cpu().numpy(), r) and np.array_equal(bits(dd.cpu().numpy()), bits(d))
+
+
+def test_scan_repeat_launch_stress(vg, gpu):
+    """Many back-to-back launches of every pipeline mode must neither hang nor change their answer
+    (regression test for the barrier-phase aliasing bug)."""
+    import torch
+
+    for elem, dims, metric, n in ((F32, 768, COSINE, 300_000), (F32, 768, L1, 100_000), (I8, 1024, L2, 400_000), (BIT, 1024, HAMMING, 2_000_000)):
+        with vg.Slab(elem, dims) as s:
+            s.fill_synthetic(seed=9, n=n, kind=1 if elem == F32 else 0)
+            q = torch.randn(dims, device="cuda") if elem == F32 else torch.randint(0, 255, (s.row_bytes,), dtype=torch.uint8, device="cuda")
+            r0, d0 = s.knn_device(q, 10, metric)
+            for _ in range(150):
+                r, d = s.knn_device(q, 10, metric)
+            torch.cuda.synchronize()
+            assert torch.equal(r, r0) and torch.equal(d, d0)
