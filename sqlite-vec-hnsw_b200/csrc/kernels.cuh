@@ -80,6 +80,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -153,6 +155,7 @@ struct F32L2 {
     }
     static constexpr bool HAS_QC = false;
     static constexpr bool ORDER_FREE = false;
+    static constexpr bool HAS_BOUND = false;
 };
 
 template <int QB>
@@ -182,13 +185,28 @@ struct F32Cos {
             for (int e = 0; e < 4; ++e) a.ab[i][e] = __fmaf_rn(qf[e], xf[e], a.ab[i][e]);
         }
     }
-    __device__ static float finish(const Acc& a, int i, const float* qc) {
-        float b2 = canon_tree(a.b2[0], a.b2[1], a.b2[2], a.b2[3]);
-        float ab = canon_tree(a.ab[i][0], a.ab[i][1], a.ab[i][2], a.ab[i][3]);
-        return cos_finish((double)ab, (double)qc[i], (double)b2);
+    struct Red {
+        float ab, b2;
+    };
+    __device__ static Red reduce(const Acc& a, int i) {
+        Red r;
+        r.b2 = canon_tree(a.b2[0], a.b2[1], a.b2[2], a.b2[3]);
+        r.ab = canon_tree(a.ab[i][0], a.ab[i][1], a.ab[i][2], a.ab[i][3]);
+        return r;
     }
+    // cheap f32 value guaranteed <= the exact f64-finished distance (|error| of the f32 path <= 6e-7 for
+    // |cos| <= 1; margin 2e-6).  -inf when a2*b2 leaves the safe range: the caller then takes the exact path.
+    __device__ static float bound(const Red& r, float a2) {
+        const float p = __fmul_rn(a2, r.b2);
+        if (!(p > 1e-30f && p < 1e30f)) return __int_as_float(0xFF800000);
+        const float c = __fmul_rn(r.ab, rsqrtf(p));
+        return __fsub_rn(__fsub_rn(1.0f, c), 2e-6f);
+    }
+    __device__ static float exact(const Red& r, float a2) { return cos_finish((double)r.ab, (double)a2, (double)r.b2); }
+    __device__ static float finish(const Acc& a, int i, const float* qc) { return exact(reduce(a, i), qc[i]); }
     static constexpr bool HAS_QC = true;
     static constexpr bool ORDER_FREE = false;
+    static constexpr bool HAS_BOUND = true;
 };
 
 template <int QB>
@@ -214,6 +232,7 @@ struct F32L1 {
     __device__ static float finish(const Acc& a, int i, const float*) { return a.s[i]; }
     static constexpr bool HAS_QC = false;
     static constexpr bool ORDER_FREE = false;
+    static constexpr bool HAS_BOUND = false;
 };
 
 // int8: exact int32 partial sums by dp4a; |q|^2 arrives as a float-encoded pair in qc (hi/lo split not
@@ -221,37 +240,61 @@ struct F32L1 {
 template <int QB, bool COS>
 struct I8Dot {
     static constexpr int LPR = 4;
-    struct Acc {
-        int bb;
-        int ab[QB];
+    struct Acc {  // four independent partial sums per quantity: IDP.4A chains stay short
+        int bb[4];
+        int ab[QB][4];
     };
     __device__ static void init(Acc& a) {
-        a.bb = 0;
 #pragma unroll
-        for (int q = 0; q < QB; ++q) a.ab[q] = 0;
+        for (int e = 0; e < 4; ++e) a.bb[e] = 0;
+#pragma unroll
+        for (int q = 0; q < QB; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.ab[q][e] = 0;
     }
     __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
         const int xw[4] = {(int)x.x, (int)x.y, (int)x.z, (int)x.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) a.bb = __dp4a(xw[e], xw[e], a.bb);
+        for (int e = 0; e < 4; ++e) a.bb[e] = __dp4a(xw[e], xw[e], a.bb[e]);
 #pragma unroll
         for (int i = 0; i < QB; ++i) {
             const int qw[4] = {(int)q[i].x, (int)q[i].y, (int)q[i].z, (int)q[i].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a.ab[i] = __dp4a(qw[e], xw[e], a.ab[i]);
+            for (int e = 0; e < 4; ++e) a.ab[i][e] = __dp4a(qw[e], xw[e], a.ab[i][e]);
         }
     }
-    __device__ static float finish(const Acc& a, int i, const float* qc) {
-        long long bb = group4_sum_i(a.bb);
-        long long ab = group4_sum_i(a.ab[i]);
-        long long a2 = (long long)__float_as_int(qc[i]);
-        if (COS) return cos_finish((double)ab, (double)a2, (double)bb);
-        long long s = a2 + bb - 2 * ab;  // == sum (a-b)^2 exactly
+    struct Red {
+        int bb, ab;
+    };
+    __device__ static Red reduce(const Acc& a, int i) {
+        Red r;
+        r.bb = group4_sum_i((a.bb[0] + a.bb[1]) + (a.bb[2] + a.bb[3]));
+        r.ab = group4_sum_i((a.ab[i][0] + a.ab[i][1]) + (a.ab[i][2] + a.ab[i][3]));
+        return r;
+    }
+    // cheap f32 lower bound of the exact distance (see F32Cos::bound); qa2 carries |q|^2 as int bits
+    __device__ static float bound(const Red& r, float qa2) {
+        const long long a2 = (long long)__float_as_int(qa2);
+        if (COS) {
+            const float p = __fmul_rn((float)a2, (float)r.bb);
+            if (!(p > 1e-30f && p < 1e30f)) return __int_as_float(0xFF800000);
+            const float c = __fmul_rn((float)r.ab, rsqrtf(p));
+            return __fsub_rn(__fsub_rn(1.0f, c), 3e-6f);
+        }
+        const long long s = a2 + (long long)r.bb - 2ll * (long long)r.ab;
+        return __fmul_rn(__fsqrt_rn((float)s), 0.9999995f);  // sqrtf((float)s) is within 2^-23 of sqrt(s)
+    }
+    __device__ static float exact(const Red& r, float qa2) {
+        const long long a2 = (long long)__float_as_int(qa2);
+        if (COS) return cos_finish((double)r.ab, (double)a2, (double)r.bb);
+        const long long s = a2 + (long long)r.bb - 2ll * (long long)r.ab;  // == sum (a-b)^2 exactly
         // src/distance/scalar.rs:65: distance.sqrt() as f32  (f64 sqrt, then cast)
         return __double2float_rn(__dsqrt_rn((double)s));
     }
+    __device__ static float finish(const Acc& a, int i, const float* qc) { return exact(reduce(a, i), qc[i]); }
     static constexpr bool HAS_QC = true;
     static constexpr bool ORDER_FREE = true;
+    static constexpr bool HAS_BOUND = true;
 };
 
 __device__ __forceinline__ unsigned absdiff_s8x4(unsigned a, unsigned b) {
@@ -264,11 +307,13 @@ template <int QB>
 struct I8L1 {
     static constexpr int LPR = 4;
     struct Acc {
-        int s[QB];
+        int s[QB][4];
     };
     __device__ static void init(Acc& a) {
 #pragma unroll
-        for (int q = 0; q < QB; ++q) a.s[q] = 0;
+        for (int q = 0; q < QB; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a.s[q][e] = 0;
     }
     __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
         const unsigned xw[4] = {x.x, x.y, x.z, x.w};
@@ -276,33 +321,40 @@ struct I8L1 {
         for (int i = 0; i < QB; ++i) {
             const unsigned qw[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a.s[i] = (int)__dp4a(absdiff_s8x4(qw[e], xw[e]), 0x01010101u, (unsigned)a.s[i]);
+            for (int e = 0; e < 4; ++e)
+                a.s[i][e] = (int)__dp4a(absdiff_s8x4(qw[e], xw[e]), 0x01010101u, (unsigned)a.s[i][e]);
         }
     }
-    __device__ static float finish(const Acc& a, int i, const float*) { return (float)group4_sum_i(a.s[i]); }
+    __device__ static float finish(const Acc& a, int i, const float*) {
+        return (float)group4_sum_i((a.s[i][0] + a.s[i][1]) + (a.s[i][2] + a.s[i][3]));
+    }
     static constexpr bool HAS_QC = false;
     static constexpr bool ORDER_FREE = true;
+    static constexpr bool HAS_BOUND = false;
 };
 
 // Hamming: one thread per row (rows are short: bit[1024] = 128 B), exact popcount
 template <int QB>
 struct BitHamming {
     static constexpr int LPR = 1;
-    struct Acc {
-        int s[QB];
+    struct Acc {  // two independent add chains
+        int s[QB][2];
     };
     __device__ static void init(Acc& a) {
 #pragma unroll
-        for (int q = 0; q < QB; ++q) a.s[q] = 0;
+        for (int q = 0; q < QB; ++q) a.s[q][0] = a.s[q][1] = 0;
     }
     __device__ static void step(Acc& a, uint4 x, const uint4 (&q)[QB]) {
 #pragma unroll
-        for (int i = 0; i < QB; ++i)
-            a.s[i] += __popc(x.x ^ q[i].x) + __popc(x.y ^ q[i].y) + __popc(x.z ^ q[i].z) + __popc(x.w ^ q[i].w);
+        for (int i = 0; i < QB; ++i) {
+            a.s[i][0] += __popc(x.x ^ q[i].x) + __popc(x.y ^ q[i].y);
+            a.s[i][1] += __popc(x.z ^ q[i].z) + __popc(x.w ^ q[i].w);
+        }
     }
-    __device__ static float finish(const Acc& a, int i, const float*) { return (float)a.s[i]; }
+    __device__ static float finish(const Acc& a, int i, const float*) { return (float)(a.s[i][0] + a.s[i][1]); }
     static constexpr bool HAS_QC = false;
     static constexpr bool ORDER_FREE = true;
+    static constexpr bool HAS_BOUND = false;
 };
 
 // |q|^2 of one query in the representation finish() expects; executed by one
@@ -407,30 +459,49 @@ __device__ __forceinline__ void list_offer(uint64_t* list, ListHdr* hdr, uint32_
     }
 }
 
+// in-place ascending bitonic sort of n (power of two) u64 keys in shared memory by the whole CTA
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, uint32_t n) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == up) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K1/K3/K4 (+K2a when QB>1): the streaming scan.
 //
-// Persistent CTAs (one per SM): warp C is the producer, warps 0..C-1 consume.
-// The slab is cut into tiles of RS rows; tile t belongs to CTA t % gridDim.x,
-// and the j-th tile of a CTA to consumer warp j % C.  Every tile travels
-// through a ring of S shared-memory stages:
+// Persistent CTAs (one per SM) of C warps.  The slab is cut into tiles of RS
+// rows; tile t belongs to CTA t % gridDim.x and the j-th tile of a CTA to warp
+// j % C.  Every warp owns a private ring of D shared-memory stages and is its
+// own producer: after it has finished reading a stage it immediately issues
+// the bulk copy of the tile D steps ahead into that stage.  Hence there is one
+// mbarrier per stage (full[s], completed by the copy's transaction bytes), no
+// "empty" barrier, no producer warp and no cross-warp protocol; a barrier is
+// only ever waited on, in phase order, by the warp that armed it.
 //   contig mode : ONE cp.async.bulk per stage (RS*row_stride contiguous bytes,
-//                 >= 16 KB, so the fixed per-copy cost of the copy engine — about
+//                 >= 8 KB, so the fixed per-copy cost of the copy engine — about
 //                 70 cycles, measured — is amortised).  Bank conflicts are
 //                 avoided without padding by rotating the order in which a lane
 //                 reads the 16-byte units of a 128-byte segment (legal for the
 //                 order-free integer metrics); the canonical-order f32 metrics
 //                 accept a 2-way conflict (shared memory has >2x headroom).
-//   per-row mode: one bulk copy per row chunk into a padded stage; used for
-//                 f32 L1 (strict order, thread-per-row needs odd unit strides)
-//                 and for rows too wide for RPW whole rows per stage.
-// Each consumer warp owns a private ring of D stages (S = C*D in total) that the
-// producer fills in tile order, so every full[]/empty[] barrier is waited on
-// strictly in phase order by one warp.  (With shared round-robin stages a warp
-// could observe the parity of an older, still incomplete phase when bulk copies
-// complete out of order — measured as sporadic launch failures.)
-// full[s] completes on the copy's transaction bytes, empty[s] on the single
-// arrival of the owning consumer warp.
+//   per-row mode: one bulk copy per row chunk (>= 1.5 KB) into a padded stage;
+//                 used for f32 L1 (strict order, thread-per-row needs odd unit
+//                 strides) and for rows too wide for RPW whole rows per stage.
+// History: a shared round-robin ring with a producer warp failed sporadically —
+// with copies completing out of order a warp could observe the parity of an
+// older, still incomplete phase (mbarrier parity waits alias every two phases).
 // ---------------------------------------------------------------------------
 struct ScanParams {
     const uint8_t* vectors;  // slab rows, row_stride bytes apart, zero padded
@@ -447,8 +518,9 @@ struct ScanParams {
     uint32_t rows_per_stage;   // RS = RPW * m   (m == 1 when n_chunks > 1); one consumer warp per stage
     uint32_t n_stages;         // D: ring depth per consumer warp (C*D stages in total)
     uint32_t contig;           // 1: a stage is one contiguous bulk copy (smem_row_stride == row_stride)
-    uint32_t n_consumers;      // C consumer warps; warp C is the producer
+    uint32_t n_consumers;      // C warps per CTA (blockDim = 32*C)
     uint32_t qc_kind;          // 0 f32 sum of squares, 1 int8
+    uint32_t list_stride;      // keys reserved per query for the C per-warp lists: pow2 >= C*k
 };
 
 // physical unit read by a lane for logical unit u (see "rotating" above)
@@ -460,7 +532,7 @@ __device__ __forceinline__ uint32_t phys_unit(uint32_t u, uint32_t units8, uint3
 }
 
 template <class T, int QB, bool EMIT>
-__global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     constexpr int LPR = T::LPR;
     constexpr int RPW = 32 / LPR;  // rows a warp scores at once
     extern __shared__ __align__(128) uint8_t smem[];
@@ -474,17 +546,14 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
     float* s_qc = (float*)(s_query + (size_t)QB * p.row_stride);
     ListHdr* s_hdr = (ListHdr*)((uint8_t*)s_qc + 64);
     uint64_t* s_list = (uint64_t*)(s_hdr + C * QB);
-    uint64_t* s_bar = s_list + (EMIT ? 0 : (size_t)C * QB * p.k);
-    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + S);
+    uint64_t* s_bar = s_list + (EMIT ? 0 : (size_t)QB * p.list_stride);  // lists are query-major: [QB][list_stride]
+    const uint32_t bar_full = smem_u32(s_bar);
 
     const uint32_t q0 = blockIdx.y * QB;  // first query of this pass
     const uint32_t nq_here = min((uint32_t)QB, p.nq_total - q0);
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
-        }
+        for (uint32_t s = 0; s < S; ++s) mbar_init(bar_full + 8 * s, 1);
         mbar_fence_init();
     }
     // stage queries (zero-fill the slots past nq_here so the arithmetic stays finite)
@@ -514,60 +583,65 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
 
     const uint64_t n_tiles = (p.n_rows + RS - 1) / RS;
 
-    if ((uint32_t)warp == C) {
-        // ================= producer warp: bulk copies global -> shared =================
-        // Parity waits alias every two phases, so every lane that waits must stay within one
-        // iteration of the lane that issues: contig mode runs on lane 0 alone, per-row mode
-        // re-converges the warp at the end of each iteration.
-        uint32_t j = 0;  // index of the tile in this CTA's tile sequence; tile j belongs to consumer j % C
-        if (p.contig) {
-            if (lane == 0) {
-                for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-                    const uint64_t row0 = tile * RS;
-                    const uint32_t valid = (uint32_t)min((uint64_t)RS, p.n_rows - row0);
-                    const uint32_t lit = j / C;  // n_chunks == 1 in contig mode
-                    const uint32_t s = (j % C) * D + lit % D, ph = (lit / D) & 1;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    const uint32_t bytes = valid * p.row_stride;  // <= ~200 KB: fits tx-count and copy size
-                    mbar_expect_tx(bar_full + 8 * s, bytes);
-                    bulk_g2s(smem_u32(s_stage + (size_t)s * stage_bytes), p.vectors + row0 * p.row_stride, bytes,
-                             bar_full + 8 * s);
-                }
-            }
-            __syncwarp();  // lanes 1..31 wait here: the CTA barrier below must be reached by a converged warp
-        } else {
-            for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-                const uint64_t row0 = tile * RS;
-                const uint32_t valid = (uint32_t)min((uint64_t)RS, p.n_rows - row0);
-                for (uint32_t c = 0; c < p.n_chunks; ++c) {
-                    const uint32_t lit = (j / C) * p.n_chunks + c;
-                    const uint32_t s = (j % C) * D + lit % D, ph = (lit / D) & 1;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    const uint32_t dst0 = smem_u32(s_stage + (size_t)s * stage_bytes);
-                    const uint32_t off = c * p.chunk_bytes;
-                    const uint32_t len = min(p.chunk_bytes, p.row_stride - off);
-                    if (lane == 0) mbar_expect_tx(bar_full + 8 * s, valid * len);
-                    __syncwarp();
-                    for (uint32_t r = lane; r < valid; r += 32)
-                        bulk_g2s(dst0 + r * p.smem_row_stride, p.vectors + (row0 + r) * p.row_stride + off, len,
-                                 bar_full + 8 * s);
-                    __syncwarp();
-                }
-            }
-        }
-    } else if ((uint32_t)warp < C) {
-        // ================= consumer warps: one warp per stage =================
+    {
+        // ================= every warp: consumer + producer of its own ring =================
         const int g = lane % LPR;
         const int rl = lane / LPR;
         const uint32_t m_steps = RS / RPW;
         const uint32_t rot = !p.contig ? 0u : (LPR == 4 ? 4u * (rl & 1) : (uint32_t)(lane & 7));
-        uint64_t* my_list = EMIT ? nullptr : s_list + (size_t)warp * QB * p.k;
+        uint64_t* my_list = EMIT ? nullptr : s_list + (size_t)warp * p.k;  // + i*list_stride for query i
         ListHdr* my_hdr = s_hdr + warp * QB;
         const uint32_t q_base = smem_u32(s_query);
-        uint32_t jl = 0;  // how many tiles this warp has taken
-        for (uint64_t tile = blockIdx.x + (uint64_t)warp * gridDim.x; tile < n_tiles;
-             tile += (uint64_t)C * gridDim.x, ++jl) {
-            const uint64_t row0 = tile * RS;
+        const uint32_t my_bar = bar_full + 8 * warp * D;
+        uint8_t* my_stage = s_stage + (size_t)warp * D * stage_bytes;
+        // number of tiles of this warp: tiles blockIdx.x + (warp + i*C)*gridDim.x < n_tiles
+        const uint64_t first_tile = blockIdx.x + (uint64_t)warp * gridDim.x;
+        const uint64_t tile_step = (uint64_t)C * gridDim.x;
+        const uint32_t my_tiles = first_tile < n_tiles ? (uint32_t)((n_tiles - first_tile + tile_step - 1) / tile_step) : 0u;
+        const uint32_t my_iters = my_tiles * p.n_chunks;
+
+        // issue the copies of ring iteration `lit` (tile lit / n_chunks, chunk lit % n_chunks) into slot lit % D
+        auto issue = [&](uint32_t lit) {
+            if (lit >= my_iters) return;
+            const uint32_t jl = lit / p.n_chunks, c = lit - jl * p.n_chunks;
+            const uint64_t row0 = (first_tile + (uint64_t)jl * tile_step) * RS;
+            const uint32_t valid = (uint32_t)min((uint64_t)RS, p.n_rows - row0);
+            const uint32_t slot = lit % D;
+            const uint32_t bar = my_bar + 8 * slot;
+            const uint32_t dst0 = smem_u32(my_stage + (size_t)slot * stage_bytes);
+            fence_proxy_async();  // the stage was read through the generic proxy; the copy writes through the async proxy
+            if (p.contig) {
+                if (lane == 0) {
+                    const uint32_t bytes = valid * p.row_stride;  // <= ~200 KB: fits tx-count and copy size
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(dst0, p.vectors + row0 * p.row_stride, bytes, bar);
+                }
+            } else {
+                const uint32_t off = c * p.chunk_bytes;
+                const uint32_t len = min(p.chunk_bytes, p.row_stride - off);
+                if (lane == 0) mbar_expect_tx(bar, valid * len);
+                __syncwarp();
+                for (uint32_t r = lane; r < valid; r += 32)
+                    bulk_g2s(dst0 + r * p.smem_row_stride, p.vectors + (row0 + r) * p.row_stride + off, len, bar);
+            }
+            __syncwarp();
+        };
+        for (uint32_t lit = 0; lit < D; ++lit) issue(lit);  // prologue: fill the ring
+
+        // thread-per-row integer path (Hamming): byte offsets of the 8 units of a 128-byte segment in this
+        // lane's rotated order, and the query in registers when a row is exactly one segment (bit[1024])
+        uint32_t offs[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) offs[t] = ((uint32_t)(t + rot) & 7u) * 16u;
+        const bool qreg_ok = (LPR == 1) && T::ORDER_FREE && (QB == 1) && p.contig && p.row_stride == 128;
+        uint4 qreg[8];
+        if (qreg_ok) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) qreg[t] = lds128(q_base + offs[t]);
+        }
+
+        for (uint32_t jl = 0; jl < my_tiles; ++jl) {
+            const uint64_t row0 = (first_tile + (uint64_t)jl * tile_step) * RS;
             const uint32_t it0 = jl * p.n_chunks;
             for (uint32_t ms = 0; ms < m_steps; ++ms) {
                 const uint32_t r_in_stage = ms * RPW + rl;
@@ -575,33 +649,114 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
                 T::init(acc);
                 for (uint32_t c = 0; c < p.n_chunks; ++c) {
                     const uint32_t lit = it0 + c;
-                    const uint32_t s = warp * D + lit % D, ph = (lit / D) & 1;
-                    if (ms == 0) mbar_wait(bar_full + 8 * s, ph);
+                    const uint32_t s = lit % D, ph = (lit / D) & 1;
+                    if (ms == 0) mbar_wait(my_bar + 8 * s, ph);
                     const uint32_t off = p.contig ? 0 : c * p.chunk_bytes;
                     const uint32_t len = p.contig ? p.row_stride : min(p.chunk_bytes, p.row_stride - off);
                     const uint32_t units = len / 16, units8 = units & ~7u;
-                    const uint32_t xb = smem_u32(s_stage + (size_t)s * stage_bytes) + r_in_stage * p.smem_row_stride;
+                    const uint32_t xb = smem_u32(my_stage + (size_t)s * stage_bytes) + r_in_stage * p.smem_row_stride;
                     const uint32_t qb = q_base + off;
                     uint32_t u = g;
+                    if constexpr (LPR == 1 && T::ORDER_FREE) {
+                        const uint32_t nseg = units >> 3;
+                        for (uint32_t sg = 0; sg < nseg; ++sg) {
+                            const uint32_t xs = xb + sg * 128, qs = qb + sg * 128;
+                            uint4 xv[8];
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) xv[t] = lds128(xs + offs[t]);
+                            if (qreg_ok) {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) {
+                                    uint4 qv[QB];
+                                    qv[0] = qreg[t];
+#pragma unroll
+                                    for (int i = 1; i < QB; ++i) qv[i] = qreg[t];
+                                    T::step(acc, xv[t], qv);
+                                }
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) {
+                                    uint4 qv[QB];
+#pragma unroll
+                                    for (int i = 0; i < QB; ++i) qv[i] = lds128(qs + i * p.row_stride + offs[t]);
+                                    T::step(acc, xv[t], qv);
+                                }
+                            }
+                        }
+                        u = nseg * 8;  // the (< 8) tail units below are read unrotated
+                    }
+                    if constexpr (LPR == 4 && T::ORDER_FREE) {
+                        // predicate-free walk over full 128-byte segments: this lane's two units of a segment sit at
+                        // oA / oB (swapped for odd rows, which is what keeps the 4-lane groups off each other's banks)
+                        const uint32_t nseg = units >> 3;
+                        const uint32_t oA = (uint32_t)(g + rot) * 16u, oB = (uint32_t)(g + 4 - rot) * 16u;
+                        uint32_t sg = 0;
+                        for (; sg + 2 <= nseg; sg += 2) {
+                            const uint32_t xs = xb + sg * 128, qs = qb + sg * 128;
+                            uint4 x0 = lds128(xs + oA), x1 = lds128(xs + oB), x2 = lds128(xs + 128 + oA),
+                                  x3 = lds128(xs + 128 + oB);
+                            uint4 q0v[QB], q1v[QB], q2v[QB], q3v[QB];
+#pragma unroll
+                            for (int i = 0; i < QB; ++i) {
+                                q0v[i] = lds128(qs + i * p.row_stride + oA);
+                                q1v[i] = lds128(qs + i * p.row_stride + oB);
+                                q2v[i] = lds128(qs + i * p.row_stride + 128 + oA);
+                                q3v[i] = lds128(qs + i * p.row_stride + 128 + oB);
+                            }
+                            T::step(acc, x0, q0v);
+                            T::step(acc, x1, q1v);
+                            T::step(acc, x2, q2v);
+                            T::step(acc, x3, q3v);
+                        }
+                        if (sg < nseg) {
+                            const uint32_t xs = xb + sg * 128, qs = qb + sg * 128;
+                            uint4 x0 = lds128(xs + oA), x1 = lds128(xs + oB);
+                            uint4 q0v[QB], q1v[QB];
+#pragma unroll
+                            for (int i = 0; i < QB; ++i) {
+                                q0v[i] = lds128(qs + i * p.row_stride + oA);
+                                q1v[i] = lds128(qs + i * p.row_stride + oB);
+                            }
+                            T::step(acc, x0, q0v);
+                            T::step(acc, x1, q1v);
+                        }
+                        u = g + nseg * 8;  // the (< 8) tail units below are read unrotated
+                    }
                     // 4 units in flight per lane
                     for (; u + 3 * LPR < units; u += 4 * LPR) {
                         const uint32_t o0 = phys_unit<T>(u, units8, rot) * 16, o1 = phys_unit<T>(u + LPR, units8, rot) * 16,
                                        o2 = phys_unit<T>(u + 2 * LPR, units8, rot) * 16,
                                        o3 = phys_unit<T>(u + 3 * LPR, units8, rot) * 16;
                         uint4 x0 = lds128(xb + o0), x1 = lds128(xb + o1), x2 = lds128(xb + o2), x3 = lds128(xb + o3);
-                        uint4 qv[QB];
+                        if constexpr (QB <= 2) {
+                            // all eight (x, q) loads in flight before the first FMA
+                            uint4 qa[QB], qb2[QB], qc2[QB], qd[QB];
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o0);
-                        T::step(acc, x0, qv);
+                            for (int i = 0; i < QB; ++i) {
+                                qa[i] = lds128(qb + i * p.row_stride + o0);
+                                qb2[i] = lds128(qb + i * p.row_stride + o1);
+                                qc2[i] = lds128(qb + i * p.row_stride + o2);
+                                qd[i] = lds128(qb + i * p.row_stride + o3);
+                            }
+                            T::step(acc, x0, qa);
+                            T::step(acc, x1, qb2);
+                            T::step(acc, x2, qc2);
+                            T::step(acc, x3, qd);
+                        } else {
+                            uint4 qv[QB];
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o1);
-                        T::step(acc, x1, qv);
+                            for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o0);
+                            T::step(acc, x0, qv);
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o2);
-                        T::step(acc, x2, qv);
+                            for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o1);
+                            T::step(acc, x1, qv);
 #pragma unroll
-                        for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o3);
-                        T::step(acc, x3, qv);
+                            for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o2);
+                            T::step(acc, x2, qv);
+#pragma unroll
+                            for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.row_stride + o3);
+                            T::step(acc, x3, qv);
+                        }
                     }
                     for (; u < units; u += LPR) {
                         const uint32_t o = phys_unit<T>(u, units8, rot) * 16;
@@ -612,8 +767,8 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
                         T::step(acc, x0, qv);
                     }
                     if (ms == m_steps - 1) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+                        __syncwarp();     // every lane has consumed its loads of this stage
+                        issue(lit + D);   // refill it with the tile D steps ahead
                     }
                 }
                 // ---- distance -> key -> fused top-k (or emit) ----
@@ -622,13 +777,22 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
                 if (live && p.skip != nullptr && g == 0) live = p.skip[row] == 0;
 #pragma unroll
                 for (int i = 0; i < QB; ++i) {
-                    float d = T::finish(acc, i, s_qc);
-                    if (EMIT) {
+                    if constexpr (EMIT) {
+                        float d = T::finish(acc, i, s_qc);
                         if (g == 0 && row < p.n_rows && (uint32_t)i < nq_here)
                             p.out_keys[(size_t)(q0 + i) * p.n_rows + row] = live ? make_key(d, (uint32_t)row) : KEY_NONE;
+                    } else if constexpr (T::HAS_BOUND) {
+                        // cheap f32 lower bound first; the f64 finish only when some row of the warp may enter the list
+                        const typename T::Red red = T::reduce(acc, i);
+                        const float tau_d = order_bits_inv((uint32_t)(my_hdr[i].tau >> 32));  // NaN while the list fills
+                        const bool cand = live && g == 0 && !(T::bound(red, s_qc[i]) > tau_d);
+                        if (__any_sync(0xffffffffu, cand)) {
+                            const float d = T::exact(red, s_qc[i]);
+                            list_offer(my_list + (size_t)i * p.list_stride, my_hdr + i, p.k, make_key(d, (uint32_t)row), cand, lane);
+                        }
                     } else {
-                        uint64_t key = make_key(d, (uint32_t)row);
-                        list_offer(my_list + (size_t)i * p.k, my_hdr + i, p.k, key, live && g == 0, lane);
+                        const float d = T::finish(acc, i, s_qc);
+                        list_offer(my_list + (size_t)i * p.list_stride, my_hdr + i, p.k, make_key(d, (uint32_t)row), live && g == 0, lane);
                     }
                 }
             }
@@ -636,25 +800,18 @@ __global__ void __launch_bounds__(288, 1) scan_kernel(const ScanParams p) {
     }
     if (EMIT) return;
     __syncthreads();
-    // ---- CTA merge: warp w folds the C lists of query i = w, w+C, ... into consumer 0's list ----
-    if ((uint32_t)warp < C) {
-        for (uint32_t i = warp; i < nq_here; i += C) {
-            uint64_t* dst = s_list + (size_t)i * p.k;  // consumer 0, query i
-            ListHdr* dh = s_hdr + i;
-            for (uint32_t w = 1; w < C; ++w) {
-                const uint64_t* src = s_list + ((size_t)w * QB + i) * p.k;
-                const uint32_t cnt = s_hdr[w * QB + i].cnt;
-                for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                    const uint32_t jj = j0 + lane;
-                    uint64_t key = jj < cnt ? src[jj] : KEY_NONE;
-                    list_offer(dst, dh, p.k, key, jj < cnt, lane);
-                }
-            }
-            __syncwarp();
-            uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
-            const uint32_t cnt = dh->cnt;
-            for (uint32_t jj = lane; jj < p.k; jj += 32) out[jj] = jj < cnt ? dst[jj] : KEY_NONE;
+    // ---- CTA merge: the C per-warp lists of a query are contiguous; blank the unused slots, bitonic-sort the
+    //      list_stride keys with the whole CTA and emit the k smallest as this CTA's partial result ----
+    for (uint32_t i = 0; i < nq_here; ++i) {
+        uint64_t* base = s_list + (size_t)i * p.list_stride;
+        for (uint32_t j = threadIdx.x; j < p.list_stride; j += blockDim.x) {
+            const uint32_t w = j / p.k, e = j - w * p.k;
+            if (w >= C || e >= s_hdr[w * QB + i].cnt) base[j] = KEY_NONE;
         }
+        __syncthreads();
+        block_bitonic_sort(base, p.list_stride);
+        uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
+        for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = base[j];
     }
 }
 
@@ -676,60 +833,17 @@ struct MergeParams {
     int64_t pad_rowid;        // value for unused slots (-1 host API, INT64_MAX device API)
 };
 
-__global__ void __launch_bounds__(256) merge_kernel(const MergeParams p) {
+// small candidate sets (n_cand <= 16384, e.g. 148 lists x k<=110): load everything, bitonic-sort, keep the first k.
+__global__ void __launch_bounds__(1024) merge_sort_kernel(const MergeParams p, uint32_t np2) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NW = 8;
-    ListHdr* hdr = (ListHdr*)smem;
-    uint64_t* lists = (uint64_t*)(hdr + NW);  // NW * k
-    uint64_t* sorted = lists + (size_t)NW * p.k;  // kp2
-    const uint64_t* keys = p.keys + (size_t)blockIdx.x * p.n_cand;
-    if (threadIdx.x < NW) {
-        hdr[threadIdx.x].tau = KEY_NONE;
-        hdr[threadIdx.x].maxpos = 0;
-        hdr[threadIdx.x].cnt = 0;
-    }
+    uint64_t* keys = (uint64_t*)smem;
+    const uint64_t* src = p.keys + (size_t)blockIdx.x * p.n_cand;
+    for (uint32_t j = threadIdx.x; j < np2; j += blockDim.x) keys[j] = j < p.n_cand ? src[j] : KEY_NONE;
     __syncthreads();
-    uint64_t* my = lists + (size_t)warp * p.k;
-    for (uint64_t j0 = (uint64_t)warp * 32; j0 < p.n_cand; j0 += NW * 32) {
-        const uint64_t j = j0 + lane;
-        uint64_t key = j < p.n_cand ? keys[j] : KEY_NONE;
-        list_offer(my, hdr + warp, p.k, key, key != KEY_NONE, lane);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < NW; ++w) {
-            const uint64_t* src = lists + (size_t)w * p.k;
-            const uint32_t cnt = hdr[w].cnt;
-            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                uint64_t key = j < cnt ? src[j] : KEY_NONE;
-                list_offer(my, hdr, p.k, key, j < cnt, lane);
-            }
-        }
-    }
-    __syncthreads();
-    const uint32_t cnt = hdr[0].cnt;
-    for (uint32_t j = threadIdx.x; j < p.kp2; j += blockDim.x) sorted[j] = j < cnt ? lists[j] : KEY_NONE;
-    __syncthreads();
-    // bitonic sort ascending over kp2 keys
-    for (uint32_t size = 2; size <= p.kp2; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < p.kp2 / 2; t += blockDim.x) {
-                uint32_t lo = 2 * t - (t & (stride - 1));
-                uint32_t hi = lo + stride;
-                bool up = (lo & size) == 0;
-                uint64_t a = sorted[lo], b = sorted[hi];
-                if ((a > b) == up) {
-                    sorted[lo] = b;
-                    sorted[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
+    block_bitonic_sort(keys, np2);
+    uint32_t cnt = 0;
     for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
-        const uint64_t key = sorted[j];
+        const uint64_t key = j < np2 ? keys[j] : KEY_NONE;
         const size_t o = (size_t)blockIdx.x * p.k + j;
         if (key == KEY_NONE) {
             p.out_rowids[o] = p.pad_rowid;
@@ -738,9 +852,44 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeParams p) {
             const uint32_t pos = (uint32_t)key;
             p.out_rowids[o] = p.rowids ? p.rowids[pos] : p.first_rowid + (int64_t)pos;
             p.out_dists[o] = order_bits_inv((uint32_t)(key >> 32));
+            ++cnt;
         }
     }
-    if (threadIdx.x == 0 && p.out_counts) p.out_counts[blockIdx.x] = cnt;
+    if (p.out_counts) {
+        __shared__ uint32_t total;
+        if (threadIdx.x == 0) total = 0;
+        __syncthreads();
+        if (cnt) atomicAdd(&total, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) p.out_counts[blockIdx.x] = total;
+    }
+}
+
+// large candidate sets: after a segmented radix sort of [nq][n_cand] keys, decode the first k of each segment
+__global__ void decode_segments_kernel(const uint64_t* keys, uint64_t n_cand, uint32_t k, const int64_t* rowids,
+                                       int64_t first_rowid, int64_t pad_rowid, int64_t* out_rowids, float* out_dists,
+                                       uint32_t* out_counts) {
+    const uint64_t* seg = keys + (size_t)blockIdx.x * n_cand;
+    __shared__ uint32_t total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    uint32_t cnt = 0;
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint64_t key = j < n_cand ? seg[j] : KEY_NONE;
+        const size_t o = (size_t)blockIdx.x * k + j;
+        if (key == KEY_NONE) {
+            out_rowids[o] = pad_rowid;
+            out_dists[o] = __int_as_float(0x7F800000);
+        } else {
+            const uint32_t pos = (uint32_t)key;
+            out_rowids[o] = rowids ? rowids[pos] : first_rowid + (int64_t)pos;
+            out_dists[o] = order_bits_inv((uint32_t)(key >> 32));
+            ++cnt;
+        }
+    }
+    if (cnt) atomicAdd(&total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && out_counts) out_counts[blockIdx.x] = total;
 }
 
 // large-k path (k > fused limit): after a full radix sort of the emitted keys

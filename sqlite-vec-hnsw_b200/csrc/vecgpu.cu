@@ -467,14 +467,23 @@ struct ScanCfg {
     size_t smem;
 };
 
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// per-query key slots for the C per-warp lists (query-major, padded to a power of two for the in-CTA bitonic merge)
+static uint32_t list_stride_for(uint32_t C, uint32_t k) { return std::max(2u, next_pow2(C * k)); }
+
 static size_t scan_fixed_smem(uint32_t C, uint32_t QB, uint32_t row_stride, uint32_t k, bool emit) {
-    return (size_t)QB * row_stride + 64 + (size_t)C * QB * sizeof(ListHdr) + (emit ? 0 : (size_t)C * QB * k * 8) +
-           2 * 32 * 8 + 128;
+    return (size_t)QB * row_stride + 64 + (size_t)C * QB * sizeof(ListHdr) +
+           (emit ? 0 : (size_t)QB * list_stride_for(C, k) * 8) + 2 * 32 * 8 + 128;
 }
 
 static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint32_t nq, bool emit, ScanCfg& c) {
     const uint32_t RPW = 32 / lpr;
-    c.C = std::min(8u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", 8)));
+    c.C = std::min(16u, std::max(1u, env_u32("VECGPU_SCAN_WARPS", 16)));
     c.QB = emit ? 1 : (nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1);
     const uint32_t qb_cap = env_u32("VECGPU_SCAN_QB", 8);
     while (c.QB > 1 && c.QB > qb_cap) c.QB >>= 1;
@@ -484,7 +493,7 @@ static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint
     const size_t fixed = scan_fixed_smem(c.C, c.QB, row_stride, k, emit);
     if (fixed + 2 * 16 * RPW > SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "row too wide for the scan kernel");
     const size_t avail = SMEM_MAX - fixed;
-    const uint32_t stage_target = std::max(1u, env_u32("VECGPU_SCAN_STAGE_KB", 16)) * 1024;
+    const uint32_t stage_target = std::max(1u, env_u32("VECGPU_SCAN_STAGE_KB", 8)) * 1024;
     const bool force_rows = env_u32("VECGPU_SCAN_PERROW", 0) != 0;
 
     if (!strict && !force_rows && (size_t)RPW * row_stride * 3 <= avail) {
@@ -501,7 +510,7 @@ static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint
         c.contig = 0;
         uint32_t cb_limit = (uint32_t)(avail / 3 / RPW);
         cb_limit = cb_limit > 128 ? ((cb_limit - 64) / 64) * 64 : 64;
-        uint32_t cb_target = std::min(std::max(64u, (env_u32("VECGPU_SCAN_CB", strict ? 1024 : 4096) / 64) * 64), cb_limit);
+        uint32_t cb_target = std::min(std::max(64u, (env_u32("VECGPU_SCAN_CB", strict ? 2048 : 4096) / 64) * 64), cb_limit);
         if (row_stride <= cb_target) {
             c.n_chunks = 1;
             c.CB = row_stride;
@@ -522,8 +531,8 @@ static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint
         c.R = RPW * m;
     }
     const size_t stage = (size_t)c.R * c.srs;
-    uint32_t s_max = (uint32_t)std::min<size_t>(32, avail / stage);
-    const uint32_t s_cap = env_u32("VECGPU_SCAN_STAGES", 32);
+    uint32_t s_max = (uint32_t)std::min<size_t>(64, avail / stage);
+    const uint32_t s_cap = env_u32("VECGPU_SCAN_STAGES", 64);
     if (s_max > s_cap && s_cap >= 1) s_max = s_cap;
     if (s_max < 2) return fail(VECGPU_ERR_INVALID_PARAM, "scan plan does not fit shared memory (row_stride=%u k=%u)", row_stride, k);
     // private ring of D >= 2 stages per consumer warp (so a warp's next stage loads while it computes)
@@ -542,7 +551,7 @@ static int launch_scan_inst(const ScanParams& p, const ScanCfg& c, dim3 grid, cu
         CU(cudaFuncSetAttribute(scan_kernel<T, QB, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         configured_for_device = dev;
     }
-    scan_kernel<T, QB, EMIT><<<grid, 32 * (c.C + 1), c.smem, st>>>(p);
+    scan_kernel<T, QB, EMIT><<<grid, 32 * c.C, c.smem, st>>>(p);
     LAUNCHED();
     return 0;
 }
@@ -579,23 +588,39 @@ static int launch_scan(int elem, int metric, const ScanParams& p, const ScanCfg&
     return launch_scan_qb<BitHamming>(p, c, emit, grid, st);
 }
 
-static uint32_t next_pow2(uint32_t v) {
-    uint32_t p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
-static int launch_merge(const MergeParams& mp, uint32_t nq, cudaStream_t st) {
-    const size_t smem = 8 * sizeof(ListHdr) + (size_t)8 * mp.k * 8 + (size_t)mp.kp2 * 8;
-    static int configured_for_device = -1;
-    int dev = 0;
-    CU(cudaGetDevice(&dev));
-    if (configured_for_device != dev) {
-        CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured_for_device = dev;
+// final selection over the per-CTA partial lists: [nq][n_cand] keys -> k smallest per query, decoded
+static int launch_merge(vecgpu_slab* s, const MergeParams& mp, uint32_t nq, cudaStream_t st) {
+    if (mp.n_cand <= 16384) {
+        // fits one CTA's shared memory: one bitonic sort per query
+        const uint32_t np2 = std::max(2u, next_pow2((uint32_t)mp.n_cand));
+        static int cfg_dev = -1;
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        if (cfg_dev != dev) {
+            CU(cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            cfg_dev = dev;
+        }
+        const uint32_t threads = std::min(1024u, std::max(32u, np2 / 2));
+        merge_sort_kernel<<<nq, threads, (size_t)np2 * 8, st>>>(mp, np2);
+        LAUNCHED();
+        return 0;
     }
-    merge_kernel<<<nq, 256, smem, st>>>(mp);
-    LAUNCHED();
+    // large candidate sets (k in the hundreds): radix-sort each query's candidates, decode the first k
+    int rc = ws_reserve(s, WS_TMP, (size_t)mp.n_cand * 8);
+    if (rc) return rc;
+    size_t sort_bytes = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, mp.keys, (uint64_t*)s->d_ws[WS_TMP], (int)mp.n_cand, 0, 64, st));
+    rc = ws_reserve(s, WS_TMP3, sort_bytes);
+    if (rc) return rc;
+    for (uint32_t q = 0; q < nq; ++q) {
+        CU(cub::DeviceRadixSort::SortKeys(s->d_ws[WS_TMP3], sort_bytes, mp.keys + (size_t)q * mp.n_cand,
+                                          (uint64_t*)s->d_ws[WS_TMP], (int)mp.n_cand, 0, 64, st));
+        g_launches.fetch_add(4, std::memory_order_relaxed);
+        decode_segments_kernel<<<1, 256, 0, st>>>((const uint64_t*)s->d_ws[WS_TMP], mp.n_cand, mp.k, mp.rowids, mp.first_rowid,
+                                                  mp.pad_rowid, mp.out_rowids + (size_t)q * mp.k,
+                                                  mp.out_dists + (size_t)q * mp.k, mp.out_counts ? mp.out_counts + q : nullptr);
+        LAUNCHED();
+    }
     return 0;
 }
 
@@ -624,7 +649,7 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
             mp.out_rowids = d_out_rowids;
             mp.out_dists = d_out_dists;
             mp.out_counts = d_out_counts;
-            return launch_merge(mp, nq, st);
+            return launch_merge(s, mp, nq, st);
         }
         for (uint32_t q = 0; q < nq; ++q) {
             decode_sorted_kernel<<<64, 256, 0, st>>>((const uint64_t*)s->d_ws[WS_PART], 0, k, nullptr, 0, pad_rowid,
@@ -662,6 +687,7 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
         p.n_stages = c.S;
         p.contig = c.contig;
         p.n_consumers = c.C;
+        p.list_stride = list_stride_for(c.C, k);
         rc = launch_scan(s->elem, metric, p, c, false, dim3(gx, gy), st);
         if (rc) return rc;
         MergeParams mp{};
@@ -675,7 +701,7 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
         mp.out_dists = d_out_dists;
         mp.out_counts = d_out_counts;
         mp.pad_rowid = pad_rowid;
-        return launch_merge(mp, nq, st);
+        return launch_merge(s, mp, nq, st);
     }
 
     // ---- large k: emit one key per row, radix sort, decode the first k ----
@@ -702,6 +728,7 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
     p.n_stages = c.S;
     p.contig = c.contig;
     p.n_consumers = c.C;
+    p.list_stride = 2;
     p.nq_total = 1;
     for (uint32_t q = 0; q < nq; ++q) {
         cub::DoubleBuffer<uint64_t> dbq((uint64_t*)s->d_ws[WS_TMP], (uint64_t*)s->d_ws[WS_TMP2]);

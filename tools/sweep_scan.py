@@ -17,17 +17,20 @@ L2, L1, COS, HAM = 0, 1, 2, 3
 
 
 def time_knn(slab, q, k, metric, iters=6):
+    """median per-launch time (ms) over `iters` launches, CUDA events on the launch stream"""
     st = torch.cuda.current_stream()
     for _ in range(2):
         slab.knn_device(q, k, metric)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(st)
+    evs = []
     for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
         slab.knn_device(q, k, metric)
-    b.record(st)
+        b.record(st)
+        evs.append((a, b))
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    return float(np.median([a.elapsed_time(b) for a, b in evs]))
 
 
 def main():
@@ -41,12 +44,15 @@ def main():
         ("bit[1024] ham k=10", BIT, 1024, HAM, 10, 64_000_000, 0),
     ]
     knobs = {
-        "VECGPU_SCAN_WARPS": ["6"] if quick else ["2", "4", "6", "8"],
-        "VECGPU_SCAN_CB": ["4096"] if quick else ["1024", "2048"],
-        "VECGPU_SCAN_STAGE_KB": ["24"] if quick else ["8", "16", "24", "48"],
+        "VECGPU_SCAN_WARPS": ["16"] if quick else ["8", "12", "16"],
+        "VECGPU_SCAN_CB": ["2048"],
+        "VECGPU_SCAN_STAGE_KB": ["8"] if quick else ["4", "8", "12"],
     }
     results = []
+    only = os.environ.get("SWEEP_ONLY")
     for name, elem, dims, metric, k, n, kind in cfgs:
+        if only and not any(o in name for o in only.split(",")):
+            continue
         slab = vg.Slab(elem, dims)
         slab.fill_synthetic(seed=7, n=n, kind=kind)
         rb = slab.row_bytes
@@ -59,7 +65,7 @@ def main():
             os.environ["VECGPU_SCAN_WARPS"], os.environ["VECGPU_SCAN_CB"], os.environ["VECGPU_SCAN_STAGE_KB"] = w, cb, skb
             signal.alarm(40)  # a hung kernel must not eat the GPU budget: default SIGALRM action kills us
             try:
-                ms = time_knn(slab, q, k, metric, iters=20)
+                ms = time_knn(slab, q, k, metric, iters=30)
             except Exception as e:  # plan may not fit
                 print(f"{name:22s} warps={w} cb={cb} stage_kb={skb}: {e}")
                 continue
