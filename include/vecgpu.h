@@ -160,6 +160,10 @@ int vecgpu_merge_device(int device, const int64_t* d_rowids, const float* d_dist
 /* Number of kernels this library has launched in this process (bench's
  * gpu_launches claim). */
 uint64_t vecgpu_launch_count(void);
+/* Batched float32 queries (nq >= 16, L2 / cosine) run as a tcgen05 3xTF32 contraction that only selects
+ * candidates, followed by an exact re-rank; a query whose candidate bound cannot be certified is re-run
+ * through the exact scan.  Counters since process start: queries served by that path / of which fell back. */
+void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks);
 
 #ifdef __cplusplus
 }

@@ -44,3 +44,12 @@ def version():
 
 def launch_count():
     return int(_lib.load().vecgpu_launch_count())
+
+
+def tc_stats():
+    """(queries served by the tensor-core batched path, of which fell back to the exact scan)."""
+    import ctypes as C
+
+    q, f = C.c_uint64(), C.c_uint64()
+    _lib.load().vecgpu_tc_stats(C.byref(q), C.byref(f))
+    return int(q.value), int(f.value)

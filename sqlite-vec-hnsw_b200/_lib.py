@@ -41,6 +41,7 @@ SIGNATURES = {
     "vecgpu_knn_device": (C.c_int, [_c_slab, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
     "vecgpu_merge_device": (C.c_int, [C.c_int, _p, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _p, _p]),
     "vecgpu_launch_count": (C.c_uint64, []),
+    "vecgpu_tc_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

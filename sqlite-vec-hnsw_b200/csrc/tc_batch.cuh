@@ -1,0 +1,380 @@
+// tc_batch.cuh — K2: batched float32 queries as a tensor-core contraction (tcgen05, kind::tf32, 3xTF32).
+//
+// Replaces, for nq >> 1 queries, the per-pair simsimd calls of the exact scan
+// (src/vtab.rs:2594-2616 -> src/distance/scalar.rs:17,48) by S = Q * X^T on the 5th-gen tensor cores:
+//     ||q - x||^2 = ||q||^2 + ||x||^2 - 2 q.x          cos(q,x) = q.x / (||q|| ||x||)
+// q.x is computed with 3xTF32 error compensation.  The tensor core TRUNCATES fp32 operands to tf32
+// (measured, tools/umma_test.cu), so with hi = x (as the hardware sees it) and lo = x - trunc_tf32(x)
+// (exact in fp32):  q.x ~= hi_q.hi_x + lo_q.hi_x + hi_q.lo_x   (the lo.lo term, ~2^-22, is dropped).
+// The result only SELECTS candidates: every query keeps its k+32 best approximate scores per CTA, a
+// rigorous error bound turns them into a candidate superset of the exact top-k, and the candidates
+// are re-scored by pair_kernel in the canonical fp32 order, so the final rowids and distances are
+// bit-identical to the single-query scan.  Queries whose bound cannot be certified (massive ties)
+// fall back to the exact scan.
+//
+// One CTA per SM, 12 warps, warp-specialised:
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of a 128x32 query chunk + 256x32 row chunk
+//   warp 1      tcgen05.mma issuer (one lane); owns the TMEM allocation (512 columns = 2 accumulators)
+//   warps 4-7   epilogue: tcgen05.ld of the 128x256 fp32 accumulator, score -> threshold -> candidate list
+//   warps 8-11  transform: lo = x - trunc(x) for both operands, written to the twin "lo" tiles
+// Pipelines: full_raw/full_lo/empty per smem stage, tmem_full/tmem_empty per accumulator.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace vg {
+
+static constexpr uint32_t TC_M = 128;      // queries per CTA tile (UMMA M)
+static constexpr uint32_t TC_N = 256;      // slab rows per tile (UMMA N)
+static constexpr uint32_t TC_KC = 32;      // floats per k-chunk = 128 bytes = one swizzle span
+static constexpr uint32_t TC_STAGES = 2;
+static constexpr uint32_t TC_A_BYTES = TC_M * 128, TC_B_BYTES = TC_N * 128;
+static constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // raw + lo of both operands = 96 KB
+static constexpr uint32_t TC_THREADS = 384;
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128
+static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
+
+struct TcParams {
+    uint64_t n_rows;
+    uint32_t nq, nk;       // queries, k-chunks (ceil(dims/32); TMA zero-fills the ragged tail)
+    uint32_t kp;           // entries kept per (CTA, query) = k + margin
+    uint32_t cosine;       // 0: L2 (v = x2 - 2s), 1: cosine (v = -s / |x|)
+    uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
+    const float* norms;    // [rows] canonical sum of squares of each slab row
+    const uint8_t* skip;   // per-row skip flags or nullptr
+    float* cand_v;         // [grid][128][kp] approximate scores kept
+    uint32_t* cand_r;      // [grid][128][kp] row positions
+    uint32_t* cand_cnt;    // [grid][128]
+    float* cand_tau;       // [grid][128] largest kept score when the list is full, else +inf
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 128-byte rows; 8-row groups 1024 B apart (SBO)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t xbits) {
+    const float x = __uint_as_float(xbits);
+    return __float_as_uint(__fsub_rn(x, __uint_as_float(xbits & 0xFFFFE000u)));  // exact
+}
+
+// thread-private candidate list in global memory: unsorted, tracked maximum (the admission bound tau)
+struct TcList {
+    uint32_t cnt, maxpos;
+    float tau;
+};
+__device__ __noinline__ TcList tc_insert(float v, uint32_t row, float* lv, uint32_t* lr, uint32_t kp, TcList st) {
+    if (st.cnt < kp) {
+        lv[st.cnt] = v;
+        lr[st.cnt] = row;
+        if (++st.cnt < kp) return st;
+    } else {
+        lv[st.maxpos] = v;
+        lr[st.maxpos] = row;
+    }
+    float best = lv[0];
+    uint32_t bp = 0;
+    for (uint32_t i = 1; i < kp; ++i) {
+        const float x = lv[i];
+        if (x > best) {
+            best = x;
+            bp = i;
+        }
+    }
+    st.tau = best;
+    st.maxpos = bp;
+    return st;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TcParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // SWIZZLE_128B tiles must sit on 1024-byte boundaries: align by hand (the launch reserves 1 KB of slack)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // layout: [stage][A_raw | A_lo | B_raw | B_lo] ... [colA[2][256] | colB[2][256]] [barriers] [tmem slot]
+    float* s_colA = (float*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    float* s_colB = s_colA + 2 * TC_N;
+    uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
+    uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
+    const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + 2), bar_empty = smem_u32(s_bar + 4),
+                   bar_tfull = smem_u32(s_bar + 6), bar_tempty = smem_u32(s_bar + 8);
+
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full_raw + 8 * s, 1);
+            mbar_init(bar_full_lo + 8 * s, 4);   // one arrival per transform warp
+            mbar_init(bar_empty + 8 * s, 1);     // tcgen05.commit
+        }
+        for (uint32_t a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);     // tcgen05.commit
+            mbar_init(bar_tempty + 8 * a, 4);    // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const uint32_t qt = blockIdx.x % p.QT, g = blockIdx.x / p.QT;
+    const uint64_t n_xt = (p.n_rows + TC_N - 1) / TC_N;
+    const uint32_t my_tiles = g < n_xt ? (uint32_t)((n_xt - g + p.G - 1) / p.G) : 0u;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+                const int row0 = (int)(((uint64_t)g + (uint64_t)ti * p.G) * TC_N);
+                for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
+                    mbar_expect_tx(bar_full_raw + 8 * s, TC_A_BYTES + TC_B_BYTES);
+                    tma_load_2d(base, &mapQ, (int)(kc * TC_KC), (int)(qt * TC_M), bar_full_raw + 8 * s);
+                    tma_load_2d(base + 2 * TC_A_BYTES, &mapX, (int)(kc * TC_KC), row0, bar_full_raw + 8 * s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+                const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_N;
+                for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), a_lo = a_raw + TC_A_BYTES,
+                                   b_raw = a_raw + 2 * TC_A_BYTES, b_lo = b_raw + TC_B_BYTES;
+                    mbar_wait(bar_full_raw + 8 * s, ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)  // hi.hi
+                        umma_tf32(d_tmem, umma_desc(a_raw + k * 32), umma_desc(b_raw + k * 32), (kc | k) != 0);
+                    mbar_wait(bar_full_lo + 8 * s, ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)  // lo_q.hi_x
+                        umma_tf32(d_tmem, umma_desc(a_lo + k * 32), umma_desc(b_raw + k * 32), 1);
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)  // hi_q.lo_x
+                        umma_tf32(d_tmem, umma_desc(a_raw + k * 32), umma_desc(b_lo + k * 32), 1);
+                    umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
+                }
+                umma_commit(bar_tfull + 8 * acc);    // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 8) {
+        // ===== transform warps: lo = x - trunc_tf32(x), same (swizzled) positions in the twin tile =====
+        const uint32_t t = threadIdx.x - 256;  // 0..127
+        uint32_t it = 0;
+        for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+            for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), b_raw = a_raw + 2 * TC_A_BYTES;
+                mbar_wait(bar_full_raw + 8 * s, ph);
+#pragma unroll 4
+                for (uint32_t u = t; u < TC_A_BYTES / 16; u += 128) {
+                    uint4 v = lds128(a_raw + u * 16);
+                    v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+                    sts128(a_raw + TC_A_BYTES + u * 16, v);
+                }
+#pragma unroll 4
+                for (uint32_t u = t; u < TC_B_BYTES / 16; u += 128) {
+                    uint4 v = lds128(b_raw + u * 16);
+                    v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+                    sts128(b_raw + TC_B_BYTES + u * 16, v);
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full_lo + 8 * s);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps: thread = query (TMEM lane), columns = slab rows of the tile =====
+        const uint32_t e = threadIdx.x - 128;        // 0..127 == TMEM lane == query within the tile
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
+        const size_t lbase = ((size_t)blockIdx.x * TC_M + e) * p.kp;
+        float* lv = p.cand_v + lbase;
+        uint32_t* lr = p.cand_r + lbase;
+        TcList st;
+        st.cnt = 0;
+        st.maxpos = 0;
+        // tile rows past nq hold zero-filled queries: they never admit anything
+        st.tau = (qt * TC_M + e < p.nq) ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
+        for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+            const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+            // per-column coefficients: v = s * a + b
+            for (uint32_t j = e; j < TC_N; j += 128) {
+                const uint64_t row = row0 + j;
+                const bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
+                const float x2 = ok ? p.norms[row] : 0.f;
+                float a, b;
+                if (p.cosine) {
+                    a = (ok && x2 > 0.f) ? -rsqrtf(x2) : 0.f;
+                    b = ok ? 0.f : __int_as_float(0x7F800000);
+                } else {
+                    a = -2.f;
+                    b = ok ? x2 : __int_as_float(0x7F800000);
+                }
+                s_colA[acc * TC_N + j] = a;
+                s_colB[acc * TC_N + j] = b;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+            mbar_wait(bar_tfull + 8 * acc, aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < TC_N / 32; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (lane_base << 16) + acc * TC_N + c * 32;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float* ca = s_colA + acc * TC_N + c * 32;
+                const float* cb = s_colB + acc * TC_N + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sc = __fmaf_rn(__uint_as_float(v[j]), ca[j], cb[j]);
+                    if (sc < st.tau) st = tc_insert(sc, (uint32_t)(row0 + c * 32 + j), lv, lr, p.kp, st);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        p.cand_cnt[(size_t)blockIdx.x * TC_M + e] = st.cnt;
+        p.cand_tau[(size_t)blockIdx.x * TC_M + e] = st.cnt == p.kp ? st.tau : __int_as_float(0x7F800000);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// canonical sum of squares of every row (the b2 / a2 of F32Cos), plus the maximum over all rows
+__global__ void __launch_bounds__(256) row_norms_kernel(const uint8_t* base, uint32_t stride, uint32_t units, uint64_t n, float* norms,
+                                                        uint32_t* max_bits) {
+    const int g = threadIdx.x & 3;
+    const uint64_t n_iter = (n + 63) / 64;
+    float mx = 0.f;
+    for (uint64_t itn = blockIdx.x; itn < n_iter; itn += gridDim.x) {
+        const uint64_t row = itn * 64 + (threadIdx.x >> 2);
+        const uint4* r = (const uint4*)(base + (row < n ? row : 0) * (uint64_t)stride);
+        const float v = query_const(r, row < n ? units : 0, g, 0);
+        if (row < n && g == 0) {
+            norms[row] = v;
+            if (v == v && v < __int_as_float(0x7F800000)) mx = fmaxf(mx, v);
+        }
+    }
+    for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    if ((threadIdx.x & 31) == 0 && max_bits) atomicMax(max_bits, __float_as_uint(mx));
+}
+
+// Per query: gather the kept approximate scores of all its CTAs, sort, derive the certified candidate set.
+struct TcCollectParams {
+    TcParams t;
+    uint32_t k, cap;            // cap: power of two >= G*kp, candidate slots per query
+    uint32_t dims;
+    const float* qnorm;         // [nq] canonical |q|^2
+    const uint32_t* x2max_bits; // max row norm
+    uint64_t n_live;
+    uint32_t* pair_q;           // [nq*cap] query index of each candidate slot
+    int64_t* pair_pos;          // [nq*cap] row position or -1
+    uint8_t* fallback;          // [nq] 1 = bound not certified, use the exact scan
+};
+__global__ void __launch_bounds__(512) tc_collect_kernel(const TcCollectParams c) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* keys = (uint64_t*)smem;  // (order_bits(v) << 32) | slot
+    const uint32_t q = blockIdx.x, qt = q / TC_M, e = q % TC_M;
+    const TcParams& p = c.t;
+    __shared__ uint32_t s_bad, s_total;
+    if (threadIdx.x == 0) { s_bad = 0; s_total = 0; }
+    __syncthreads();
+    const uint32_t total_slots = p.G * p.kp;
+    for (uint32_t j = threadIdx.x; j < c.cap; j += blockDim.x) {
+        uint64_t key = KEY_NONE;
+        if (j < total_slots) {
+            const uint32_t gg = j / p.kp, i = j - gg * p.kp;
+            const size_t cta = (size_t)gg * p.QT + qt;
+            if (i < p.cand_cnt[cta * TC_M + e]) {
+                key = ((uint64_t)order_bits(p.cand_v[(cta * TC_M + e) * p.kp + i]) << 32) | j;
+                atomicAdd(&s_total, 1u);
+            }
+        }
+        keys[j] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, c.cap);
+    const uint32_t total = s_total;
+    // error bound of the approximate score (worst case over D fp32 accumulations of 3xTF32 partial products)
+    const float q2 = c.qnorm[q], x2max = __uint_as_float(*c.x2max_bits);
+    const float unit = (float)(c.dims + 32) * 4.76837158e-7f;  // (D+32) * 2^-21
+    const float eps = p.cosine ? unit * sqrtf(q2) : unit * (q2 + x2max);
+    float bound = __int_as_float(0x7F800000);
+    if (total >= c.k) bound = order_bits_inv((uint32_t)(keys[c.k - 1] >> 32)) + 2.f * eps;
+    // every full per-CTA list must have dropped only scores above the bound
+    for (uint32_t gg = threadIdx.x; gg < p.G; gg += blockDim.x) {
+        const size_t cta = (size_t)gg * p.QT + qt;
+        if (p.cand_cnt[cta * TC_M + e] == p.kp && !(p.cand_tau[cta * TC_M + e] > bound)) atomicExch(&s_bad, 1u);
+    }
+    if (threadIdx.x == 0 && total < c.k && (uint64_t)total < c.n_live) s_bad = 1;  // NaN/inf scores hid rows
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < c.cap; j += blockDim.x) {
+        const uint64_t key = keys[j];
+        int64_t pos = -1;
+        if (key != KEY_NONE && !(order_bits_inv((uint32_t)(key >> 32)) > bound)) {
+            const uint32_t slot = (uint32_t)key, gg = slot / p.kp, i = slot - gg * p.kp;
+            const size_t cta = (size_t)gg * p.QT + qt;
+            pos = (int64_t)p.cand_r[(cta * TC_M + e) * p.kp + i];
+        }
+        c.pair_q[(size_t)q * c.cap + j] = q;
+        c.pair_pos[(size_t)q * c.cap + j] = pos;
+    }
+    if (threadIdx.x == 0) c.fallback[q] = (uint8_t)s_bad;
+}
+
+// exact distances of the candidate pairs -> ranking keys (KEY_NONE for empty slots)
+__global__ void tc_keys_kernel(const float* dist, const int64_t* pos, uint64_t n, uint64_t* keys) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = pos[i] >= 0 ? make_key(dist[i], (uint32_t)pos[i]) : KEY_NONE;
+}
+
+}  // namespace vg

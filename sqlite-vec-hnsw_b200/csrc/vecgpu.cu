@@ -15,6 +15,7 @@
 
 #include "../../include/vecgpu.h"
 #include "kernels.cuh"
+#include "tc_batch.cuh"
 
 using namespace vg;
 
@@ -23,6 +24,7 @@ using namespace vg;
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_tc_queries{0}, g_tc_fallbacks{0};
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -80,14 +82,21 @@ struct vecgpu_slab {
     std::vector<uint8_t> h_skip;
     uint8_t* d_skip = nullptr;
     uint64_t cap_skip = 0, n_skip = 0;
+    // canonical |row|^2 cache for the tensor-core batched path (invalidated by any vector write)
+    float* d_norms = nullptr;
+    uint32_t* d_x2max = nullptr;
+    uint64_t cap_norms = 0;
+    bool norms_valid = false;
     // workspaces
-    void* d_ws[8] = {nullptr};
-    size_t ws_cap[8] = {0};
+    void* d_ws[20] = {nullptr};
+    size_t ws_cap[20] = {0};
     void* h_pin[2] = {nullptr};
     size_t pin_cap[2] = {0};
 };
 
-enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7 };
+enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7,
+       WS_TC_CANDV = 8, WS_TC_CANDR = 9, WS_TC_CNT = 10, WS_TC_TAU = 11, WS_TC_PAIRQ = 12, WS_TC_PAIRPOS = 13, WS_TC_DIST = 14,
+       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_COUNT = 20 };
 
 static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
     if (bytes <= s->ws_cap[i]) return 0;
@@ -197,6 +206,7 @@ static int slab_set_skip(vecgpu_slab* s, uint64_t pos, uint8_t v) {
 // copy n host rows (row_bytes each) into slab rows [pos, pos+n)
 static int slab_write_rows(vecgpu_slab* s, uint64_t pos, const void* vectors, uint64_t n) {
     if (n == 0) return 0;
+    s->norms_valid = false;
     uint8_t* dst = s->d_vec + pos * s->row_stride;
     if (s->row_bytes == s->row_stride) {
         CU(cudaMemcpy(dst, vectors, (size_t)n * s->row_bytes, cudaMemcpyHostToDevice));
@@ -213,6 +223,10 @@ extern "C" {
 const char* vecgpu_last_error(void) { return g_err; }
 const char* vecgpu_version(void) { return "vecgpu 0.1.0 sm_100a"; }
 uint64_t vecgpu_launch_count(void) { return g_launches.load(); }
+void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks) {
+    if (queries) *queries = g_tc_queries.load();
+    if (fallbacks) *fallbacks = g_tc_fallbacks.load();
+}
 
 int vecgpu_device_count(void) {
     int n = 0;
@@ -300,7 +314,9 @@ extern "C" void vecgpu_slab_destroy(vecgpu_slab* s) {
     cudaFree(s->d_vec);
     cudaFree(s->d_rowids);
     cudaFree(s->d_skip);
-    for (int i = 0; i < 8; ++i) cudaFree(s->d_ws[i]);
+    for (int i = 0; i < WS_COUNT; ++i) cudaFree(s->d_ws[i]);
+    cudaFree(s->d_norms);
+    cudaFree(s->d_x2max);
     for (int i = 0; i < 2; ++i)
         if (s->h_pin[i]) cudaFreeHost(s->h_pin[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -412,6 +428,7 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
                            cudaMemcpyDeviceToDevice, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
+    s->norms_valid = false;
     s->h_rowids.insert(s->h_rowids.begin() + (ptrdiff_t)ins, rowid);
     if (!s->h_skip.empty()) {
         s->h_skip.resize(s->rows, 0);
@@ -625,7 +642,7 @@ static int launch_merge(vecgpu_slab* s, const MergeParams& mp, uint32_t nq, cuda
 }
 
 // queries already on the device, padded to row_stride.  Results to device arrays.
-static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
+static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
     int rc;
     if (k == 0 || nq == 0) return 0;
@@ -744,6 +761,190 @@ static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k,
         LAUNCHED();
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K2: tensor-core batched path (tc_batch.cuh)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_f32_map(CUtensorMap* m, const void* base, uint32_t dims, uint64_t rows, uint32_t stride_bytes, uint32_t box_rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn) return fail(VECGPU_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    cuuint64_t gdim[2] = {dims, rows};
+    cuuint64_t gstr[1] = {stride_bytes};
+    cuuint32_t box[2] = {TC_KC, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VECGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
+    if (s->norms_valid) return 0;
+    if (s->rows > s->cap_norms) {
+        if (s->d_norms) CU(cudaFree(s->d_norms));
+        s->d_norms = nullptr;
+        s->cap_norms = std::max<uint64_t>(s->rows, s->cap);
+        CU(cudaMalloc((void**)&s->d_norms, s->cap_norms * sizeof(float)));
+    }
+    if (!s->d_x2max) CU(cudaMalloc((void**)&s->d_x2max, 4));
+    CU(cudaMemsetAsync(s->d_x2max, 0, 4, st));
+    row_norms_kernel<<<(uint32_t)s->num_sms * 8, 256, 0, st>>>(s->d_vec, s->row_stride, s->row_stride / 16, s->rows, s->d_norms,
+                                                               s->d_x2max);
+    LAUNCHED();
+    s->norms_valid = true;
+    return 0;
+}
+
+static bool tc_eligible(const vecgpu_slab* s, uint32_t nq, uint32_t k, int metric) {
+    if (env_u32("VECGPU_TC", 1) == 0) return false;
+    return s->elem == VECGPU_F32 && (metric == VECGPU_L2 || metric == VECGPU_COSINE) && nq >= env_u32("VECGPU_TC_MIN_NQ", 16) &&
+           s->rows >= 8192 && s->rows < 0x7FFFFFFFull && k <= 96 && s->dims >= 16;
+}
+
+static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
+                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st);
+static int launch_pairs(int elem, int metric, const PairParams& p, int num_sms, cudaStream_t st);
+
+static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t k, int metric, int64_t* d_out_rowids,
+                  float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
+    int rc = slab_ensure_norms(s, st);
+    if (rc) return rc;
+    static int cfg_dev = -1;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const size_t smem = TC_STAGES * TC_STAGE_BYTES + 2 * 2 * TC_N * 4 + 16 * 8 + 64 + 1024;  // + alignment slack
+    if (cfg_dev != dev) {
+        CU(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(tc_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CU(cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        cfg_dev = dev;
+    }
+    const uint32_t kp = ((k + 32 + 7) / 8) * 8;
+    const uint64_t n_xt = (s->rows + TC_N - 1) / TC_N;
+    const uint32_t max_qt = std::max(1u, std::min(16u, (uint32_t)s->num_sms));  // <= 2048 queries per launch
+    CUtensorMap mapX;
+    if ((rc = make_f32_map(&mapX, s->d_vec, s->dims, s->rows, s->row_stride, TC_N))) return rc;
+    const uint64_t live = s->rows - s->n_skip;
+
+    for (uint32_t qoff = 0; qoff < nq_all; qoff += max_qt * TC_M) {
+        const uint32_t nq = std::min(nq_all - qoff, max_qt * TC_M);
+        const uint8_t* dq = d_q + (size_t)qoff * s->row_stride;
+        const uint32_t QT = (nq + TC_M - 1) / TC_M;
+        uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms / QT, n_xt));
+        while (G > 1 && next_pow2(G * kp) > 8192) --G;
+        const uint32_t cap = std::max(2u, next_pow2(G * kp));
+        const uint32_t grid = QT * G;
+        const size_t lists = (size_t)grid * TC_M;
+        if ((rc = ws_reserve(s, WS_TC_CANDV, lists * kp * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_CANDR, lists * kp * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_CNT, lists * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_TAU, lists * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_PAIRQ, (size_t)nq * cap * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_PAIRPOS, (size_t)nq * cap * 8))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_DIST, (size_t)nq * cap * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_KEYS, (size_t)nq * cap * 8))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_QNORM, (size_t)nq * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_FLAGS, (size_t)nq))) return rc;
+
+        // |q|^2 in the canonical order
+        row_norms_kernel<<<std::max(1u, std::min((nq + 63) / 64, 1024u)), 256, 0, st>>>(dq, s->row_stride, s->row_stride / 16, nq,
+                                                                                        (float*)s->d_ws[WS_TC_QNORM], nullptr);
+        LAUNCHED();
+        CUtensorMap mapQ;
+        if ((rc = make_f32_map(&mapQ, dq, s->dims, nq, s->row_stride, TC_M))) return rc;
+        TcParams tp{};
+        tp.n_rows = s->rows;
+        tp.nq = nq;
+        tp.nk = (s->dims + TC_KC - 1) / TC_KC;
+        tp.kp = kp;
+        tp.cosine = metric == VECGPU_COSINE ? 1u : 0u;
+        tp.QT = QT;
+        tp.G = G;
+        tp.norms = s->d_norms;
+        tp.skip = s->n_skip ? s->d_skip : nullptr;
+        tp.cand_v = (float*)s->d_ws[WS_TC_CANDV];
+        tp.cand_r = (uint32_t*)s->d_ws[WS_TC_CANDR];
+        tp.cand_cnt = (uint32_t*)s->d_ws[WS_TC_CNT];
+        tp.cand_tau = (float*)s->d_ws[WS_TC_TAU];
+        tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(mapQ, mapX, tp);
+        LAUNCHED();
+
+        TcCollectParams cp{};
+        cp.t = tp;
+        cp.k = (uint32_t)std::min<uint64_t>(k, live);
+        cp.cap = cap;
+        cp.dims = s->dims;
+        cp.qnorm = (const float*)s->d_ws[WS_TC_QNORM];
+        cp.x2max_bits = s->d_x2max;
+        cp.n_live = live;
+        cp.pair_q = (uint32_t*)s->d_ws[WS_TC_PAIRQ];
+        cp.pair_pos = (int64_t*)s->d_ws[WS_TC_PAIRPOS];
+        cp.fallback = (uint8_t*)s->d_ws[WS_TC_FLAGS];
+        if (cp.k == 0) cp.k = 1;
+        tc_collect_kernel<<<nq, 512, (size_t)cap * 8, st>>>(cp);
+        LAUNCHED();
+
+        // exact re-rank of the certified candidates in the canonical order
+        PairParams pp{};
+        pp.a_base = dq;
+        pp.b_base = s->d_vec;
+        pp.a_stride = pp.b_stride = s->row_stride;
+        pp.units = s->row_stride / 16;
+        pp.a_index = cp.pair_q;
+        pp.b_index = cp.pair_pos;
+        pp.n_pairs = (uint64_t)nq * cap;
+        pp.out = (float*)s->d_ws[WS_TC_DIST];
+        pp.qc_kind = 0;
+        if ((rc = launch_pairs(s->elem, metric, pp, s->num_sms, st))) return rc;
+        tc_keys_kernel<<<(uint32_t)std::min<uint64_t>((pp.n_pairs + 255) / 256, 4096), 256, 0, st>>>(
+            pp.out, cp.pair_pos, pp.n_pairs, (uint64_t*)s->d_ws[WS_TC_KEYS]);
+        LAUNCHED();
+        MergeParams mp{};
+        mp.keys = (const uint64_t*)s->d_ws[WS_TC_KEYS];
+        mp.n_cand = cap;
+        mp.k = k;
+        mp.kp2 = next_pow2(k);
+        mp.rowids = s->dense ? nullptr : s->d_rowids;
+        mp.first_rowid = s->first_rowid;
+        mp.out_rowids = d_out_rowids + (size_t)qoff * k;
+        mp.out_dists = d_out_dists + (size_t)qoff * k;
+        mp.out_counts = d_out_counts ? d_out_counts + qoff : nullptr;
+        mp.pad_rowid = pad_rowid;
+        if ((rc = launch_merge(s, mp, nq, st))) return rc;
+
+        // queries whose candidate bound could not be certified: exact scan (rare: massive ties, non-finite data)
+        std::vector<uint8_t> flags(nq);
+        CU(cudaMemcpyAsync(flags.data(), s->d_ws[WS_TC_FLAGS], nq, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        g_tc_queries.fetch_add(nq, std::memory_order_relaxed);
+        for (uint32_t q = 0; q < nq; ++q)
+            if (flags[q]) {
+                g_tc_fallbacks.fetch_add(1, std::memory_order_relaxed);
+                rc = knn_exact(s, dq + (size_t)q * s->row_stride, 1, k, metric, d_out_rowids + (size_t)(qoff + q) * k,
+                               d_out_dists + (size_t)(qoff + q) * k, d_out_counts ? d_out_counts + qoff + q : nullptr, pad_rowid, st);
+                if (rc) return rc;
+            }
+    }
+    return 0;
+}
+
+static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
+                    float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
+    if (nq && k && tc_eligible(s, nq, k, metric))
+        return knn_tc(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
+    return knn_exact(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
 }
 
 // stage nq host queries (row_bytes each) into the slab's padded device query buffer
@@ -1063,6 +1264,7 @@ extern "C" int vecgpu_slab_fill_synthetic(vecgpu_slab* s, uint64_t seed, int64_t
     if (rc) return rc;
     s->first_rowid = first_rowid;
     s->rows = n;
+    s->norms_valid = false;
     if (n == 0) return 0;
     const uint32_t grid = (uint32_t)s->num_sms * 16;
     if (s->elem == VECGPU_F32)
