@@ -37,6 +37,11 @@ static constexpr uint32_t TC_THREADS = 384;
 // kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128
 static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
+// A squared norm outside this range (zero, denormal-ish, huge, inf, NaN) makes the approximate score of the row
+// meaningless (overflow / cancellation), so the row bypasses the contraction and is always re-ranked exactly.
+static constexpr uint32_t TC_MAX_UNSAFE = 64;
+__host__ __device__ __forceinline__ bool tc_norm_safe(float x2) { return x2 > 1e-30f && x2 < 1e30f; }
+
 struct TcParams {
     uint64_t n_rows;
     uint32_t nq, nk;       // queries, k-chunks (ceil(dims/32); TMA zero-fills the ragged tail)
@@ -240,8 +245,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             // per-column coefficients: v = s * a + b
             for (uint32_t j = e; j < TC_N; j += 128) {
                 const uint64_t row = row0 + j;
-                const bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
+                bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
                 const float x2 = ok ? p.norms[row] : 0.f;
+                ok = ok && tc_norm_safe(x2);  // unsafe rows are handled by the exact re-rank alone
                 float a, b;
                 if (p.cosine) {
                     a = (ok && x2 > 0.f) ? -rsqrtf(x2) : 0.f;
@@ -289,9 +295,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-// canonical sum of squares of every row (the b2 / a2 of F32Cos), plus the maximum over all rows
+// canonical sum of squares of every row (the b2 / a2 of F32Cos), the maximum over the safe rows, and the list
+// of unsafe rows (unsafe[0] = count, unsafe[1..] = positions of the first TC_MAX_UNSAFE)
 __global__ void __launch_bounds__(256) row_norms_kernel(const uint8_t* base, uint32_t stride, uint32_t units, uint64_t n, float* norms,
-                                                        uint32_t* max_bits) {
+                                                        uint32_t* max_bits, uint32_t* unsafe) {
     const int g = threadIdx.x & 3;
     const uint64_t n_iter = (n + 63) / 64;
     float mx = 0.f;
@@ -301,7 +308,11 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const uint8_t* base, uin
         const float v = query_const(r, row < n ? units : 0, g, 0);
         if (row < n && g == 0) {
             norms[row] = v;
-            if (v == v && v < __int_as_float(0x7F800000)) mx = fmaxf(mx, v);
+            if (tc_norm_safe(v)) mx = fmaxf(mx, v);
+            else if (unsafe) {
+                const uint32_t slot = atomicAdd(unsafe, 1u);
+                if (slot < TC_MAX_UNSAFE) unsafe[1 + slot] = (uint32_t)row;
+            }
         }
     }
     for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
@@ -319,6 +330,7 @@ struct TcCollectParams {
     uint32_t* pair_q;           // [nq*cap] query index of each candidate slot
     int64_t* pair_pos;          // [nq*cap] row position or -1
     uint8_t* fallback;          // [nq] 1 = bound not certified, use the exact scan
+    const uint32_t* unsafe;     // [1 + TC_MAX_UNSAFE] rows that bypass the contraction
 };
 __global__ void __launch_bounds__(512) tc_collect_kernel(const TcCollectParams c) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -355,7 +367,8 @@ __global__ void __launch_bounds__(512) tc_collect_kernel(const TcCollectParams c
         const size_t cta = (size_t)gg * p.QT + qt;
         if (p.cand_cnt[cta * TC_M + e] == p.kp && !(p.cand_tau[cta * TC_M + e] > bound)) atomicExch(&s_bad, 1u);
     }
-    if (threadIdx.x == 0 && total < c.k && (uint64_t)total < c.n_live) s_bad = 1;  // NaN/inf scores hid rows
+    if (threadIdx.x == 0 && total < c.k && (uint64_t)total < c.n_live) s_bad = 1;  // non-finite scores hid rows
+    if (threadIdx.x == 0 && !tc_norm_safe(q2)) s_bad = 1;                           // the query itself is unsafe
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < c.cap; j += blockDim.x) {
         const uint64_t key = keys[j];
@@ -364,6 +377,12 @@ __global__ void __launch_bounds__(512) tc_collect_kernel(const TcCollectParams c
             const uint32_t slot = (uint32_t)key, gg = slot / p.kp, i = slot - gg * p.kp;
             const size_t cta = (size_t)gg * p.QT + qt;
             pos = (int64_t)p.cand_r[(cta * TC_M + e) * p.kp + i];
+        }
+        // the last TC_MAX_UNSAFE slots are always free (cap >= G*kp + TC_MAX_UNSAFE): unsafe rows go there
+        const uint32_t n_unsafe = min(c.unsafe[0], TC_MAX_UNSAFE);
+        if (j >= c.cap - n_unsafe) {
+            const uint32_t row = c.unsafe[1 + (c.cap - 1 - j)];
+            pos = (p.skip && p.skip[row]) ? -1 : (int64_t)row;
         }
         c.pair_q[(size_t)q * c.cap + j] = q;
         c.pair_pos[(size_t)q * c.cap + j] = pos;

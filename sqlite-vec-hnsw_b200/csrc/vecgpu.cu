@@ -85,6 +85,8 @@ struct vecgpu_slab {
     // canonical |row|^2 cache for the tensor-core batched path (invalidated by any vector write)
     float* d_norms = nullptr;
     uint32_t* d_x2max = nullptr;
+    uint32_t* d_unsafe = nullptr;   // [1 + TC_MAX_UNSAFE]: count + positions of rows with unusable norms
+    uint32_t n_unsafe = 0;
     uint64_t cap_norms = 0;
     bool norms_valid = false;
     // workspaces
@@ -317,6 +319,7 @@ extern "C" void vecgpu_slab_destroy(vecgpu_slab* s) {
     for (int i = 0; i < WS_COUNT; ++i) cudaFree(s->d_ws[i]);
     cudaFree(s->d_norms);
     cudaFree(s->d_x2max);
+    cudaFree(s->d_unsafe);
     for (int i = 0; i < 2; ++i)
         if (s->h_pin[i]) cudaFreeHost(s->h_pin[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -799,10 +802,14 @@ static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
         CU(cudaMalloc((void**)&s->d_norms, s->cap_norms * sizeof(float)));
     }
     if (!s->d_x2max) CU(cudaMalloc((void**)&s->d_x2max, 4));
+    if (!s->d_unsafe) CU(cudaMalloc((void**)&s->d_unsafe, (1 + TC_MAX_UNSAFE) * 4));
     CU(cudaMemsetAsync(s->d_x2max, 0, 4, st));
+    CU(cudaMemsetAsync(s->d_unsafe, 0, (1 + TC_MAX_UNSAFE) * 4, st));
     row_norms_kernel<<<(uint32_t)s->num_sms * 8, 256, 0, st>>>(s->d_vec, s->row_stride, s->row_stride / 16, s->rows, s->d_norms,
-                                                               s->d_x2max);
+                                                               s->d_x2max, s->d_unsafe);
     LAUNCHED();
+    CU(cudaMemcpyAsync(&s->n_unsafe, s->d_unsafe, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     s->norms_valid = true;
     return 0;
 }
@@ -821,6 +828,8 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
                   float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
     int rc = slab_ensure_norms(s, st);
     if (rc) return rc;
+    if (s->n_unsafe > TC_MAX_UNSAFE)  // too many rows with unusable norms: the whole batch goes through the exact scan
+        return knn_exact(s, d_q, nq_all, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
     static int cfg_dev = -1;
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -843,8 +852,8 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         const uint8_t* dq = d_q + (size_t)qoff * s->row_stride;
         const uint32_t QT = (nq + TC_M - 1) / TC_M;
         uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms / QT, n_xt));
-        while (G > 1 && next_pow2(G * kp) > 8192) --G;
-        const uint32_t cap = std::max(2u, next_pow2(G * kp));
+        while (G > 1 && next_pow2(G * kp + TC_MAX_UNSAFE) > 8192) --G;
+        const uint32_t cap = std::max(2u, next_pow2(G * kp + TC_MAX_UNSAFE));
         const uint32_t grid = QT * G;
         const size_t lists = (size_t)grid * TC_M;
         if ((rc = ws_reserve(s, WS_TC_CANDV, lists * kp * 4))) return rc;
@@ -860,7 +869,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
 
         // |q|^2 in the canonical order
         row_norms_kernel<<<std::max(1u, std::min((nq + 63) / 64, 1024u)), 256, 0, st>>>(dq, s->row_stride, s->row_stride / 16, nq,
-                                                                                        (float*)s->d_ws[WS_TC_QNORM], nullptr);
+                                                                                        (float*)s->d_ws[WS_TC_QNORM], nullptr, nullptr);
         LAUNCHED();
         CUtensorMap mapQ;
         if ((rc = make_f32_map(&mapQ, dq, s->dims, nq, s->row_stride, TC_M))) return rc;
@@ -892,6 +901,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         cp.pair_q = (uint32_t*)s->d_ws[WS_TC_PAIRQ];
         cp.pair_pos = (int64_t*)s->d_ws[WS_TC_PAIRPOS];
         cp.fallback = (uint8_t*)s->d_ws[WS_TC_FLAGS];
+        cp.unsafe = s->d_unsafe;
         if (cp.k == 0) cp.k = 1;
         tc_collect_kernel<<<nq, 512, (size_t)cap * 8, st>>>(cp);
         LAUNCHED();

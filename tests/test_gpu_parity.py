@@ -463,3 +463,79 @@ def test_scan_repeat_launch_stress(vg, gpu):
                 r, d = s.knn_device(q, 10, metric)
             torch.cuda.synchronize()
             assert torch.equal(r, r0) and torch.equal(d, d0)
+
+
+# ------------------------------------------------------------------ K2: tensor-core batched path (tcgen05 3xTF32 + exact re-rank)
+@pytest.mark.parametrize("metric", [L2, COSINE], ids=["l2", "cos"])
+@pytest.mark.parametrize("dims,nq,k", [(96, 16, 10), (768, 130, 10), (100, 33, 5), (384, 257, 32), (64, 40, 96), (17, 20, 3)])
+def test_tc_batched_matches_oracle(vg, orc, gpu, metric, dims, nq, k):
+    n = 30000
+    kind = 1 if metric == COSINE else 0
+    with vg.Slab(F32, dims) as s:
+        s.fill_synthetic(seed=21, n=n, kind=kind)
+        cpu = orc.synth_rows(F32, 21, 1, n, dims, kind)
+        q = orc.synth_rows(F32, 22, 1, nq, dims, kind)
+        before = vg.tc_stats()
+        r, d, c = s.knn(q, k, metric)
+        after = vg.tc_stats()
+    assert after[0] - before[0] == nq, "the batch must have gone through the tensor-core path"
+    er, ed, ec = orc.knn(F32, dims, cpu, q, k, metric)
+    assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+
+
+def test_tc_batched_ties_fall_back_to_exact(vg, orc, gpu):
+    # a tiny alphabet makes thousands of rows tie at the k-th distance: the candidate bound cannot be
+    # certified, the affected queries must be re-run by the exact scan and still match bit for bit
+    n, dims, nq, k = 20000, 32, 24, 10
+    v = random_rows(F32, n, dims, seed=31, ties=True)
+    q = random_rows(F32, nq, dims, seed=32, ties=True)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        before = vg.tc_stats()
+        for metric in (L2, COSINE):
+            r, d, c = s.knn(q, k, metric)
+            er, ed, ec = orc.knn(F32, dims, v, q, k, metric)
+            assert np.array_equal(r, er) and same_bits(d, ed)
+        after = vg.tc_stats()
+    assert after[0] - before[0] == 2 * nq
+
+
+def test_tc_batched_skips_and_sparse_rowids(vg, orc, gpu):
+    n, dims, nq, k = 25000, 48, 64, 12
+    v = random_rows(F32, n, dims, seed=41)
+    q = random_rows(F32, nq, dims, seed=42)
+    q[:8] = v[100:108]  # exact self matches: distance 0 must survive the ||q||^2+||x||^2-2qx cancellation
+    rowids = (np.arange(n, dtype="<i8") * 3 + 7)
+    skip = np.zeros(n, dtype="u1")
+    skip[[100, 5000, n - 1]] = 1
+    with vg.Slab(F32, dims) as s:
+        s.load(v, rowids)
+        for i in np.flatnonzero(skip):
+            s.delete(int(rowids[i]))
+        for metric in (L2, COSINE):
+            r, d, c = s.knn(q, k, metric)
+            er, ed, ec = orc.knn(F32, dims, v, q, k, metric, rowids=rowids, skip=skip)
+            assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+        # a write invalidates the cached row norms
+        v[200] = q[20]
+        s.upsert(int(rowids[200]), v[200].tobytes())
+        r, d, c = s.knn(q, k, L2)
+        er, ed, ec = orc.knn(F32, dims, v, q, k, L2, rowids=rowids, skip=skip)
+        assert np.array_equal(r, er) and same_bits(d, ed) and r[20, 0] == rowids[200] and d[20, 0] == 0.0
+
+
+def test_tc_batched_special_values(vg, orc, gpu):
+    n, dims, nq, k = 16384, 40, 20, 10
+    v = random_rows(F32, n, dims, seed=51)
+    v[7] = 0
+    v[8] = 3e38
+    v[9, 2] = np.nan
+    v[10] = 1e-30
+    q = random_rows(F32, nq, dims, seed=52)
+    q[3] = 0
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        for metric in (L2, COSINE):
+            r, d, c = s.knn(q, k, metric)
+            er, ed, ec = orc.knn(F32, dims, v, q, k, metric)
+            assert np.array_equal(r, er) and same_bits(d, ed)
