@@ -47,6 +47,7 @@ struct TcParams {
     uint32_t nq, nk;       // queries, k-chunks (ceil(dims/32); TMA zero-fills the ragged tail)
     uint32_t kp;           // entries kept per (CTA, query) = k + margin
     uint32_t cosine;       // 0: L2 (v = x2 - 2s), 1: cosine (v = -s / |x|)
+    uint32_t lists_smem;   // 1: the kept scores live in shared memory ([kp][128] floats) during the scan
     uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
     const float* norms;    // [rows] canonical sum of squares of each slab row
     const uint8_t* skip;   // per-row skip flags or nullptr
@@ -90,19 +91,20 @@ struct TcList {
     uint32_t cnt, maxpos;
     float tau;
 };
-__device__ __noinline__ TcList tc_insert(float v, uint32_t row, float* lv, uint32_t* lr, uint32_t kp, TcList st) {
+// lv[i * vstride] is entry i of this thread's score list (shared memory, transposed: vstride = 128; or global: 1)
+__device__ __noinline__ TcList tc_insert(float v, uint32_t row, float* lv, uint32_t vstride, uint32_t* lr, uint32_t kp, TcList st) {
     if (st.cnt < kp) {
-        lv[st.cnt] = v;
+        lv[st.cnt * vstride] = v;
         lr[st.cnt] = row;
         if (++st.cnt < kp) return st;
     } else {
-        lv[st.maxpos] = v;
+        lv[st.maxpos * vstride] = v;
         lr[st.maxpos] = row;
     }
     float best = lv[0];
     uint32_t bp = 0;
     for (uint32_t i = 1; i < kp; ++i) {
-        const float x = lv[i];
+        const float x = lv[i * vstride];
         if (x > best) {
             best = x;
             bp = i;
@@ -124,6 +126,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     float* s_colB = s_colA + 2 * TC_N;
     uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
+    float* s_lists = (float*)(s_bar + 32);  // [kp][128] when p.lists_smem
     const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + 2), bar_empty = smem_u32(s_bar + 4),
                    bar_tfull = smem_u32(s_bar + 6), bar_tempty = smem_u32(s_bar + 8);
 
@@ -232,7 +235,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         const uint32_t e = threadIdx.x - 128;        // 0..127 == TMEM lane == query within the tile
         const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
         const size_t lbase = ((size_t)blockIdx.x * TC_M + e) * p.kp;
-        float* lv = p.cand_v + lbase;
+        float* lv = p.lists_smem ? s_lists + e : p.cand_v + lbase;
+        const uint32_t vstride = p.lists_smem ? TC_M : 1u;
         uint32_t* lr = p.cand_r + lbase;
         TcList st;
         st.cnt = 0;
@@ -280,13 +284,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float sc = __fmaf_rn(__uint_as_float(v[j]), ca[j], cb[j]);
-                    if (sc < st.tau) st = tc_insert(sc, (uint32_t)(row0 + c * 32 + j), lv, lr, p.kp, st);
+                    if (sc < st.tau) st = tc_insert(sc, (uint32_t)(row0 + c * 32 + j), lv, vstride, lr, p.kp, st);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (p.lists_smem)
+            for (uint32_t i = 0; i < st.cnt; ++i) p.cand_v[lbase + i] = lv[i * TC_M];
         p.cand_cnt[(size_t)blockIdx.x * TC_M + e] = st.cnt;
         p.cand_tau[(size_t)blockIdx.x * TC_M + e] = st.cnt == p.kp ? st.tau : __int_as_float(0x7F800000);
     }

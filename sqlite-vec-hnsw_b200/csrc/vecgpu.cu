@@ -833,14 +833,16 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
     static int cfg_dev = -1;
     int dev = 0;
     CU(cudaGetDevice(&dev));
-    const size_t smem = TC_STAGES * TC_STAGE_BYTES + 2 * 2 * TC_N * 4 + 16 * 8 + 64 + 1024;  // + alignment slack
+    const uint32_t kp = ((k + 32 + 7) / 8) * 8;
+    size_t smem = TC_STAGES * TC_STAGE_BYTES + 2 * 2 * TC_N * 4 + 32 * 8 + 1024;  // + alignment slack
+    const bool lists_smem = smem + (size_t)kp * TC_M * 4 <= SMEM_MAX;          // kept scores in shared memory when they fit
+    if (lists_smem) smem += (size_t)kp * TC_M * 4;
     if (cfg_dev != dev) {
-        CU(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         CU(cudaFuncSetAttribute(tc_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CU(cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         cfg_dev = dev;
     }
-    const uint32_t kp = ((k + 32 + 7) / 8) * 8;
     const uint64_t n_xt = (s->rows + TC_N - 1) / TC_N;
     const uint32_t max_qt = std::max(1u, std::min(16u, (uint32_t)s->num_sms));  // <= 2048 queries per launch
     CUtensorMap mapX;
@@ -879,6 +881,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         tp.nk = (s->dims + TC_KC - 1) / TC_KC;
         tp.kp = kp;
         tp.cosine = metric == VECGPU_COSINE ? 1u : 0u;
+        tp.lists_smem = lists_smem ? 1u : 0u;
         tp.QT = QT;
         tp.G = G;
         tp.norms = s->d_norms;
