@@ -256,7 +256,67 @@ def run_ours(args):
     barrier()
     t_e2e = time.perf_counter() - t0  # host-synchronous API: wall clock brackets device work + copies
 
-    clocks = sampler.summary() if rank == 0 else None
+    clocks = sampler.summary() if rank == 0 else None  # clocks of the headline timed regions only
+
+    # ---- extras (N=1 only, outside the headline timing): 1024-query batches on the same corpus through the
+    #      tensor-core path, and the other BASELINE.json configs at single-GPU sizes
+    extras = {}
+    if world == 1 and not args.no_extras:
+        def timed(fn, iters):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(iters):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+
+        qb = torch.from_numpy(oracle.synth_rows(F32, QSEED, 1, 1024, DIMS, GAUSS4).copy()).to(dev)
+        tc0 = vg.tc_stats()
+        ms = timed(lambda: sh.slab.knn_device(qb, K, COSINE, stream=stream.cuda_stream), 3)
+        tc1 = vg.tc_stats()
+        bf16 = None
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
+        exec_tflops = 3 * 2.0 * 1024 * rows_local * DIMS / (ms / 1e3) / 1e12
+        extras["batched_1024"] = {
+            "workload": f"1024-query batches, same {N_ROWS}x{DIMS} f32 cosine k={K} corpus (BASELINE.json configs[1], batch mode)",
+            "queries_per_s": 1024 / (ms / 1e3), "ms_per_batch": ms,
+            "roofline": {"bound": "tensor", "achieved": exec_tflops, "unit": "TFLOP/s (executed TF32, 3 MMA terms)",
+                         "algorithmic_tflops": exec_tflops / 3,
+                         "peak": bf16 / 2 if bf16 else 830.0,
+                         "peak_source": "half of the measured cuBLAS bf16 burst peak (TF32 runs at half the bf16 MAC rate)" if bf16 else "fallback: 1.59 PF bf16 / 2",
+                         "frac": exec_tflops / (bf16 / 2 if bf16 else 830.0)},
+            "tc_queries": tc1[0] - tc0[0], "tc_fallbacks": tc1[1] - tc0[1],
+            "kernel": "tc_scan_kernel (tcgen05 kind::tf32, 3xTF32) + exact re-rank (pair_kernel) + merge",
+        }
+        sh.close()
+        sh = None
+        torch.cuda.empty_cache()
+        for name, elem, dims, metric, k, n, kind in [
+            ("cfg3_i8_1024_l2_k100", 1, 1024, 0, 100, int(os.environ.get("VECGPU_BENCH_ROWS_I8", 50_000_000)), 0),
+            ("cfg4_bit_1024_hamming_k10_per_gpu_share", 2, 1024, 3, 10, int(os.environ.get("VECGPU_BENCH_ROWS_BIT", 62_500_000)), 0),
+            ("cfg1_f32_384_l2_k10_10k", 0, 384, 0, 10, 10_000, 0),
+        ]:
+            sl = vg.Slab(elem, dims)
+            sl.fill_synthetic(seed=4 + elem, n=n, kind=kind)
+            q1 = torch.from_numpy(oracle.synth_rows(elem, 77, 1, 100, dims, kind).copy()).to(dev)
+            ms1 = timed(lambda: sl.knn_device(q1[0], k, metric, stream=stream.cuda_stream), 10)
+            gbs = n * sl.row_bytes / (ms1 / 1e3) / 1e9
+            ent = {"rows": n, "single_query_ms": ms1, "single_query_qps": 1e3 / ms1, "achieved_gbs": gbs,
+                   "frac_of_measured_hbm": gbs / load_peaks()[0]}
+            if name.startswith("cfg1"):
+                msb = timed(lambda: sl.knn_device(q1, k, metric, stream=stream.cuda_stream), 10)
+                ent["batch100_ms"] = msb
+                ent["batch100_qps"] = 100 / (msb / 1e3)
+            extras[name] = ent
+            sl.close()
+            torch.cuda.empty_cache()
+
 
     # max over ranks
     tt = torch.tensor([t_dev, t_e2e, scan_ms], device=dev, dtype=torch.float64)
@@ -291,11 +351,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_baseline()
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
-    sh.close()
+    if sh is not None:
+        sh.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -307,6 +370,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batched / other-config extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
