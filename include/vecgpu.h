@@ -165,6 +165,31 @@ uint64_t vecgpu_launch_count(void);
  * through the exact scan.  Counters since process start: queries served by that path / of which fell back. */
 void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks);
 
+/* ---- HNSW with GPU-batched candidate scoring (BASELINE config 5) -------------------------------------
+ * The graph (levels, adjacency, stored edge distances) lives in host memory next to a slab that holds the
+ * STORED node vectors (normalised for cosine columns, int8 when index_quantization=int8:
+ * src/hnsw/insert.rs:300-322); `metric` is the INTERNAL metric (src/hnsw/mod.rs:129-137).  B inserts or
+ * queries advance in lockstep and each expansion round scores all their unvisited neighbours in one launch. */
+typedef struct vecgpu_hnsw vecgpu_hnsw;
+
+/* M in [2,100], ef_construction in [10,2000] as vec_rebuild_hnsw validates (src/sql_functions.rs:442-469);
+ * max_m0 = 2M (:489-505).  `seed` makes level assignment reproducible. */
+int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uint32_t ef_construction, uint64_t seed, vecgpu_hnsw** out);
+void vecgpu_hnsw_destroy(vecgpu_hnsw* h);
+/* vec_rebuild_hnsw (src/sql_functions.rs:436-534 -> src/hnsw/insert.rs:279-532): rebuild over every live row of
+ * the slab, at most `batch` inserts in lockstep (0 = 4096). */
+int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch);
+/* search_hnsw (src/hnsw/search.rs:267-335): ef = max(ef_search, k); results closest first, distances in the
+ * internal metric (apply convert_distance_for_output for cosine columns); unused slots rowid -1 / +inf. */
+int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef_search,
+                       int64_t* out_rowids, float* out_dists, uint32_t* out_counts);
+int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edges, int32_t* entry_level, uint64_t* distances_scored,
+                      uint64_t* rounds);
+/* Edge list for a bulk write-back into {t}_{c}_hnsw_edges (src/shadow.rs:478-487; insert_edges_batch shape,
+ * src/hnsw/storage.rs:346-383).  cap = 0 only counts. */
+int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* from_rowids, int64_t* to_rowids, int32_t* levels,
+                             float* dists, uint64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ from . import _lib
 from .vec0 import (  # noqa: F401
     DimensionMismatch,
     DistanceMetric,
+    HnswIndex,
     InvalidDistanceMetric,
     InvalidParameter,
     InvalidState,

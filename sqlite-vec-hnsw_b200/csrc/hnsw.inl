@@ -1,0 +1,559 @@
+// hnsw.inl — batched HNSW build / search driver on top of the gathered scoring kernel (K5).
+// Included by vecgpu.cu (needs vecgpu_slab, launch_pairs, ws_reserve, pin_reserve, CU, LAUNCHED, fail).
+//
+// What it replaces in the reference: insert_hnsw (src/hnsw/insert.rs:279-532), search_hnsw / search_layer
+// (src/hnsw/search.rs:267-543) and the SQL node/edge fetches behind them (src/hnsw/storage.rs), for the
+// rebuild (src/sql_functions.rs:436-534) and for queries.  The reference walks the graph one query at a
+// time and scores 1-32 neighbours per expansion step through SQLite lookups; here B inserts
+// (or queries) advance in lockstep and every round scores ALL their unvisited neighbours in one launch of
+// pair_kernel over the HBM-resident slab.  Graph state (adjacency + stored edge distances) lives in host
+// memory and can be exported for a bulk write-back into {t}_{c}_hnsw_edges (src/shadow.rs:478-487).
+//
+// Semantics kept from the reference:
+//   - layer search: entry scored first (search.rs:385-398); pop closest candidate, stop when it is farther
+//     than the worst result (strict >, :406-410); neighbours filtered by a visited set before scoring
+//     (:424-434); admission `len < ef || d < worst` (strict <, :516); results trimmed to ef (:528-531).
+//   - insert: greedy descent with ef=1 above the node's level (insert.rs:396-405), ef_construction search
+//     per level, the closest max_connections results become neighbours (max_m0 = 2M at level 0, M above;
+//     :421-430), bidirectional edges carrying the distance (:463-470), overfull neighbours pruned by
+//     keeping the closest by STORED distance (simple_prune, :144-222), entry point raised when the new
+//     node's level exceeds it.
+//   - levels: floor(-ln(u) * 1/ln(M)), capped at max_level-1 = 15 (insert.rs:114-137, hnsw/mod.rs:35-47);
+//     u comes from a counter-based hash of (seed, position), so builds are reproducible (the reference's
+//     are not: SURVEY F7).
+// Deviation: nodes of one batch do not see each other while searching (they are linked afterwards, in
+// order); batches start small and grow with the graph to keep the effect negligible.  Judged by recall.
+
+struct HCand {
+    float d;
+    uint32_t node;
+};
+struct HMinCmp {  // std heap with this comparator = min-heap on (d, node)
+    bool operator()(const HCand& a, const HCand& b) const { return a.d > b.d || (a.d == b.d && a.node > b.node); }
+};
+struct HMaxCmp {  // max-heap on (d, node)
+    bool operator()(const HCand& a, const HCand& b) const { return a.d < b.d || (a.d == b.d && a.node < b.node); }
+};
+
+struct HVisited {  // open addressing, cleared by replaying the inserted slots
+    std::vector<uint32_t> tab;
+    std::vector<uint32_t> used;
+    uint32_t mask = 0;
+    void init(uint32_t cap_pow2) {
+        tab.assign(cap_pow2, 0xFFFFFFFFu);
+        mask = cap_pow2 - 1;
+        used.clear();
+    }
+    void clear() {
+        for (uint32_t s : used) tab[s] = 0xFFFFFFFFu;
+        used.clear();
+    }
+    void grow() {
+        std::vector<uint32_t> old;
+        old.reserve(used.size());
+        for (uint32_t s : used) old.push_back(tab[s]);
+        init((mask + 1) * 2);
+        for (uint32_t k : old) insert(k);
+    }
+    bool insert(uint32_t key) {  // true if newly inserted
+        if (used.size() * 2 > mask) grow();
+        uint32_t h = (key * 2654435761u) & mask;
+        while (true) {
+            const uint32_t v = tab[h];
+            if (v == key) return false;
+            if (v == 0xFFFFFFFFu) {
+                tab[h] = key;
+                used.push_back(h);
+                return true;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+};
+
+struct HQuery {
+    uint32_t a_index = 0;       // row of the query in the a-operand buffer (slab position for inserts)
+    int level = 0;              // layer being searched
+    int stop_level = 0;         // last layer to search (0)
+    int node_level = -1;        // insert: the new node's level; search: -1 (only layer 0 collects ef results)
+    uint32_t ef = 1, ef_wide = 1;  // ef of the current layer; ef of the layers that collect results
+    uint32_t entry = 0;
+    bool started = false, done = false;
+    std::vector<HCand> cand, res;
+    HVisited visited;
+    std::vector<uint32_t> pending;            // nodes submitted for scoring this round
+    std::vector<std::vector<HCand>> layers;   // sorted results of the layers <= node_level (insert) / layer 0 (search)
+};
+
+struct vecgpu_hnsw {
+    vecgpu_slab* slab = nullptr;
+    int metric = VECGPU_L2;
+    uint32_t M = 16, max_m0 = 32, efc = 200;
+    uint64_t seed = 0;
+    int max_level = 16;
+    double level_factor = 1.0 / std::log(16.0);
+    uint64_t n_nodes = 0;
+    int64_t entry = -1;
+    int entry_level = -1;
+    std::vector<int8_t> node_level;
+    // level 0 adjacency: [node][max_m0]; upper levels: node with level L owns L consecutive M-wide lists
+    std::vector<uint32_t> nbr0;
+    std::vector<float> dist0;
+    std::vector<uint16_t> deg0;
+    std::vector<uint32_t> upper_base;
+    std::vector<uint32_t> nbrU;
+    std::vector<float> distU;
+    std::vector<uint16_t> degU;
+    uint64_t scored = 0, rounds = 0;
+    std::mutex mu;
+    // pinned staging + device buffers for the per-round pair lists
+    void* h_pin = nullptr;
+    size_t pin_cap = 0;
+    void* d_buf = nullptr;
+    size_t d_cap = 0;
+    void* d_queries = nullptr;
+    size_t dq_cap = 0;
+};
+
+static inline uint64_t h_mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static int hnsw_level_for(const vecgpu_hnsw* h, uint64_t pos) {
+    const uint64_t r = h_mix64(h->seed * 0x9E3779B97F4A7C15ull + pos + 1);
+    double u = (double)(r % 1000000ull) / 1000000.0;  // [0,1), insert.rs:129
+    if (u < 1e-9) u = 1e-9;
+    int level = (int)std::floor(-std::log(u) * h->level_factor);
+    return std::max(0, std::min(level, h->max_level - 1));
+}
+
+static inline uint32_t* h_nbr(vecgpu_hnsw* h, uint32_t node, int level, float** dist, uint16_t** deg, uint32_t* maxc) {
+    if (level == 0) {
+        *dist = &h->dist0[(size_t)node * h->max_m0];
+        *deg = &h->deg0[node];
+        *maxc = h->max_m0;
+        return &h->nbr0[(size_t)node * h->max_m0];
+    }
+    const size_t slot = (size_t)h->upper_base[node] + (size_t)(level - 1);
+    *dist = &h->distU[slot * h->M];
+    *deg = &h->degU[slot];
+    *maxc = h->M;
+    return &h->nbrU[slot * h->M];
+}
+
+// add edge from -> to with stored distance; an overfull list keeps the closest maxc by (distance, node)
+static void h_add_edge(vecgpu_hnsw* h, uint32_t from, uint32_t to, float d, int level) {
+    float* dist;
+    uint16_t* deg;
+    uint32_t maxc;
+    uint32_t* nb = h_nbr(h, from, level, &dist, &deg, &maxc);
+    for (uint32_t i = 0; i < *deg; ++i)
+        if (nb[i] == to) {
+            dist[i] = d;
+            return;
+        }
+    if (*deg < maxc) {
+        nb[*deg] = to;
+        dist[*deg] = d;
+        ++*deg;
+        return;
+    }
+    uint32_t worst = 0;
+    for (uint32_t i = 1; i < maxc; ++i)
+        if (dist[i] > dist[worst] || (dist[i] == dist[worst] && nb[i] > nb[worst])) worst = i;
+    if (d < dist[worst] || (d == dist[worst] && to < nb[worst])) {
+        nb[worst] = to;
+        dist[worst] = d;
+    }
+}
+
+// ---- one GPU launch for all (query, node) pairs of a round ---------------------------------------------
+static int hnsw_score_round(vecgpu_hnsw* h, const uint8_t* a_base, const std::vector<uint32_t>& a_idx,
+                            const std::vector<uint32_t>& b_pos, std::vector<float>& out) {
+    vecgpu_slab* s = h->slab;
+    const size_t n = a_idx.size();
+    out.resize(n);
+    if (n == 0) return 0;
+    const size_t up = n * 4 + n * 8;
+    if (up > h->pin_cap) {
+        if (h->h_pin) CU(cudaFreeHost(h->h_pin));
+        h->h_pin = nullptr;
+        h->pin_cap = std::max(up * 2, (size_t)1 << 20);
+        CU(cudaMallocHost(&h->h_pin, h->pin_cap));
+    }
+    const size_t dbytes = n * 16;
+    if (dbytes > h->d_cap) {
+        if (h->d_buf) CU(cudaFree(h->d_buf));
+        h->d_buf = nullptr;
+        h->d_cap = std::max(dbytes * 2, (size_t)1 << 20);
+        CU(cudaMalloc(&h->d_buf, h->d_cap));
+    }
+    uint8_t* hp = (uint8_t*)h->h_pin;
+    int64_t* hb = (int64_t*)hp;
+    uint32_t* ha = (uint32_t*)(hp + n * 8);
+    for (size_t i = 0; i < n; ++i) {
+        hb[i] = (int64_t)b_pos[i];
+        ha[i] = a_idx[i];
+    }
+    uint8_t* db = (uint8_t*)h->d_buf;
+    CU(cudaMemcpyAsync(db, hp, up, cudaMemcpyHostToDevice, s->stream));
+    PairParams p{};
+    p.a_base = a_base;
+    p.b_base = s->d_vec;
+    p.a_stride = p.b_stride = s->row_stride;
+    p.units = s->row_stride / 16;
+    p.b_index = (const int64_t*)db;
+    p.a_index = (const uint32_t*)(db + n * 8);
+    p.n_pairs = n;
+    p.out = (float*)(db + n * 12);
+    p.qc_kind = s->elem == VECGPU_I8 ? 1u : 0u;
+    int rc = launch_pairs(s->elem, h->metric, p, s->num_sms, s->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hp, p.out, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(out.data(), hp, n * 4);
+    h->scored += n;
+    h->rounds += 1;
+    return 0;
+}
+
+// start the search of `q.level` from q.entry
+static void hq_start_layer(HQuery& q) {
+    q.cand.clear();
+    q.res.clear();
+    q.visited.clear();
+    q.started = false;
+}
+
+// finish the current layer: record / descend.  Returns with q.done set when nothing is left.
+static void hq_finish_layer(vecgpu_hnsw* h, HQuery& q) {
+    std::vector<HCand> sorted = q.res;
+    std::sort(sorted.begin(), sorted.end(), [](const HCand& a, const HCand& b) { return a.d < b.d || (a.d == b.d && a.node < b.node); });
+    const bool collect = q.node_level < 0 ? q.level == 0 : q.level <= q.node_level;
+    if (!sorted.empty()) q.entry = sorted[0].node;  // closest becomes the entry of the next layer (insert.rs / search.rs:318-323)
+    if (collect) {
+        if ((int)q.layers.size() <= q.level) q.layers.resize(q.level + 1);
+        q.layers[q.level] = std::move(sorted);
+    }
+    if (q.level == q.stop_level) {
+        q.done = true;
+        return;
+    }
+    q.level -= 1;
+    const bool wide = q.node_level < 0 ? q.level == 0 : q.level <= q.node_level;
+    q.ef = wide ? q.ef_wide : 1;
+    hq_start_layer(q);
+}
+
+// advance all queries until every one is done; a_base = device rows the queries live in
+static int hnsw_run_batch(vecgpu_hnsw* h, std::vector<HQuery>& qs, size_t nqs, const uint8_t* a_base) {
+    std::vector<uint32_t> a_idx, b_pos, offs(nqs + 1);
+    std::vector<float> dists;
+    while (true) {
+        // ---- prepare: each query pops until it has neighbours to score (or finishes)
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int64_t qi = 0; qi < (int64_t)nqs; ++qi) {
+            HQuery& q = qs[qi];
+            q.pending.clear();
+            while (!q.done && q.pending.empty()) {
+                if (!q.started) {
+                    q.pending.push_back(q.entry);  // the entry point is scored first
+                    q.visited.insert(q.entry);
+                    break;
+                }
+                if (q.cand.empty()) {
+                    hq_finish_layer(h, q);
+                    continue;
+                }
+                std::pop_heap(q.cand.begin(), q.cand.end(), HMinCmp());
+                const HCand c = q.cand.back();
+                q.cand.pop_back();
+                if (!q.res.empty() && c.d > q.res.front().d) {  // farther than the worst result: layer done
+                    hq_finish_layer(h, q);
+                    continue;
+                }
+                float* nd;
+                uint16_t* deg;
+                uint32_t maxc;
+                const uint32_t* nb = h_nbr(h, c.node, q.level, &nd, &deg, &maxc);
+                for (uint32_t i = 0; i < *deg; ++i)
+                    if (q.visited.insert(nb[i])) q.pending.push_back(nb[i]);
+            }
+        }
+        // ---- gather
+        size_t total = 0;
+        for (size_t qi = 0; qi < nqs; ++qi) {
+            offs[qi] = (uint32_t)total;
+            total += qs[qi].pending.size();
+        }
+        offs[nqs] = (uint32_t)total;
+        if (total == 0) break;
+        a_idx.resize(total);
+        b_pos.resize(total);
+#pragma omp parallel for schedule(static)
+        for (int64_t qi = 0; qi < (int64_t)nqs; ++qi) {
+            const HQuery& q = qs[qi];
+            for (size_t j = 0; j < q.pending.size(); ++j) {
+                a_idx[offs[qi] + j] = q.a_index;
+                b_pos[offs[qi] + j] = q.pending[j];
+            }
+        }
+        // ---- one launch scores every pending pair of the batch
+        int rc = hnsw_score_round(h, a_base, a_idx, b_pos, dists);
+        if (rc) return rc;
+        // ---- update heaps (admission rule of search.rs:516-531)
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int64_t qi = 0; qi < (int64_t)nqs; ++qi) {
+            HQuery& q = qs[qi];
+            for (size_t j = 0; j < q.pending.size(); ++j) {
+                const HCand c{dists[offs[qi] + j], q.pending[j]};
+                if (c.d != c.d) continue;  // NaN: node missing
+                if (!q.started || q.res.size() < q.ef || c.d < q.res.front().d) {
+                    q.cand.push_back(c);
+                    std::push_heap(q.cand.begin(), q.cand.end(), HMinCmp());
+                    q.res.push_back(c);
+                    std::push_heap(q.res.begin(), q.res.end(), HMaxCmp());
+                    while (q.res.size() > q.ef) {
+                        std::pop_heap(q.res.begin(), q.res.end(), HMaxCmp());
+                        q.res.pop_back();
+                    }
+                }
+                q.started = true;
+            }
+            if (!q.pending.empty()) q.started = true;
+        }
+    }
+    return 0;
+}
+
+
+// ---- C ABI ------------------------------------------------------------------------------------------------
+static int64_t h_rowid_of(const vecgpu_slab* s, uint32_t pos) { return s->dense ? s->first_rowid + (int64_t)pos : s->h_rowids[pos]; }
+
+extern "C" int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uint32_t ef_construction, uint64_t seed,
+                                  vecgpu_hnsw** out) {
+    if (!slab || !out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    *out = nullptr;
+    int rc = check_pair(slab->elem, metric);
+    if (rc) return rc;
+    // argument ranges of vec_rebuild_hnsw (src/sql_functions.rs:442-469)
+    if (M < 2 || M > 100) return fail(VECGPU_ERR_INVALID_PARAM, "M must be between 2 and 100");
+    if (ef_construction < 10 || ef_construction > 2000) return fail(VECGPU_ERR_INVALID_PARAM, "ef_construction must be between 10 and 2000");
+    vecgpu_hnsw* h = new (std::nothrow) vecgpu_hnsw();
+    if (!h) return fail(VECGPU_ERR_CUDA, "out of host memory");
+    h->slab = slab;
+    h->metric = metric;
+    h->M = M;
+    h->max_m0 = 2 * M;  // src/sql_functions.rs:489-505: max_m0 = 2m
+    h->efc = ef_construction;
+    h->seed = seed;
+    h->level_factor = 1.0 / std::log((double)M);
+    *out = h;
+    return 0;
+}
+
+extern "C" void vecgpu_hnsw_destroy(vecgpu_hnsw* h) {
+    if (!h) return;
+    if (h->slab) cudaSetDevice(h->slab->device);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    cudaFree(h->d_buf);
+    cudaFree(h->d_queries);
+    cudaGetLastError();
+    delete h;
+}
+
+static void hq_init(vecgpu_hnsw* h, HQuery& q, uint32_t a_index, int node_level, uint32_t ef_wide) {
+    q.a_index = a_index;
+    q.node_level = node_level;
+    q.level = h->entry_level;
+    q.stop_level = 0;
+    q.ef_wide = ef_wide;
+    const bool wide = node_level < 0 ? q.level == 0 : q.level <= node_level;
+    q.ef = wide ? ef_wide : 1;
+    q.entry = (uint32_t)h->entry;
+    q.done = false;
+    q.layers.clear();
+    if (q.visited.tab.empty()) q.visited.init(1024);
+    hq_start_layer(q);
+}
+
+// vec_rebuild_hnsw: (re)build the graph over every live row of the slab, `batch` inserts in lockstep
+extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    vecgpu_slab* s = h->slab;
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    if (batch == 0) batch = 4096;
+    const uint64_t n = s->rows;
+    if (n >= 0xFFFFFFFFull) return fail(VECGPU_ERR_INVALID_PARAM, "too many rows");
+    h->n_nodes = 0;
+    h->entry = -1;
+    h->entry_level = -1;
+    h->scored = h->rounds = 0;
+    h->node_level.assign(n, 0);
+    h->upper_base.assign(n, 0);
+    uint64_t upper_slots = 0;
+    for (uint64_t pos = 0; pos < n; ++pos) {
+        const int L = hnsw_level_for(h, pos);
+        h->node_level[pos] = (int8_t)L;
+        h->upper_base[pos] = (uint32_t)upper_slots;
+        upper_slots += (uint64_t)L;
+    }
+    h->nbr0.assign((size_t)n * h->max_m0, 0);
+    h->dist0.assign((size_t)n * h->max_m0, 0.f);
+    h->deg0.assign(n, 0);
+    h->nbrU.assign((size_t)upper_slots * h->M, 0);
+    h->distU.assign((size_t)upper_slots * h->M, 0.f);
+    h->degU.assign(upper_slots, 0);
+
+    std::vector<HQuery> qs;
+    std::vector<uint32_t> nodes;
+    uint64_t pos = 0;
+    while (pos < n) {
+        const uint64_t want = std::min<uint64_t>(batch, std::max<uint64_t>(1, h->n_nodes / 4));
+        nodes.clear();
+        while (pos < n && nodes.size() < want) {
+            if (s->h_skip.empty() || !s->h_skip[pos]) nodes.push_back((uint32_t)pos);
+            ++pos;
+        }
+        if (nodes.empty()) break;
+        size_t first = 0;
+        if (h->entry < 0) {  // very first node: it becomes the entry point, nothing to search
+            h->entry = nodes[0];
+            h->entry_level = h->node_level[nodes[0]];
+            h->n_nodes = 1;
+            first = 1;
+        }
+        const size_t nb = nodes.size() - first;
+        if (nb == 0) continue;
+        if (qs.size() < nb) qs.resize(nb);
+        const int search_entry_level = h->entry_level;
+        for (size_t i = 0; i < nb; ++i) hq_init(h, qs[i], nodes[first + i], h->node_level[nodes[first + i]], h->efc);
+        rc = hnsw_run_batch(h, qs, nb, s->d_vec);
+        if (rc) return rc;
+        // ---- link, in insertion order (insert.rs:408-498)
+        for (size_t i = 0; i < nb; ++i) {
+            HQuery& q = qs[i];
+            const uint32_t node = nodes[first + i];
+            const int L = h->node_level[node];
+            for (int lv = std::min(L, search_entry_level); lv >= 0; --lv) {
+                if ((int)q.layers.size() <= lv) continue;
+                const uint32_t maxc = lv == 0 ? h->max_m0 : h->M;
+                const std::vector<HCand>& w = q.layers[lv];
+                const size_t take = std::min<size_t>(maxc, w.size());
+                for (size_t j = 0; j < take; ++j) {
+                    if (w[j].node == node) continue;
+                    h_add_edge(h, node, w[j].node, w[j].d, lv);
+                    h_add_edge(h, w[j].node, node, w[j].d, lv);
+                }
+            }
+            if (L > h->entry_level) {
+                h->entry = node;
+                h->entry_level = L;
+            }
+        }
+        h->n_nodes += nb;
+    }
+    return 0;
+}
+
+// search_hnsw (src/hnsw/search.rs:267-335) for nq queries in lockstep; distances are in the graph's (internal) metric
+extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef_search,
+                                  int64_t* out_rowids, float* out_dists, uint32_t* out_counts) {
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    if (nq == 0 || k == 0) return 0;
+    if (!queries || !out_rowids || !out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    vecgpu_slab* s = h->slab;
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    for (size_t i = 0; i < (size_t)nq * k; ++i) {
+        out_rowids[i] = -1;
+        out_dists[i] = INFINITY;
+    }
+    if (out_counts) memset(out_counts, 0, (size_t)nq * 4);
+    if (h->entry < 0) return 0;  // empty index: no rows (search.rs:279-281)
+    const uint32_t ef = std::max(ef_search, k);  // search.rs:282
+    const size_t qbytes = (size_t)nq * s->row_stride;
+    if (qbytes > h->dq_cap) {
+        if (h->d_queries) CU(cudaFree(h->d_queries));
+        h->d_queries = nullptr;
+        h->dq_cap = std::max(qbytes, (size_t)1 << 16);
+        CU(cudaMalloc(&h->d_queries, h->dq_cap));
+    }
+    CU(cudaMemsetAsync(h->d_queries, 0, qbytes, s->stream));
+    CU(cudaMemcpy2DAsync(h->d_queries, s->row_stride, queries, s->row_bytes, s->row_bytes, nq, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    const uint32_t chunk = 8192;
+    std::vector<HQuery> qs;
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t m = std::min(chunk, nq - q0);
+        qs.clear();
+        qs.resize(m);
+        for (uint32_t i = 0; i < m; ++i) hq_init(h, qs[i], q0 + i, -1, ef);
+        rc = hnsw_run_batch(h, qs, m, (const uint8_t*)h->d_queries);
+        if (rc) return rc;
+        for (uint32_t i = 0; i < m; ++i) {
+            if (qs[i].layers.empty()) continue;
+            const std::vector<HCand>& w = qs[i].layers[0];
+            const uint32_t cnt = (uint32_t)std::min<size_t>(k, w.size());
+            for (uint32_t j = 0; j < cnt; ++j) {
+                out_rowids[(size_t)(q0 + i) * k + j] = h_rowid_of(s, w[j].node);
+                out_dists[(size_t)(q0 + i) * k + j] = w[j].d;
+            }
+            if (out_counts) out_counts[q0 + i] = cnt;
+        }
+    }
+    return 0;
+}
+
+extern "C" int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edges, int32_t* entry_level, uint64_t* distances_scored,
+                                 uint64_t* rounds) {
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (nodes) *nodes = h->n_nodes;
+    if (edges) {
+        uint64_t e = 0;
+        for (uint16_t d : h->deg0) e += d;
+        for (uint16_t d : h->degU) e += d;
+        *edges = e;
+    }
+    if (entry_level) *entry_level = h->entry_level;
+    if (distances_scored) *distances_scored = h->scored;
+    if (rounds) *rounds = h->rounds;
+    return 0;
+}
+
+// edge list for a bulk write-back into {t}_{c}_hnsw_edges(from_rowid, to_rowid, level, distance) (src/shadow.rs:478-487).
+// Call with cap = 0 to get the count in *n_out.
+extern "C" int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* from_rowids, int64_t* to_rowids, int32_t* levels,
+                                        float* dists, uint64_t* n_out) {
+    if (!h || !n_out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    vecgpu_slab* s = h->slab;
+    uint64_t n = 0;
+    const uint64_t rows = h->node_level.size();
+    for (uint64_t node = 0; node < rows; ++node) {
+        for (int lv = 0; lv <= h->node_level[node]; ++lv) {
+            float* dist;
+            uint16_t* deg;
+            uint32_t maxc;
+            const uint32_t* nb = h_nbr(h, (uint32_t)node, lv, &dist, &deg, &maxc);
+            for (uint32_t i = 0; i < *deg; ++i, ++n) {
+                if (n < cap) {
+                    from_rowids[n] = h_rowid_of(s, (uint32_t)node);
+                    to_rowids[n] = h_rowid_of(s, nb[i]);
+                    levels[n] = lv;
+                    dists[n] = dist[i];
+                }
+            }
+        }
+    }
+    *n_out = n;
+    return 0;
+}

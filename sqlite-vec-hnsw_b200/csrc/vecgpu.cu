@@ -4,6 +4,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -1299,3 +1300,8 @@ extern "C" int vecgpu_slab_device_view(vecgpu_slab* s, void** d_vectors, uint32_
     if (rows) *rows = s->rows;
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// batched HNSW driver (config 5)
+// ---------------------------------------------------------------------------
+#include "hnsw.inl"

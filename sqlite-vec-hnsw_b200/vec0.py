@@ -473,3 +473,66 @@ def brute_force_search(slab, query_vector, k, distance_metric):
     rowids, dists, counts = slab.knn(q, k, distance_metric)
     n = int(counts[0])
     return [(int(rowids[0, i]), float(dists[0, i])) for i in range(n)]
+
+
+# ---------------------------------------------------------------- HNSW (src/hnsw/{insert,search,rebuild}.rs)
+class HnswIndex:
+    """Graph over the rows of a slab that holds the STORED node vectors; built and searched with GPU-batched
+    candidate scoring.  `metric` is the column's metric; cosine columns must load normalised vectors and are
+    searched with L2 internally, distances converted on output (src/hnsw/mod.rs:129-146)."""
+
+    def __init__(self, slab, metric, M=32, ef_construction=400, seed=42, normalize_vectors=True):
+        # defaults of HnswParams (src/hnsw/mod.rs:35-47)
+        self.slab = slab
+        self.metric = DistanceMetric(metric)
+        self.normalize_vectors = bool(normalize_vectors)
+        self.internal = internal_distance_metric(self.metric, self.normalize_vectors)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _check(self._lib.vecgpu_hnsw_create(slab._h, int(self.internal), M, ef_construction, seed, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.vecgpu_hnsw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def rebuild(self, batch=4096):
+        """vec_rebuild_hnsw (src/sql_functions.rs:436-534): index every live row of the slab."""
+        _check(self._lib.vecgpu_hnsw_build(self._h, batch))
+        return self.stats()["nodes"]
+
+    def stats(self):
+        n, e, r, sc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lvl = C.c_int32()
+        _check(self._lib.vecgpu_hnsw_stats(self._h, C.byref(n), C.byref(e), C.byref(lvl), C.byref(sc), C.byref(r)))
+        return dict(nodes=n.value, edges=e.value, entry_level=lvl.value, distances_scored=sc.value, rounds=r.value)
+
+    def search(self, queries, k, ef_search=200):
+        """search_hnsw (src/hnsw/search.rs:267-335).  Queries are raw column vectors; cosine queries are
+        normalised here (search.rs:291-293).  -> (rowids [nq,k], distances in the column's metric, counts)."""
+        q = _as_raw(queries, self.slab.vec_type)
+        if self.metric == DistanceMetric.Cosine and self.normalize_vectors and self.slab.vec_type == VectorType.Float32:
+            q = normalize(np.frombuffer(q.tobytes(), dtype="<f4").reshape(-1, self.slab.dims), self.slab.device)
+        nbytes = q.size * q.itemsize
+        if nbytes == 0 or nbytes % self.slab.row_bytes:
+            raise DimensionMismatch(f"Dimension mismatch: expected {self.slab.dims}", self.slab.dims, None)
+        nq = nbytes // self.slab.row_bytes
+        rowids = np.full((nq, k), -1, dtype="<i8")
+        dists = np.full((nq, k), np.inf, dtype="<f4")
+        counts = np.zeros(nq, dtype="<u4")
+        _check(self._lib.vecgpu_hnsw_search(self._h, _ptr(np.ascontiguousarray(q)), nq, k, ef_search, _ptr(rowids), _ptr(dists), _ptr(counts)))
+        if self.internal != self.metric:  # cosine: d_out = d_L2^2 / 2
+            with np.errstate(invalid="ignore"):
+                dists = ((dists * dists) / np.float32(2.0)).astype("<f4")
+        return rowids, dists, counts
+
+    def export_edges(self):
+        """-> (from_rowid, to_rowid, level, distance) arrays in the shape of the {t}_{c}_hnsw_edges table."""
+        n = C.c_uint64()
+        _check(self._lib.vecgpu_hnsw_export_edges(self._h, 0, None, None, None, None, C.byref(n)))
+        fr, to = np.empty(n.value, dtype="<i8"), np.empty(n.value, dtype="<i8")
+        lv, ds = np.empty(n.value, dtype="<i4"), np.empty(n.value, dtype="<f4")
+        _check(self._lib.vecgpu_hnsw_export_edges(self._h, n.value, _ptr(fr), _ptr(to), _ptr(lv), _ptr(ds), C.byref(n)))
+        return fr, to, lv, ds
