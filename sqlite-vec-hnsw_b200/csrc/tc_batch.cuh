@@ -279,12 +279,26 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const float* ca = s_colA + acc * TC_N + c * 32;
-                const float* cb = s_colB + acc * TC_N + c * 32;
+                // branch-free common case: all 32 scores and a pass mask first, the (rare) inserts afterwards
+                const float4* ca4 = (const float4*)(s_colA + acc * TC_N + c * 32);
+                const float4* cb4 = (const float4*)(s_colB + acc * TC_N + c * 32);
+                float sc[32];
+                uint32_t mask = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float sc = __fmaf_rn(__uint_as_float(v[j]), ca[j], cb[j]);
-                    if (sc < st.tau) st = tc_insert(sc, (uint32_t)(row0 + c * 32 + j), lv, vstride, lr, p.kp, st);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 a = ca4[j4], b = cb4[j4];
+                    sc[4 * j4 + 0] = __fmaf_rn(__uint_as_float(v[4 * j4 + 0]), a.x, b.x);
+                    sc[4 * j4 + 1] = __fmaf_rn(__uint_as_float(v[4 * j4 + 1]), a.y, b.y);
+                    sc[4 * j4 + 2] = __fmaf_rn(__uint_as_float(v[4 * j4 + 2]), a.z, b.z);
+                    sc[4 * j4 + 3] = __fmaf_rn(__uint_as_float(v[4 * j4 + 3]), a.w, b.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mask |= (sc[j] < st.tau ? 1u : 0u) << j;
+                if (mask) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (((mask >> j) & 1u) && sc[j] < st.tau)
+                            st = tc_insert(sc[j], (uint32_t)(row0 + c * 32 + j), lv, vstride, lr, p.kp, st);
                 }
             }
             tc_fence_before();
@@ -400,6 +414,238 @@ __global__ void __launch_bounds__(512) tc_collect_kernel(const TcCollectParams c
 __global__ void tc_keys_kernel(const float* dist, const int64_t* pos, uint64_t n, uint64_t* keys) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
         keys[i] = pos[i] >= 0 ? make_key(dist[i], (uint32_t)pos[i]) : KEY_NONE;
+}
+
+}  // namespace vg
+
+// =====================================================================================================
+// K3 (batched): int8 L2 on the tensor cores — tcgen05 kind::i8, exact int32 accumulation.
+//   ||q - x||^2 = |q|^2 + |x|^2 - 2 q.x  is an exact integer, so the epilogue produces the FINAL ranking keys
+//   ((float)sqrt((double)s), row) itself — no re-rank, no error bound.  Same pipeline as tc_scan_kernel minus
+//   the lo-split: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 epilogue; 4 smem stages of 48 KB.
+//   Each epilogue thread (= one query) keeps its k best keys as a binary max-heap in global memory, written
+//   straight into the [query][part][k] layout the final merge reads.
+// =====================================================================================================
+namespace vg {
+
+static constexpr uint32_t TCI_STAGES = 4;
+static constexpr uint32_t TCI_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
+// kind::i8 instruction descriptor: D=S32, A=B=S8, both K-major, N=256, M=128
+static constexpr uint32_t TCI_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
+
+struct TciParams {
+    uint64_t n_rows;
+    uint32_t nq, nk, k;    // nk = ceil(row bytes / 128)
+    uint32_t QT, G;
+    const int* norms;      // [rows] exact |x|^2
+    const int* qnorms;     // [nq] exact |q|^2
+    const uint8_t* skip;
+    uint64_t* out_keys;    // [nq][G][k]
+    uint32_t debug;        // bit0: skip the epilogue arithmetic (pipeline-only timing experiments)
+};
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(TCI_IDESC), "r"(accumulate)
+        : "memory");
+}
+
+// replace the root (current worst) of a full max-heap of `k` keys and restore the heap property
+__device__ __noinline__ uint64_t heap_replace_root(uint64_t* heap, uint32_t k, uint64_t key) {
+    uint32_t i = 0;
+    while (true) {
+        const uint32_t l = 2 * i + 1, r = l + 1;
+        if (l >= k) break;
+        uint64_t cl = heap[l], cr = r < k ? heap[r] : 0ull;
+        const uint32_t c = (r < k && cr > cl) ? r : l;
+        const uint64_t cv = c == l ? cl : cr;
+        if (cv <= key) break;
+        heap[i] = cv;
+        i = c;
+    }
+    heap[i] = key;
+    return heap[0];
+}
+__device__ __noinline__ void heap_push(uint64_t* heap, uint32_t cnt, uint64_t key) {  // cnt = size before the push
+    uint32_t i = cnt;
+    while (i > 0) {
+        const uint32_t p = (i - 1) >> 1;
+        const uint64_t pv = heap[p];
+        if (pv >= key) break;
+        heap[i] = pv;
+        i = p;
+    }
+    heap[i] = key;
+}
+
+__global__ void __launch_bounds__(256, 1)
+tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TciParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* s_colB = (int*)(smem + TCI_STAGES * TCI_STAGE_BYTES);      // [2][256] |x|^2, -1 = row not eligible
+    uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
+    uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 4), bar_tfull = smem_u32(s_bar + 8),
+                   bar_tempty = smem_u32(s_bar + 10);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < TCI_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (uint32_t a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t qt = blockIdx.x % p.QT, g = blockIdx.x / p.QT;
+    const uint64_t n_xt = (p.n_rows + TC_N - 1) / TC_N;
+    const uint32_t my_tiles = g < n_xt ? (uint32_t)((n_xt - g + p.G - 1) / p.G) : 0u;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+                const int row0 = (int)(((uint64_t)g + (uint64_t)ti * p.G) * TC_N);
+                for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                    const uint32_t s = it % TCI_STAGES, ph = (it / TCI_STAGES) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t base = smem_u32(smem + s * TCI_STAGE_BYTES);
+                    mbar_expect_tx(bar_full + 8 * s, TCI_STAGE_BYTES);
+                    tma_load_2d(base, &mapQ, (int)(kc * 128), (int)(qt * TC_M), bar_full + 8 * s);
+                    tma_load_2d(base + TC_A_BYTES, &mapX, (int)(kc * 128), row0, bar_full + 8 * s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+                const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_N;
+                for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                    const uint32_t s = it % TCI_STAGES, ph = (it / TCI_STAGES) & 1;
+                    const uint32_t a = smem_u32(smem + s * TCI_STAGE_BYTES), b = a + TC_A_BYTES;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)  // 4 x K=32 int8 per 128-byte chunk
+                        umma_i8(d_tmem, umma_desc(a + k * 32), umma_desc(b + k * 32), (kc | k) != 0);
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_tfull + 8 * acc);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const uint32_t e = threadIdx.x - 128;
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
+        const uint32_t q = qt * TC_M + e;
+        const bool q_ok = q < p.nq;
+        uint64_t* heap = p.out_keys + ((size_t)(q_ok ? q : 0) * p.G + g) * p.k;
+        const int a2 = q_ok ? p.qnorms[q] : 0;
+        uint32_t cnt = 0;
+        uint64_t tau_key = KEY_NONE;   // heap root once full
+        int tau_s = 0x7FFFFFFE;        // every s above this is certainly not better than the root (0x7FFFFFFF = ineligible row)
+        for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+            const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+            for (uint32_t j = e; j < TC_N; j += 128) {
+                const uint64_t row = row0 + j;
+                const bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
+                s_colB[acc * TC_N + j] = ok ? p.norms[row] : -1;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_tfull + 8 * acc, aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t c = 0; c < ((p.debug & 1) ? 0u : TC_N / 32); ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (lane_base << 16) + acc * TC_N + c * 32;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // branch-free common case: exact s = |q|^2 + |x|^2 - 2 q.x for all 32 columns and a pass mask first
+                const int4* cb4 = (const int4*)(s_colB + acc * TC_N + c * 32);
+                int sv[32];
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const int4 b = cb4[j4];
+                    // rows that are not eligible carry |x|^2 = -1: force s above every threshold
+                    sv[4 * j4 + 0] = b.x < 0 ? 0x7FFFFFFF : a2 + b.x - 2 * (int)v[4 * j4 + 0];
+                    sv[4 * j4 + 1] = b.y < 0 ? 0x7FFFFFFF : a2 + b.y - 2 * (int)v[4 * j4 + 1];
+                    sv[4 * j4 + 2] = b.z < 0 ? 0x7FFFFFFF : a2 + b.z - 2 * (int)v[4 * j4 + 2];
+                    sv[4 * j4 + 3] = b.w < 0 ? 0x7FFFFFFF : a2 + b.w - 2 * (int)v[4 * j4 + 3];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mask |= (sv[j] <= tau_s ? 1u : 0u) << j;
+                if (mask && q_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int s = sv[j];
+                        if (((mask >> j) & 1u) && s <= tau_s && s != 0x7FFFFFFF) {
+                            // src/distance/scalar.rs:65: f64 sqrt, then cast — the same final value as the scan
+                            const float d = __double2float_rn(__dsqrt_rn((double)s));
+                            const uint64_t key = make_key(d, (uint32_t)(row0 + c * 32 + j));
+                            if (cnt < p.k) {
+                                heap_push(heap, cnt, key);
+                                if (++cnt == p.k) tau_key = heap[0];
+                            } else if (key < tau_key) {
+                                tau_key = heap_replace_root(heap, p.k, key);
+                            }
+                            if (cnt == p.k) {
+                                // any s beyond (next float after the root's distance)^2 has a strictly larger f32 distance
+                                const float dr = order_bits_inv((uint32_t)(tau_key >> 32));
+                                const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
+                                const double lim = dn * dn;
+                                tau_s = lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (q_ok)
+            for (uint32_t i = cnt; i < p.k; ++i) heap[i] = KEY_NONE;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// exact |row|^2 of int8 rows (int32)
+__global__ void __launch_bounds__(256) row_norms_i8_kernel(const uint8_t* base, uint32_t stride, uint32_t units, uint64_t n, int* norms) {
+    const int g = threadIdx.x & 3;
+    const uint64_t n_iter = (n + 63) / 64;
+    for (uint64_t itn = blockIdx.x; itn < n_iter; itn += gridDim.x) {
+        const uint64_t row = itn * 64 + (threadIdx.x >> 2);
+        const uint4* r = (const uint4*)(base + (row < n ? row : 0) * (uint64_t)stride);
+        const float v = query_const(r, row < n ? units : 0, g, 1);
+        if (row < n && g == 0) norms[row] = __float_as_int(v);
+    }
 }
 
 }  // namespace vg

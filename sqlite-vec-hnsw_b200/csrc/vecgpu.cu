@@ -774,7 +774,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_f32_map(CUtensorMap* m, const void* base, uint32_t dims, uint64_t rows, uint32_t stride_bytes, uint32_t box_rows) {
+static int make_tile_map(CUtensorMap* m, CUtensorMapDataType dtype, uint32_t inner_elems_total, uint32_t box_inner, const void* base,
+                         uint64_t rows, uint32_t stride_bytes, uint32_t box_rows) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         cudaDriverEntryPointQueryResult qres;
@@ -783,15 +784,17 @@ static int make_f32_map(CUtensorMap* m, const void* base, uint32_t dims, uint64_
         if (!fn) return fail(VECGPU_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
         encode = (EncodeTiledFn)fn;
     }
-    cuuint64_t gdim[2] = {dims, rows};
+    cuuint64_t gdim[2] = {inner_elems_total, rows};
     cuuint64_t gstr[1] = {stride_bytes};
-    cuuint32_t box[2] = {TC_KC, box_rows};
+    cuuint32_t box[2] = {box_inner, box_rows};  // inner box = 128 bytes = one SWIZZLE_128B span
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(m, dtype, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(VECGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
+}
+static int make_f32_map(CUtensorMap* m, const void* base, uint32_t dims, uint64_t rows, uint32_t stride_bytes, uint32_t box_rows) {
+    return make_tile_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims, TC_KC, base, rows, stride_bytes, box_rows);
 }
 
 static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
@@ -801,6 +804,13 @@ static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
         s->d_norms = nullptr;
         s->cap_norms = std::max<uint64_t>(s->rows, s->cap);
         CU(cudaMalloc((void**)&s->d_norms, s->cap_norms * sizeof(float)));
+    }
+    if (s->elem == VECGPU_I8) {  // exact int32 |x|^2 (same 4-byte slots)
+        row_norms_i8_kernel<<<(uint32_t)s->num_sms * 8, 256, 0, st>>>(s->d_vec, s->row_stride, s->row_stride / 16, s->rows, (int*)s->d_norms);
+        LAUNCHED();
+        s->n_unsafe = 0;
+        s->norms_valid = true;
+        return 0;
     }
     if (!s->d_x2max) CU(cudaMalloc((void**)&s->d_x2max, 4));
     if (!s->d_unsafe) CU(cudaMalloc((void**)&s->d_unsafe, (1 + TC_MAX_UNSAFE) * 4));
@@ -954,8 +964,78 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
     return 0;
 }
 
+static bool tci8_eligible(const vecgpu_slab* s, uint32_t nq, uint32_t k, int metric) {
+    if (env_u32("VECGPU_TC", 1) == 0) return false;
+    return s->elem == VECGPU_I8 && metric == VECGPU_L2 && nq >= env_u32("VECGPU_TC_MIN_NQ", 16) && s->rows >= 8192 &&
+           s->rows < 0x7FFFFFFFull && k <= 1024 && s->dims >= 16 && s->dims <= 16384;
+}
+
+// int8 L2 batches: exact on the tensor cores (tci8_scan_kernel) + the ordinary final merge
+static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t k, int metric, int64_t* d_out_rowids,
+                    float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
+    (void)metric;
+    int rc = slab_ensure_norms(s, st);
+    if (rc) return rc;
+    static int cfg_dev = -1;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + 2 * TC_N * 4 + 32 * 8 + 1024;
+    if (cfg_dev != dev) {
+        CU(cudaFuncSetAttribute(tci8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        cfg_dev = dev;
+    }
+    const uint64_t n_xt = (s->rows + TC_N - 1) / TC_N;
+    const uint32_t max_qt = 16;
+    CUtensorMap mapX;
+    if ((rc = make_tile_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->dims, 128, s->d_vec, s->rows, s->row_stride, TC_N))) return rc;
+    for (uint32_t qoff = 0; qoff < nq_all; qoff += max_qt * TC_M) {
+        const uint32_t nq = std::min(nq_all - qoff, max_qt * TC_M);
+        const uint8_t* dq = d_q + (size_t)qoff * s->row_stride;
+        const uint32_t QT = (nq + TC_M - 1) / TC_M;
+        uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms / QT, n_xt));
+        while (G > 1 && (uint64_t)G * k > 16384) --G;  // keep the final merge in one CTA's shared memory
+        if ((rc = ws_reserve(s, WS_PART, (size_t)nq * G * k * 8))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_QNORM, (size_t)nq * 4))) return rc;
+        row_norms_i8_kernel<<<std::max(1u, std::min((nq + 63) / 64, 1024u)), 256, 0, st>>>(dq, s->row_stride, s->row_stride / 16, nq,
+                                                                                           (int*)s->d_ws[WS_TC_QNORM]);
+        LAUNCHED();
+        CUtensorMap mapQ;
+        if ((rc = make_tile_map(&mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->dims, 128, dq, nq, s->row_stride, TC_M))) return rc;
+        TciParams tp{};
+        tp.n_rows = s->rows;
+        tp.nq = nq;
+        tp.nk = (s->dims + 127) / 128;
+        tp.k = k;
+        tp.QT = QT;
+        tp.G = G;
+        tp.norms = (const int*)s->d_norms;
+        tp.qnorms = (const int*)s->d_ws[WS_TC_QNORM];
+        tp.skip = s->n_skip ? s->d_skip : nullptr;
+        tp.out_keys = (uint64_t*)s->d_ws[WS_PART];
+        tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
+        tci8_scan_kernel<<<QT * G, 256, smem, st>>>(mapQ, mapX, tp);
+        LAUNCHED();
+        g_tc_queries.fetch_add(nq, std::memory_order_relaxed);
+        MergeParams mp{};
+        mp.keys = tp.out_keys;
+        mp.n_cand = (uint64_t)G * k;
+        mp.k = k;
+        mp.kp2 = next_pow2(k);
+        mp.rowids = s->dense ? nullptr : s->d_rowids;
+        mp.first_rowid = s->first_rowid;
+        mp.out_rowids = d_out_rowids + (size_t)qoff * k;
+        mp.out_dists = d_out_dists + (size_t)qoff * k;
+        mp.out_counts = d_out_counts ? d_out_counts + qoff : nullptr;
+        mp.pad_rowid = pad_rowid;
+        if ((rc = launch_merge(s, mp, nq, st))) return rc;
+    }
+    return 0;
+}
+
 static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
+    if (nq && k && tci8_eligible(s, nq, k, metric))
+        return knn_tci8(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
     if (nq && k && tc_eligible(s, nq, k, metric))
         return knn_tc(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
     return knn_exact(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);

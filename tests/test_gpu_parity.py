@@ -646,3 +646,39 @@ def test_hnsw_empty_and_tiny(vg, gpu):
         with pytest.raises(vg.InvalidParameter):
             vg.HnswIndex(s, L2, M=1)  # M must be in [2,100] (src/sql_functions.rs:442-469)
         idx.close()
+
+
+# ------------------------------------------------------------------ K3 batched: int8 L2 on the tensor cores (tcgen05 kind::i8), exact
+@pytest.mark.parametrize("dims,nq,k", [(1024, 64, 100), (128, 16, 10), (100, 130, 7), (33, 40, 1), (2000, 20, 33)])
+def test_tc_int8_batched_matches_oracle(vg, orc, gpu, dims, nq, k):
+    n = 30000
+    v = random_rows(I8, n, dims, seed=61)
+    q = random_rows(I8, nq, dims, seed=62)
+    rowids = np.arange(n, dtype="<i8") * 5 - 1000
+    skip = np.zeros(n, dtype="u1")
+    skip[[0, 777, n - 1]] = 1
+    with vg.Slab(I8, dims) as s:
+        s.load(v, rowids)
+        for i in np.flatnonzero(skip):
+            s.delete(int(rowids[i]))
+        before = vg.tc_stats()
+        r, d, c = s.knn(q, k, L2)
+        assert vg.tc_stats()[0] - before[0] == nq, "the batch must have gone through the int8 tensor-core path"
+    er, ed, ec = orc.knn(I8, dims, v, q, k, L2, rowids=rowids, skip=skip)
+    assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed)) and np.array_equal(c, ec)
+
+
+def test_tc_int8_batched_heavy_ties_and_extremes(vg, orc, gpu):
+    # tiny alphabet: thousands of equal distances, the rowid tie-break decides every rank; plus +-128/127 rows
+    n, dims, nq, k = 20000, 64, 32, 50
+    v = random_rows(I8, n, dims, seed=71, ties=True)
+    v[5] = -128
+    v[6] = 127
+    q = random_rows(I8, nq, dims, seed=72, ties=True)
+    q[1] = 127
+    q[2] = -128
+    with vg.Slab(I8, dims) as s:
+        s.load(v)
+        r, d, c = s.knn(q, k, L2)
+    er, ed, ec = orc.knn(I8, dims, v, q, k, L2)
+    assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed))
