@@ -1,0 +1,150 @@
+"""vec0-compatible SQLite reader that exercises the C-ABI boundary end to end.
+
+The reference stores a vec0 table as plain SQLite shadow tables (src/shadow.rs:105-184):
+
+    "{t}_data"(rowid INTEGER PRIMARY KEY, vec00 BLOB, vec01 BLOB, ..., col00 T, ...)   one BLOB per row and vector column
+    "{t}_info"(key TEXT PRIMARY KEY, value)                                            CREATE_VERSION*, STORAGE_SCHEMA='unified'
+
+A BLOB is the raw little-endian element array (src/vector.rs:223-242, 592-600).  This module reads and writes that
+format with Python's sqlite3 — no Rust extension needed — and keeps an HBM slab in step with it:
+
+    stage()                      SELECT rowid, vecNN FROM "{t}_data" ORDER BY rowid  ->  vecgpu_slab_load
+                                 (src/shadow.rs:853-868 order; NULL / empty / wrong-length blobs become skipped rows,
+                                 src/vtab.rs:2596-2613)
+    knn(query_blob, k)           the body of brute_force_search (src/vtab.rs:2573-2623) on the GPU
+    insert / update / delete     the hooks of Vec0Tab::insert/update/delete (src/vtab.rs:1409, 1684, 1326): SQLite first,
+                                 then vecgpu_slab_upsert / vecgpu_slab_delete
+    is_stale()                   (COUNT(*), MAX(rowid), total_changes) heuristic of SURVEY H5 for writers that bypass us
+"""
+import numpy as np
+
+from . import vec0
+
+
+def data_table_ddl(table, n_vector_columns=1, data_columns=()):
+    """The CREATE TABLE statement of src/shadow.rs:111-129 (schema "main")."""
+    sql = f'CREATE TABLE "main"."{table}_data" (rowid INTEGER PRIMARY KEY'
+    for i in range(n_vector_columns):
+        sql += f", vec{i:02d} BLOB"
+    for i, col_type in enumerate(data_columns):
+        sql += f", col{i:02d} {col_type}"
+    return sql + ");"
+
+
+INFO_ROWS = [  # src/shadow.rs:141-181
+    ("CREATE_VERSION", "0.2.0"), ("CREATE_VERSION_MAJOR", 0), ("CREATE_VERSION_MINOR", 2), ("CREATE_VERSION_PATCH", 0),
+    ("STORAGE_SCHEMA", "unified"),
+]
+
+
+def create_shadow_tables(conn, table, n_vector_columns=1, data_columns=()):
+    """Create "{t}_data" and "{t}_info" exactly as the reference does (src/shadow.rs:105-184)."""
+    conn.execute(data_table_ddl(table, n_vector_columns, data_columns))
+    conn.execute(f'CREATE TABLE "main"."{table}_info" (key TEXT PRIMARY KEY, value);')
+    conn.executemany(f'INSERT INTO "main"."{table}_info" (key, value) VALUES (?, ?)', INFO_ROWS)
+
+
+def storage_schema(conn, table):
+    row = conn.execute(f'SELECT value FROM "main"."{table}_info" WHERE key = \'STORAGE_SCHEMA\'').fetchone()
+    return None if row is None else row[0]
+
+
+def read_column(conn, table, column_idx, row_bytes):
+    """-> (rowids int64[n], vectors uint8[n, row_bytes], skip uint8[n]) in ascending rowid order."""
+    cur = conn.execute(f'SELECT rowid, vec{column_idx:02d} FROM "main"."{table}_data" ORDER BY rowid')
+    rowids, chunks, skip = [], [], []
+    zero = bytes(row_bytes)
+    for rowid, blob in cur:
+        rowids.append(rowid)
+        if blob is None or len(blob) != row_bytes:  # empty / NULL / wrong length: the scan skips the row
+            chunks.append(zero)
+            skip.append(1)
+        else:
+            chunks.append(bytes(blob))
+            skip.append(0)
+    n = len(rowids)
+    vec = np.frombuffer(b"".join(chunks), dtype="u1").reshape(n, row_bytes) if n else np.zeros((0, row_bytes), dtype="u1")
+    return np.asarray(rowids, dtype="<i8"), vec, np.asarray(skip, dtype="u1")
+
+
+class Vec0Table:
+    """One vector column of one vec0 table, served from an HBM slab."""
+
+    def __init__(self, conn, table, vec_type, dims, distance_metric=vec0.DistanceMetric.Cosine, column_idx=0, device=0,
+                 slab_factory=None):
+        # the column's metric defaults to Cosine (src/vtab.rs:240-248)
+        self.conn, self.table, self.column_idx = conn, table, column_idx
+        self.vec_type = vec0.VectorType(vec_type)
+        self.dims = int(dims)
+        self.metric = vec0.DistanceMetric(distance_metric)
+        self.row_bytes = self.vec_type.row_bytes(self.dims)
+        schema = storage_schema(conn, table)
+        if schema != "unified":
+            raise vec0.InvalidState(f"{table}: unsupported STORAGE_SCHEMA {schema!r} (expected 'unified')")
+        self._slab_factory = slab_factory or (lambda: vec0.Slab(self.vec_type, self.dims, device=device))
+        self.slab = None
+        self._fingerprint = None
+
+    # ---- staging
+    def _current_fingerprint(self):
+        cnt, mx = self.conn.execute(f'SELECT COUNT(*), MAX(rowid) FROM "main"."{self.table}_data"').fetchone()
+        return (cnt, mx, self.conn.total_changes)
+
+    def is_stale(self):
+        return self.slab is None or self._fingerprint != self._current_fingerprint()
+
+    def stage(self):
+        rowids, vec, skip = read_column(self.conn, self.table, self.column_idx, self.row_bytes)
+        if self.slab is None:
+            self.slab = self._slab_factory()
+        if len(rowids):
+            self.slab.load(vec, rowids)
+            for i in np.flatnonzero(skip):
+                self.slab.upsert(int(rowids[i]), b"")
+        else:
+            self.slab.load(np.zeros((0, self.row_bytes), dtype="u1"), np.zeros(0, dtype="<i8"))
+        self._fingerprint = self._current_fingerprint()
+        return len(rowids)
+
+    # ---- the KNN arm of Vec0TabCursor::filter (src/vtab.rs:2286-2305)
+    def knn(self, query, k, metric=None):
+        """query: blob, or a JSON array text as vec_f32('[...]') accepts (src/vtab.rs:2119-2143)."""
+        if isinstance(query, str):
+            query = vec0.Vector.from_json(query, self.vec_type).as_bytes()
+        if self.is_stale():
+            self.stage()
+        return vec0.brute_force_search(self.slab, query, k, self.metric if metric is None else metric)
+
+    # ---- write hooks: SQLite first (shadow::insert_row / update_row / delete_row), then the slab
+    def next_rowid(self):
+        mx = self.conn.execute(f'SELECT MAX(rowid) FROM "main"."{self.table}_data"').fetchone()[0]
+        return 1 if mx is None else mx + 1  # src/shadow.rs:888-900
+
+    def insert(self, blob, rowid=None):
+        rowid = self.next_rowid() if rowid is None else int(rowid)
+        if blob is not None and len(blob) not in (0, self.row_bytes):
+            # the vtab rejects wrong-length vectors on insert (src/vtab.rs:1474-1498)
+            raise vec0.DimensionMismatch(
+                f"Dimension mismatch: expected {self.dims}, got {len(blob)} bytes", self.dims, None)
+        self.conn.execute(f'INSERT INTO "main"."{self.table}_data" (rowid, vec{self.column_idx:02d}) VALUES (?, ?)', (rowid, blob))
+        if self.slab is not None:
+            self.slab.upsert(rowid, blob or b"")
+            self._fingerprint = self._current_fingerprint()
+        return rowid
+
+    def update(self, rowid, blob):
+        self.conn.execute(f'UPDATE "main"."{self.table}_data" SET vec{self.column_idx:02d} = ? WHERE rowid = ?', (blob, int(rowid)))
+        if self.slab is not None:
+            self.slab.upsert(int(rowid), blob or b"")
+            self._fingerprint = self._current_fingerprint()
+
+    def delete(self, rowid):
+        self.conn.execute(f'DELETE FROM "main"."{self.table}_data" WHERE rowid = ?', (int(rowid),))
+        if self.slab is not None:
+            self.slab.delete(int(rowid))
+            self._fingerprint = self._current_fingerprint()
+
+    def close(self):
+        if self.slab is not None:
+            self.slab.close()
+            self.slab = None

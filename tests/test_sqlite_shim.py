@@ -1,0 +1,120 @@
+"""SQLite-side shim: the reference's on-disk format read / written with Python's sqlite3 and served from a slab."""
+import sqlite3
+
+import numpy as np
+import pytest
+
+from helpers import COSINE, F32, I8, L2, random_rows
+
+
+def _shim():
+    from sqlite_vec_hnsw_b200 import sqlite_shim
+
+    return sqlite_shim
+
+
+def test_shadow_ddl_matches_reference():
+    sh = _shim()
+    # src/shadow.rs:111-129
+    assert sh.data_table_ddl("t") == 'CREATE TABLE "main"."t_data" (rowid INTEGER PRIMARY KEY, vec00 BLOB);'
+    assert (sh.data_table_ddl("docs", 2, ["TEXT", "INTEGER"])
+            == 'CREATE TABLE "main"."docs_data" (rowid INTEGER PRIMARY KEY, vec00 BLOB, vec01 BLOB, col00 TEXT, col01 INTEGER);')
+    conn = sqlite3.connect(":memory:")
+    sh.create_shadow_tables(conn, "t", 1, ["TEXT"])
+    info = dict(conn.execute('SELECT key, value FROM "t_info"').fetchall())
+    assert info["STORAGE_SCHEMA"] == "unified" and info["CREATE_VERSION"] == "0.2.0"  # src/shadow.rs:141-181
+    assert sh.storage_schema(conn, "t") == "unified"
+
+
+def test_read_column_order_and_skips():
+    sh = _shim()
+    conn = sqlite3.connect(":memory:")
+    sh.create_shadow_tables(conn, "t")
+    v = random_rows(F32, 6, 4, seed=1)
+    for rid, blob in [(7, v[0].tobytes()), (2, v[1].tobytes()), (9, None), (4, b""), (5, v[2].tobytes()[:8]), (11, v[3].tobytes())]:
+        conn.execute('INSERT INTO "t_data" (rowid, vec00) VALUES (?, ?)', (rid, blob))
+    rowids, vec, skip = sh.read_column(conn, "t", 0, 16)
+    assert list(rowids) == [2, 4, 5, 7, 9, 11]  # ORDER BY rowid (src/shadow.rs:853-868)
+    assert list(skip) == [0, 1, 1, 0, 1, 0]  # empty / wrong length / NULL are skipped (src/vtab.rs:2596-2613)
+    assert vec[0].tobytes() == v[1].tobytes() and vec[3].tobytes() == v[0].tobytes() and not vec[1].any()
+
+
+class _RecorderSlab:
+    """Stands in for the HBM slab on CPU-only hosts: records the staging calls."""
+
+    def __init__(self):
+        self.calls = []
+
+    def load(self, vec, rowids):
+        self.calls.append(("load", len(rowids)))
+
+    def upsert(self, rowid, blob):
+        self.calls.append(("upsert", rowid, len(blob)))
+
+    def delete(self, rowid):
+        self.calls.append(("delete", rowid))
+
+    def close(self):
+        pass
+
+
+def test_staging_and_hooks_drive_the_slab():
+    sh = _shim()
+    conn = sqlite3.connect(":memory:")
+    sh.create_shadow_tables(conn, "t")
+    rec = _RecorderSlab()
+    t = sh.Vec0Table(conn, "t", F32, 4, slab_factory=lambda: rec)
+    assert t.is_stale()
+    v = random_rows(F32, 3, 4, seed=2)
+    conn.execute('INSERT INTO "t_data" (rowid, vec00) VALUES (1, ?)', (v[0].tobytes(),))
+    conn.execute('INSERT INTO "t_data" (rowid, vec00) VALUES (2, ?)', (b"",))
+    assert t.stage() == 2 and rec.calls == [("load", 2), ("upsert", 2, 0)] and not t.is_stale()
+    assert t.insert(v[1].tobytes()) == 3  # auto rowid = MAX+1 (src/shadow.rs:888-900)
+    t.update(1, v[2].tobytes())
+    t.delete(3)
+    assert rec.calls[2:] == [("upsert", 3, 16), ("upsert", 1, 16), ("delete", 3)] and not t.is_stale()
+    conn.execute('INSERT INTO "t_data" (rowid, vec00) VALUES (50, ?)', (v[0].tobytes(),))  # a writer that bypasses the hooks
+    assert t.is_stale()
+    with pytest.raises(Exception):
+        t.insert(b"\x00" * 5)  # wrong-length vectors are rejected on insert (src/vtab.rs:1474-1498)
+
+
+@pytest.mark.gpu
+def test_end_to_end_knn_from_sqlite(vg, orc, gpu, tmp_path):
+    sh = _shim()
+    conn = sqlite3.connect(str(tmp_path / "vec.db"))  # a file database, like tests/test_disk_persistence.rs
+    sh.create_shadow_tables(conn, "items", 1, ["TEXT"])
+    n, dims = 3000, 24
+    v = random_rows(F32, n, dims, seed=3)
+    rowids = np.arange(n) * 2 + 1
+    conn.executemany('INSERT INTO "items_data" (rowid, vec00, col00) VALUES (?, ?, ?)',
+                     [(int(r), v[i].tobytes(), f"doc{i}") for i, r in enumerate(rowids)])
+    conn.execute('UPDATE "items_data" SET vec00 = NULL WHERE rowid = 5')
+    conn.commit()
+    t = sh.Vec0Table(conn, "items", F32, dims)  # default metric: cosine
+    skip = np.zeros(n, dtype="u1")
+    skip[2] = 1
+    res = t.knn(v[10].tobytes(), 5)
+    er, ed, _ = orc.knn(F32, dims, v, v[10], 5, COSINE, rowids=rowids, skip=skip)
+    assert [r for r, _ in res] == list(er[0]) and np.array_equal(np.array([d for _, d in res], dtype="<f4").view("<u4"), ed[0].view("<u4"))
+    # JSON query text == blob (tests/integration_test.rs:1076-1128)
+    js = "[" + ",".join(repr(float(x)) for x in v[10]) + "]"
+    assert t.knn(js, 5) == res
+    # write through the hooks, then query again
+    nv = random_rows(F32, 2, dims, seed=4)
+    new_id = t.insert(nv[0].tobytes())
+    t.update(int(rowids[0]), nv[1].tobytes())
+    t.delete(int(rowids[10]))
+    v2 = np.concatenate([v, nv[:1]])
+    v2[0] = nv[1]
+    rowids2 = np.concatenate([rowids, [new_id]])
+    skip2 = np.concatenate([skip, [0]]).astype("u1")
+    skip2[10] = 1
+    res = t.knn(nv[0].tobytes(), 4, metric=L2)
+    er, ed, _ = orc.knn(F32, dims, v2, nv[0], 4, L2, rowids=rowids2, skip=skip2)
+    assert [r for r, _ in res] == list(er[0]) and res[0] == (new_id, 0.0)
+    # an external writer is noticed and the slab re-staged
+    conn.execute('DELETE FROM "items_data" WHERE rowid = ?', (new_id,))
+    res = t.knn(nv[0].tobytes(), 1, metric=L2)
+    assert res[0][0] != new_id
+    t.close()
