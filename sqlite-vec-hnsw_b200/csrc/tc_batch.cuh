@@ -48,6 +48,7 @@ struct TcParams {
     uint32_t kp;           // entries kept per (CTA, query) = k + margin
     uint32_t cosine;       // 0: L2 (v = x2 - 2s), 1: cosine (v = -s / |x|)
     uint32_t lists_smem;   // 1: the kept scores live in shared memory ([kp][128] floats) during the scan
+    uint32_t debug;        // bit0: skip the epilogue arithmetic (pipeline-only timing experiments)
     uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
     const float* norms;    // [rows] canonical sum of squares of each slab row
     const uint8_t* skip;   // per-row skip flags or nullptr
@@ -267,7 +268,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
 #pragma unroll 1
-            for (uint32_t c = 0; c < TC_N / 32; ++c) {
+            for (uint32_t c = 0; c < ((p.debug & 1) ? 0u : TC_N / 32); ++c) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (lane_base << 16) + acc * TC_N + c * 32;
                 asm volatile(
@@ -440,7 +441,9 @@ struct TciParams {
     const int* norms;      // [rows] exact |x|^2
     const int* qnorms;     // [nq] exact |q|^2
     const uint8_t* skip;
-    uint64_t* out_keys;    // [nq][G][k]
+    uint64_t* out_keys;    // [nq][G][k]   final per-(query, CTA) results, KEY_NONE padded
+    uint64_t* buf_keys;    // [nq][G][cap] per-thread append buffers (cap: power of two >= 2k + 64)
+    uint32_t cap;
     uint32_t debug;        // bit0: skip the epilogue arithmetic (pipeline-only timing experiments)
 };
 
@@ -451,32 +454,32 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         : "memory");
 }
 
-// replace the root (current worst) of a full max-heap of `k` keys and restore the heap property
-__device__ __noinline__ uint64_t heap_replace_root(uint64_t* heap, uint32_t k, uint64_t key) {
-    uint32_t i = 0;
-    while (true) {
-        const uint32_t l = 2 * i + 1, r = l + 1;
-        if (l >= k) break;
-        uint64_t cl = heap[l], cr = r < k ? heap[r] : 0ull;
-        const uint32_t c = (r < k && cr > cl) ? r : l;
-        const uint64_t cv = c == l ? cl : cr;
-        if (cv <= key) break;
-        heap[i] = cv;
-        i = c;
+// Warp-cooperative compaction of one thread's append buffer: copy its `cnt` keys (padded with KEY_NONE to `cap`)
+// into the warp's shared-memory scratch, bitonic-sort ascending, write the k smallest back to the front of the
+// buffer.  Returns (to every lane) the new k-th smallest key, or KEY_NONE when fewer than k keys exist.
+__device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint32_t cap, uint32_t k, uint64_t* scratch, int lane) {
+    __syncwarp();  // the owner lane's appends become visible to the helping lanes
+    for (uint32_t i = lane; i < cap; i += 32) scratch[i] = i < cnt ? buf[i] : KEY_NONE;
+    __syncwarp();
+    for (uint32_t size = 2; size <= cap; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < cap / 2; t += 32) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = scratch[lo], b = scratch[hi];
+                if ((a > b) == up) {
+                    scratch[lo] = b;
+                    scratch[hi] = a;
+                }
+            }
+            __syncwarp();
+        }
     }
-    heap[i] = key;
-    return heap[0];
-}
-__device__ __noinline__ void heap_push(uint64_t* heap, uint32_t cnt, uint64_t key) {  // cnt = size before the push
-    uint32_t i = cnt;
-    while (i > 0) {
-        const uint32_t p = (i - 1) >> 1;
-        const uint64_t pv = heap[p];
-        if (pv >= key) break;
-        heap[i] = pv;
-        i = p;
-    }
-    heap[i] = key;
+    for (uint32_t i = lane; i < k; i += 32) buf[i] = scratch[i];
+    const uint64_t kth = scratch[k - 1];
+    __syncwarp();
+    return kth;
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -487,6 +490,7 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     int* s_colB = (int*)(smem + TCI_STAGES * TCI_STAGE_BYTES);      // [2][256] |x|^2, -1 = row not eligible
     uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
+    uint64_t* s_scratch = s_bar + 32;                                // [4 epilogue warps][cap] compaction scratch
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 4), bar_tfull = smem_u32(s_bar + 8),
                    bar_tempty = smem_u32(s_bar + 10);
     if (warp == 1) {
@@ -555,11 +559,14 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
         const uint32_t q = qt * TC_M + e;
         const bool q_ok = q < p.nq;
-        uint64_t* heap = p.out_keys + ((size_t)(q_ok ? q : 0) * p.G + g) * p.k;
+        // per-thread append buffer: keys that beat the (lazily refreshed) threshold are simply appended; when a
+        // buffer is nearly full the warp compacts it cooperatively and the thread's threshold tightens
+        uint64_t* buf = p.buf_keys + ((size_t)(q_ok ? q : 0) * p.G + g) * p.cap;
+        uint64_t* scratch = s_scratch + (size_t)(warp & 3) * p.cap;
         const int a2 = q_ok ? p.qnorms[q] : 0;
         uint32_t cnt = 0;
-        uint64_t tau_key = KEY_NONE;   // heap root once full
-        int tau_s = 0x7FFFFFFE;        // every s above this is certainly not better than the root (0x7FFFFFFF = ineligible row)
+        uint64_t tau_key = KEY_NONE;   // k-th best key as of the last compaction
+        int tau_s = 0x7FFFFFFE;        // every s above this is certainly not better than tau_key (0x7FFFFFFF = ineligible row)
         for (uint32_t ti = 0; ti < my_tiles; ++ti) {
             const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
             const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
@@ -607,19 +614,27 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             // src/distance/scalar.rs:65: f64 sqrt, then cast — the same final value as the scan
                             const float d = __double2float_rn(__dsqrt_rn((double)s));
                             const uint64_t key = make_key(d, (uint32_t)(row0 + c * 32 + j));
-                            if (cnt < p.k) {
-                                heap_push(heap, cnt, key);
-                                if (++cnt == p.k) tau_key = heap[0];
-                            } else if (key < tau_key) {
-                                tau_key = heap_replace_root(heap, p.k, key);
-                            }
-                            if (cnt == p.k) {
-                                // any s beyond (next float after the root's distance)^2 has a strictly larger f32 distance
-                                const float dr = order_bits_inv((uint32_t)(tau_key >> 32));
-                                const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
-                                const double lim = dn * dn;
-                                tau_s = lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
-                            }
+                            if (key < tau_key) buf[cnt++] = key;
+                        }
+                    }
+                }
+                // a buffer that could overflow during the next 32 columns is compacted now (warp-uniform loop)
+                unsigned need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint64_t bp = shfl_u64((uint64_t)(uintptr_t)buf, src);
+                    const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
+                    const uint64_t kth = warp_compact((uint64_t*)(uintptr_t)bp, bc, p.cap, p.k, scratch, lane);
+                    if (lane == src) {
+                        cnt = min(bc, p.k);
+                        tau_key = kth;
+                        if (kth != KEY_NONE) {
+                            // any s beyond (next float after the k-th distance)^2 has a strictly larger f32 distance
+                            const float dr = order_bits_inv((uint32_t)(kth >> 32));
+                            const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
+                            const double lim = dn * dn;
+                            tau_s = lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
                         }
                     }
                 }
@@ -628,8 +643,17 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
-        if (q_ok)
-            for (uint32_t i = cnt; i < p.k; ++i) heap[i] = KEY_NONE;
+        // final compaction of every lane's buffer -> the k best keys of this (query, CTA), KEY_NONE padded
+        for (int src = 0; src < 32; ++src) {
+            const uint64_t bp = shfl_u64((uint64_t)(uintptr_t)buf, src);
+            const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
+            const uint32_t qs = __shfl_sync(0xffffffffu, q, src);
+            if (qs >= p.nq) continue;  // warp-uniform
+            warp_compact((uint64_t*)(uintptr_t)bp, bc, p.cap, p.k, scratch, lane);
+            uint64_t* out = p.out_keys + ((size_t)qs * p.G + g) * p.k;
+            for (uint32_t i = lane; i < p.k; i += 32) out[i] = scratch[i];
+            __syncwarp();
+        }
     }
     tc_fence_before();
     __syncthreads();

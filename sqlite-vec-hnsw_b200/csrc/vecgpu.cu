@@ -893,6 +893,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         tp.kp = kp;
         tp.cosine = metric == VECGPU_COSINE ? 1u : 0u;
         tp.lists_smem = lists_smem ? 1u : 0u;
+        tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
         tp.QT = QT;
         tp.G = G;
         tp.norms = s->d_norms;
@@ -967,7 +968,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
 static bool tci8_eligible(const vecgpu_slab* s, uint32_t nq, uint32_t k, int metric) {
     if (env_u32("VECGPU_TC", 1) == 0) return false;
     return s->elem == VECGPU_I8 && metric == VECGPU_L2 && nq >= env_u32("VECGPU_TC_MIN_NQ", 16) && s->rows >= 8192 &&
-           s->rows < 0x7FFFFFFFull && k <= 1024 && s->dims >= 16 && s->dims <= 16384;
+           s->rows < 0x7FFFFFFFull && k <= 224 && s->dims >= 16 && s->dims <= 16384;
 }
 
 // int8 L2 batches: exact on the tensor cores (tci8_scan_kernel) + the ordinary final merge
@@ -979,7 +980,8 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
     static int cfg_dev = -1;
     int dev = 0;
     CU(cudaGetDevice(&dev));
-    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + 2 * TC_N * 4 + 32 * 8 + 1024;
+    const uint32_t cap = std::max(128u, next_pow2(2 * k + 64));  // per-thread append buffer; k <= 224 -> cap <= 512
+    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + 2 * TC_N * 4 + 32 * 8 + 4 * (size_t)cap * 8 + 1024;
     if (cfg_dev != dev) {
         CU(cudaFuncSetAttribute(tci8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         cfg_dev = dev;
@@ -995,6 +997,7 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
         uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms / QT, n_xt));
         while (G > 1 && (uint64_t)G * k > 16384) --G;  // keep the final merge in one CTA's shared memory
         if ((rc = ws_reserve(s, WS_PART, (size_t)nq * G * k * 8))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_KEYS, (size_t)nq * G * cap * 8))) return rc;
         if ((rc = ws_reserve(s, WS_TC_QNORM, (size_t)nq * 4))) return rc;
         row_norms_i8_kernel<<<std::max(1u, std::min((nq + 63) / 64, 1024u)), 256, 0, st>>>(dq, s->row_stride, s->row_stride / 16, nq,
                                                                                            (int*)s->d_ws[WS_TC_QNORM]);
@@ -1012,6 +1015,8 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
         tp.qnorms = (const int*)s->d_ws[WS_TC_QNORM];
         tp.skip = s->n_skip ? s->d_skip : nullptr;
         tp.out_keys = (uint64_t*)s->d_ws[WS_PART];
+        tp.buf_keys = (uint64_t*)s->d_ws[WS_TC_KEYS];
+        tp.cap = cap;
         tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
         tci8_scan_kernel<<<QT * G, 256, smem, st>>>(mapQ, mapX, tp);
         LAUNCHED();
