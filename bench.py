@@ -313,6 +313,13 @@ def run_ours(args):
                 msb = timed(lambda: sl.knn_device(q1, k, metric, stream=stream.cuda_stream), 10)
                 ent["batch100_ms"] = msb
                 ent["batch100_qps"] = 100 / (msb / 1e3)
+            if name.startswith("cfg3"):
+                qb8 = torch.from_numpy(oracle.synth_rows(elem, 78, 1, 1024, dims, kind).copy()).to(dev)
+                msb = timed(lambda: sl.knn_device(qb8, k, metric, stream=stream.cuda_stream), 2)
+                ent["batch1024_ms"] = msb
+                ent["batch1024_qps"] = 1024 / (msb / 1e3)
+                ent["batch1024_tops"] = 2.0 * 1024 * n * dims / (msb / 1e3) / 1e12
+                ent["batch1024_kernel"] = "tci8_scan_kernel (tcgen05 kind::i8, exact) + merge"
             extras[name] = ent
             sl.close()
             torch.cuda.empty_cache()
