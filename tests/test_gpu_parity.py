@@ -682,3 +682,30 @@ def test_tc_int8_batched_heavy_ties_and_extremes(vg, orc, gpu):
         r, d, c = s.knn(q, k, L2)
     er, ed, ec = orc.knn(I8, dims, v, q, k, L2)
     assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed))
+
+
+def test_sharded_batched_queries_through_tensor_cores(vg, orc, gpu):
+    """Rowid-range shards (emulated on one device) + tensor-core batches + cross-shard merge == one big slab."""
+    import torch
+
+    from sqlite_vec_hnsw_b200.dist import pack_local, shard_range, unpack_gathered
+
+    dims, n, k, nq, world = 64, 40000, 10, 48, 3
+    v = orc.synth_rows(F32, 31, 1, n, dims, 1)
+    q = orc.synth_rows(F32, 32, 1, nq, dims, 1)
+    dq = torch.from_numpy(q.copy()).cuda()
+    parts = []
+    before = vg.tc_stats()[0]
+    for rank in range(world):
+        lo, hi = shard_range(n, rank, world)
+        s = vg.Slab(F32, dims)
+        s.load(v[lo:hi], np.arange(1 + lo, 1 + hi, dtype="<i8"))
+        r, d = s.knn_device(dq, k, COSINE)
+        torch.cuda.synchronize()
+        parts.append(pack_local(r, d))
+        s.close()
+    assert vg.tc_stats()[0] - before == world * nq
+    mr, md = vg.merge_device(*unpack_gathered(torch.stack(parts)))
+    torch.cuda.synchronize()
+    er, ed, _ = orc.knn(F32, dims, v, q, k, COSINE)
+    assert np.array_equal(mr.cpu().numpy(), er) and np.array_equal(bits(md.cpu().numpy()), bits(ed))
