@@ -709,3 +709,50 @@ def test_sharded_batched_queries_through_tensor_cores(vg, orc, gpu):
     torch.cuda.synchronize()
     er, ed, _ = orc.knn(F32, dims, v, q, k, COSINE)
     assert np.array_equal(mr.cpu().numpy(), er) and np.array_equal(bits(md.cpu().numpy()), bits(ed))
+
+
+# ------------------------------------------------------------------ randomized sweep: every dispatch path vs the oracle
+@pytest.mark.parametrize("seed", range(40))
+def test_knn_fuzz(vg, orc, gpu, seed):
+    rng = np.random.default_rng(1000 + seed)
+    elem, metric = PAIRS[rng.integers(len(PAIRS))]
+    dims = int(rng.choice([1, 2, 5, 8, 15, 16, 31, 32, 33, 63, 64, 96, 127, 128, 200, 256, 384, 513, 768, 1000, 1536]))
+    if elem == BIT:
+        dims = int(rng.choice([1, 7, 8, 9, 64, 100, 128, 1000, 1024, 2048, 4100]))
+    n = int(rng.choice([1, 2, 17, 100, 1000, 5000, 9000, 20000]))
+    nq = int(rng.choice([1, 1, 2, 3, 7, 8, 9, 16, 17, 40]))
+    k = int(rng.choice([1, 2, 5, 10, 31, 32, 33, 100, 129]))
+    ties = bool(rng.integers(4) == 0)
+    v = random_rows(elem, n, dims, seed=seed * 3 + 1, ties=ties)
+    q = random_rows(elem, nq, dims, seed=seed * 3 + 2, ties=ties)
+    rowids = None
+    if rng.integers(2):
+        rowids = np.cumsum(rng.integers(1, 1000, size=n)).astype("<i8") - int(rng.integers(0, 10**6))
+    skip = None
+    if rng.integers(2) and n > 3:
+        skip = np.zeros(n, dtype="u1")
+        skip[rng.choice(n, size=max(1, n // 10), replace=False)] = 1
+    check_knn(vg, orc, elem, dims, v, q, k, metric, rowids=rowids, skip=skip)
+
+
+# ------------------------------------------------------------------ size-independent properties at BASELINE's full single-GPU sizes
+@pytest.mark.parametrize("elem,dims,metric,k,n", [(I8, 1024, L2, 100, 50_000_000), (BIT, 1024, HAMMING, 10, 62_500_000)])
+def test_full_size_properties_int8_and_bit(vg, orc, gpu, elem, dims, metric, k, n):
+    with vg.Slab(elem, dims) as s:
+        s.fill_synthetic(seed=4 + elem, n=n, kind=0)
+        probe = [1, 31_415_926, n]
+        q = np.concatenate([orc.synth_rows(elem, 4 + elem, rid, 1, dims, 0) for rid in probe])
+        r, d, c = s.knn(q, k, metric)
+        assert list(r[:, 0]) == probe and np.all(d[:, 0] == 0)          # every probe row is its own nearest neighbour
+        assert np.all(np.diff(d, axis=1) >= 0) and np.all(c == k)          # sorted, full
+        for qi in range(3):                                               # ties broken by ascending rowid
+            same = d[qi, 1:] == d[qi, :-1]
+            assert np.all(r[qi, 1:][same] > r[qi, :-1][same])
+        r2, d2, _ = s.knn(q, k, metric)
+        assert np.array_equal(r, r2) and np.array_equal(bits(d), bits(d2))  # deterministic
+        rk, _, _ = s.knn(q, max(1, k // 2), metric)
+        assert np.array_equal(rk, r[:, : max(1, k // 2)])                  # top-k/2 is a prefix of top-k
+        for qi in range(3):                                               # returned distances are the oracle's for those rows
+            rows = np.concatenate([orc.synth_rows(elem, 4 + elem, int(x), 1, dims, 0) for x in r[qi]])
+            want = orc.distances(elem, dims, rows, q[qi], metric)
+            assert np.array_equal(bits(d[qi]), bits(want))
