@@ -673,3 +673,124 @@ __global__ void __launch_bounds__(256) row_norms_i8_kernel(const uint8_t* base, 
 }
 
 }  // namespace vg
+
+// =====================================================================================================
+// f32 L1 scan with swizzled TMA boxes.  L1 must add |a_i - b_i| strictly left to right
+// (src/distance/scalar.rs:31-35), i.e. one thread per row, which makes plain row-major shared memory
+// 8-way bank-conflicted.  A 2-D tensor-map load with SWIZZLE_128B stores unit u of row r at u ^ (r & 7), so
+// the 8 lanes of a quarter-warp (8 consecutive rows) hit 8 different 16-byte units: conflict-free, one TMA
+// instruction per 32-row x 128-byte box (4 KB) instead of 32 padded per-row copies.
+// Warp w owns tiles w, w+C, ... of 32 rows and a private ring of D boxes which it refills itself.
+// =====================================================================================================
+namespace vg {
+
+struct L1Params {
+    const uint8_t* skip;
+    const uint8_t* queries;   // nq_total rows of row_stride bytes (device)
+    uint64_t* out_keys;       // [nq_total][gridDim.x][k]
+    uint64_t n_rows;
+    uint32_t nq_total, k, row_stride, q_stride;  // q_stride: row_stride rounded up to 128 (shared-memory query pitch)
+    uint32_t n_chunks;        // ceil(row_stride / 128)
+    uint32_t ring;            // D
+    uint32_t n_warps;         // C
+    uint32_t list_stride;
+};
+
+template <int QB>
+__global__ void __launch_bounds__(512, 1) scan_l1_tma_kernel(const __grid_constant__ CUtensorMap mapX, const L1Params p) {
+    using T = F32L1<QB>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t C = p.n_warps, D = p.ring;
+    // layout: [C*D boxes of 4 KB][queries QB*q_stride][hdr C*QB][lists QB*list_stride][barriers C*D]
+    uint8_t* s_box = smem;
+    uint8_t* s_query = s_box + (size_t)C * D * 4096;
+    ListHdr* s_hdr = (ListHdr*)(s_query + (size_t)QB * p.q_stride);
+    uint64_t* s_list = (uint64_t*)(s_hdr + C * QB);
+    uint64_t* s_bar = s_list + (size_t)QB * p.list_stride;
+    const uint32_t q0 = blockIdx.y * QB;
+    const uint32_t nq_here = min((uint32_t)QB, p.nq_total - q0);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < C * D; ++s) mbar_init(smem_u32(s_bar + s), 1);
+        mbar_fence_init();
+    }
+    {
+        const uint32_t qunits = p.q_stride / 16, runits = p.row_stride / 16;
+        uint4* sq = (uint4*)s_query;
+        for (uint32_t i = threadIdx.x; i < QB * qunits; i += blockDim.x) {
+            const uint32_t qi = i / qunits, u = i - qi * qunits;
+            sq[i] = (qi < nq_here && u < runits) ? ((const uint4*)(p.queries + (size_t)(q0 + qi) * p.row_stride))[u] : make_uint4(0, 0, 0, 0);
+        }
+        for (uint32_t i = threadIdx.x; i < C * QB; i += blockDim.x) {
+            s_hdr[i].tau = KEY_NONE;
+            s_hdr[i].maxpos = 0;
+            s_hdr[i].cnt = 0;
+        }
+    }
+    __syncthreads();
+    const uint64_t n_tiles = (p.n_rows + 31) / 32;
+    const uint64_t first_tile = blockIdx.x + (uint64_t)warp * gridDim.x, tile_step = (uint64_t)C * gridDim.x;
+    const uint32_t my_tiles = first_tile < n_tiles ? (uint32_t)((n_tiles - first_tile + tile_step - 1) / tile_step) : 0u;
+    const uint32_t my_iters = my_tiles * p.n_chunks;
+    const uint32_t my_bar = smem_u32(s_bar + warp * D);
+    const uint32_t my_box = smem_u32(s_box + (size_t)warp * D * 4096);
+    auto issue = [&](uint32_t lit) {
+        if (lit >= my_iters) return;
+        fence_proxy_async();
+        if (lane == 0) {
+            const uint32_t jl = lit / p.n_chunks, c = lit - jl * p.n_chunks, slot = lit % D;
+            mbar_expect_tx(my_bar + 8 * slot, 4096);
+            tma_load_2d(my_box + slot * 4096, &mapX, (int)(c * 128), (int)((first_tile + (uint64_t)jl * tile_step) * 32), my_bar + 8 * slot);
+        }
+        __syncwarp();
+    };
+    for (uint32_t lit = 0; lit < D; ++lit) issue(lit);
+    uint64_t* my_list = s_list + (size_t)warp * p.k;
+    ListHdr* my_hdr = s_hdr + warp * QB;
+    const uint32_t q_base = smem_u32(s_query);
+    const uint32_t sw = (uint32_t)(lane & 7);
+    for (uint32_t jl = 0; jl < my_tiles; ++jl) {
+        const uint64_t row = (first_tile + (uint64_t)jl * tile_step) * 32 + lane;
+        typename T::Acc acc;
+        T::init(acc);
+        for (uint32_t c = 0; c < p.n_chunks; ++c) {
+            const uint32_t lit = jl * p.n_chunks + c, slot = lit % D;
+            mbar_wait(my_bar + 8 * slot, (lit / D) & 1);
+            const uint32_t xb = my_box + slot * 4096 + lane * 128, qb = q_base + c * 128;
+            uint4 xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = lds128(xb + (((uint32_t)u ^ sw) << 4));  // de-swizzle: conflict-free
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {  // strict left-to-right order over the row
+                uint4 qv[QB];
+#pragma unroll
+                for (int i = 0; i < QB; ++i) qv[i] = lds128(qb + i * p.q_stride + u * 16);
+                T::step(acc, xv[u], qv);
+            }
+            __syncwarp();
+            issue(lit + D);
+        }
+        bool live = row < p.n_rows;
+        if (live && p.skip != nullptr) live = p.skip[row] == 0;
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const float d = T::finish(acc, i, nullptr);
+            list_offer(my_list + (size_t)i * p.list_stride, my_hdr + i, p.k, make_key(d, (uint32_t)row), live, lane);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = 0; i < nq_here; ++i) {
+        uint64_t* base = s_list + (size_t)i * p.list_stride;
+        for (uint32_t j = threadIdx.x; j < p.list_stride; j += blockDim.x) {
+            const uint32_t w = j / p.k, e = j - w * p.k;
+            if (w >= C || e >= s_hdr[w * QB + i].cnt) base[j] = KEY_NONE;
+        }
+        __syncthreads();
+        block_bitonic_sort(base, p.list_stride);
+        uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
+        for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = base[j];
+    }
+}
+
+}  // namespace vg

@@ -645,6 +645,66 @@ static int launch_merge(vecgpu_slab* s, const MergeParams& mp, uint32_t nq, cuda
     return 0;
 }
 
+// f32 L1 single/batched scan through swizzled TMA boxes (scan_l1_tma_kernel); returns 1 if not applicable
+static int make_tile_map(CUtensorMap* m, CUtensorMapDataType dtype, uint32_t inner_elems_total, uint32_t box_inner, const void* base,
+                         uint64_t rows, uint32_t stride_bytes, uint32_t box_rows);
+template <int QB>
+static int launch_l1_inst(const CUtensorMap& map, const L1Params& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static int cfg_dev = -1;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (cfg_dev != dev) {
+        CU(cudaFuncSetAttribute(scan_l1_tma_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        cfg_dev = dev;
+    }
+    scan_l1_tma_kernel<QB><<<grid, 32 * p.n_warps, smem, st>>>(map, p);
+    LAUNCHED();
+    return 0;
+}
+static int knn_l1_tma(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, uint64_t** out_keys, uint32_t* out_gx, cudaStream_t st) {
+    if (env_u32("VECGPU_L1_TMA", 1) == 0 || s->rows >= 0x7FFFFFFFull || s->row_stride < 128 || k > 256) return 1;
+    uint32_t QB = nq >= 8 ? 8 : nq >= 4 ? 4 : nq >= 2 ? 2 : 1;
+    const uint32_t q_stride = (s->row_stride + 127u) & ~127u;
+    uint32_t C = 12, D = 4;
+    auto fixed = [&](uint32_t c, uint32_t qb) {
+        return (size_t)qb * q_stride + (size_t)c * qb * sizeof(ListHdr) + (size_t)qb * list_stride_for(c, k) * 8 + (size_t)c * D * 8 + 1024 + 256;
+    };
+    while (QB > 1 && fixed(C, QB) > SMEM_MAX / 3) QB >>= 1;
+    while (C > 2 && (size_t)C * D * 4096 + fixed(C, QB) > SMEM_MAX) --C;
+    if ((size_t)C * D * 4096 + fixed(C, QB) > SMEM_MAX) return 1;
+    const size_t smem = (size_t)C * D * 4096 + fixed(C, QB);
+    CUtensorMap map;
+    int rc = make_tile_map(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->row_stride, 128, s->d_vec, s->rows, s->row_stride, 32);
+    if (rc) return rc;
+    const uint64_t n_tiles = (s->rows + 31) / 32;
+    const uint32_t gx = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, n_tiles / 4), (uint64_t)s->num_sms);
+    const uint32_t gy = (nq + QB - 1) / QB;
+    if ((rc = ws_reserve(s, WS_PART, (size_t)nq * gx * k * 8))) return rc;
+    L1Params p{};
+    p.skip = s->n_skip ? s->d_skip : nullptr;
+    p.queries = d_q;
+    p.out_keys = (uint64_t*)s->d_ws[WS_PART];
+    p.n_rows = s->rows;
+    p.nq_total = nq;
+    p.k = k;
+    p.row_stride = s->row_stride;
+    p.q_stride = q_stride;
+    p.n_chunks = q_stride / 128;
+    p.ring = D;
+    p.n_warps = C;
+    p.list_stride = list_stride_for(C, k);
+    switch (QB) {
+        case 1: rc = launch_l1_inst<1>(map, p, dim3(gx, gy), smem, st); break;
+        case 2: rc = launch_l1_inst<2>(map, p, dim3(gx, gy), smem, st); break;
+        case 4: rc = launch_l1_inst<4>(map, p, dim3(gx, gy), smem, st); break;
+        default: rc = launch_l1_inst<8>(map, p, dim3(gx, gy), smem, st); break;
+    }
+    if (rc) return rc;
+    *out_keys = p.out_keys;
+    *out_gx = gx;
+    return 0;
+}
+
 // queries already on the device, padded to row_stride.  Results to device arrays.
 static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
@@ -690,6 +750,27 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
     p.row_stride = s->row_stride;
     p.qc_kind = metric_qc_kind(s->elem);
 
+    if (metric_strict(s->elem, metric) && k <= K_FUSED_MAX) {
+        // strict-order f32 L1: swizzled TMA boxes (conflict-free thread-per-row) when applicable
+        uint64_t* keys = nullptr;
+        uint32_t gx = 0;
+        rc = knn_l1_tma(s, d_q, nq, k, &keys, &gx, st);
+        if (rc == 0) {
+            MergeParams mp{};
+            mp.keys = keys;
+            mp.n_cand = (uint64_t)gx * k;
+            mp.k = k;
+            mp.kp2 = next_pow2(k);
+            mp.rowids = d_rowids;
+            mp.first_rowid = s->first_rowid;
+            mp.out_rowids = d_out_rowids;
+            mp.out_dists = d_out_dists;
+            mp.out_counts = d_out_counts;
+            mp.pad_rowid = pad_rowid;
+            return launch_merge(s, mp, nq, st);
+        }
+        if (rc != 1) return rc;
+    }
     if (k <= K_FUSED_MAX) {
         ScanCfg c;
         rc = plan_scan(lpr, metric_strict(s->elem, metric), s->row_stride, k, nq, false, c);
