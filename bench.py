@@ -277,9 +277,10 @@ def run_ours(args):
         tc0 = vg.tc_stats()
         ms = timed(lambda: sh.slab.knn_device(qb, K, COSINE, stream=stream.cuda_stream), 3)
         tc1 = vg.tc_stats()
-        bf16 = None
+        bf16 = bf16_sus = None
         try:
-            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            bf16, bf16_sus = float(peaks["bf16_tflops"]), float(peaks.get("bf16_tflops_sustained", 0)) or None
         except Exception:
             pass
         exec_tflops = 3 * 2.0 * 1024 * rows_local * DIMS / (ms / 1e3) / 1e12
@@ -290,7 +291,10 @@ def run_ours(args):
                          "algorithmic_tflops": exec_tflops / 3,
                          "peak": bf16 / 2 if bf16 else 830.0,
                          "peak_source": "half of the measured cuBLAS bf16 burst peak (TF32 runs at half the bf16 MAC rate)" if bf16 else "fallback: 1.59 PF bf16 / 2",
-                         "frac": exec_tflops / (bf16 / 2 if bf16 else 830.0)},
+                         "frac": exec_tflops / (bf16 / 2 if bf16 else 830.0),
+                         "peak_sustained": bf16_sus / 2 if bf16_sus else None,
+                         "frac_of_sustained": exec_tflops / (bf16_sus / 2) if bf16_sus else None,
+                         "note": "a 70+ ms batch runs under the 1 kW power cap: the sustained figure is the relevant denominator"},
             "tc_queries": tc1[0] - tc0[0], "tc_fallbacks": tc1[1] - tc0[1],
             "kernel": "tc_scan_kernel (tcgen05 kind::tf32, 3xTF32) + exact re-rank (pair_kernel) + merge",
         }

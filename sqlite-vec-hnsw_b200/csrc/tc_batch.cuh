@@ -29,11 +29,18 @@ namespace vg {
 
 static constexpr uint32_t TC_M = 128;      // queries per CTA tile (UMMA M)
 static constexpr uint32_t TC_N = 256;      // slab rows per tile (UMMA N)
-static constexpr uint32_t TC_KC = 32;      // floats per k-chunk = 128 bytes = one swizzle span
+// f32 kernel: k-chunks of 32 floats = 128-byte rows (SWIZZLE_128B), two 96 KB stages.  (16-float chunks with
+// SWIZZLE_64B and four 48 KB stages were measured 10 % slower: twice the barrier round trips per K.)
+static constexpr uint32_t TC_KC = 32;
+static constexpr uint32_t TC_ROW_BYTES = TC_KC * 4;
+static constexpr uint32_t TC_KSTEPS = TC_ROW_BYTES / 32;  // tf32 MMAs (K=8) per chunk
 static constexpr uint32_t TC_STAGES = 2;
-static constexpr uint32_t TC_A_BYTES = TC_M * 128, TC_B_BYTES = TC_N * 128;
+static constexpr uint32_t TC_A_BYTES = TC_M * TC_ROW_BYTES, TC_B_BYTES = TC_N * TC_ROW_BYTES;
 static constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // raw + lo of both operands = 96 KB
-static constexpr uint32_t TC_THREADS = 384;
+static constexpr uint32_t TC_THREADS = 384;            // warps 0-1 TMA/MMA, 4-7 epilogue, 8-11 lo-split transform
+static constexpr uint32_t TC_XFORM_THREADS = 128;     // (8 transform warps were measured: no gain)
+// int8 kernel: 128-byte rows (SWIZZLE_128B)
+static constexpr uint32_t TCI_A_BYTES = TC_M * 128, TCI_B_BYTES = TC_N * 128;
 // kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128
 static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
@@ -64,9 +71,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 128-byte rows; 8-row groups 1024 B apart (SBO)
+// shared-memory matrix descriptors, K-major: 8-row groups are SBO bytes apart; layout 2 = SWIZZLE_128B (128-byte rows),
+// layout 4 = SWIZZLE_64B (64-byte rows).  Both verified on the device (tools/umma_test.cu, tools/umma_test_sw64.cu).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -128,8 +139,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
     float* s_lists = (float*)(s_bar + 32);  // [kp][128] when p.lists_smem
-    const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + 2), bar_empty = smem_u32(s_bar + 4),
-                   bar_tfull = smem_u32(s_bar + 6), bar_tempty = smem_u32(s_bar + 8);
+    const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + TC_STAGES), bar_empty = smem_u32(s_bar + 2 * TC_STAGES),
+                   bar_tfull = smem_u32(s_bar + 3 * TC_STAGES), bar_tempty = smem_u32(s_bar + 3 * TC_STAGES + 2);
 
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
@@ -138,7 +149,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < TC_STAGES; ++s) {
             mbar_init(bar_full_raw + 8 * s, 1);
-            mbar_init(bar_full_lo + 8 * s, 4);   // one arrival per transform warp
+            mbar_init(bar_full_lo + 8 * s, TC_XFORM_THREADS / 32);   // one arrival per transform warp
             mbar_init(bar_empty + 8 * s, 1);     // tcgen05.commit
         }
         for (uint32_t a = 0; a < 2; ++a) {
@@ -175,39 +186,59 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        // The hi.hi MMAs of a chunk only need the TMA data, the two lo terms also need the lo-split.  While the issuer
+        // waits for the lo-split of chunk `it` it opportunistically issues hi.hi of chunk it+1 as soon as that chunk's
+        // data has landed (non-blocking probes), so the tensor pipe has work during the transform.
         if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t ti = 0; ti < my_tiles; ++ti) {
-                const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);  // epilogue has drained this accumulator
+            const uint32_t total = my_tiles * p.nk;
+            uint32_t next_hihi = 0;  // first chunk whose hi.hi MMAs have not been issued yet
+            auto hihi_ready = [&](uint32_t it) {
+                const uint32_t ti = it / p.nk, kc = it - ti * p.nk;
+                if (kc == 0 && !mbar_test(bar_tempty + 8 * (ti & 1), ((ti >> 1) & 1) ^ 1)) return false;
+                return mbar_test(bar_full_raw + 8 * (it % TC_STAGES), (it / TC_STAGES) & 1);
+            };
+            auto issue_hihi = [&](uint32_t it) {  // blocking
+                const uint32_t ti = it / p.nk, kc = it - ti * p.nk;
+                const uint32_t acc = ti & 1, s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                if (kc == 0) mbar_wait(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), b_raw = a_raw + 2 * TC_A_BYTES;
+                mbar_wait(bar_full_raw + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * TC_N;
-                for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
-                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-                    const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), a_lo = a_raw + TC_A_BYTES,
-                                   b_raw = a_raw + 2 * TC_A_BYTES, b_lo = b_raw + TC_B_BYTES;
-                    mbar_wait(bar_full_raw + 8 * s, ph);
-                    tc_fence_after();
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k)  // hi.hi
-                        umma_tf32(d_tmem, umma_desc(a_raw + k * 32), umma_desc(b_raw + k * 32), (kc | k) != 0);
-                    mbar_wait(bar_full_lo + 8 * s, ph);
-                    tc_fence_after();
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k)  // lo_q.hi_x
-                        umma_tf32(d_tmem, umma_desc(a_lo + k * 32), umma_desc(b_raw + k * 32), 1);
-#pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k)  // hi_q.lo_x
-                        umma_tf32(d_tmem, umma_desc(a_raw + k * 32), umma_desc(b_lo + k * 32), 1);
-                    umma_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
+                for (uint32_t k = 0; k < TC_KSTEPS; ++k)
+                    umma_tf32(tmem_base + acc * TC_N, umma_desc(a_raw + k * 32), umma_desc(b_raw + k * 32), (kc | k) != 0);
+            };
+            for (uint32_t it = 0; it < total; ++it) {
+                if (next_hihi <= it) {
+                    issue_hihi(it);
+                    next_hihi = it + 1;
                 }
-                umma_commit(bar_tfull + 8 * acc);    // accumulator complete
+                const uint32_t ti = it / p.nk, kc = it - ti * p.nk;
+                const uint32_t acc = ti & 1, s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                while (!mbar_test(bar_full_lo + 8 * s, ph)) {
+                    if (next_hihi == it + 1 && next_hihi < total && hihi_ready(next_hihi)) {
+                        issue_hihi(next_hihi);
+                        ++next_hihi;
+                    }
+                }
+                tc_fence_after();
+                const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), a_lo = a_raw + TC_A_BYTES,
+                               b_raw = a_raw + 2 * TC_A_BYTES, b_lo = b_raw + TC_B_BYTES;
+                const uint32_t d_tmem = tmem_base + acc * TC_N;
+#pragma unroll
+                for (uint32_t k = 0; k < TC_KSTEPS; ++k)  // lo_q.hi_x
+                    umma_tf32(d_tmem, umma_desc(a_lo + k * 32), umma_desc(b_raw + k * 32), 1);
+#pragma unroll
+                for (uint32_t k = 0; k < TC_KSTEPS; ++k)  // hi_q.lo_x
+                    umma_tf32(d_tmem, umma_desc(a_raw + k * 32), umma_desc(b_lo + k * 32), 1);
+                umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs have read it
+                if (kc == p.nk - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
             }
         }
         __syncwarp();
     } else if (warp >= 8) {
         // ===== transform warps: lo = x - trunc_tf32(x), same (swizzled) positions in the twin tile =====
-        const uint32_t t = threadIdx.x - 256;  // 0..127
+        const uint32_t t = threadIdx.x - 256;  // 0..TC_XFORM_THREADS-1
         uint32_t it = 0;
         for (uint32_t ti = 0; ti < my_tiles; ++ti) {
             for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
@@ -215,13 +246,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), b_raw = a_raw + 2 * TC_A_BYTES;
                 mbar_wait(bar_full_raw + 8 * s, ph);
 #pragma unroll 4
-                for (uint32_t u = t; u < TC_A_BYTES / 16; u += 128) {
+                for (uint32_t u = t; u < TC_A_BYTES / 16; u += TC_XFORM_THREADS) {
                     uint4 v = lds128(a_raw + u * 16);
                     v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
                     sts128(a_raw + TC_A_BYTES + u * 16, v);
                 }
 #pragma unroll 4
-                for (uint32_t u = t; u < TC_B_BYTES / 16; u += 128) {
+                for (uint32_t u = t; u < TC_B_BYTES / 16; u += TC_XFORM_THREADS) {
                     uint4 v = lds128(b_raw + u * 16);
                     v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
                     sts128(b_raw + TC_B_BYTES + u * 16, v);
@@ -430,7 +461,7 @@ __global__ void tc_keys_kernel(const float* dist, const int64_t* pos, uint64_t n
 namespace vg {
 
 static constexpr uint32_t TCI_STAGES = 4;
-static constexpr uint32_t TCI_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
+static constexpr uint32_t TCI_STAGE_BYTES = TCI_A_BYTES + TCI_B_BYTES;  // 48 KB
 // kind::i8 instruction descriptor: D=S32, A=B=S8, both K-major, N=256, M=128
 static constexpr uint32_t TCI_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
@@ -527,7 +558,7 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     const uint32_t base = smem_u32(smem + s * TCI_STAGE_BYTES);
                     mbar_expect_tx(bar_full + 8 * s, TCI_STAGE_BYTES);
                     tma_load_2d(base, &mapQ, (int)(kc * 128), (int)(qt * TC_M), bar_full + 8 * s);
-                    tma_load_2d(base + TC_A_BYTES, &mapX, (int)(kc * 128), row0, bar_full + 8 * s);
+                    tma_load_2d(base + TCI_A_BYTES, &mapX, (int)(kc * 128), row0, bar_full + 8 * s);
                 }
             }
         }
@@ -542,7 +573,7 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const uint32_t d_tmem = tmem_base + acc * TC_N;
                 for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
                     const uint32_t s = it % TCI_STAGES, ph = (it / TCI_STAGES) & 1;
-                    const uint32_t a = smem_u32(smem + s * TCI_STAGE_BYTES), b = a + TC_A_BYTES;
+                    const uint32_t a = smem_u32(smem + s * TCI_STAGE_BYTES), b = a + TCI_A_BYTES;
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
 #pragma unroll

@@ -647,7 +647,7 @@ static int launch_merge(vecgpu_slab* s, const MergeParams& mp, uint32_t nq, cuda
 
 // f32 L1 single/batched scan through swizzled TMA boxes (scan_l1_tma_kernel); returns 1 if not applicable
 static int make_tile_map(CUtensorMap* m, CUtensorMapDataType dtype, uint32_t inner_elems_total, uint32_t box_inner, const void* base,
-                         uint64_t rows, uint32_t stride_bytes, uint32_t box_rows);
+                         uint64_t rows, uint32_t stride_bytes, uint32_t box_rows, CUtensorMapSwizzle swz);
 template <int QB>
 static int launch_l1_inst(const CUtensorMap& map, const L1Params& p, dim3 grid, size_t smem, cudaStream_t st) {
     static int cfg_dev = -1;
@@ -674,7 +674,7 @@ static int knn_l1_tma(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t 
     if ((size_t)C * D * 4096 + fixed(C, QB) > SMEM_MAX) return 1;
     const size_t smem = (size_t)C * D * 4096 + fixed(C, QB);
     CUtensorMap map;
-    int rc = make_tile_map(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->row_stride, 128, s->d_vec, s->rows, s->row_stride, 32);
+    int rc = make_tile_map(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->row_stride, 128, s->d_vec, s->rows, s->row_stride, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const uint64_t n_tiles = (s->rows + 31) / 32;
     const uint32_t gx = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, n_tiles / 4), (uint64_t)s->num_sms);
@@ -856,7 +856,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_tile_map(CUtensorMap* m, CUtensorMapDataType dtype, uint32_t inner_elems_total, uint32_t box_inner, const void* base,
-                         uint64_t rows, uint32_t stride_bytes, uint32_t box_rows) {
+                         uint64_t rows, uint32_t stride_bytes, uint32_t box_rows, CUtensorMapSwizzle swz) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         cudaDriverEntryPointQueryResult qres;
@@ -867,15 +867,15 @@ static int make_tile_map(CUtensorMap* m, CUtensorMapDataType dtype, uint32_t inn
     }
     cuuint64_t gdim[2] = {inner_elems_total, rows};
     cuuint64_t gstr[1] = {stride_bytes};
-    cuuint32_t box[2] = {box_inner, box_rows};  // inner box = 128 bytes = one SWIZZLE_128B span
+    cuuint32_t box[2] = {box_inner, box_rows};  // inner box = one swizzle span (128 or 64 bytes)
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(m, dtype, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(VECGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 static int make_f32_map(CUtensorMap* m, const void* base, uint32_t dims, uint64_t rows, uint32_t stride_bytes, uint32_t box_rows) {
-    return make_tile_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims, TC_KC, base, rows, stride_bytes, box_rows);
+    return make_tile_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims, TC_KC, base, rows, stride_bytes, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
@@ -1070,7 +1070,7 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
     const uint64_t n_xt = (s->rows + TC_N - 1) / TC_N;
     const uint32_t max_qt = 16;
     CUtensorMap mapX;
-    if ((rc = make_tile_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->dims, 128, s->d_vec, s->rows, s->row_stride, TC_N))) return rc;
+    if ((rc = make_tile_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->dims, 128, s->d_vec, s->rows, s->row_stride, TC_N, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     for (uint32_t qoff = 0; qoff < nq_all; qoff += max_qt * TC_M) {
         const uint32_t nq = std::min(nq_all - qoff, max_qt * TC_M);
         const uint8_t* dq = d_q + (size_t)qoff * s->row_stride;
@@ -1084,7 +1084,7 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
                                                                                            (int*)s->d_ws[WS_TC_QNORM]);
         LAUNCHED();
         CUtensorMap mapQ;
-        if ((rc = make_tile_map(&mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->dims, 128, dq, nq, s->row_stride, TC_M))) return rc;
+        if ((rc = make_tile_map(&mapQ, CU_TENSOR_MAP_DATA_TYPE_UINT8, s->dims, 128, dq, nq, s->row_stride, TC_M, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         TciParams tp{};
         tp.n_rows = s->rows;
         tp.nq = nq;
