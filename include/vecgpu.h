@@ -166,10 +166,13 @@ uint64_t vecgpu_launch_count(void);
 void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks);
 
 /* ---- HNSW with GPU-batched candidate scoring (BASELINE config 5) -------------------------------------
- * The graph (levels, adjacency, stored edge distances) lives in host memory next to a slab that holds the
- * STORED node vectors (normalised for cosine columns, int8 when index_quantization=int8:
- * src/hnsw/insert.rs:300-322); `metric` is the INTERNAL metric (src/hnsw/mod.rs:129-137).  B inserts or
- * queries advance in lockstep and each expansion round scores all their unvisited neighbours in one launch. */
+ * The graph (levels, adjacency, stored edge distances) lives in host memory, with a copy of the adjacency in HBM,
+ * next to a slab that holds the STORED node vectors (normalised for cosine columns, int8 when
+ * index_quantization=int8: src/hnsw/insert.rs:300-322); `metric` is the INTERNAL metric (src/hnsw/mod.rs:129-137).
+ * Searches (queries, and the search half of every insert of a rebuild batch) run wholly on the device, one warp per
+ * query walking all layers (search_layer, src/hnsw/search.rs:340-543).  With VECGPU_HNSW_DEVICE=0 in the environment
+ * the lockstep driver is used instead: B inserts or queries advance together and each expansion round scores all
+ * their unvisited neighbours in one launch.  Both give identical results. */
 typedef struct vecgpu_hnsw vecgpu_hnsw;
 
 /* M in [2,100], ef_construction in [10,2000] as vec_rebuild_hnsw validates (src/sql_functions.rs:442-469);
@@ -185,6 +188,12 @@ int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_
                        int64_t* out_rowids, float* out_dists, uint32_t* out_counts);
 int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edges, int32_t* entry_level, uint64_t* distances_scored,
                       uint64_t* rounds);
+/* Entry point of the graph (rowid, level) for the {t}_{c}_hnsw_meta row (HnswMetadata.entry_point_rowid / entry_point_level, src/hnsw/mod.rs:97-103); rowid -1 / level -1
+ * when the index is empty. */
+int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* level);
+/* Device-search counters: queries (or inserts) answered by the search kernel, how many of those hit a device capacity
+ * limit and were re-run by the lockstep driver, and the number of search launches. */
+int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallbacks, uint64_t* launches);
 /* Edge list for a bulk write-back into {t}_{c}_hnsw_edges (src/shadow.rs:478-487; insert_edges_batch shape,
  * src/hnsw/storage.rs:346-383).  cap = 0 only counts. */
 int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* from_rowids, int64_t* to_rowids, int32_t* levels,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "vecgpu_hnsw_search": (C.c_int, [C.c_void_p, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _p, _p]),
     "vecgpu_hnsw_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vecgpu_hnsw_entry_point": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "vecgpu_hnsw_device_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_export_edges": (C.c_int, [C.c_void_p, C.c_uint64, _p, _p, _p, _p, C.POINTER(C.c_uint64)]),
     "vecgpu_launch_count": (C.c_uint64, []),
     "vecgpu_tc_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

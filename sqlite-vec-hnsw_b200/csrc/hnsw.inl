@@ -113,6 +113,23 @@ struct vecgpu_hnsw {
     size_t d_cap = 0;
     void* d_queries = nullptr;
     size_t dq_cap = 0;
+    // K6: adjacency resident in HBM for the one-warp-per-query search kernel (hnsw_dev.cuh)
+    uint32_t* d_nbr0 = nullptr;
+    uint16_t* d_deg0 = nullptr;
+    uint32_t* d_upper_base = nullptr;
+    uint32_t* d_nbrU = nullptr;
+    uint16_t* d_degU = nullptr;
+    size_t dn_rows = 0, dn_slots = 0;
+    bool dev_valid = false;              // device copy exists and matches the host lists except for the dirty ones
+    std::vector<uint8_t> dirty0, dirtyU;
+    std::vector<uint32_t> dirty0_list, dirtyU_list;
+    uint32_t* d_visited = nullptr;
+    size_t vis_cap = 0;
+    uint8_t* d_sw = nullptr;             // per-launch arrays of the search kernel
+    size_t sw_cap = 0;
+    uint8_t* h_sw = nullptr;             // pinned twin
+    size_t hsw_cap = 0;
+    uint64_t dev_queries = 0, dev_fallbacks = 0, dev_launches = 0;
 };
 
 static inline uint64_t h_mix64(uint64_t z) {
@@ -143,12 +160,28 @@ static inline uint32_t* h_nbr(vecgpu_hnsw* h, uint32_t node, int level, float** 
     return &h->nbrU[slot * h->M];
 }
 
-// add edge from -> to with stored distance; an overfull list keeps the closest maxc by (distance, node)
-static void h_add_edge(vecgpu_hnsw* h, uint32_t from, uint32_t to, float d, int level) {
+// add edge from -> to with stored distance; an overfull list keeps the closest maxc by (distance, node).
+// `dirty` (optional) collects the lists that changed, for the incremental upload of the device copy.
+static void h_add_edge(vecgpu_hnsw* h, uint32_t from, uint32_t to, float d, int level, std::vector<uint32_t>* dirty0 = nullptr,
+                       std::vector<uint32_t>* dirtyU = nullptr) {
     float* dist;
     uint16_t* deg;
     uint32_t maxc;
     uint32_t* nb = h_nbr(h, from, level, &dist, &deg, &maxc);
+    if (dirty0) {
+        if (level == 0) {
+            if (!h->dirty0[from]) {
+                h->dirty0[from] = 1;
+                dirty0->push_back(from);
+            }
+        } else {
+            const uint32_t slot = h->upper_base[from] + (uint32_t)(level - 1);
+            if (!h->dirtyU[slot]) {
+                h->dirtyU[slot] = 1;
+                dirtyU->push_back(slot);
+            }
+        }
+    }
     for (uint32_t i = 0; i < *deg; ++i)
         if (nb[i] == to) {
             dist[i] = d;
@@ -329,6 +362,226 @@ static int hnsw_run_batch(vecgpu_hnsw* h, std::vector<HQuery>& qs, size_t nqs, c
 }
 
 
+// ---- K6: device-resident graph + one-warp-per-query search (hnsw_dev.cuh) ------------------------------------
+static bool hnsw_device_enabled(const vecgpu_hnsw* h) {
+    const char* e = getenv("VECGPU_HNSW_DEVICE");
+    if (e && e[0] == '0') return false;
+    return h->node_level.size() < 0x7FFFFFFFull;  // node << 1 must fit the low key word
+}
+
+static void hnsw_dev_free_graph(vecgpu_hnsw* h) {
+    cudaFree(h->d_nbr0);
+    cudaFree(h->d_deg0);
+    cudaFree(h->d_upper_base);
+    cudaFree(h->d_nbrU);
+    cudaFree(h->d_degU);
+    h->d_nbr0 = h->d_upper_base = h->d_nbrU = nullptr;
+    h->d_deg0 = h->d_degU = nullptr;
+    h->dn_rows = h->dn_slots = 0;
+    h->dev_valid = false;
+}
+
+// (re)create the device copy from the host lists
+static int hnsw_dev_upload_all(vecgpu_hnsw* h) {
+    vecgpu_slab* s = h->slab;
+    const size_t n = h->node_level.size(), slots = h->degU.size();
+    hnsw_dev_free_graph(h);
+    cudaGetLastError();
+    CU(cudaMalloc(&h->d_nbr0, std::max<size_t>(1, n * h->max_m0) * 4));
+    CU(cudaMalloc(&h->d_deg0, std::max<size_t>(1, n) * 2));
+    CU(cudaMalloc(&h->d_upper_base, std::max<size_t>(1, n) * 4));
+    CU(cudaMalloc(&h->d_nbrU, std::max<size_t>(1, slots * h->M) * 4));
+    CU(cudaMalloc(&h->d_degU, std::max<size_t>(1, slots) * 2));
+    h->dn_rows = n;
+    h->dn_slots = slots;
+    if (n) {
+        CU(cudaMemcpyAsync(h->d_nbr0, h->nbr0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(h->d_deg0, h->deg0.data(), n * 2, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(h->d_upper_base, h->upper_base.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (slots) {
+        CU(cudaMemcpyAsync(h->d_nbrU, h->nbrU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(h->d_degU, h->degU.data(), slots * 2, cudaMemcpyHostToDevice, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    h->dirty0.assign(n, 0);
+    h->dirtyU.assign(slots, 0);
+    h->dirty0_list.clear();
+    h->dirtyU_list.clear();
+    h->dev_valid = true;
+    return 0;
+}
+
+static int hnsw_sw_reserve(vecgpu_hnsw* h, size_t bytes) {
+    if (bytes > h->sw_cap) {
+        if (h->d_sw) CU(cudaFree(h->d_sw));
+        h->d_sw = nullptr;
+        h->sw_cap = std::max(bytes * 2, (size_t)1 << 20);
+        CU(cudaMalloc(&h->d_sw, h->sw_cap));
+    }
+    if (bytes > h->hsw_cap) {
+        if (h->h_sw) CU(cudaFreeHost(h->h_sw));
+        h->h_sw = nullptr;
+        h->hsw_cap = std::max(bytes * 2, (size_t)1 << 20);
+        CU(cudaMallocHost(&h->h_sw, h->hsw_cap));
+    }
+    return 0;
+}
+
+// push the lists changed since the last flush: [id][deg][width ids] items, scattered by hnsw_scatter_kernel
+static int hnsw_dev_flush_dirty(vecgpu_hnsw* h) {
+    vecgpu_slab* s = h->slab;
+    for (int upper = 0; upper < 2; ++upper) {
+        std::vector<uint32_t>& list = upper ? h->dirtyU_list : h->dirty0_list;
+        if (list.empty()) continue;
+        const uint32_t width = upper ? h->M : h->max_m0;
+        const size_t item = (size_t)width + 2, bytes = list.size() * item * 4;
+        int rc = hnsw_sw_reserve(h, bytes);
+        if (rc) return rc;
+        uint32_t* st = (uint32_t*)h->h_sw;
+        const uint32_t* nbr = upper ? h->nbrU.data() : h->nbr0.data();
+        const uint16_t* deg = upper ? h->degU.data() : h->deg0.data();
+        uint8_t* flags = upper ? h->dirtyU.data() : h->dirty0.data();
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)list.size(); ++i) {
+            const uint32_t id = list[i];
+            uint32_t* d = st + (size_t)i * item;
+            d[0] = id;
+            d[1] = deg[id];
+            memcpy(d + 2, nbr + (size_t)id * width, (size_t)width * 4);
+            flags[id] = 0;
+        }
+        CU(cudaMemcpyAsync(h->d_sw, st, bytes, cudaMemcpyHostToDevice, s->stream));
+        const uint32_t n_items = (uint32_t)list.size();
+        const uint32_t blocks = std::max(1u, std::min((n_items + 7) / 8, (uint32_t)s->num_sms * 8));
+        hnsw_scatter_kernel<<<blocks, 256, 0, s->stream>>>((const uint32_t*)h->d_sw, n_items, width, upper ? h->d_nbrU : h->d_nbr0,
+                                                            upper ? h->d_degU : h->d_deg0);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(s->stream));  // the staging buffers are reused right away
+        list.clear();
+    }
+    return 0;
+}
+
+struct HDevOut {  // host view of one launch's results (pinned memory, valid until the next launch)
+    const uint32_t* cnt = nullptr;
+    const uint32_t* status = nullptr;
+    const uint64_t* keys = nullptr;
+    uint32_t take = 0;
+};
+
+template <class T>
+static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) {
+    vecgpu_slab* s = h->slab;
+    uint32_t wpb = 8;
+    while (wpb > 1 && wpb * per_warp > 200 * 1024) wpb >>= 1;
+    if (wpb * per_warp > SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "ef too large for the device search");
+    CU(cudaFuncSetAttribute(hnsw_search_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    int bps = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, hnsw_search_kernel<T>, (int)wpb * 32, wpb * per_warp));
+    int bps_max = 4;
+    if (const char* e = getenv("VECGPU_HNSW_BPS")) bps_max = std::max(1, atoi(e));
+    bps = std::max(1, std::min(bps, bps_max));
+    uint32_t grid = (uint32_t)s->num_sms * (uint32_t)bps;
+    if ((uint64_t)grid * wpb > p.nq) {  // few queries: spread them, one or a few warps per CTA
+        grid = std::min(grid, p.nq);
+        wpb = (p.nq + grid - 1) / grid;
+    }
+    const size_t vis_bytes = (size_t)grid * wpb * p.vis_size * 4;
+    if (vis_bytes > h->vis_cap) {
+        if (h->d_visited) CU(cudaFree(h->d_visited));
+        h->d_visited = nullptr;
+        h->vis_cap = 0;
+        CU(cudaMalloc(&h->d_visited, vis_bytes));
+        h->vis_cap = vis_bytes;
+    }
+    p.visited = h->d_visited;
+    hnsw_search_kernel<T><<<grid, wpb * 32, wpb * per_warp, s->stream>>>(p);
+    LAUNCHED();
+    return 0;
+}
+
+// One launch: every query walks all its layers on the device.  a_index / node_level / out_off are host arrays (or NULL).
+static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t* a_index, const int8_t* node_level, uint32_t nq,
+                           uint32_t ef_wide, uint32_t take, const uint32_t* out_off, uint32_t n_slots, HDevOut* out) {
+    vecgpu_slab* s = h->slab;
+    int rc;
+    if (!h->dev_valid && (rc = hnsw_dev_upload_all(h))) return rc;
+    if ((rc = hnsw_dev_flush_dirty(h))) return rc;
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    // upload block: [a_index][out_off][node_level]   download block: [cnt][status][scored][keys]
+    const size_t o_ai = 0, o_off = al(o_ai + (size_t)nq * 4), o_lvl = al(o_off + (size_t)nq * 4), up_end = al(o_lvl + nq);
+    const size_t o_cnt = up_end, o_status = al(o_cnt + (size_t)n_slots * 4), o_scored = al(o_status + (size_t)nq * 4),
+                 o_next = o_scored + 8, o_keys = al(o_scored + 16), total = o_keys + (size_t)n_slots * take * 8;
+    if ((rc = hnsw_sw_reserve(h, total))) return rc;
+    uint8_t* hp = h->h_sw;
+    uint8_t* dp = h->d_sw;
+    if (a_index) memcpy(hp + o_ai, a_index, (size_t)nq * 4);
+    if (out_off) memcpy(hp + o_off, out_off, (size_t)nq * 4);
+    if (node_level) memcpy(hp + o_lvl, node_level, nq);
+    CU(cudaMemcpyAsync(dp, hp, up_end, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(dp + o_cnt, 0, o_keys - o_cnt, s->stream));
+
+    HSearchParams p{};
+    p.g.nbr0 = h->d_nbr0;
+    p.g.deg0 = h->d_deg0;
+    p.g.upper_base = h->d_upper_base;
+    p.g.nbrU = h->d_nbrU;
+    p.g.degU = h->d_degU;
+    p.g.max_m0 = h->max_m0;
+    p.g.M = h->M;
+    p.a_base = a_base;
+    p.a_stride = s->row_stride;
+    p.a_index = a_index ? (const uint32_t*)(dp + o_ai) : nullptr;
+    p.b_base = s->d_vec;
+    p.b_stride = s->row_stride;
+    p.units = s->row_stride / 16;
+    p.qc_kind = s->elem == VECGPU_I8 ? 1u : 0u;
+    p.nq = nq;
+    p.entry = (uint32_t)h->entry;
+    p.entry_level = h->entry_level;
+    p.node_level = node_level ? (const int8_t*)(dp + o_lvl) : nullptr;
+    p.ef_wide = ef_wide;
+    p.cap = ((2 * ef_wide + 32 + 31) / 32) * 32;  // the array never holds more than 2 ef - 1 entries (ties behind ef < ef)
+    p.take = take;
+    p.vis_size = std::min<uint32_t>(1u << 18, std::max<uint32_t>(4096u, next_pow2((uint32_t)std::min<uint64_t>(1u << 18, 4ull * ef_wide * h->max_m0))));
+    if (const char* e = getenv("VECGPU_HNSW_VIS_LOG2")) p.vis_size = 1u << std::max(12, std::min(18, atoi(e)));
+    p.out_off = out_off ? (const uint32_t*)(dp + o_off) : nullptr;
+    p.out_cnt = (uint32_t*)(dp + o_cnt);
+    p.status = (uint32_t*)(dp + o_status);
+    p.scored = (unsigned long long*)(dp + o_scored);
+    p.next_q = (unsigned int*)(dp + o_next);
+    p.out_keys = (uint64_t*)(dp + o_keys);
+    p.max_steps = 1u << 20;
+    const size_t per_warp = (size_t)p.cap * 8 + (size_t)((h->max_m0 + 31u) & ~31u) * 4;
+    const int elem = s->elem, metric = h->metric;
+    if (elem == VECGPU_F32) {
+        if (metric == VECGPU_L2) rc = hnsw_dev_launch_t<F32L2<1>>(h, p, per_warp);
+        else if (metric == VECGPU_L1) rc = hnsw_dev_launch_t<F32L1<1>>(h, p, per_warp);
+        else rc = hnsw_dev_launch_t<F32Cos<1>>(h, p, per_warp);
+    } else if (elem == VECGPU_I8) {
+        if (metric == VECGPU_L2) rc = hnsw_dev_launch_t<I8Dot<1, false>>(h, p, per_warp);
+        else if (metric == VECGPU_L1) rc = hnsw_dev_launch_t<I8L1<1>>(h, p, per_warp);
+        else rc = hnsw_dev_launch_t<I8Dot<1, true>>(h, p, per_warp);
+    } else {
+        rc = hnsw_dev_launch_t<BitHamming<1>>(h, p, per_warp);
+    }
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hp + o_cnt, dp + o_cnt, total - o_cnt, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    h->scored += *(const unsigned long long*)(hp + o_scored);
+    h->rounds += 1;
+    h->dev_launches += 1;
+    h->dev_queries += nq;
+    out->cnt = (const uint32_t*)(hp + o_cnt);
+    out->status = (const uint32_t*)(hp + o_status);
+    out->keys = (const uint64_t*)(hp + o_keys);
+    out->take = take;
+    return 0;
+}
+
+static inline HCand h_decode(uint64_t key) { return HCand{order_bits_inv((uint32_t)(key >> 32)), (uint32_t)(key & 0xFFFFFFFFull) >> 1}; }
+
 // ---- C ABI ------------------------------------------------------------------------------------------------
 static int64_t h_rowid_of(const vecgpu_slab* s, uint32_t pos) { return s->dense ? s->first_rowid + (int64_t)pos : s->h_rowids[pos]; }
 
@@ -360,6 +613,10 @@ extern "C" void vecgpu_hnsw_destroy(vecgpu_hnsw* h) {
     if (h->h_pin) cudaFreeHost(h->h_pin);
     cudaFree(h->d_buf);
     cudaFree(h->d_queries);
+    hnsw_dev_free_graph(h);
+    cudaFree(h->d_visited);
+    cudaFree(h->d_sw);
+    if (h->h_sw) cudaFreeHost(h->h_sw);
     cudaGetLastError();
     delete h;
 }
@@ -410,8 +667,24 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     h->distU.assign((size_t)upper_slots * h->M, 0.f);
     h->degU.assign(upper_slots, 0);
 
-    std::vector<HQuery> qs;
-    std::vector<uint32_t> nodes;
+    const bool use_dev = hnsw_device_enabled(h);
+    if (use_dev) {
+        if ((rc = hnsw_dev_upload_all(h))) return rc;  // empty lists; kept in sync batch by batch
+    } else {
+        hnsw_dev_free_graph(h);
+    }
+
+    struct HOp {
+        uint32_t from, to;
+        float d;
+        int32_t level;
+    };
+    std::vector<HQuery> qs, fq;
+    std::vector<uint32_t> nodes, off, fb;
+    std::vector<int8_t> lv8;
+    std::vector<HOp> ops;
+    const int nthreads = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<uint32_t>> t_dirty0(nthreads), t_dirtyU(nthreads);
     uint64_t pos = 0;
     while (pos < n) {
         const uint64_t want = std::min<uint64_t>(batch, std::max<uint64_t>(1, h->n_nodes / 4));
@@ -432,10 +705,53 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
         if (nb == 0) continue;
         if (qs.size() < nb) qs.resize(nb);
         const int search_entry_level = h->entry_level;
-        for (size_t i = 0; i < nb; ++i) hq_init(h, qs[i], nodes[first + i], h->node_level[nodes[first + i]], h->efc);
-        rc = hnsw_run_batch(h, qs, nb, s->d_vec);
-        if (rc) return rc;
-        // ---- link, in insertion order (insert.rs:408-498)
+        if (use_dev) {
+            // ---- one launch: every insert of the batch walks all its layers on the device (K6)
+            off.resize(nb);
+            lv8.resize(nb);
+            uint32_t slots = 0;
+            for (size_t i = 0; i < nb; ++i) {
+                const int L = h->node_level[nodes[first + i]];
+                lv8[i] = (int8_t)L;
+                off[i] = slots;
+                slots += (uint32_t)std::min(L, search_entry_level) + 1u;
+            }
+            HDevOut o;
+            rc = hnsw_dev_search(h, s->d_vec, nodes.data() + first, lv8.data(), (uint32_t)nb, h->efc, h->max_m0, off.data(), slots, &o);
+            if (rc) return rc;
+            fb.clear();
+            for (size_t i = 0; i < nb; ++i) {
+                HQuery& q = qs[i];
+                q.layers.clear();
+                if (o.status[i]) {
+                    fb.push_back((uint32_t)i);
+                    continue;
+                }
+                const int nl = std::min((int)lv8[i], search_entry_level) + 1;
+                q.layers.resize(nl);
+                for (int lv = 0; lv < nl; ++lv) {
+                    const uint32_t slot = off[i] + (uint32_t)lv, c = o.cnt[slot];
+                    q.layers[lv].resize(c);
+                    for (uint32_t j = 0; j < c; ++j) q.layers[lv][j] = h_decode(o.keys[(size_t)slot * o.take + j]);
+                }
+            }
+            if (!fb.empty()) {  // capacity overflow on the device: the lockstep driver answers those
+                h->dev_fallbacks += fb.size();
+                if (fq.size() < fb.size()) fq.resize(fb.size());
+                for (size_t j = 0; j < fb.size(); ++j) hq_init(h, fq[j], nodes[first + fb[j]], h->node_level[nodes[first + fb[j]]], h->efc);
+                rc = hnsw_run_batch(h, fq, fb.size(), s->d_vec);
+                if (rc) return rc;
+                for (size_t j = 0; j < fb.size(); ++j) qs[fb[j]].layers = fq[j].layers;
+            }
+        } else {
+            for (size_t i = 0; i < nb; ++i) hq_init(h, qs[i], nodes[first + i], h->node_level[nodes[first + i]], h->efc);
+            rc = hnsw_run_batch(h, qs, nb, s->d_vec);
+            if (rc) return rc;
+        }
+        // ---- link, in insertion order (insert.rs:408-498).  The edge operations are listed in order, then every
+        //      host thread replays the list and applies the operations of the adjacency lists it owns: each list
+        //      sees its operations in the sequential order, so the result equals the one-thread loop.
+        ops.clear();
         for (size_t i = 0; i < nb; ++i) {
             HQuery& q = qs[i];
             const uint32_t node = nodes[first + i];
@@ -447,8 +763,8 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
                 const size_t take = std::min<size_t>(maxc, w.size());
                 for (size_t j = 0; j < take; ++j) {
                     if (w[j].node == node) continue;
-                    h_add_edge(h, node, w[j].node, w[j].d, lv);
-                    h_add_edge(h, w[j].node, node, w[j].d, lv);
+                    ops.push_back(HOp{node, w[j].node, w[j].d, lv});
+                    ops.push_back(HOp{w[j].node, node, w[j].d, lv});
                 }
             }
             if (L > h->entry_level) {
@@ -456,8 +772,24 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
                 h->entry_level = L;
             }
         }
+#pragma omp parallel num_threads(nthreads)
+        {
+            const uint32_t tid = (uint32_t)omp_get_thread_num(), nt = (uint32_t)omp_get_num_threads();
+            std::vector<uint32_t>* d0 = use_dev ? &t_dirty0[tid] : nullptr;
+            std::vector<uint32_t>* dU = use_dev ? &t_dirtyU[tid] : nullptr;
+            for (const HOp& op : ops)
+                if (((op.from * 2654435761u) >> 12) % nt == tid) h_add_edge(h, op.from, op.to, op.d, op.level, d0, dU);
+        }
+        if (use_dev)
+            for (int t = 0; t < nthreads; ++t) {
+                h->dirty0_list.insert(h->dirty0_list.end(), t_dirty0[t].begin(), t_dirty0[t].end());
+                h->dirtyU_list.insert(h->dirtyU_list.end(), t_dirtyU[t].begin(), t_dirtyU[t].end());
+                t_dirty0[t].clear();
+                t_dirtyU[t].clear();
+            }
         h->n_nodes += nb;
     }
+    if (use_dev && (rc = hnsw_dev_flush_dirty(h))) return rc;
     return 0;
 }
 
@@ -489,26 +821,55 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
     CU(cudaMemsetAsync(h->d_queries, 0, qbytes, s->stream));
     CU(cudaMemcpy2DAsync(h->d_queries, s->row_stride, queries, s->row_bytes, s->row_bytes, nq, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    const uint32_t chunk = 8192;
     std::vector<HQuery> qs;
-    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
-        const uint32_t m = std::min(chunk, nq - q0);
+    auto emit = [&](uint32_t qi, const std::vector<HCand>& w) {
+        const uint32_t cnt = (uint32_t)std::min<size_t>(k, w.size());
+        for (uint32_t j = 0; j < cnt; ++j) {
+            out_rowids[(size_t)qi * k + j] = h_rowid_of(s, w[j].node);
+            out_dists[(size_t)qi * k + j] = w[j].d;
+        }
+        if (out_counts) out_counts[qi] = cnt;
+    };
+    // lockstep driver (one scoring launch per expansion round) for the queries listed in `which` (NULL: q0..q0+m)
+    auto host_loop = [&](const uint32_t* which, uint32_t q0, uint32_t m) -> int {
         qs.clear();
         qs.resize(m);
-        for (uint32_t i = 0; i < m; ++i) hq_init(h, qs[i], q0 + i, -1, ef);
-        rc = hnsw_run_batch(h, qs, m, (const uint8_t*)h->d_queries);
-        if (rc) return rc;
-        for (uint32_t i = 0; i < m; ++i) {
-            if (qs[i].layers.empty()) continue;
-            const std::vector<HCand>& w = qs[i].layers[0];
-            const uint32_t cnt = (uint32_t)std::min<size_t>(k, w.size());
-            for (uint32_t j = 0; j < cnt; ++j) {
-                out_rowids[(size_t)(q0 + i) * k + j] = h_rowid_of(s, w[j].node);
-                out_dists[(size_t)(q0 + i) * k + j] = w[j].d;
+        for (uint32_t i = 0; i < m; ++i) hq_init(h, qs[i], which ? which[i] : q0 + i, -1, ef);
+        int r = hnsw_run_batch(h, qs, m, (const uint8_t*)h->d_queries);
+        if (r) return r;
+        for (uint32_t i = 0; i < m; ++i)
+            if (!qs[i].layers.empty()) emit(which ? which[i] : q0 + i, qs[i].layers[0]);
+        return 0;
+    };
+    if (hnsw_device_enabled(h)) {
+        // K6: the whole layered search on the device, one warp per query
+        const uint32_t chunk = 1u << 16;
+        std::vector<uint32_t> fb;
+        std::vector<HCand> w;
+        for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+            const uint32_t m = std::min(chunk, nq - q0);
+            HDevOut o;
+            rc = hnsw_dev_search(h, (const uint8_t*)h->d_queries + (size_t)q0 * s->row_stride, nullptr, nullptr, m, ef, k, nullptr, m, &o);
+            if (rc) return rc;
+            for (uint32_t i = 0; i < m; ++i) {
+                if (o.status[i]) {
+                    fb.push_back(q0 + i);
+                    continue;
+                }
+                w.resize(o.cnt[i]);
+                for (uint32_t j = 0; j < o.cnt[i]; ++j) w[j] = h_decode(o.keys[(size_t)i * o.take + j]);
+                emit(q0 + i, w);
             }
-            if (out_counts) out_counts[q0 + i] = cnt;
         }
+        if (!fb.empty()) {
+            h->dev_fallbacks += fb.size();
+            if ((rc = host_loop(fb.data(), 0, (uint32_t)fb.size()))) return rc;
+        }
+        return 0;
     }
+    const uint32_t chunk = 8192;
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk)
+        if ((rc = host_loop(nullptr, q0, std::min(chunk, nq - q0)))) return rc;
     return 0;
 }
 
@@ -526,6 +887,25 @@ extern "C" int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edge
     if (entry_level) *entry_level = h->entry_level;
     if (distances_scored) *distances_scored = h->scored;
     if (rounds) *rounds = h->rounds;
+    return 0;
+}
+
+extern "C" int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* level) {
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (rowid) *rowid = h->entry < 0 ? -1 : h_rowid_of(h->slab, (uint32_t)h->entry);
+    if (level) *level = h->entry < 0 ? -1 : h->entry_level;
+    return 0;
+}
+
+// K6 counters: queries answered by the device search kernel, how many of them overflowed a device capacity and were
+// re-run through the lockstep driver, and the number of search launches.
+extern "C" int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallbacks, uint64_t* launches) {
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (queries) *queries = h->dev_queries;
+    if (fallbacks) *fallbacks = h->dev_fallbacks;
+    if (launches) *launches = h->dev_launches;
     return 0;
 }
 

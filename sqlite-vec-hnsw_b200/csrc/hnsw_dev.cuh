@@ -1,0 +1,278 @@
+// hnsw_dev.cuh — K6: the whole layered HNSW search on the device, one warp per query.
+//
+// Replaces search_hnsw / search_layer (src/hnsw/search.rs:267-543) and the search half of insert_hnsw
+// (src/hnsw/insert.rs:396-430) when the adjacency lists are resident in HBM: no host round trip per
+// expansion step.  The traversal is the reference's, statement for statement:
+//   - the entry point is scored first (search.rs:385-398);
+//   - pop the closest unexpanded candidate; the layer ends when it is farther than the worst result (:406-410);
+//   - its neighbours are filtered through a visited set BEFORE scoring (:424-434), scored (K5 arithmetic, canonical
+//     order, bit-identical to pair_kernel) and admitted IN ADJACENCY ORDER with `len < ef || d < worst` (:516),
+//     results trimmed to ef by evicting the largest (d, node) (:528-531);
+//   - the closest result seeds the next layer (:318-323); layers above the collecting ones run with ef = 1.
+//
+// Data structure: ONE sorted array per warp in shared memory holds both heaps of the reference.  Key =
+// order_bits(d) << 32 | node << 1 | expanded.  The first min(len, ef) entries are the result set; the unexpanded
+// entries are the candidate heap.  An admitted entry that falls behind position ef with a distance strictly larger
+// than the worst result can never be expanded (the reference would stop on popping it), so it is dropped; entries
+// behind ef that TIE with the worst result's distance stay (the reference does expand those).  With that rule the
+// reference's stop condition is exactly "no unexpanded entry left".
+// The visited set is an open-addressing table in global memory (L2-resident), one per warp.  At most ef - 1 entries can sit behind position ef (they are copies of the worst result's distance pushed out one
+// admission at a time), so an array of 2 ef slots never overflows.
+// The visited set is bounded: when it is 3/4 full (or the step limit is hit) status[q] = 1 and the host re-runs that
+// query through the lockstep driver: never a silent approximation.
+#pragma once
+#include "kernels.cuh"
+
+namespace vg {
+
+struct HGraphDev {
+    const uint32_t* nbr0;        // [node][max_m0]
+    const uint16_t* deg0;        // [node]
+    const uint32_t* upper_base;  // [node] first upper-level slot of the node
+    const uint32_t* nbrU;        // [slot][M]
+    const uint16_t* degU;        // [slot]
+    uint32_t max_m0, M;
+};
+
+struct HSearchParams {
+    HGraphDev g;
+    const uint8_t* a_base;       // query rows
+    uint32_t a_stride;
+    const uint32_t* a_index;     // row of query q in a_base (NULL: q)
+    const uint8_t* b_base;       // slab rows
+    uint32_t b_stride, units, qc_kind;
+    uint32_t nq, entry;
+    int32_t entry_level;
+    const int8_t* node_level;    // inserts: level of the new node (layers <= it collect ef_wide results); NULL: queries
+    uint32_t ef_wide, cap, take; // cap = array capacity (> ef_wide), take = entries written per collected layer
+    uint32_t* visited;           // [warp][vis_size], vis_size a power of two
+    uint32_t vis_size;
+    const uint32_t* out_off;     // first output slot of query q (NULL: q); layer lv goes to slot out_off[q] + lv
+    uint64_t* out_keys;          // [slot][take]
+    uint32_t* out_cnt;           // [slot]
+    uint32_t* status;            // [q]
+    unsigned int* next_q;        // work counter
+    unsigned long long* scored;  // distances computed
+    uint32_t max_steps;
+};
+
+static constexpr uint32_t HV_EMPTY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ bool hvis_insert(uint32_t* t, uint32_t mask, uint32_t key) {  // true if newly inserted
+    uint32_t h = (key * 2654435761u) & mask;
+    while (true) {
+        const uint32_t old = atomicCAS(&t[h], HV_EMPTY, key);
+        if (old == HV_EMPTY) return true;
+        if (old == key) return false;
+        h = (h + 1) & mask;
+    }
+}
+
+// insert x into the ascending array L[0..len) (order = key >> 1; nodes are unique so there are no equal keys).
+// Warp-uniform arguments; returns the position.
+__device__ __forceinline__ uint32_t hlist_insert(uint64_t* L, uint32_t len, uint64_t x, int lane) {
+    const uint64_t xk = x | 1ull;
+    uint32_t pos = 0;
+    for (uint32_t c = 0; c < len; c += 32) {
+        const uint32_t i = c + lane;
+        const bool lt = i < len && (L[i] | 1ull) < xk;
+        const uint32_t m = __ballot_sync(0xffffffffu, lt);
+        pos += __popc(m);
+        if (m != 0xffffffffu) break;
+    }
+    if (len > 0) {  // shift [pos, len) up by one, highest chunk first
+        for (int c = (int)((len - 1) >> 5); c >= (int)(pos >> 5); --c) {
+            const uint32_t i = ((uint32_t)c << 5) + lane;
+            const bool mv = i < len && i >= pos;
+            const uint64_t v = mv ? L[i] : 0ull;
+            __syncwarp();
+            if (mv) L[i + 1] = v;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) L[pos] = x;
+    __syncwarp();
+    return pos;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p) {
+    constexpr int LPR = T::LPR;
+    constexpr int GPW = 32 / LPR;  // rows scored per pass of the warp
+    extern __shared__ __align__(16) uint8_t h_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane % LPR;
+    const uint32_t pend_cap = (p.g.max_m0 + 31u) & ~31u;
+    const size_t per_warp = (size_t)p.cap * 8 + (size_t)pend_cap * 4;
+    uint64_t* L = (uint64_t*)(h_smem + (size_t)warp * per_warp);
+    uint32_t* pend = (uint32_t*)(L + p.cap);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    uint32_t* vt = p.visited + (size_t)gw * p.vis_size;
+
+    while (true) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(p.next_q, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= p.nq) break;
+        const uint32_t ai = p.a_index ? p.a_index[q] : q;
+        const uint4* a = (const uint4*)(p.a_base + (uint64_t)ai * p.a_stride);
+        float qc = 0.f;
+        if (T::HAS_QC) qc = query_const(a, p.units, lane & 3, p.qc_kind);
+        const int nlev = p.node_level ? (int)p.node_level[q] : -1;
+        const uint32_t slot0 = p.out_off ? p.out_off[q] : q;
+        uint32_t entry = p.entry;
+        uint32_t status = 0;
+        unsigned long long nscored = 0;
+
+        for (int level = p.entry_level; level >= 0 && !status; --level) {
+            const bool wide = nlev < 0 ? level == 0 : level <= nlev;
+            const uint32_t ef = wide ? p.ef_wide : 1u;
+            const uint32_t vsz = ef == 1u ? min(p.vis_size, 4096u) : p.vis_size;
+            const uint32_t vmask = vsz - 1, vlimit = vsz - (vsz >> 2);
+            for (uint32_t i = (uint32_t)lane * 4; i < vsz; i += 128) *(uint4*)(vt + i) = make_uint4(HV_EMPTY, HV_EMPTY, HV_EMPTY, HV_EMPTY);
+            __syncwarp();
+            uint32_t len = 0, lo = 0, vcount = 1, npend = 1, steps = 0;
+            uint32_t worst_hi = 0xFFFFFFFFu;
+            if (lane == 0) {
+                pend[0] = entry;
+                hvis_insert(vt, vmask, entry);
+            }
+            __syncwarp();
+
+            while (true) {
+                // ---- score the pending nodes, GPW at a time, and admit them in order
+                for (uint32_t base = 0; base < npend && !status; base += GPW) {
+                    const uint32_t r = base + (uint32_t)(lane / LPR);
+                    const bool valid = r < npend;
+                    const uint32_t node = valid ? pend[r] : 0u;
+                    typename T::Acc acc;
+                    T::init(acc);
+                    if (valid) {
+                        const uint4* b = (const uint4*)(p.b_base + (uint64_t)node * p.b_stride);
+#pragma unroll 4
+                        for (uint32_t u = g; u < p.units; u += LPR) {
+                            const uint4 x = __ldg(b + u);
+                            const uint4 qv[1] = {__ldg(a + u)};
+                            T::step(acc, x, qv);
+                        }
+                    }
+                    const float d = T::finish(acc, 0, &qc);
+                    const uint32_t cnt = min((uint32_t)GPW, npend - base);
+                    for (uint32_t j = 0; j < cnt; ++j) {
+                        const float dj = __shfl_sync(0xffffffffu, d, (int)j * LPR);
+                        const uint32_t nj = __shfl_sync(0xffffffffu, node, (int)j * LPR);
+                        if (dj != dj) continue;  // NaN never enters a heap
+                        const uint32_t oj = order_bits(dj);
+                        if (len < ef || oj < worst_hi) {  // search.rs:516 (strict <)
+                            const uint64_t key = ((uint64_t)oj << 32) | ((uint64_t)nj << 1);
+                            const uint32_t pos = hlist_insert(L, len, key, lane);
+                            ++len;
+                            if (pos < lo) lo = pos;
+                            if (len > ef) {  // keep only the entries behind ef that tie with the worst result
+                                const uint32_t wd = (uint32_t)(L[ef - 1] >> 32);
+                                uint32_t keep = ef;
+                                for (uint32_t c = ef; c < len; c += 32) {
+                                    const uint32_t i = c + lane;
+                                    const bool tie = i < len && (uint32_t)(L[i] >> 32) == wd;
+                                    const uint32_t m = __ballot_sync(0xffffffffu, tie);
+                                    keep += __popc(m);
+                                    if (m != 0xffffffffu) break;
+                                }
+                                len = keep;
+                            }
+                            worst_hi = (uint32_t)(L[min(len, ef) - 1] >> 32);
+                            if (len >= p.cap) {
+                                status = 1;
+                                break;
+                            }
+                        }
+                    }
+                }
+                nscored += npend;
+                if (status) break;
+
+                // ---- pop the closest unexpanded entry until one has unvisited neighbours
+                npend = 0;
+                bool layer_done = false;
+                while (npend == 0) {
+                    uint32_t ci = 0xFFFFFFFFu;
+                    for (uint32_t c = lo & ~31u; c < len; c += 32) {
+                        const uint32_t i = c + lane;
+                        const bool un = i < len && i >= lo && !(L[i] & 1ull);
+                        const uint32_t m = __ballot_sync(0xffffffffu, un);
+                        if (m) {
+                            ci = c + (uint32_t)__ffs(m) - 1u;
+                            break;
+                        }
+                    }
+                    if (ci == 0xFFFFFFFFu) {  // == the reference's stop: every remaining candidate is farther than the worst result
+                        layer_done = true;
+                        break;
+                    }
+                    const uint64_t ck = L[ci];
+                    __syncwarp();
+                    if (lane == 0) L[ci] = ck | 1ull;
+                    __syncwarp();
+                    lo = ci + 1;
+                    const uint32_t cn = (uint32_t)(ck & 0xFFFFFFFFull) >> 1;
+                    const uint32_t* nb;
+                    uint32_t deg;
+                    if (level == 0) {
+                        nb = p.g.nbr0 + (size_t)cn * p.g.max_m0;
+                        deg = p.g.deg0[cn];
+                    } else {
+                        const size_t slot = (size_t)p.g.upper_base[cn] + (size_t)(level - 1);
+                        nb = p.g.nbrU + slot * p.g.M;
+                        deg = p.g.degU[slot];
+                    }
+                    if (vcount + deg > vlimit || ++steps > p.max_steps) {
+                        status = 1;
+                        break;
+                    }
+                    for (uint32_t i0 = 0; i0 < deg; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        uint32_t v = 0;
+                        bool isnew = false;
+                        if (i < deg) {
+                            v = nb[i];
+                            isnew = hvis_insert(vt, vmask, v);
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+                        if (isnew) pend[npend + __popc(m & ((1u << lane) - 1u))] = v;
+                        npend += __popc(m);
+                    }
+                    vcount += npend;
+                    __syncwarp();
+                }
+                if (layer_done || status) break;
+            }
+            if (status) break;
+            if (len > 0) entry = (uint32_t)(L[0] & 0xFFFFFFFFull) >> 1;  // closest result seeds the next layer
+            if (wide) {
+                const uint32_t slot = slot0 + (uint32_t)level;
+                const uint32_t cnt = min(min(len, ef), p.take);
+                for (uint32_t i = lane; i < cnt; i += 32) p.out_keys[(size_t)slot * p.take + i] = L[i];
+                if (lane == 0) p.out_cnt[slot] = cnt;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            p.status[q] = status;
+            atomicAdd(p.scored, nscored);
+        }
+    }
+}
+
+// scatter staged adjacency lists into the device graph: item = [list id][degree][width x u32]
+__global__ void hnsw_scatter_kernel(const uint32_t* staged, uint32_t n_items, uint32_t width, uint32_t* nbr, uint16_t* deg) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t it = w; it < n_items; it += nw) {
+        const uint32_t* src = staged + (size_t)it * (width + 2);
+        const uint32_t id = src[0];
+        if (lane == 0) deg[id] = (uint16_t)src[1];
+        for (uint32_t i = lane; i < width; i += 32) nbr[(size_t)id * width + i] = src[2 + i];
+    }
+}
+
+}  // namespace vg

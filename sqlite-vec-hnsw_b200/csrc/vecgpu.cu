@@ -15,8 +15,11 @@
 #include <vector>
 
 #include "../../include/vecgpu.h"
+#include <omp.h>
+
 #include "kernels.cuh"
 #include "tc_batch.cuh"
+#include "hnsw_dev.cuh"
 
 using namespace vg;
 

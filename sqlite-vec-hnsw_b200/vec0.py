@@ -509,6 +509,18 @@ class HnswIndex:
         _check(self._lib.vecgpu_hnsw_stats(self._h, C.byref(n), C.byref(e), C.byref(lvl), C.byref(sc), C.byref(r)))
         return dict(nodes=n.value, edges=e.value, entry_level=lvl.value, distances_scored=sc.value, rounds=r.value)
 
+    def entry_point(self):
+        """-> (rowid, level) of the graph's entry point, (-1, -1) when empty."""
+        r, l = C.c_int64(), C.c_int32()
+        _check(self._lib.vecgpu_hnsw_entry_point(self._h, C.byref(r), C.byref(l)))
+        return r.value, l.value
+
+    def device_stats(self):
+        """Counters of the on-device search kernel: queries/inserts it answered, capacity fallbacks, launches."""
+        q, f, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._lib.vecgpu_hnsw_device_stats(self._h, C.byref(q), C.byref(f), C.byref(l)))
+        return dict(queries=q.value, fallbacks=f.value, launches=l.value)
+
     def search(self, queries, k, ef_search=200):
         """search_hnsw (src/hnsw/search.rs:267-335).  Queries are raw column vectors; cosine queries are
         normalised here (search.rs:291-293).  -> (rowids [nq,k], distances in the column's metric, counts)."""

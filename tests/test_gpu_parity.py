@@ -648,6 +648,149 @@ def test_hnsw_empty_and_tiny(vg, gpu):
         idx.close()
 
 
+# ------------------------------------------------------------------ K6: whole search_layer on the device (one warp per query)
+class _hnsw_mode:
+    """VECGPU_HNSW_DEVICE=0 selects the lockstep driver (one scoring launch per expansion round)."""
+
+    def __init__(self, device):
+        self.v = "1" if device else "0"
+
+    def __enter__(self):
+        self.old = os.environ.get("VECGPU_HNSW_DEVICE")
+        os.environ["VECGPU_HNSW_DEVICE"] = self.v
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("VECGPU_HNSW_DEVICE", None)
+        else:
+            os.environ["VECGPU_HNSW_DEVICE"] = self.old
+
+
+@pytest.mark.parametrize(
+    "elem,metric,dims,n,M,efc",
+    [
+        (F32, L2, 48, 6000, 16, 200),
+        (F32, COSINE, 40, 3000, 8, 64),
+        (F32, L1, 24, 2500, 6, 40),
+        (I8, L2, 8, 4000, 16, 100),      # tiny int8 rows: distances tie all the time -> the tie rules are exercised
+        (I8, COSINE, 64, 2000, 12, 80),
+        (I8, L1, 16, 2000, 5, 30),
+        (BIT, HAMMING, 64, 5000, 16, 120),  # integer distances 0..64: massive ties
+        (F32, L2, 16, 3000, 50, 30),     # max_m0 = 100 > ef: every list longer than a warp, take > ef
+    ],
+)
+def test_hnsw_device_search_equals_lockstep_and_restatement(vg, orc, gpu, elem, metric, dims, n, M, efc):
+    from oracle import hnsw_ref
+
+    v = random_rows(elem, n, dims, seed=401)
+    q = random_rows(elem, 96, dims, seed=402)
+    rowids = np.arange(n, dtype="<i8") * 3 + 11
+    with vg.Slab(elem, dims) as s:
+        s.load(v, rowids)
+        with _hnsw_mode(True):
+            idx = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=5, normalize_vectors=False)
+            idx.rebuild(batch=256)
+            ds = idx.device_stats()
+            assert ds["queries"] == n - 1 and ds["launches"] > 0  # every insert but the first searched on the device
+        with _hnsw_mode(False):
+            idx_h = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=5, normalize_vectors=False)
+            idx_h.rebuild(batch=256)
+            assert idx_h.device_stats()["queries"] == 0
+        # identical graphs: same lists in the same order with the same stored distances
+        e_d, e_h = idx.export_edges(), idx_h.export_edges()
+        for a, b in zip(e_d, e_h):
+            assert np.array_equal(a.view("u1"), b.view("u1"))
+        assert idx.entry_point() == idx_h.entry_point()
+        for k, ef in ((10, 64), (1, 1), (7, 300), (40, 10)):
+            with _hnsw_mode(True):
+                r1, d1, c1 = idx.search(q, k, ef_search=ef)
+            with _hnsw_mode(False):
+                r2, d2, c2 = idx.search(q, k, ef_search=ef)       # device-built graph, lockstep walk
+                r3, d3, c3 = idx_h.search(q, k, ef_search=ef)
+            assert np.array_equal(r1, r2) and same_bits(d1, d2) and np.array_equal(c1, c2)
+            assert np.array_equal(r1, r3) and same_bits(d1, d3)
+        # literal restatement of search_hnsw (oracle/hnsw_ref.py) over the exported graph
+        fr, to, lv, _ = e_d
+        nbrs = hnsw_ref.adjacency_from_edges(fr, to, lv)
+        entry, entry_level = idx.entry_point()
+        k, ef = 10, 50
+        with _hnsw_mode(True):
+            r1, d1, c1 = idx.search(q[:12], k, ef_search=ef)
+        for qi in range(12):
+            dist_of = lambda rid: float(orc.distance(elem, q[qi], v[(rid - 11) // 3], metric))
+            want = hnsw_ref.search_hnsw(dist_of, nbrs, entry, entry_level, k, ef)
+            assert c1[qi] == len(want)
+            assert [int(x) for x in r1[qi, : len(want)]] == [w[0] for w in want]
+            assert same_bits(d1[qi, : len(want)], np.array([w[1] for w in want], dtype="<f4"))
+        assert idx.device_stats()["fallbacks"] <= ds["fallbacks"] + 96 * 8  # counters move, nothing else to assert
+        idx.close()
+        idx_h.close()
+
+
+def test_hnsw_device_capacity_fallback_is_exact(vg, orc, gpu):
+    # a visited table that is too small for the beam: the kernel flags the query and the lockstep driver answers it
+    n, dims = 8000, 16
+    v = random_rows(F32, n, dims, seed=421)
+    q = random_rows(F32, 40, dims, seed=422)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=16, ef_construction=100, seed=1)
+        idx.rebuild()
+        before = idx.device_stats()
+        os.environ["VECGPU_HNSW_VIS_LOG2"] = "12"  # 4096 slots, 3072 usable: ef=1500 visits more than that
+        try:
+            r1, d1, c1 = idx.search(q, 10, ef_search=1500)
+        finally:
+            del os.environ["VECGPU_HNSW_VIS_LOG2"]
+        after = idx.device_stats()
+        assert after["fallbacks"] - before["fallbacks"] > 0
+        with _hnsw_mode(False):
+            r2, d2, c2 = idx.search(q, 10, ef_search=1500)
+        assert np.array_equal(r1, r2) and same_bits(d1, d2) and np.array_equal(c1, c2)
+        r3, d3, c3 = idx.search(q, 10, ef_search=1500)  # full-size table: no fallback, same answer
+        assert idx.device_stats()["fallbacks"] == after["fallbacks"]
+        assert np.array_equal(r1, r3) and same_bits(d1, d3)
+        # massive ties (two distinct points, thousands of copies): the sorted array never overflows (<= 2 ef - 1 entries)
+        vt = np.zeros((3000, 8), dtype="i1")
+        vt[:, 0] = (np.arange(3000) % 2).astype("i1")
+        with vg.Slab(I8, 8) as st:
+            st.load(vt)
+            with _hnsw_mode(True):
+                it = vg.HnswIndex(st, L2, M=8, ef_construction=40, seed=1)
+                it.rebuild(batch=128)
+                ra, da, ca = it.search(np.zeros((4, 8), dtype="i1"), 10, ef_search=32)
+                assert it.device_stats()["fallbacks"] == 0
+            with _hnsw_mode(False):
+                ih = vg.HnswIndex(st, L2, M=8, ef_construction=40, seed=1)
+                ih.rebuild(batch=128)
+                rb, db, cb = ih.search(np.zeros((4, 8), dtype="i1"), 10, ef_search=32)
+            for a_, b_ in zip(it.export_edges(), ih.export_edges()):
+                assert np.array_equal(a_.view("u1"), b_.view("u1"))
+            assert np.array_equal(ra, rb) and same_bits(da, db) and np.array_equal(ca, cb)
+            it.close()
+            ih.close()
+        idx.close()
+
+
+def test_hnsw_device_large_batch_throughput_path(vg, orc, gpu):
+    # many queries in one launch (more than one wave of warps), results independent of the launch shape
+    n, dims, nq = 20000, 32, 20000
+    v = random_rows(F32, n, dims, seed=411)
+    q = random_rows(F32, nq, dims, seed=412)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=16, ef_construction=100, seed=3)
+        idx.rebuild()
+        r_all, d_all, c_all = idx.search(q, 10, ef_search=64)
+        for lo in (0, 7777, nq - 5):
+            r1, d1, c1 = idx.search(q[lo : lo + 5], 10, ef_search=64)
+            assert np.array_equal(r1, r_all[lo : lo + 5]) and same_bits(d1, d_all[lo : lo + 5])
+        er, _, _ = orc.knn(F32, dims, v, q[:300], 10, L2)
+        assert _recall(r_all[:300], er) >= 0.80
+        assert idx.device_stats()["fallbacks"] == 0
+        idx.close()
+
+
 # ------------------------------------------------------------------ K3 batched: int8 L2 on the tensor cores (tcgen05 kind::i8), exact
 @pytest.mark.parametrize("dims,nq,k", [(1024, 64, 100), (128, 16, 10), (100, 130, 7), (33, 40, 1), (2000, 20, 33)])
 def test_tc_int8_batched_matches_oracle(vg, orc, gpu, dims, nq, k):
