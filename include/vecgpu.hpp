@@ -304,6 +304,14 @@ public:
         for (uint32_t i = 0; i < count; ++i) out.emplace_back(rowids[i], convert_distance_for_output(metric_, normalize_, dists[i]));
         return out;
     }
+    // HnswMetadata.entry_point_rowid / entry_point_level (src/hnsw/mod.rs:97-103); (-1, -1) when empty
+    Result<std::pair<int64_t, int32_t>> entry_point() {
+        int64_t rowid = -1;
+        int32_t level = -1;
+        int rc = vecgpu_hnsw_entry_point(h_, &rowid, &level);
+        if (rc) return Error::from_status(rc);
+        return std::make_pair(rowid, level);
+    }
 };
 
 }  // namespace vecgpu

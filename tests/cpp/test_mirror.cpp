@@ -122,6 +122,8 @@ int main() {
         auto res = idx->search(blob_f32({1, 0, 0}), 2).unwrap();
         CHECK(res.size() == 2 && res[0].first == 1 && res[1].first == 2 && res[0].second < 1e-6f);
         CHECK(std::fabs(res[1].second - 0.2f) < 1e-5f);  // cosine distance of (1,0,0) and (0.8,0.6,0) via d_L2^2/2
+        auto ep = idx->entry_point().unwrap();           // -> _hnsw_meta entry_point_rowid / _level (src/hnsw/mod.rs:97-103)
+        CHECK(ep.first >= 1 && ep.first <= 3 && ep.second >= 0);
         CHECK(HnswIndex::create(*slab, DistanceMetric::Cosine, 1, 400).is_err());  // M in [2,100] (src/sql_functions.rs:442-469)
         delete idx;
         delete slab;
