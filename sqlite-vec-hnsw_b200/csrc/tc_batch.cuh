@@ -461,6 +461,7 @@ __global__ void tc_keys_kernel(const float* dist, const int64_t* pos, uint64_t n
 namespace vg {
 
 static constexpr uint32_t TCI_STAGES = 4;
+static constexpr int TCI_INEL = 0x40000000;  // |x|^2 stand-in of a row that must not be returned (valid values < 2^30 for dims <= 16384)
 static constexpr uint32_t TCI_STAGE_BYTES = TCI_A_BYTES + TCI_B_BYTES;  // 48 KB
 // kind::i8 instruction descriptor: D=S32, A=B=S8, both K-major, N=256, M=128
 static constexpr uint32_t TCI_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
@@ -518,10 +519,11 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* s_colB = (int*)(smem + TCI_STAGES * TCI_STAGE_BYTES);      // [2][256] |x|^2, -1 = row not eligible
-    uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
+    int* s_colB = (int*)(smem + TCI_STAGES * TCI_STAGE_BYTES);      // [4 epilogue warps][256] |x|^2 of the current tile
+    uint64_t* s_bar = (uint64_t*)(s_colB + 4 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
-    uint64_t* s_scratch = s_bar + 32;                                // [4 epilogue warps][cap] compaction scratch
+    uint64_t* s_scratch = s_bar + 32;                                // [4 epilogue warps] compaction scratch / chunk staging
+    const size_t scratch_bytes = max((size_t)p.cap * 8, (size_t)4096);
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 4), bar_tfull = smem_u32(s_bar + 8),
                    bar_tempty = smem_u32(s_bar + 10);
     if (warp == 1) {
@@ -586,27 +588,41 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
         __syncwarp();
     } else if (warp >= 4) {
+        const uint32_t ew = (uint32_t)(warp & 3);
         const uint32_t e = threadIdx.x - 128;
-        const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
+        const uint32_t lane_base = ew * 32;
         const uint32_t q = qt * TC_M + e;
         const bool q_ok = q < p.nq;
         // per-thread append buffer: keys that beat the (lazily refreshed) threshold are simply appended; when a
         // buffer is nearly full the warp compacts it cooperatively and the thread's threshold tightens
         uint64_t* buf = p.buf_keys + ((size_t)(q_ok ? q : 0) * p.G + g) * p.cap;
-        uint64_t* scratch = s_scratch + (size_t)(warp & 3) * p.cap;
+        uint64_t* scratch = (uint64_t*)((uint8_t*)s_scratch + (size_t)ew * scratch_bytes);
+        int* stage = (int*)scratch;            // [32 columns][32 lanes] staging of one chunk for the rare path
+        int* my_colB = s_colB + ew * TC_N;     // this warp's copy of the tile's |x|^2 (TCI_INEL = row not eligible)
         const int a2 = q_ok ? p.qnorms[q] : 0;
         uint32_t cnt = 0;
         uint64_t tau_key = KEY_NONE;   // k-th best key as of the last compaction
-        int tau_s = 0x7FFFFFFE;        // every s above this is certainly not better than tau_key (0x7FFFFFFF = ineligible row)
+        int tau_s = 0x7FFFFFFE;        // every s above this is certainly not better than tau_key
+        int tau_a = q_ok ? tau_s - a2 : (int)0x80000000;  // same bound on t = |x|^2 - 2 q.x; nothing passes for a padding query
+        // |x|^2 of the next tile is fetched one tile ahead (registers), so the loads never sit in front of the MMA wait
+        int nb[TC_N / 32];
+        auto fetch_norms = [&](uint32_t ti) {
+            const uint64_t r0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+#pragma unroll
+            for (int i = 0; i < TC_N / 32; ++i) {
+                const uint64_t row = r0 + (uint64_t)(i * 32 + lane);
+                const bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
+                nb[i] = ok ? p.norms[row] : TCI_INEL;
+            }
+        };
+        if (my_tiles) fetch_norms(0);
         for (uint32_t ti = 0; ti < my_tiles; ++ti) {
             const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
             const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
-            for (uint32_t j = e; j < TC_N; j += 128) {
-                const uint64_t row = row0 + j;
-                const bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
-                s_colB[acc * TC_N + j] = ok ? p.norms[row] : -1;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < TC_N / 32; ++i) my_colB[i * 32 + lane] = nb[i];
+            __syncwarp();
+            if (ti + 1 < my_tiles) fetch_norms(ti + 1);
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
 #pragma unroll 1
@@ -622,32 +638,38 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // branch-free common case: exact s = |q|^2 + |x|^2 - 2 q.x for all 32 columns and a pass mask first
-                const int4* cb4 = (const int4*)(s_colB + acc * TC_N + c * 32);
-                int sv[32];
+                // common case, branch-free: t = |x|^2 - 2 q.x for the 32 columns and a pass mask against tau_a
+                // (s = |q|^2 + t is the exact squared distance; ineligible rows carry a huge |x|^2)
+                const int4* cb4 = (const int4*)(my_colB + c * 32);
+                int tv[32];
                 uint32_t mask = 0;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     const int4 b = cb4[j4];
-                    // rows that are not eligible carry |x|^2 = -1: force s above every threshold
-                    sv[4 * j4 + 0] = b.x < 0 ? 0x7FFFFFFF : a2 + b.x - 2 * (int)v[4 * j4 + 0];
-                    sv[4 * j4 + 1] = b.y < 0 ? 0x7FFFFFFF : a2 + b.y - 2 * (int)v[4 * j4 + 1];
-                    sv[4 * j4 + 2] = b.z < 0 ? 0x7FFFFFFF : a2 + b.z - 2 * (int)v[4 * j4 + 2];
-                    sv[4 * j4 + 3] = b.w < 0 ? 0x7FFFFFFF : a2 + b.w - 2 * (int)v[4 * j4 + 3];
+                    tv[4 * j4 + 0] = b.x - 2 * (int)v[4 * j4 + 0];
+                    tv[4 * j4 + 1] = b.y - 2 * (int)v[4 * j4 + 1];
+                    tv[4 * j4 + 2] = b.z - 2 * (int)v[4 * j4 + 2];
+                    tv[4 * j4 + 3] = b.w - 2 * (int)v[4 * j4 + 3];
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mask |= (sv[j] <= tau_s ? 1u : 0u) << j;
-                if (mask && q_ok) {
+                for (int j = 0; j < 32; ++j) mask |= (tv[j] <= tau_a ? 1u : 0u) << j;
+                // rare path (warp-uniform entry): the chunk is staged in shared memory so that the few passing columns
+                // can be picked by index in a compact loop; the exact key is (float)sqrt((double)s)
+                if (__any_sync(0xffffffffu, mask != 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int s = sv[j];
-                        if (((mask >> j) & 1u) && s <= tau_s && s != 0x7FFFFFFF) {
+                    for (int j = 0; j < 32; ++j) stage[j * 32 + lane] = tv[j];
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int s = a2 + stage[j * 32 + lane];
+                        if (my_colB[c * 32 + j] < TCI_INEL) {
                             // src/distance/scalar.rs:65: f64 sqrt, then cast — the same final value as the scan
                             const float d = __double2float_rn(__dsqrt_rn((double)s));
                             const uint64_t key = make_key(d, (uint32_t)(row0 + c * 32 + j));
                             if (key < tau_key) buf[cnt++] = key;
                         }
                     }
+                    __syncwarp();
                 }
                 // a buffer that could overflow during the next 32 columns is compacted now (warp-uniform loop)
                 unsigned need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
@@ -666,6 +688,7 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
                             const double lim = dn * dn;
                             tau_s = lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
+                            tau_a = tau_s - a2;
                         }
                     }
                 }

@@ -1065,7 +1065,7 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
     int dev = 0;
     CU(cudaGetDevice(&dev));
     const uint32_t cap = std::max(128u, next_pow2(2 * k + 64));  // per-thread append buffer; k <= 224 -> cap <= 512
-    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + 2 * TC_N * 4 + 32 * 8 + 4 * (size_t)cap * 8 + 1024;
+    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + 4 * TC_N * 4 + 32 * 8 + 4 * std::max((size_t)cap * 8, (size_t)4096) + 1024;
     if (cfg_dev != dev) {
         CU(cudaFuncSetAttribute(tci8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         cfg_dev = dev;
