@@ -486,6 +486,15 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         : "memory");
 }
 
+// (float)sqrt((double)s) for an exact non-negative integer s (src/distance/scalar.rs:65).  Below 2^24 the integer is a
+// float, and the correctly rounded float square root equals the double-rounded value (double rounding is innocuous for
+// sqrt when the wide format has >= 2*24+2 bits), so no FP64 instruction is needed; tests/test_oracle_golden.py checks
+// the identity exhaustively on the CPU.
+__device__ __forceinline__ float exact_sqrt_int(int s) {
+    if (s < (1 << 24)) return __fsqrt_rn((float)s);
+    return __double2float_rn(__dsqrt_rn((double)s));
+}
+
 // Warp-cooperative compaction of one thread's append buffer: copy its `cnt` keys (padded with KEY_NONE to `cap`)
 // into the warp's shared-memory scratch, bitonic-sort ascending, write the k smallest back to the front of the
 // buffer.  Returns (to every lane) the new k-th smallest key, or KEY_NONE when fewer than k keys exist.
@@ -495,6 +504,7 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint3
     __syncwarp();
     for (uint32_t size = 2; size <= cap; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll 4
             for (uint32_t t = lane; t < cap / 2; t += 32) {
                 const uint32_t lo = 2 * t - (t & (stride - 1));
                 const uint32_t hi = lo + stride;
@@ -513,6 +523,25 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint3
     __syncwarp();
     return kth;
 }
+
+// TMEM -> registers, 32 lanes x 32 columns; the wait names the registers so that no use is scheduled before it
+#define TCI_LD32(v, addr)                                                                                                  \
+    asm volatile(                                                                                                          \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),    \
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),       \
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),       \
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                               \
+        : "r"(addr))
+#define TCI_WAIT32(v)                                                                                                      \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                          \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),      \
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),           \
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),          \
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])                        \
+                 :                                                                                                         \
+                 : "memory")
 
 __global__ void __launch_bounds__(256, 1)
 tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TciParams p) {
@@ -625,19 +654,8 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             if (ti + 1 < my_tiles) fetch_norms(ti + 1);
             mbar_wait(bar_tfull + 8 * acc, aph);
             tc_fence_after();
-#pragma unroll 1
-            for (uint32_t c = 0; c < ((p.debug & 1) ? 0u : TC_N / 32); ++c) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + (lane_base << 16) + acc * TC_N + c * 32;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // accumulators come out of TMEM 32 columns at a time, the next chunk's load in flight while this one is ranked
+            auto process = [&](uint32_t (&v)[32], const uint32_t c) {
                 // common case, branch-free: t = |x|^2 - 2 q.x for the 32 columns and a pass mask against tau_a
                 // (s = |q|^2 + t is the exact squared distance; ineligible rows carry a huge |x|^2)
                 const int4* cb4 = (const int4*)(my_colB + c * 32);
@@ -664,7 +682,7 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         const int s = a2 + stage[j * 32 + lane];
                         if (my_colB[c * 32 + j] < TCI_INEL) {
                             // src/distance/scalar.rs:65: f64 sqrt, then cast — the same final value as the scan
-                            const float d = __double2float_rn(__dsqrt_rn((double)s));
+                            const float d = exact_sqrt_int(s);
                             const uint64_t key = make_key(d, (uint32_t)(row0 + c * 32 + j));
                             if (key < tau_key) buf[cnt++] = key;
                         }
@@ -691,6 +709,20 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             tau_a = tau_s - a2;
                         }
                     }
+                }
+                        };
+            if (!(p.debug & 1)) {
+                uint32_t va[32], vb[32];
+                const uint32_t tbase = tmem_base + (lane_base << 16) + acc * TC_N;
+                TCI_LD32(va, tbase);
+#pragma unroll 1
+                for (uint32_t c = 0; c < TC_N / 32; c += 2) {
+                    TCI_WAIT32(va);
+                    TCI_LD32(vb, tbase + (c + 1) * 32);
+                    process(va, c);
+                    TCI_WAIT32(vb);
+                    if (c + 2 < TC_N / 32) TCI_LD32(va, tbase + (c + 2) * 32);
+                    process(vb, c + 1);
                 }
             }
             tc_fence_before();

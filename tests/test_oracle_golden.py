@@ -313,3 +313,12 @@ def test_oracle_reproduces_golden(orc, case):
     assert np.array_equal(r, z["out_rowids"])
     assert np.array_equal(d.view("<u4"), z["out_dists"].view("<u4"))
     assert np.array_equal(c, z["out_counts"])
+
+
+def test_int_sqrt_identity_below_2_24():
+    # the int8 tensor-core epilogue computes (float)sqrt((double)s) of an exact integer s (src/distance/scalar.rs:65) as
+    # sqrtf((float)s) when s < 2^24: double rounding is innocuous for sqrt (53 >= 2*24+2), checked here exhaustively
+    s = np.arange(1 << 24, dtype=np.int64)
+    via_double = np.sqrt(s.astype(np.float64)).astype(np.float32)
+    via_float = np.sqrt(s.astype(np.float32))
+    assert via_float.dtype == np.float32 and np.array_equal(via_double.view(np.uint32), via_float.view(np.uint32))
