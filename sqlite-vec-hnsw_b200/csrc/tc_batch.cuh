@@ -55,7 +55,7 @@ struct TcParams {
     uint32_t kp;           // entries kept per (CTA, query) = k + margin
     uint32_t cosine;       // 0: L2 (v = x2 - 2s), 1: cosine (v = -s / |x|)
     uint32_t lists_smem;   // 1: the kept scores live in shared memory ([kp][128] floats) during the scan
-    uint32_t debug;        // bit0: skip the epilogue arithmetic (pipeline-only timing experiments)
+    uint32_t debug;        // timing experiments (results invalid): 1 = no epilogue work, 2 = common path only, 4 = no norm loads
     uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
     const float* norms;    // [rows] canonical sum of squares of each slab row
     const uint8_t* skip;   // per-row skip flags or nullptr
@@ -461,6 +461,9 @@ __global__ void tc_keys_kernel(const float* dist, const int64_t* pos, uint64_t n
 namespace vg {
 
 static constexpr uint32_t TCI_STAGES = 4;
+static constexpr uint32_t TCI_EPI_WARPS = 8;             // two groups of four: each ranks one 128-column half of every tile
+static constexpr uint32_t TCI_HALF = TC_N / 2;
+static constexpr uint32_t TCI_THREADS = (4 + TCI_EPI_WARPS) * 32;
 static constexpr int TCI_INEL = 0x40000000;  // |x|^2 stand-in of a row that must not be returned (valid values < 2^30 for dims <= 16384)
 static constexpr uint32_t TCI_STAGE_BYTES = TCI_A_BYTES + TCI_B_BYTES;  // 48 KB
 // kind::i8 instruction descriptor: D=S32, A=B=S8, both K-major, N=256, M=128
@@ -473,10 +476,13 @@ struct TciParams {
     const int* norms;      // [rows] exact |x|^2
     const int* qnorms;     // [nq] exact |q|^2
     const uint8_t* skip;
-    uint64_t* out_keys;    // [nq][G][k]   final per-(query, CTA) results, KEY_NONE padded
-    uint64_t* buf_keys;    // [nq][G][cap] per-thread append buffers (cap: power of two >= 2k + 64)
+    uint64_t* out_keys;    // [nq][2G][k]   final per-(query, CTA, column half) results, KEY_NONE padded
+    uint64_t* buf_keys;    // [nq][2G][cap] per-thread append buffers (cap: power of two >= k + 64)
     uint32_t cap;
-    uint32_t debug;        // bit0: skip the epilogue arithmetic (pipeline-only timing experiments)
+    uint64_t tile_begin, tile_end;  // 256-row tiles this launch scans
+    uint32_t part_base, parts_total; // this launch writes parts part_base .. part_base + 2G - 1 of out_keys[q][parts_total][k]
+    const uint64_t* tau_init;        // [nq] or NULL: a key every result must beat (k-th best of an earlier launch), KEY_NONE = none
+    uint32_t debug;        // timing experiments (results invalid): 1 = no epilogue work, 2 = common path only, 4 = no norm loads
 };
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -495,31 +501,83 @@ __device__ __forceinline__ float exact_sqrt_int(int s) {
     return __double2float_rn(__dsqrt_rn((double)s));
 }
 
-// Warp-cooperative compaction of one thread's append buffer: copy its `cnt` keys (padded with KEY_NONE to `cap`)
-// into the warp's shared-memory scratch, bitonic-sort ascending, write the k smallest back to the front of the
-// buffer.  Returns (to every lane) the new k-th smallest key, or KEY_NONE when fewer than k keys exist.
-__device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint32_t cap, uint32_t k, uint64_t* scratch, int lane) {
+// Integer bound that goes with a key bound: any squared distance s beyond (next float after the key's distance)^2
+// has a strictly larger f32 distance, so it can never beat the key.
+__device__ __forceinline__ int tci_tau_s(uint64_t key) {
+    const float dr = order_bits_inv((uint32_t)(key >> 32));
+    const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
+    const double lim = dn * dn;
+    return lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
+}
+
+// Warp-cooperative compaction of one thread's append buffer (at most 256 keys): the keys are loaded 8 per lane,
+// sorted ascending across the warp with a bitonic network that lives entirely in registers (strides below 8 are
+// register-to-register compare-exchanges, larger strides are lane shuffles; the "flip" form of the network needs no
+// direction flags), and the k smallest are written back to the front of the buffer (and to `out` when given).
+// Returns (to every lane) the k-th smallest key, KEY_NONE when fewer than k keys exist.  ~1.2k instructions per
+// lane: cheap enough that a compaction no longer stalls the accumulator pipeline.
+__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
+
+__device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint32_t k, uint64_t* out, int lane) {
     __syncwarp();  // the owner lane's appends become visible to the helping lanes
-    for (uint32_t i = lane; i < cap; i += 32) scratch[i] = i < cnt ? buf[i] : KEY_NONE;
-    __syncwarp();
-    for (uint32_t size = 2; size <= cap; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll 4
-            for (uint32_t t = lane; t < cap / 2; t += 32) {
-                const uint32_t lo = 2 * t - (t & (stride - 1));
-                const uint32_t hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const uint64_t a = scratch[lo], b = scratch[hi];
-                if ((a > b) == up) {
-                    scratch[lo] = b;
-                    scratch[hi] = a;
+    uint64_t v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = (uint32_t)lane * 8 + r;
+        v[r] = i < cnt ? buf[i] : KEY_NONE;
+    }
+#pragma unroll
+    for (int size = 2; size <= 256; size <<= 1) {
+        if (size <= 8) {  // element i against i ^ (size - 1), both in this lane
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int pr = r ^ (size - 1);
+                if (pr > r) {
+                    const uint64_t a = v[r], b = v[pr];
+                    v[r] = u64min(a, b);
+                    v[pr] = u64max(a, b);
                 }
             }
-            __syncwarp();
+        } else {          // partner lane = lane ^ (size/8 - 1), partner register = 7 - r
+            const bool keep_min = (lane & (size / 16)) == 0;
+            uint64_t o[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = shfl_xor_u64(v[7 - r], size / 8 - 1);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = keep_min ? u64min(v[r], o[r]) : u64max(v[r], o[r]);
+        }
+#pragma unroll
+        for (int stride = size / 4; stride >= 1; stride >>= 1) {  // element i against i ^ stride
+            if (stride >= 8) {
+                const bool keep_min = (lane & (stride / 8)) == 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint64_t o = shfl_xor_u64(v[r], stride / 8);
+                    v[r] = keep_min ? u64min(v[r], o) : u64max(v[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if ((r & stride) == 0) {
+                        const uint64_t a = v[r], b = v[r ^ stride];
+                        v[r] = u64min(a, b);
+                        v[r ^ stride] = u64max(a, b);
+                    }
+            }
         }
     }
-    for (uint32_t i = lane; i < k; i += 32) buf[i] = scratch[i];
-    const uint64_t kth = scratch[k - 1];
+    uint64_t mine = v[0];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = (uint32_t)lane * 8 + r;
+        if (i < k) {
+            buf[i] = v[r];
+            if (out) out[i] = v[r];
+        }
+        if (((k - 1) & 7u) == (uint32_t)r) mine = v[r];
+    }
+    const uint64_t kth = shfl_u64(mine, (int)((k - 1) >> 3));
     __syncwarp();
     return kth;
 }
@@ -543,16 +601,16 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint3
                  :                                                                                                         \
                  : "memory")
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TCI_THREADS, 1)
 tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TciParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* s_colB = (int*)(smem + TCI_STAGES * TCI_STAGE_BYTES);      // [4 epilogue warps][256] |x|^2 of the current tile
-    uint64_t* s_bar = (uint64_t*)(s_colB + 4 * TC_N);
+    int* s_colB = (int*)(smem + TCI_STAGES * TCI_STAGE_BYTES);      // [8 epilogue warps][128] |x|^2 of the warp's half tile
+    uint64_t* s_bar = (uint64_t*)(s_colB + TCI_EPI_WARPS * TCI_HALF);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
-    uint64_t* s_scratch = s_bar + 32;                                // [4 epilogue warps] compaction scratch / chunk staging
-    const size_t scratch_bytes = max((size_t)p.cap * 8, (size_t)4096);
+    uint64_t* s_scratch = s_bar + 32;                                // [8 epilogue warps] staging of half a chunk (rare path)
+    const size_t scratch_bytes = 2048;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + 4), bar_tfull = smem_u32(s_bar + 8),
                    bar_tempty = smem_u32(s_bar + 10);
     if (warp == 1) {
@@ -566,7 +624,7 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, 4);
+            mbar_init(bar_tempty + 8 * a, TCI_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -575,14 +633,15 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     const uint32_t qt = blockIdx.x % p.QT, g = blockIdx.x / p.QT;
-    const uint64_t n_xt = (p.n_rows + TC_N - 1) / TC_N;
+    const uint64_t n_xt = p.tile_end - p.tile_begin;
     const uint32_t my_tiles = g < n_xt ? (uint32_t)((n_xt - g + p.G - 1) / p.G) : 0u;
+    const uint64_t tile0 = p.tile_begin + g;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
             for (uint32_t ti = 0; ti < my_tiles; ++ti) {
-                const int row0 = (int)(((uint64_t)g + (uint64_t)ti * p.G) * TC_N);
+                const int row0 = (int)((tile0 + (uint64_t)ti * p.G) * TC_N);
                 for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
                     const uint32_t s = it % TCI_STAGES, ph = (it / TCI_STAGES) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -617,39 +676,47 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
         __syncwarp();
     } else if (warp >= 4) {
-        const uint32_t ew = (uint32_t)(warp & 3);
-        const uint32_t e = threadIdx.x - 128;
-        const uint32_t lane_base = ew * 32;
+        // two epilogue groups: warps 4-7 rank columns 0..127 of every tile, warps 8-11 columns 128..255; warp w may only
+        // touch TMEM lanes 32 (w % 4) .. +31, so both groups see all 128 queries
+        const uint32_t ew = (uint32_t)(warp - 4);          // 0..7
+        const uint32_t half = ew >> 2;                     // column half of the tile
+        const uint32_t lane_base = (ew & 3) * 32;
+        const uint32_t e = lane_base + lane;               // TMEM lane == query within the tile
+        const uint32_t col0 = half * TCI_HALF;
+        const uint32_t lpart = g * 2 + half;               // this thread's partial list of its query within this launch
         const uint32_t q = qt * TC_M + e;
         const bool q_ok = q < p.nq;
         // per-thread append buffer: keys that beat the (lazily refreshed) threshold are simply appended; when a
         // buffer is nearly full the warp compacts it cooperatively and the thread's threshold tightens
-        uint64_t* buf = p.buf_keys + ((size_t)(q_ok ? q : 0) * p.G + g) * p.cap;
-        uint64_t* scratch = (uint64_t*)((uint8_t*)s_scratch + (size_t)ew * scratch_bytes);
-        int* stage = (int*)scratch;            // [32 columns][32 lanes] staging of one chunk for the rare path
-        int* my_colB = s_colB + ew * TC_N;     // this warp's copy of the tile's |x|^2 (TCI_INEL = row not eligible)
+        uint64_t* buf = p.buf_keys + ((size_t)(q_ok ? q : 0) * (p.G * 2) + lpart) * p.cap;
+        int* stage = (int*)((uint8_t*)s_scratch + (size_t)ew * scratch_bytes);  // [16 columns][32 lanes]
+        int* my_colB = s_colB + ew * TCI_HALF; // this warp's copy of its half tile's |x|^2 (TCI_INEL = row not eligible)
         const int a2 = q_ok ? p.qnorms[q] : 0;
         uint32_t cnt = 0;
         uint64_t tau_key = KEY_NONE;   // k-th best key as of the last compaction
         int tau_s = 0x7FFFFFFE;        // every s above this is certainly not better than tau_key
+        if (q_ok && p.tau_init && p.tau_init[q] != KEY_NONE) {  // k better rows are already known from a sample of the slab
+            tau_key = p.tau_init[q];
+            tau_s = tci_tau_s(tau_key);
+        }
         int tau_a = q_ok ? tau_s - a2 : (int)0x80000000;  // same bound on t = |x|^2 - 2 q.x; nothing passes for a padding query
         // |x|^2 of the next tile is fetched one tile ahead (registers), so the loads never sit in front of the MMA wait
-        int nb[TC_N / 32];
+        int nb[TCI_HALF / 32];
         auto fetch_norms = [&](uint32_t ti) {
-            const uint64_t r0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+            const uint64_t r0 = (tile0 + (uint64_t)ti * p.G) * TC_N + col0;
 #pragma unroll
-            for (int i = 0; i < TC_N / 32; ++i) {
+            for (int i = 0; i < (int)TCI_HALF / 32; ++i) {
                 const uint64_t row = r0 + (uint64_t)(i * 32 + lane);
                 const bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
-                nb[i] = ok ? p.norms[row] : TCI_INEL;
+                nb[i] = (p.debug & 4) ? 1 : ok ? p.norms[row] : TCI_INEL;
             }
         };
         if (my_tiles) fetch_norms(0);
         for (uint32_t ti = 0; ti < my_tiles; ++ti) {
             const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-            const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+            const uint64_t row0 = (tile0 + (uint64_t)ti * p.G) * TC_N + col0;
 #pragma unroll
-            for (int i = 0; i < TC_N / 32; ++i) my_colB[i * 32 + lane] = nb[i];
+            for (int i = 0; i < (int)TCI_HALF / 32; ++i) my_colB[i * 32 + lane] = nb[i];
             __syncwarp();
             if (ti + 1 < my_tiles) fetch_norms(ti + 1);
             mbar_wait(bar_tfull + 8 * acc, aph);
@@ -671,23 +738,29 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) mask |= (tv[j] <= tau_a ? 1u : 0u) << j;
+                if (p.debug & 2) mask = mask == 0x12345678u ? 1u : 0u;  // timing experiments: common path only
                 // rare path (warp-uniform entry): the chunk is staged in shared memory so that the few passing columns
                 // can be picked by index in a compact loop; the exact key is (float)sqrt((double)s)
-                if (__any_sync(0xffffffffu, mask != 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stage[j * 32 + lane] = tv[j];
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int s = a2 + stage[j * 32 + lane];
-                        if (my_colB[c * 32 + j] < TCI_INEL) {
-                            // src/distance/scalar.rs:65: f64 sqrt, then cast — the same final value as the scan
-                            const float d = exact_sqrt_int(s);
-                            const uint64_t key = make_key(d, (uint32_t)(row0 + c * 32 + j));
-                            if (key < tau_key) buf[cnt++] = key;
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t m16 = (mask >> (16 * hh)) & 0xFFFFu;
+                    if (__any_sync(0xffffffffu, m16 != 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) stage[j * 32 + lane] = tv[16 * hh + j];
+                        while (m16) {
+                            const int j = __ffs(m16) - 1;
+                            m16 &= m16 - 1;
+                            const int s = a2 + stage[j * 32 + lane];
+                            const uint32_t col = c * 32 + 16 * hh + (uint32_t)j;
+                            if (my_colB[col] < TCI_INEL) {
+                                // src/distance/scalar.rs:65: f64 sqrt, then cast — the same final value as the scan
+                                const float d = exact_sqrt_int(s);
+                                const uint64_t key = make_key(d, (uint32_t)(row0 + col));
+                                if (key < tau_key) buf[cnt++] = key;
+                            }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 // a buffer that could overflow during the next 32 columns is compacted now (warp-uniform loop)
                 unsigned need = __ballot_sync(0xffffffffu, cnt + 32 > p.cap);
@@ -696,16 +769,12 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     need &= need - 1;
                     const uint64_t bp = shfl_u64((uint64_t)(uintptr_t)buf, src);
                     const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
-                    const uint64_t kth = warp_compact((uint64_t*)(uintptr_t)bp, bc, p.cap, p.k, scratch, lane);
+                    const uint64_t kth = warp_compact((uint64_t*)(uintptr_t)bp, bc, p.k, nullptr, lane);
                     if (lane == src) {
                         cnt = min(bc, p.k);
                         tau_key = kth;
                         if (kth != KEY_NONE) {
-                            // any s beyond (next float after the k-th distance)^2 has a strictly larger f32 distance
-                            const float dr = order_bits_inv((uint32_t)(kth >> 32));
-                            const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
-                            const double lim = dn * dn;
-                            tau_s = lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
+                            tau_s = tci_tau_s(kth);
                             tau_a = tau_s - a2;
                         }
                     }
@@ -713,15 +782,15 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         };
             if (!(p.debug & 1)) {
                 uint32_t va[32], vb[32];
-                const uint32_t tbase = tmem_base + (lane_base << 16) + acc * TC_N;
+                const uint32_t tbase = tmem_base + (lane_base << 16) + acc * TC_N + col0;
                 TCI_LD32(va, tbase);
 #pragma unroll 1
-                for (uint32_t c = 0; c < TC_N / 32; c += 2) {
+                for (uint32_t c = 0; c < TCI_HALF / 32; c += 2) {
                     TCI_WAIT32(va);
                     TCI_LD32(vb, tbase + (c + 1) * 32);
                     process(va, c);
                     TCI_WAIT32(vb);
-                    if (c + 2 < TC_N / 32) TCI_LD32(va, tbase + (c + 2) * 32);
+                    if (c + 2 < TCI_HALF / 32) TCI_LD32(va, tbase + (c + 2) * 32);
                     process(vb, c + 1);
                 }
             }
@@ -735,15 +804,24 @@ tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
             const uint32_t qs = __shfl_sync(0xffffffffu, q, src);
             if (qs >= p.nq) continue;  // warp-uniform
-            warp_compact((uint64_t*)(uintptr_t)bp, bc, p.cap, p.k, scratch, lane);
-            uint64_t* out = p.out_keys + ((size_t)qs * p.G + g) * p.k;
-            for (uint32_t i = lane; i < p.k; i += 32) out[i] = scratch[i];
-            __syncwarp();
+            warp_compact((uint64_t*)(uintptr_t)bp, bc, p.k, p.out_keys + ((size_t)qs * p.parts_total + p.part_base + lpart) * p.k, lane);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// k-th smallest key per query over the partial lists of a sample launch -> the admission bound of the main launch
+__global__ void __launch_bounds__(1024) tci8_tau_kernel(const uint64_t* keys, uint32_t n_keys, uint64_t q_stride, uint32_t k, uint32_t np2,
+                                                        uint64_t* tau) {
+    extern __shared__ __align__(16) uint8_t tau_smem[];
+    uint64_t* sk = (uint64_t*)tau_smem;
+    const uint64_t* src = keys + (uint64_t)blockIdx.x * q_stride;
+    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) sk[i] = i < n_keys ? src[i] : KEY_NONE;
+    __syncthreads();
+    block_bitonic_sort(sk, np2);
+    if (threadIdx.x == 0) tau[blockIdx.x] = sk[k - 1];
 }
 
 // exact |row|^2 of int8 rows (int32)

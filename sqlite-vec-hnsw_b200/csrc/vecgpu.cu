@@ -1052,7 +1052,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
 static bool tci8_eligible(const vecgpu_slab* s, uint32_t nq, uint32_t k, int metric) {
     if (env_u32("VECGPU_TC", 1) == 0) return false;
     return s->elem == VECGPU_I8 && metric == VECGPU_L2 && nq >= env_u32("VECGPU_TC_MIN_NQ", 16) && s->rows >= 8192 &&
-           s->rows < 0x7FFFFFFFull && k <= 224 && s->dims >= 16 && s->dims <= 16384;
+           s->rows < 0x7FFFFFFFull && k <= 192 && s->dims >= 16 && s->dims <= 16384;
 }
 
 // int8 L2 batches: exact on the tensor cores (tci8_scan_kernel) + the ordinary final merge
@@ -1064,10 +1064,12 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
     static int cfg_dev = -1;
     int dev = 0;
     CU(cudaGetDevice(&dev));
-    const uint32_t cap = std::max(128u, next_pow2(2 * k + 64));  // per-thread append buffer; k <= 224 -> cap <= 512
-    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + 4 * TC_N * 4 + 32 * 8 + 4 * std::max((size_t)cap * 8, (size_t)4096) + 1024;
+    const uint32_t cap = std::max(128u, next_pow2(k + 64));  // per-thread append buffer; k <= 192 -> cap <= 256
+    const size_t smem = TCI_STAGES * TCI_STAGE_BYTES + TCI_EPI_WARPS * TCI_HALF * 4 + 32 * 8 +
+                        TCI_EPI_WARPS * (size_t)2048 + 1024;
     if (cfg_dev != dev) {
         CU(cudaFuncSetAttribute(tci8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        CU(cudaFuncSetAttribute(tci8_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         cfg_dev = dev;
     }
     const uint64_t n_xt = (s->rows + TC_N - 1) / TC_N;
@@ -1079,10 +1081,18 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
         const uint8_t* dq = d_q + (size_t)qoff * s->row_stride;
         const uint32_t QT = (nq + TC_M - 1) / TC_M;
         uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms / QT, n_xt));
-        while (G > 1 && (uint64_t)G * k > 16384) --G;  // keep the final merge in one CTA's shared memory
-        if ((rc = ws_reserve(s, WS_PART, (size_t)nq * G * k * 8))) return rc;
-        if ((rc = ws_reserve(s, WS_TC_KEYS, (size_t)nq * G * cap * 8))) return rc;
+        while (G > 1 && (uint64_t)2 * G * k > 16384) --G;  // keep the final merge in one CTA's shared memory
+        // Thresholds from a sample: a first launch ranks a small prefix of the slab, the k-th best key of every query then
+        // bounds the main launch from its first tile on (instead of each thread rediscovering it on its 1/2G of the rows)
+        uint64_t samp_tiles = std::max<uint64_t>(n_xt / 32, std::min<uint64_t>(n_xt / 8, 1024));  // ~3 % of the slab, at least 256 k rows
+        if (const char* e = getenv("VECGPU_TCI_SAMPLE")) samp_tiles = std::min<uint64_t>(n_xt / 2, (uint64_t)atoll(e));
+        const bool sample = samp_tiles >= 2ull * G && (uint64_t)4 * G * k <= 16384;
+        if (!sample) samp_tiles = 0;
+        const uint32_t parts = sample ? 4 * G : 2 * G;
+        if ((rc = ws_reserve(s, WS_PART, (size_t)nq * parts * k * 8))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_KEYS, (size_t)nq * 2 * G * cap * 8))) return rc;
         if ((rc = ws_reserve(s, WS_TC_QNORM, (size_t)nq * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_TC_TAU, (size_t)nq * 8))) return rc;
         row_norms_i8_kernel<<<std::max(1u, std::min((nq + 63) / 64, 1024u)), 256, 0, st>>>(dq, s->row_stride, s->row_stride / 16, nq,
                                                                                            (int*)s->d_ws[WS_TC_QNORM]);
         LAUNCHED();
@@ -1101,13 +1111,30 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
         tp.out_keys = (uint64_t*)s->d_ws[WS_PART];
         tp.buf_keys = (uint64_t*)s->d_ws[WS_TC_KEYS];
         tp.cap = cap;
+        tp.parts_total = parts;
         tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
-        tci8_scan_kernel<<<QT * G, 256, smem, st>>>(mapQ, mapX, tp);
+        if (sample) {
+            tp.tile_begin = 0;
+            tp.tile_end = samp_tiles;
+            tp.part_base = 0;
+            tp.tau_init = nullptr;
+            tci8_scan_kernel<<<QT * G, TCI_THREADS, smem, st>>>(mapQ, mapX, tp);
+            LAUNCHED();
+            const uint32_t n_keys = 2 * G * k, np2 = std::max(2u, next_pow2(n_keys));
+            tci8_tau_kernel<<<nq, std::min(1024u, std::max(32u, np2 / 2)), (size_t)np2 * 8, st>>>(tp.out_keys, n_keys, (uint64_t)parts * k, k, np2,
+                                                                                                  (uint64_t*)s->d_ws[WS_TC_TAU]);
+            LAUNCHED();
+        }
+        tp.tile_begin = samp_tiles;
+        tp.tile_end = n_xt;
+        tp.part_base = sample ? 2 * G : 0;
+        tp.tau_init = sample ? (const uint64_t*)s->d_ws[WS_TC_TAU] : nullptr;
+        tci8_scan_kernel<<<QT * G, TCI_THREADS, smem, st>>>(mapQ, mapX, tp);
         LAUNCHED();
         g_tc_queries.fetch_add(nq, std::memory_order_relaxed);
         MergeParams mp{};
         mp.keys = tp.out_keys;
-        mp.n_cand = (uint64_t)G * k;
+        mp.n_cand = (uint64_t)parts * k;
         mp.k = k;
         mp.kp2 = next_pow2(k);
         mp.rowids = s->dense ? nullptr : s->d_rowids;

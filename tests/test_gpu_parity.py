@@ -811,6 +811,33 @@ def test_tc_int8_batched_matches_oracle(vg, orc, gpu, dims, nq, k):
     assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed)) and np.array_equal(c, ec)
 
 
+@pytest.mark.parametrize("sample_tiles", ["0", "40"])
+@pytest.mark.parametrize("ties", [False, True])
+def test_tc_int8_sampled_thresholds_are_exact(vg, orc, gpu, sample_tiles, ties):
+    # nq = 1024 -> 8 query tiles, 18 row groups: the launch that ranks a prefix of the slab first and hands its k-th
+    # key to the main launch as the admission bound (VECGPU_TCI_SAMPLE forces / disables it) must not change any result;
+    # with ties the bound is hit by equal distances all the time
+    n, dims, nq, k = 30000, 64, 1024, 100
+    v = random_rows(I8, n, dims, seed=81, ties=ties)
+    q = random_rows(I8, nq, dims, seed=82, ties=ties)
+    rowids = np.arange(n, dtype="<i8") * 2 + 7
+    skip = np.zeros(n, dtype="u1")
+    skip[[3, 5000, 9999, n - 2]] = 1   # skipped rows inside the sampled prefix and outside it
+    os.environ["VECGPU_TCI_SAMPLE"] = sample_tiles
+    try:
+        with vg.Slab(I8, dims) as s:
+            s.load(v, rowids)
+            for i in np.flatnonzero(skip):
+                s.delete(int(rowids[i]))
+            before = vg.tc_stats()
+            r, d, c = s.knn(q, k, L2)
+            assert vg.tc_stats()[0] - before[0] == nq
+    finally:
+        del os.environ["VECGPU_TCI_SAMPLE"]
+    er, ed, ec = orc.knn(I8, dims, v, q, k, L2, rowids=rowids, skip=skip)
+    assert np.array_equal(r, er) and np.array_equal(bits(d), bits(ed)) and np.array_equal(c, ec)
+
+
 def test_tc_int8_batched_heavy_ties_and_extremes(vg, orc, gpu):
     # tiny alphabet: thousands of equal distances, the rowid tie-break decides every rank; plus +-128/127 rows
     n, dims, nq, k = 20000, 64, 32, 50
