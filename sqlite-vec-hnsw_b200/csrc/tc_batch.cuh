@@ -54,6 +54,7 @@ struct TcParams {
     uint32_t nq, nk;       // queries, k-chunks (ceil(dims/32); TMA zero-fills the ragged tail)
     uint32_t kp;           // entries kept per (CTA, query) = k + margin
     uint32_t cosine;       // 0: L2 (v = x2 - 2s), 1: cosine (v = -s / |x|)
+    uint32_t terms;        // 3: 3xTF32 (hi.hi + lo.hi + hi.lo), 1: one TF32 pass (wider certified bound)
     uint32_t lists_smem;   // 1: the kept scores live in shared memory ([kp][128] floats) during the scan
     uint32_t debug;        // timing experiments (results invalid): 1 = no epilogue work, 2 = common path only, 4 = no norm loads
     uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
@@ -139,15 +140,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
     float* s_lists = (float*)(s_bar + 32);  // [kp][128] when p.lists_smem
-    const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + TC_STAGES), bar_empty = smem_u32(s_bar + 2 * TC_STAGES),
-                   bar_tfull = smem_u32(s_bar + 3 * TC_STAGES), bar_tempty = smem_u32(s_bar + 3 * TC_STAGES + 2);
+    // terms == 3: two 96 KB stages [A_raw | A_lo | B_raw | B_lo]; terms == 1: four 48 KB stages [A | B], no lo-split
+    const uint32_t n_stages = p.terms == 1 ? 2 * TC_STAGES : TC_STAGES;
+    const uint32_t stage_bytes = p.terms == 1 ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
+    const uint32_t b_off = p.terms == 1 ? TC_A_BYTES : 2 * TC_A_BYTES;
+    const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + n_stages), bar_empty = smem_u32(s_bar + 2 * n_stages),
+                   bar_tfull = smem_u32(s_bar + 3 * n_stages), bar_tempty = smem_u32(s_bar + 3 * n_stages + 2);
 
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < TC_STAGES; ++s) {
+        for (uint32_t s = 0; s < n_stages; ++s) {
             mbar_init(bar_full_raw + 8 * s, 1);
             mbar_init(bar_full_lo + 8 * s, TC_XFORM_THREADS / 32);   // one arrival per transform warp
             mbar_init(bar_empty + 8 * s, 1);     // tcgen05.commit
@@ -174,12 +179,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             for (uint32_t ti = 0; ti < my_tiles; ++ti) {
                 const int row0 = (int)(((uint64_t)g + (uint64_t)ti * p.G) * TC_N);
                 for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
-                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                    const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    const uint32_t base = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint32_t base = smem_u32(smem + s * stage_bytes);
                     mbar_expect_tx(bar_full_raw + 8 * s, TC_A_BYTES + TC_B_BYTES);
                     tma_load_2d(base, &mapQ, (int)(kc * TC_KC), (int)(qt * TC_M), bar_full_raw + 8 * s);
-                    tma_load_2d(base + 2 * TC_A_BYTES, &mapX, (int)(kc * TC_KC), row0, bar_full_raw + 8 * s);
+                    tma_load_2d(base + b_off, &mapX, (int)(kc * TC_KC), row0, bar_full_raw + 8 * s);
                 }
             }
         }
@@ -189,7 +194,27 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         // The hi.hi MMAs of a chunk only need the TMA data, the two lo terms also need the lo-split.  While the issuer
         // waits for the lo-split of chunk `it` it opportunistically issues hi.hi of chunk it+1 as soon as that chunk's
         // data has landed (non-blocking probes), so the tensor pipe has work during the transform.
-        if (lane == 0) {
+        if (lane == 0 && p.terms == 1) {
+            // single TF32 pass: the operands are used as they are (the tensor core truncates them to TF32); the wider
+            // error bound is paid for by a slightly larger certified candidate set, not by two more MMAs
+            uint32_t it = 0;
+            for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+                const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_N;
+                for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                    const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+                    const uint32_t a = smem_u32(smem + s * stage_bytes), b = a + b_off;
+                    mbar_wait(bar_full_raw + 8 * s, ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (uint32_t k = 0; k < TC_KSTEPS; ++k) umma_tf32(d_tmem, umma_desc(a + k * 32), umma_desc(b + k * 32), (kc | k) != 0);
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_tfull + 8 * acc);
+            }
+        } else if (lane == 0) {
             const uint32_t total = my_tiles * p.nk;
             uint32_t next_hihi = 0;  // first chunk whose hi.hi MMAs have not been issued yet
             auto hihi_ready = [&](uint32_t it) {
@@ -240,7 +265,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         // ===== transform warps: lo = x - trunc_tf32(x), same (swizzled) positions in the twin tile =====
         const uint32_t t = threadIdx.x - 256;  // 0..TC_XFORM_THREADS-1
         uint32_t it = 0;
-        for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+        for (uint32_t ti = 0; ti < (p.terms == 1 ? 0u : my_tiles); ++ti) {
             for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
                 const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                 const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), b_raw = a_raw + 2 * TC_A_BYTES;
@@ -410,7 +435,9 @@ __global__ void __launch_bounds__(512) tc_collect_kernel(const TcCollectParams c
     const uint32_t total = s_total;
     // error bound of the approximate score (worst case over D fp32 accumulations of 3xTF32 partial products)
     const float q2 = c.qnorm[q], x2max = __uint_as_float(*c.x2max_bits);
-    const float unit = (float)(c.dims + 32) * 4.76837158e-7f;  // (D+32) * 2^-21
+    // (D+32) * 2^-21 covers the fp32 accumulation of the partial products; a single TF32 pass adds the truncation of both
+    // operands to 10 mantissa bits: |q.x - tf32(q).tf32(x)| <= (2^-10 + 2^-10) |q||x| by Cauchy-Schwarz (+1 % slack)
+    const float unit = (float)(c.dims + 32) * 4.76837158e-7f + (p.terms == 1 ? 1.97265625e-3f : 0.f);
     const float eps = p.cosine ? unit * sqrtf(q2) : unit * (q2 + x2max);
     float bound = __int_as_float(0x7F800000);
     if (total >= c.k) bound = order_bits_inv((uint32_t)(keys[c.k - 1] >> 32)) + 2.f * eps;

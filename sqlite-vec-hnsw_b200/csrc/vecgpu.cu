@@ -976,6 +976,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         tp.nk = (s->dims + TC_KC - 1) / TC_KC;
         tp.kp = kp;
         tp.cosine = metric == VECGPU_COSINE ? 1u : 0u;
+        tp.terms = env_u32("VECGPU_TC_TERMS", 1) == 3 ? 3u : 1u;  // 1: one TF32 pass + wider certified bound (default); 3: 3xTF32
         tp.lists_smem = lists_smem ? 1u : 0u;
         tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
         tp.QT = QT;

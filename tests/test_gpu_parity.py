@@ -465,10 +465,22 @@ def test_scan_repeat_launch_stress(vg, gpu):
             assert torch.equal(r, r0) and torch.equal(d, d0)
 
 
-# ------------------------------------------------------------------ K2: tensor-core batched path (tcgen05 3xTF32 + exact re-rank)
+# ------------------------------------------------------------------ K2: tensor-core batched path (tcgen05 TF32 candidate pass + exact re-rank)
+@pytest.fixture(params=["1", "3"], ids=["tf32x1", "tf32x3"])
+def tc_terms(request):
+    """Both candidate passes: one TF32 MMA per product (default, wider certified bound) and 3xTF32."""
+    old = os.environ.get("VECGPU_TC_TERMS")
+    os.environ["VECGPU_TC_TERMS"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("VECGPU_TC_TERMS", None)
+    else:
+        os.environ["VECGPU_TC_TERMS"] = old
+
+
 @pytest.mark.parametrize("metric", [L2, COSINE], ids=["l2", "cos"])
 @pytest.mark.parametrize("dims,nq,k", [(96, 16, 10), (768, 130, 10), (100, 33, 5), (384, 257, 32), (64, 40, 96), (17, 20, 3)])
-def test_tc_batched_matches_oracle(vg, orc, gpu, metric, dims, nq, k):
+def test_tc_batched_matches_oracle(vg, orc, gpu, tc_terms, metric, dims, nq, k):
     n = 30000
     kind = 1 if metric == COSINE else 0
     with vg.Slab(F32, dims) as s:
@@ -483,7 +495,7 @@ def test_tc_batched_matches_oracle(vg, orc, gpu, metric, dims, nq, k):
     assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
 
 
-def test_tc_batched_ties_fall_back_to_exact(vg, orc, gpu):
+def test_tc_batched_ties_fall_back_to_exact(vg, orc, gpu, tc_terms):
     # a tiny alphabet makes thousands of rows tie at the k-th distance: the candidate bound cannot be
     # certified, the affected queries must be re-run by the exact scan and still match bit for bit
     n, dims, nq, k = 20000, 32, 24, 10
@@ -500,7 +512,7 @@ def test_tc_batched_ties_fall_back_to_exact(vg, orc, gpu):
     assert after[0] - before[0] == 2 * nq
 
 
-def test_tc_batched_skips_and_sparse_rowids(vg, orc, gpu):
+def test_tc_batched_skips_and_sparse_rowids(vg, orc, gpu, tc_terms):
     n, dims, nq, k = 25000, 48, 64, 12
     v = random_rows(F32, n, dims, seed=41)
     q = random_rows(F32, nq, dims, seed=42)
@@ -524,7 +536,7 @@ def test_tc_batched_skips_and_sparse_rowids(vg, orc, gpu):
         assert np.array_equal(r, er) and same_bits(d, ed) and r[20, 0] == rowids[200] and d[20, 0] == 0.0
 
 
-def test_tc_batched_special_values(vg, orc, gpu):
+def test_tc_batched_special_values(vg, orc, gpu, tc_terms):
     n, dims, nq, k = 16384, 40, 20, 10
     v = random_rows(F32, n, dims, seed=51)
     v[7] = 0
