@@ -102,7 +102,7 @@ struct vecgpu_slab {
 
 enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7,
        WS_TC_CANDV = 8, WS_TC_CANDR = 9, WS_TC_CNT = 10, WS_TC_TAU = 11, WS_TC_PAIRQ = 12, WS_TC_PAIRPOS = 13, WS_TC_DIST = 14,
-       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_COUNT = 20 };
+       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_COUNT = 20 };
 
 static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
     if (bytes <= s->ws_cap[i]) return 0;
@@ -987,6 +987,13 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         tp.cand_r = (uint32_t*)s->d_ws[WS_TC_CANDR];
         tp.cand_cnt = (uint32_t*)s->d_ws[WS_TC_CNT];
         tp.cand_tau = (float*)s->d_ws[WS_TC_TAU];
+        tp.lockstep = nullptr;
+        if (QT > 1 && QT <= 32 && env_u32("VECGPU_TC_LOCKSTEP", 1)) {  // the QT CTAs of a row group stream their tiles together
+            if ((rc = ws_reserve(s, WS_TC_LOCK, (size_t)G * 32 * 4))) return rc;
+            CU(cudaMemsetAsync(s->d_ws[WS_TC_LOCK], 0, (size_t)G * 32 * 4, st));
+            tp.lockstep = (uint32_t*)s->d_ws[WS_TC_LOCK];
+            tp.lock_slack = env_u32("VECGPU_TC_LOCKSLACK", 0);
+        }
         tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(mapQ, mapX, tp);
         LAUNCHED();
 
@@ -1114,7 +1121,13 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
         tp.cap = cap;
         tp.parts_total = parts;
         tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
+        // measured: with 5 us int8 tiles the coupling costs more than the L2 misses it saves (off by default, VECGPU_TCI_LOCKSTEP=1 enables)
+        const bool lockstep = QT > 1 && QT <= 32 && env_u32("VECGPU_TCI_LOCKSTEP", 0);
+        if (lockstep && (rc = ws_reserve(s, WS_TC_LOCK, (size_t)G * 32 * 4))) return rc;
+        tp.lockstep = lockstep ? (uint32_t*)s->d_ws[WS_TC_LOCK] : nullptr;
+        tp.lock_slack = env_u32("VECGPU_TC_LOCKSLACK", 1);
         if (sample) {
+            if (lockstep) CU(cudaMemsetAsync(s->d_ws[WS_TC_LOCK], 0, (size_t)G * 32 * 4, st));
             tp.tile_begin = 0;
             tp.tile_end = samp_tiles;
             tp.part_base = 0;
@@ -1130,6 +1143,7 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
         tp.tile_end = n_xt;
         tp.part_base = sample ? 2 * G : 0;
         tp.tau_init = sample ? (const uint64_t*)s->d_ws[WS_TC_TAU] : nullptr;
+        if (lockstep) CU(cudaMemsetAsync(s->d_ws[WS_TC_LOCK], 0, (size_t)G * 32 * 4, st));
         tci8_scan_kernel<<<QT * G, TCI_THREADS, smem, st>>>(mapQ, mapX, tp);
         LAUNCHED();
         g_tc_queries.fetch_add(nq, std::memory_order_relaxed);
