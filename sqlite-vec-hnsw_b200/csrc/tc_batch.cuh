@@ -60,6 +60,7 @@ struct TcParams {
     uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
     uint32_t* lockstep;    // [G][32] tile counters of the query-tile CTAs of each row group (zeroed before the launch), or NULL
     uint32_t lock_slack;   // how many tiles a peer may be behind
+    uint32_t cs;           // cluster size (1, 2, 4, 8; divides QT): the CTAs of a cluster share every row tile through TMA multicast
     const float* norms;    // [rows] canonical sum of squares of each slab row
     const uint8_t* skip;   // per-row skip flags or nullptr
     float* cand_v;         // [grid][128][kp] approximate scores kept
@@ -90,6 +91,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// cluster variants: a row-tile slice is loaded once and written into the same shared-memory offset of every CTA in `mask`
+// (each destination's mbarrier at the same offset receives the bytes); the commit arrives on the barrier of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// mbarrier wait that traps instead of spinning forever (a protocol bug must not hang the GPU)
+__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; spins < (1u << 28); ++spins)
+        if (mbar_test(bar, parity)) return;
+    __trap();
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,7 +196,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         for (uint32_t s = 0; s < n_stages; ++s) {
             mbar_init(bar_full_raw + 8 * s, 1);
             mbar_init(bar_full_lo + 8 * s, TC_XFORM_THREADS / 32);   // one arrival per transform warp
-            mbar_init(bar_empty + 8 * s, 1);     // tcgen05.commit
+            mbar_init(bar_empty + 8 * s, p.cs);  // tcgen05.commit of every CTA that receives the multicast row tiles
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);     // tcgen05.commit
@@ -185,7 +207,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cs > 1) cluster_sync_all();  // every CTA's barriers exist before the first multicast can land
     const uint32_t tmem_base = *s_tmem;
+    const uint32_t crank = blockIdx.x % p.cs;                    // rank in the cluster (consecutive query tiles of one row group)
+    const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+    const uint32_t slice_rows = TC_N / p.cs;                     // rows of every tile this CTA fetches for the whole cluster
 
     const uint32_t qt = blockIdx.x % p.QT, g = blockIdx.x / p.QT;
     const uint64_t n_xt = (p.n_rows + TC_N - 1) / TC_N;
@@ -201,11 +227,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 const int row0 = (int)(((uint64_t)g + (uint64_t)ti * p.G) * TC_N);
                 for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_wait_b(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t base = smem_u32(smem + s * stage_bytes);
                     mbar_expect_tx(bar_full_raw + 8 * s, TC_A_BYTES + TC_B_BYTES);
                     tma_load_2d(base, &mapQ, (int)(kc * TC_KC), (int)(qt * TC_M), bar_full_raw + 8 * s);
-                    tma_load_2d(base + b_off, &mapX, (int)(kc * TC_KC), row0, bar_full_raw + 8 * s);
+                    if (p.cs > 1)
+                        tma_load_2d_mc(base + b_off + crank * slice_rows * TC_ROW_BYTES, &mapX, (int)(kc * TC_KC),
+                                       row0 + (int)(crank * slice_rows), bar_full_raw + 8 * s, cmask);
+                    else
+                        tma_load_2d(base + b_off, &mapX, (int)(kc * TC_KC), row0, bar_full_raw + 8 * s);
                 }
             }
             __syncwarp();
@@ -221,17 +251,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             uint32_t it = 0;
             for (uint32_t ti = 0; ti < my_tiles; ++ti) {
                 const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+                mbar_wait_b(bar_tempty + 8 * acc, aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TC_N;
                 for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                     const uint32_t a = smem_u32(smem + s * stage_bytes), b = a + b_off;
-                    mbar_wait(bar_full_raw + 8 * s, ph);
+                    mbar_wait_b(bar_full_raw + 8 * s, ph);
                     tc_fence_after();
 #pragma unroll
                     for (uint32_t k = 0; k < TC_KSTEPS; ++k) umma_tf32(d_tmem, umma_desc(a + k * 32), umma_desc(b + k * 32), (kc | k) != 0);
-                    umma_commit(bar_empty + 8 * s);
+                    if (p.cs > 1) umma_commit_mc(bar_empty + 8 * s, cmask);
+                    else umma_commit(bar_empty + 8 * s);
                 }
                 umma_commit(bar_tfull + 8 * acc);
             }
@@ -246,9 +277,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             auto issue_hihi = [&](uint32_t it) {  // blocking
                 const uint32_t ti = it / p.nk, kc = it - ti * p.nk;
                 const uint32_t acc = ti & 1, s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-                if (kc == 0) mbar_wait(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                if (kc == 0) mbar_wait_b(bar_tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), b_raw = a_raw + 2 * TC_A_BYTES;
-                mbar_wait(bar_full_raw + 8 * s, ph);
+                mbar_wait_b(bar_full_raw + 8 * s, ph);
                 tc_fence_after();
 #pragma unroll
                 for (uint32_t k = 0; k < TC_KSTEPS; ++k)
@@ -277,7 +308,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
                 for (uint32_t k = 0; k < TC_KSTEPS; ++k)  // hi_q.lo_x
                     umma_tf32(d_tmem, umma_desc(a_raw + k * 32), umma_desc(b_lo + k * 32), 1);
-                umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs have read it
+                if (p.cs > 1) umma_commit_mc(bar_empty + 8 * s, cmask);  // stage reusable once these MMAs have read it
+                else umma_commit(bar_empty + 8 * s);
                 if (kc == p.nk - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
             }
         }
@@ -290,7 +322,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
                 const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                 const uint32_t a_raw = smem_u32(smem + s * TC_STAGE_BYTES), b_raw = a_raw + 2 * TC_A_BYTES;
-                mbar_wait(bar_full_raw + 8 * s, ph);
+                mbar_wait_b(bar_full_raw + 8 * s, ph);
 #pragma unroll 4
                 for (uint32_t u = t; u < TC_A_BYTES / 16; u += TC_XFORM_THREADS) {
                     uint4 v = lds128(a_raw + u * 16);
@@ -342,7 +374,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 s_colB[acc * TC_N + j] = b;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-            mbar_wait(bar_tfull + 8 * acc, aph);
+            mbar_wait_b(bar_tfull + 8 * acc, aph);
             tc_fence_after();
 #pragma unroll 1
             for (uint32_t c = 0; c < ((p.debug & 1) ? 0u : TC_N / 32); ++c) {
@@ -390,6 +422,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cs > 1) cluster_sync_all();  // peers may still arrive on this CTA's barriers until they are done too
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 

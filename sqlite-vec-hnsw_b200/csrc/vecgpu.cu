@@ -949,6 +949,36 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         const uint8_t* dq = d_q + (size_t)qoff * s->row_stride;
         const uint32_t QT = (nq + TC_M - 1) / TC_M;
         uint32_t G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms / QT, n_xt));
+        // thread-block clusters: the CTAs of consecutive query tiles share every row tile through TMA multicast (each loads
+        // 1/cs of it for all), so the slab crosses L2 -> SM once per cluster instead of once per query tile
+        uint32_t cs = 1;
+        {
+            // measured on 1024 x 10 M x 768: 31.8 / 30.8 / 31.2 / 30.9 ms at cs = 8 / 4 / 2 / 1 (with the soft lockstep at cs = 1):
+            // the single-pass kernel is bound by the depth of its 4 x 48 KB operand pipeline, not by L2 traffic, so clusters
+            // are off by default (VECGPU_TC_CLUSTER = 2, 4, 8 enables them)
+            const uint32_t want = std::min(8u, env_u32("VECGPU_TC_CLUSTER", 1));
+            while (cs * 2 <= want && QT % (cs * 2) == 0) cs *= 2;
+        }
+        if (cs > 1) {
+            cudaLaunchConfig_t occ{};
+            occ.gridDim = dim3(QT * G);
+            occ.blockDim = dim3(TC_THREADS);
+            occ.dynamicSmemBytes = smem;
+            cudaLaunchAttribute oa{};
+            oa.id = cudaLaunchAttributeClusterDimension;
+            oa.val.clusterDim.x = cs;
+            oa.val.clusterDim.y = oa.val.clusterDim.z = 1;
+            occ.attrs = &oa;
+            occ.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_scan_kernel, &occ) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                cs = 1;
+            } else {
+                // all clusters must be co-resident (one wave): fewer row groups when the GPCs cannot hold QT*G/cs clusters
+                G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(G, (uint64_t)max_clusters * cs / QT));
+            }
+        }
         while (G > 1 && next_pow2(G * kp + TC_MAX_UNSAFE) > 8192) --G;
         const uint32_t cap = std::max(2u, next_pow2(G * kp + TC_MAX_UNSAFE));
         const uint32_t grid = QT * G;
@@ -994,7 +1024,26 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             tp.lockstep = (uint32_t*)s->d_ws[WS_TC_LOCK];
             tp.lock_slack = env_u32("VECGPU_TC_LOCKSLACK", 0);
         }
-        tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(mapQ, mapX, tp);
+        tp.cs = cs;
+        if (cs > 1) {
+            CUtensorMap mapXs;  // row-tile slices of TC_N / cs rows
+            if ((rc = make_f32_map(&mapXs, s->d_vec, s->dims, s->rows, s->row_stride, TC_N / cs))) return rc;
+            if (cs == QT) tp.lockstep = nullptr;  // the shared stages already keep the whole row group together
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3(grid);
+            lc.blockDim = dim3(TC_THREADS);
+            lc.dynamicSmemBytes = smem;
+            lc.stream = st;
+            cudaLaunchAttribute la{};
+            la.id = cudaLaunchAttributeClusterDimension;
+            la.val.clusterDim.x = cs;
+            la.val.clusterDim.y = la.val.clusterDim.z = 1;
+            lc.attrs = &la;
+            lc.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&lc, tc_scan_kernel, mapQ, mapXs, tp));
+        } else {
+            tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(mapQ, mapX, tp);
+        }
         LAUNCHED();
 
         TcCollectParams cp{};

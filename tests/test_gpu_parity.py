@@ -495,6 +495,27 @@ def test_tc_batched_matches_oracle(vg, orc, gpu, tc_terms, metric, dims, nq, k):
     assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
 
 
+@pytest.mark.parametrize("cluster,nq", [("8", 1024), ("4", 512), ("2", 260), ("8", 1500)])
+def test_tc_batched_cluster_multicast_matches_oracle(vg, orc, gpu, tc_terms, cluster, nq):
+    # thread-block clusters: the CTAs of consecutive query tiles receive every row tile through TMA multicast
+    # (VECGPU_TC_CLUSTER; 1500 queries = 12 query tiles -> clusters of 4)
+    n, dims, k = 30000, 72, 10
+    os.environ["VECGPU_TC_CLUSTER"] = cluster
+    try:
+        with vg.Slab(F32, dims) as s:
+            s.fill_synthetic(seed=23, n=n, kind=1)
+            cpu = orc.synth_rows(F32, 23, 1, n, dims, 1)
+            q = orc.synth_rows(F32, 24, 1, nq, dims, 1)
+            before = vg.tc_stats()
+            for metric in (L2, COSINE):
+                r, d, c = s.knn(q, k, metric)
+                er, ed, ec = orc.knn(F32, dims, cpu, q, k, metric)
+                assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+            assert vg.tc_stats()[0] - before[0] == 2 * nq
+    finally:
+        del os.environ["VECGPU_TC_CLUSTER"]
+
+
 def test_tc_batched_ties_fall_back_to_exact(vg, orc, gpu, tc_terms):
     # a tiny alphabet makes thousands of rows tie at the k-th distance: the candidate bound cannot be
     # certified, the affected queries must be re-run by the exact scan and still match bit for bit
