@@ -130,6 +130,13 @@ struct vecgpu_hnsw {
     uint8_t* h_sw = nullptr;             // pinned twin
     size_t hsw_cap = 0;
     uint64_t dev_queries = 0, dev_fallbacks = 0, dev_launches = 0;
+    // device-side linking: stored edge distances on the device, scratch for the operation sort; while a rebuild links on
+    // the device the host lists are stale until hnsw_ensure_host() downloads them
+    float* d_dist0 = nullptr;
+    float* d_distU = nullptr;
+    bool host_stale = false;
+    uint8_t* d_link = nullptr;
+    size_t link_cap = 0;
 };
 
 static inline uint64_t h_mix64(uint64_t z) {
@@ -375,8 +382,11 @@ static void hnsw_dev_free_graph(vecgpu_hnsw* h) {
     cudaFree(h->d_upper_base);
     cudaFree(h->d_nbrU);
     cudaFree(h->d_degU);
+    cudaFree(h->d_dist0);
+    cudaFree(h->d_distU);
     h->d_nbr0 = h->d_upper_base = h->d_nbrU = nullptr;
     h->d_deg0 = h->d_degU = nullptr;
+    h->d_dist0 = h->d_distU = nullptr;
     h->dn_rows = h->dn_slots = 0;
     h->dev_valid = false;
 }
@@ -392,16 +402,20 @@ static int hnsw_dev_upload_all(vecgpu_hnsw* h) {
     CU(cudaMalloc(&h->d_upper_base, std::max<size_t>(1, n) * 4));
     CU(cudaMalloc(&h->d_nbrU, std::max<size_t>(1, slots * h->M) * 4));
     CU(cudaMalloc(&h->d_degU, std::max<size_t>(1, slots) * 2));
+    CU(cudaMalloc(&h->d_dist0, std::max<size_t>(1, n * h->max_m0) * 4));
+    CU(cudaMalloc(&h->d_distU, std::max<size_t>(1, slots * h->M) * 4));
     h->dn_rows = n;
     h->dn_slots = slots;
     if (n) {
         CU(cudaMemcpyAsync(h->d_nbr0, h->nbr0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemcpyAsync(h->d_deg0, h->deg0.data(), n * 2, cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemcpyAsync(h->d_upper_base, h->upper_base.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(h->d_dist0, h->dist0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
     }
     if (slots) {
         CU(cudaMemcpyAsync(h->d_nbrU, h->nbrU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
         CU(cudaMemcpyAsync(h->d_degU, h->degU.data(), slots * 2, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(h->d_distU, h->distU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
     }
     CU(cudaStreamSynchronize(s->stream));
     h->dirty0.assign(n, 0);
@@ -409,6 +423,26 @@ static int hnsw_dev_upload_all(vecgpu_hnsw* h) {
     h->dirty0_list.clear();
     h->dirtyU_list.clear();
     h->dev_valid = true;
+    return 0;
+}
+
+// bring the host lists up to date after a rebuild that linked on the device
+static int hnsw_ensure_host(vecgpu_hnsw* h) {
+    if (!h->host_stale) return 0;
+    vecgpu_slab* s = h->slab;
+    const size_t n = h->node_level.size(), slots = h->degU.size();
+    if (n) {
+        CU(cudaMemcpyAsync(h->nbr0.data(), h->d_nbr0, n * h->max_m0 * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h->dist0.data(), h->d_dist0, n * h->max_m0 * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h->deg0.data(), h->d_deg0, n * 2, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (slots) {
+        CU(cudaMemcpyAsync(h->nbrU.data(), h->d_nbrU, slots * h->M * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h->distU.data(), h->d_distU, slots * h->M * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h->degU.data(), h->d_degU, slots * 2, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    h->host_stale = false;
     return 0;
 }
 
@@ -468,6 +502,13 @@ struct HDevOut {  // host view of one launch's results (pinned memory, valid unt
     const uint32_t* status = nullptr;
     const uint64_t* keys = nullptr;
     uint32_t take = 0;
+    // device twins (valid until the next launch on the stream)
+    const uint32_t* d_ai = nullptr;
+    const uint32_t* d_off = nullptr;
+    const int8_t* d_lvl = nullptr;
+    const uint32_t* d_cnt = nullptr;
+    const uint64_t* d_keys = nullptr;
+    size_t keys_bytes = 0;
 };
 
 template <class T>
@@ -503,7 +544,7 @@ static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) 
 
 // One launch: every query walks all its layers on the device.  a_index / node_level / out_off are host arrays (or NULL).
 static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t* a_index, const int8_t* node_level, uint32_t nq,
-                           uint32_t ef_wide, uint32_t take, const uint32_t* out_off, uint32_t n_slots, HDevOut* out) {
+                           uint32_t ef_wide, uint32_t take, const uint32_t* out_off, uint32_t n_slots, HDevOut* out, bool fetch_keys = true) {
     vecgpu_slab* s = h->slab;
     int rc;
     if (!h->dev_valid && (rc = hnsw_dev_upload_all(h))) return rc;
@@ -567,7 +608,7 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
         rc = hnsw_dev_launch_t<BitHamming<1>>(h, p, per_warp);
     }
     if (rc) return rc;
-    CU(cudaMemcpyAsync(hp + o_cnt, dp + o_cnt, total - o_cnt, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(hp + o_cnt, dp + o_cnt, (fetch_keys ? total : o_keys) - o_cnt, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     h->scored += *(const unsigned long long*)(hp + o_scored);
     h->rounds += 1;
@@ -577,6 +618,62 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     out->status = (const uint32_t*)(hp + o_status);
     out->keys = (const uint64_t*)(hp + o_keys);
     out->take = take;
+    out->d_ai = (const uint32_t*)(dp + o_ai);
+    out->d_off = (const uint32_t*)(dp + o_off);
+    out->d_lvl = (const int8_t*)(dp + o_lvl);
+    out->d_cnt = (const uint32_t*)(dp + o_cnt);
+    out->d_keys = (const uint64_t*)(dp + o_keys);
+    out->keys_bytes = total - o_keys;
+    return 0;
+}
+
+// link a whole batch on the device from the search kernel's results (still in the launch workspace)
+static int hnsw_dev_link(vecgpu_hnsw* h, const HDevOut& o, uint32_t nq, uint32_t n_slots, int search_entry_level) {
+    vecgpu_slab* s = h->slab;
+    const uint32_t n_ops = n_slots * o.take;
+    if (n_ops == 0) return 0;
+    size_t sort_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint64_t*)nullptr,
+                                       (uint64_t*)nullptr, (int)n_ops, 0, 64, s->stream));
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t arr = al((size_t)n_ops * 8), need = 4 * arr + al(sort_bytes);
+    if (need > h->link_cap) {
+        if (h->d_link) CU(cudaFree(h->d_link));
+        h->d_link = nullptr;
+        h->link_cap = std::max(need * 2, (size_t)1 << 20);
+        CU(cudaMalloc(&h->d_link, h->link_cap));
+    }
+    HLinkParams p{};
+    p.nbr0 = h->d_nbr0;
+    p.dist0 = h->d_dist0;
+    p.deg0 = h->d_deg0;
+    p.upper_base = h->d_upper_base;
+    p.nbrU = h->d_nbrU;
+    p.distU = h->d_distU;
+    p.degU = h->d_degU;
+    p.max_m0 = h->max_m0;
+    p.M = h->M;
+    p.n_rows = (uint32_t)h->node_level.size();
+    p.a_index = o.d_ai;
+    p.out_off = o.d_off;
+    p.node_level = o.d_lvl;
+    p.entry_level = search_entry_level;
+    p.nq = nq;
+    p.take = o.take;
+    p.out_keys = o.d_keys;
+    p.out_cnt = o.d_cnt;
+    p.op_key = (uint64_t*)h->d_link;
+    p.op_val = (uint64_t*)(h->d_link + arr);
+    p.n_ops = n_ops;
+    uint64_t* skey = (uint64_t*)(h->d_link + 2 * arr);
+    uint64_t* sval = (uint64_t*)(h->d_link + 3 * arr);
+    hnsw_link_forward_kernel<<<std::max(1u, std::min((nq + 7) / 8, (uint32_t)s->num_sms * 8)), 256, 0, s->stream>>>(p);
+    LAUNCHED();
+    CU(cub::DeviceRadixSort::SortPairs(h->d_link + 4 * arr, sort_bytes, p.op_key, skey, p.op_val, sval, (int)n_ops, 0, 64, s->stream));
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    hnsw_link_reverse_kernel<<<std::max(1u, std::min((n_ops + 255) / 256, (uint32_t)s->num_sms * 8)), 256, 0, s->stream>>>(p, skey, sval);
+    LAUNCHED();
+    h->host_stale = true;
     return 0;
 }
 
@@ -616,6 +713,7 @@ extern "C" void vecgpu_hnsw_destroy(vecgpu_hnsw* h) {
     hnsw_dev_free_graph(h);
     cudaFree(h->d_visited);
     cudaFree(h->d_sw);
+    cudaFree(h->d_link);
     if (h->h_sw) cudaFreeHost(h->h_sw);
     cudaGetLastError();
     delete h;
@@ -668,6 +766,13 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     h->degU.assign(upper_slots, 0);
 
     const bool use_dev = hnsw_device_enabled(h);
+    h->host_stale = false;  // the host lists were just reset
+    // device search + device linking by default; VECGPU_HNSW_LINK=host keeps the ordered edge replay on the host threads
+    const char* link_env = getenv("VECGPU_HNSW_LINK");
+    const bool dev_link = use_dev && !(link_env && link_env[0] == 'h') && batch <= 32768 && h->max_m0 <= 256;
+    const bool timing = getenv("VECGPU_HNSW_TIMING") != nullptr;
+    double t_search = 0, t_decode = 0, t_ops = 0, t_link = 0, t_flush = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     if (use_dev) {
         if ((rc = hnsw_dev_upload_all(h))) return rc;  // empty lists; kept in sync batch by batch
     } else {
@@ -717,8 +822,35 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
                 slots += (uint32_t)std::min(L, search_entry_level) + 1u;
             }
             HDevOut o;
-            rc = hnsw_dev_search(h, s->d_vec, nodes.data() + first, lv8.data(), (uint32_t)nb, h->efc, h->max_m0, off.data(), slots, &o);
+            double t0 = now();
+            rc = hnsw_dev_search(h, s->d_vec, nodes.data() + first, lv8.data(), (uint32_t)nb, h->efc, h->max_m0, off.data(), slots, &o, !dev_link);
             if (rc) return rc;
+            t_search += now() - t0;
+            t0 = now();
+            if (dev_link) {
+                bool any_fb = false;
+                for (size_t i = 0; i < nb && !any_fb; ++i) any_fb = o.status[i] != 0;
+                if (!any_fb) {
+                    // ---- the common case: link on the device too; the host only tracks the entry point
+                    if ((rc = hnsw_dev_link(h, o, (uint32_t)nb, slots, search_entry_level))) return rc;
+                    for (size_t i = 0; i < nb; ++i) {
+                        const uint32_t node = nodes[first + i];
+                        const int L = h->node_level[node];
+                        if (L > h->entry_level) {
+                            h->entry = node;
+                            h->entry_level = L;
+                        }
+                    }
+                    h->n_nodes += nb;
+                    t_link += now() - t0;
+                    continue;
+                }
+                // a query overflowed a device capacity: this batch is linked by the host loop (which needs the keys and
+                // current host lists); the device copy is rebuilt from the host afterwards
+                CU(cudaMemcpyAsync((void*)o.keys, o.d_keys, o.keys_bytes, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
+                if ((rc = hnsw_ensure_host(h))) return rc;
+            }
             fb.clear();
             for (size_t i = 0; i < nb; ++i) {
                 HQuery& q = qs[i];
@@ -743,6 +875,7 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
                 if (rc) return rc;
                 for (size_t j = 0; j < fb.size(); ++j) qs[fb[j]].layers = fq[j].layers;
             }
+            t_decode += now() - t0;
         } else {
             for (size_t i = 0; i < nb; ++i) hq_init(h, qs[i], nodes[first + i], h->node_level[nodes[first + i]], h->efc);
             rc = hnsw_run_batch(h, qs, nb, s->d_vec);
@@ -751,6 +884,7 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
         // ---- link, in insertion order (insert.rs:408-498).  The edge operations are listed in order, then every
         //      host thread replays the list and applies the operations of the adjacency lists it owns: each list
         //      sees its operations in the sequential order, so the result equals the one-thread loop.
+        double t1 = now();
         ops.clear();
         for (size_t i = 0; i < nb; ++i) {
             HQuery& q = qs[i];
@@ -772,6 +906,8 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
                 h->entry_level = L;
             }
         }
+        t_ops += now() - t1;
+        t1 = now();
 #pragma omp parallel num_threads(nthreads)
         {
             const uint32_t tid = (uint32_t)omp_get_thread_num(), nt = (uint32_t)omp_get_num_threads();
@@ -787,9 +923,16 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
                 t_dirty0[t].clear();
                 t_dirtyU[t].clear();
             }
+        if (dev_link) h->dev_valid = false;  // (overflow batch) the stored distances on the device are stale: full re-upload
+        t_link += now() - t1;
         h->n_nodes += nb;
     }
-    if (use_dev && (rc = hnsw_dev_flush_dirty(h))) return rc;
+    double t2 = now();
+    if (use_dev && h->dev_valid && (rc = hnsw_dev_flush_dirty(h))) return rc;
+    t_flush += now() - t2;
+    if (timing)
+        fprintf(stderr, "[vecgpu hnsw build] search+flush %.3f s  decode %.3f s  ops %.3f s  link %.3f s  (threads %d, %s linking)\n",
+                t_search + t_flush, t_decode, t_ops, t_link, nthreads, dev_link ? "device" : "host");
     return 0;
 }
 
@@ -832,6 +975,8 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
     };
     // lockstep driver (one scoring launch per expansion round) for the queries listed in `which` (NULL: q0..q0+m)
     auto host_loop = [&](const uint32_t* which, uint32_t q0, uint32_t m) -> int {
+        int r0 = hnsw_ensure_host(h);  // the lockstep driver walks the host lists
+        if (r0) return r0;
         qs.clear();
         qs.resize(m);
         for (uint32_t i = 0; i < m; ++i) hq_init(h, qs[i], which ? which[i] : q0 + i, -1, ef);
@@ -878,6 +1023,10 @@ extern "C" int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edge
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
     if (nodes) *nodes = h->n_nodes;
+    if (edges && h->host_stale) {
+        int rc = use_device(h->slab->device);
+        if (rc || (rc = hnsw_ensure_host(h))) return rc;
+    }
     if (edges) {
         uint64_t e = 0;
         for (uint16_t d : h->deg0) e += d;
@@ -916,6 +1065,10 @@ extern "C" int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* f
     if (!h || !n_out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     vecgpu_slab* s = h->slab;
+    if (h->host_stale) {
+        int rc = use_device(s->device);
+        if (rc || (rc = hnsw_ensure_host(h))) return rc;
+    }
     uint64_t n = 0;
     const uint64_t rows = h->node_level.size();
     for (uint64_t node = 0; node < rows; ++node) {

@@ -263,6 +263,159 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
     }
 }
 
+// ---- linking on the device (insert.rs:408-498 for a whole batch) ---------------------------------------------------
+// The search kernel left, per (insert, layer), the sorted closest results in out_keys.  Forward edges: the new node's own
+// list is exactly its first min(cnt, maxc) results, in order.  Reverse edges: every (neighbour, layer) list receives the
+// new nodes in the order the sequential loop would add them (insert order, layers top-down, results closest first);
+// the operations are keyed (list id, sequence number), radix-sorted, and one thread per list replays its run with the
+// reference's rule: append while there is room, else replace the worst (distance, node) if the newcomer is better
+// (simple_prune keeps the closest, src/hnsw/insert.rs:144-222).  Same lists, same order, same stored distances as the
+// host loop (tests compare the exported graphs byte for byte).
+struct HLinkParams {
+    uint32_t* nbr0;
+    float* dist0;
+    uint16_t* deg0;
+    const uint32_t* upper_base;
+    uint32_t* nbrU;
+    float* distU;
+    uint16_t* degU;
+    uint32_t max_m0, M;
+    uint32_t n_rows;             // level-0 list id = node, upper list id = n_rows + slot
+    const uint32_t* a_index;     // [nq] the new nodes
+    const uint32_t* out_off;     // [nq] first result slot of each insert
+    const int8_t* node_level;    // [nq]
+    int32_t entry_level;         // entry level the batch searched from
+    uint32_t nq, take;
+    const uint64_t* out_keys;    // [slot][take]
+    const uint32_t* out_cnt;     // [slot]
+    uint64_t* op_key;            // [slots * take] (list id << 32) | sequence, ~0 = no operation
+    uint64_t* op_val;            // [slots * take] (distance bits << 32) | new node
+    uint32_t n_ops;
+};
+
+__device__ __forceinline__ void hlink_list(const HLinkParams& p, uint32_t lid, uint32_t** nb, float** dist, uint16_t** deg, uint32_t* maxc) {
+    if (lid < p.n_rows) {
+        *nb = p.nbr0 + (size_t)lid * p.max_m0;
+        *dist = p.dist0 + (size_t)lid * p.max_m0;
+        *deg = p.deg0 + lid;
+        *maxc = p.max_m0;
+    } else {
+        const size_t slot = lid - p.n_rows;
+        *nb = p.nbrU + slot * p.M;
+        *dist = p.distU + slot * p.M;
+        *deg = p.degU + slot;
+        *maxc = p.M;
+    }
+}
+
+// one warp per insert: write the new node's own lists and emit the reverse-edge operations
+__global__ void __launch_bounds__(256) hnsw_link_forward_kernel(const HLinkParams p) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = w; i < p.nq; i += nw) {
+        const uint32_t node = p.a_index[i];
+        const int nl = min((int)p.node_level[i], p.entry_level) + 1;
+        for (int lv = 0; lv < nl; ++lv) {
+            const uint32_t slot = p.out_off[i] + (uint32_t)lv;
+            const uint32_t lid = lv == 0 ? node : p.n_rows + p.upper_base[node] + (uint32_t)(lv - 1);
+            uint32_t* nb;
+            float* dist;
+            uint16_t* deg;
+            uint32_t maxc;
+            hlink_list(p, lid, &nb, &dist, &deg, &maxc);
+            const uint32_t tk = min(p.out_cnt[slot], maxc);
+            for (uint32_t j = lane; j < p.take; j += 32) {
+                const size_t o = (size_t)slot * p.take + j;
+                if (j < tk) {
+                    const uint64_t key = p.out_keys[o];
+                    const uint32_t wn = (uint32_t)(key & 0xFFFFFFFFull) >> 1;
+                    const float d = order_bits_inv((uint32_t)(key >> 32));
+                    nb[j] = wn;
+                    dist[j] = d;
+                    const uint32_t tl = lv == 0 ? wn : p.n_rows + p.upper_base[wn] + (uint32_t)(lv - 1);
+                    const uint32_t seq = ((i * 16u + (uint32_t)(15 - lv)) << 8) | j;
+                    p.op_key[o] = ((uint64_t)tl << 32) | seq;
+                    p.op_val[o] = ((uint64_t)__float_as_uint(d) << 32) | node;
+                } else {
+                    p.op_key[o] = ~0ull;
+                }
+            }
+            if (lane == 0) *deg = (uint16_t)tk;
+        }
+    }
+}
+
+// One warp per list: the warp that finds the head of a list's run in its 32-operation window replays the whole run in
+// order with the list held in registers (entry e*32+lane in k[e] as (order_bits(distance) << 32) | node, so the worst
+// entry is a warp-wide maximum).  Hub nodes receive thousands of reverse edges per batch: a run costs ~30 instructions
+// per operation instead of a 32-entry scan of global memory.
+__global__ void __launch_bounds__(256) hnsw_link_reverse_kernel(const HLinkParams p, const uint64_t* skey, const uint64_t* sval) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = w * 32; base < p.n_ops; base += nw * 32) {
+        const uint32_t t = base + lane;
+        bool head = false;
+        if (t < p.n_ops) {
+            const uint64_t key = skey[t];
+            if (key != ~0ull) head = t == 0 || (uint32_t)(skey[t - 1] >> 32) != (uint32_t)(key >> 32);
+        }
+        uint32_t hm = __ballot_sync(0xffffffffu, head);
+        while (hm) {
+            const uint32_t t0 = base + (uint32_t)__ffs(hm) - 1u;
+            hm &= hm - 1;
+            const uint32_t lid = (uint32_t)(skey[t0] >> 32);
+            uint32_t* nb;
+            float* dist;
+            uint16_t* deg;
+            uint32_t maxc;
+            hlink_list(p, lid, &nb, &dist, &deg, &maxc);
+            uint32_t d = *deg;
+            uint64_t k[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t idx = (uint32_t)e * 32 + lane;
+                k[e] = idx < d ? (((uint64_t)order_bits(dist[idx]) << 32) | nb[idx]) : 0ull;
+            }
+            for (uint32_t u = t0; u < p.n_ops; ++u) {
+                const uint64_t ku = skey[u];
+                if (ku == ~0ull || (uint32_t)(ku >> 32) != lid) break;
+                const uint64_t v = sval[u];
+                const uint64_t nk = ((uint64_t)order_bits(__uint_as_float((uint32_t)(v >> 32))) << 32) | (uint32_t)v;
+                if (d < maxc) {  // room: append (insert.rs: no pruning needed)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if ((uint32_t)e == (d >> 5) && lane == (d & 31)) k[e] = nk;
+                    ++d;
+                } else {         // full: the newcomer replaces the worst (distance, node) if it is better
+                    uint64_t mx = k[0];
+#pragma unroll
+                    for (int e = 1; e < 8; ++e) mx = k[e] > mx ? k[e] : mx;
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) {
+                        const uint64_t o = shfl_xor_u64(mx, m);
+                        mx = o > mx ? o : mx;
+                    }
+                    if (nk < mx) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (k[e] == mx) k[e] = nk;
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t idx = (uint32_t)e * 32 + lane;
+                if (idx < d) {
+                    nb[idx] = (uint32_t)k[e];
+                    dist[idx] = order_bits_inv((uint32_t)(k[e] >> 32));
+                }
+            }
+            if (lane == 0) *deg = (uint16_t)d;
+            __syncwarp();
+        }
+    }
+}
+
 // scatter staged adjacency lists into the device graph: item = [list id][degree][width x u32]
 __global__ void hnsw_scatter_kernel(const uint32_t* staged, uint32_t n_items, uint32_t width, uint32_t* nbr, uint16_t* deg) {
     const uint32_t lane = threadIdx.x & 31;

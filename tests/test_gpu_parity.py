@@ -733,6 +733,17 @@ def test_hnsw_device_search_equals_lockstep_and_restatement(vg, orc, gpu, elem, 
         e_d, e_h = idx.export_edges(), idx_h.export_edges()
         for a, b in zip(e_d, e_h):
             assert np.array_equal(a.view("u1"), b.view("u1"))
+        # device search with the ordered edge replay on the host threads instead of the device link kernels: same graph
+        os.environ["VECGPU_HNSW_LINK"] = "host"
+        try:
+            with _hnsw_mode(True):
+                idx_hl = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=5, normalize_vectors=False)
+                idx_hl.rebuild(batch=256)
+        finally:
+            del os.environ["VECGPU_HNSW_LINK"]
+        for a, b in zip(e_d, idx_hl.export_edges()):
+            assert np.array_equal(a.view("u1"), b.view("u1"))
+        idx_hl.close()
         assert idx.entry_point() == idx_h.entry_point()
         for k, ef in ((10, 64), (1, 1), (7, 300), (40, 10)):
             with _hnsw_mode(True):
@@ -803,6 +814,35 @@ def test_hnsw_device_capacity_fallback_is_exact(vg, orc, gpu):
             it.close()
             ih.close()
         idx.close()
+
+
+def test_hnsw_device_build_overflow_batches_are_exact(vg, orc, gpu):
+    # a rebuild whose inserts overflow the (shrunk) visited table: those batches are linked by the host loop after the
+    # host lists have been refreshed from the device, the device copy is rebuilt, and the result is still the same graph
+    n, dims = 6000, 12
+    v = random_rows(F32, n, dims, seed=431)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        os.environ["VECGPU_HNSW_VIS_LOG2"] = "12"
+        try:
+            with _hnsw_mode(True):
+                idx = vg.HnswIndex(s, L2, M=16, ef_construction=1200, seed=2)
+                idx.rebuild(batch=512)
+                st = idx.device_stats()
+        finally:
+            del os.environ["VECGPU_HNSW_VIS_LOG2"]
+        assert st["fallbacks"] > 0 and st["queries"] == n - 1
+        with _hnsw_mode(False):
+            idx_h = vg.HnswIndex(s, L2, M=16, ef_construction=1200, seed=2)
+            idx_h.rebuild(batch=512)
+        for a, b in zip(idx.export_edges(), idx_h.export_edges()):
+            assert np.array_equal(a.view("u1"), b.view("u1"))
+        q = random_rows(F32, 20, dims, seed=432)
+        r1, d1, _ = idx.search(q, 10, ef_search=100)
+        r2, d2, _ = idx_h.search(q, 10, ef_search=100)
+        assert np.array_equal(r1, r2) and same_bits(d1, d2)
+        idx.close()
+        idx_h.close()
 
 
 def test_hnsw_device_large_batch_throughput_path(vg, orc, gpu):
