@@ -180,7 +180,7 @@ typedef struct vecgpu_hnsw vecgpu_hnsw;
 int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uint32_t ef_construction, uint64_t seed, vecgpu_hnsw** out);
 void vecgpu_hnsw_destroy(vecgpu_hnsw* h);
 /* vec_rebuild_hnsw (src/sql_functions.rs:436-534 -> src/hnsw/insert.rs:279-532): rebuild over every live row of
- * the slab, at most `batch` inserts in lockstep (0 = 4096). */
+ * the slab, at most `batch` inserts per search launch (0 = 16384; never more than a quarter of the graph built so far). */
 int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch);
 /* search_hnsw (src/hnsw/search.rs:267-335): ef = max(ef_search, k); results closest first, distances in the
  * internal metric (apply convert_distance_for_output for cosine columns); unused slots rowid -1 / +inf. */

@@ -288,7 +288,7 @@ public:
         if (rc) return Error::from_status(rc);
         return idx;
     }
-    Result<Unit> rebuild(uint32_t batch = 4096) {  // vec_rebuild_hnsw
+    Result<Unit> rebuild(uint32_t batch = 0) {  // vec_rebuild_hnsw; 0 = library default (16384 inserts per launch)
         int rc = vecgpu_hnsw_build(h_, batch);
         if (rc) return Error::from_status(rc);
         return Unit{};

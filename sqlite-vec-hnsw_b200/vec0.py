@@ -498,7 +498,7 @@ class HnswIndex:
 
     __del__ = close
 
-    def rebuild(self, batch=4096):
+    def rebuild(self, batch=0):
         """vec_rebuild_hnsw (src/sql_functions.rs:436-534): index every live row of the slab."""
         _check(self._lib.vecgpu_hnsw_build(self._h, batch))
         return self.stats()["nodes"]
