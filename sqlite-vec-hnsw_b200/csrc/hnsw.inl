@@ -594,7 +594,8 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     p.next_q = (unsigned int*)(dp + o_next);
     p.out_keys = (uint64_t*)(dp + o_keys);
     p.max_steps = 1u << 20;
-    const size_t per_warp = (size_t)p.cap * 8 + (size_t)((h->max_m0 + 31u) & ~31u) * 4;
+    p.q_smem = s->row_stride <= 16384 ? 1u : 0u;
+    const size_t per_warp = (size_t)p.cap * 8 + (size_t)((h->max_m0 + 31u) & ~31u) * 4 + (p.q_smem ? (size_t)s->row_stride : 0);
     const int elem = s->elem, metric = h->metric;
     if (elem == VECGPU_F32) {
         if (metric == VECGPU_L2) rc = hnsw_dev_launch_t<F32L2<1>>(h, p, per_warp);

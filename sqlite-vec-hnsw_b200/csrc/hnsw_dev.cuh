@@ -54,6 +54,7 @@ struct HSearchParams {
     unsigned int* next_q;        // work counter
     unsigned long long* scored;  // distances computed
     uint32_t max_steps;
+    uint32_t q_smem;             // 1: each warp stages its query in shared memory (units * 16 bytes per warp)
 };
 
 static constexpr uint32_t HV_EMPTY = 0xFFFFFFFFu;
@@ -103,9 +104,10 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane % LPR;
     const uint32_t pend_cap = (p.g.max_m0 + 31u) & ~31u;
-    const size_t per_warp = (size_t)p.cap * 8 + (size_t)pend_cap * 4;
+    const size_t per_warp = (size_t)p.cap * 8 + (size_t)pend_cap * 4 + (p.q_smem ? (size_t)p.units * 16 : 0);
     uint64_t* L = (uint64_t*)(h_smem + (size_t)warp * per_warp);
     uint32_t* pend = (uint32_t*)(L + p.cap);
+    uint4* sq = (uint4*)(pend + pend_cap);  // the query, staged once: the row stream evicts it from L1 between passes
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
     uint32_t* vt = p.visited + (size_t)gw * p.vis_size;
 
@@ -116,6 +118,12 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
         if (q >= p.nq) break;
         const uint32_t ai = p.a_index ? p.a_index[q] : q;
         const uint4* a = (const uint4*)(p.a_base + (uint64_t)ai * p.a_stride);
+        if (p.q_smem) {
+            __syncwarp();
+            for (uint32_t u = lane; u < p.units; u += 32) sq[u] = __ldg(a + u);
+            __syncwarp();
+            a = sq;
+        }
         float qc = 0.f;
         if (T::HAS_QC) qc = query_const(a, p.units, lane & 3, p.qc_kind);
         const int nlev = p.node_level ? (int)p.node_level[q] : -1;
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
 #pragma unroll 4
                         for (uint32_t u = g; u < p.units; u += LPR) {
                             const uint4 x = __ldg(b + u);
-                            const uint4 qv[1] = {__ldg(a + u)};
+                            const uint4 qv[1] = {a[u]};
                             T::step(acc, x, qv);
                         }
                     }
