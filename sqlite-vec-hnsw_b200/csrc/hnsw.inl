@@ -520,7 +520,7 @@ static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) 
     CU(cudaFuncSetAttribute(hnsw_search_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     int bps = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, hnsw_search_kernel<T>, (int)wpb * 32, wpb * per_warp));
-    int bps_max = 4;
+    int bps_max = 6;
     if (const char* e = getenv("VECGPU_HNSW_BPS")) bps_max = std::max(1, atoi(e));
     bps = std::max(1, std::min(bps, bps_max));
     uint32_t grid = (uint32_t)s->num_sms * (uint32_t)bps;
