@@ -47,6 +47,7 @@ static constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N
 // A squared norm outside this range (zero, denormal-ish, huge, inf, NaN) makes the approximate score of the row
 // meaningless (overflow / cancellation), so the row bypasses the contraction and is always re-ranked exactly.
 static constexpr uint32_t TC_MAX_UNSAFE = 64;
+static constexpr uint32_t TC_BUF_CAP = 256;     // per-thread append buffer of the epilogue (kp + 32 <= TC_BUF_CAP)
 __host__ __device__ __forceinline__ bool tc_norm_safe(float x2) { return x2 > 1e-30f && x2 < 1e30f; }
 
 struct TcParams {
@@ -55,7 +56,6 @@ struct TcParams {
     uint32_t kp;           // entries kept per (CTA, query) = k + margin
     uint32_t cosine;       // 0: L2 (v = x2 - 2s), 1: cosine (v = -s / |x|)
     uint32_t terms;        // 3: 3xTF32 (hi.hi + lo.hi + hi.lo), 1: one TF32 pass (wider certified bound)
-    uint32_t lists_smem;   // 1: the kept scores live in shared memory ([kp][128] floats) during the scan
     uint32_t debug;        // timing experiments (results invalid): 1 = no epilogue work, 2 = common path only, 4 = no norm loads
     uint32_t QT, G;        // query tiles, row-tile groups; grid = QT*G, CTA c -> (qt = c % QT, g = c / QT)
     uint32_t* lockstep;    // [G][32] tile counters of the query-tile CTAs of each row group (zeroed before the launch), or NULL
@@ -63,6 +63,7 @@ struct TcParams {
     uint32_t cs;           // cluster size (1, 2, 4, 8; divides QT): the CTAs of a cluster share every row tile through TMA multicast
     const float* norms;    // [rows] canonical sum of squares of each slab row
     const uint8_t* skip;   // per-row skip flags or nullptr
+    uint64_t* buf_keys;    // [grid][128][TC_BUF_CAP] per-thread append buffers
     float* cand_v;         // [grid][128][kp] approximate scores kept
     uint32_t* cand_r;      // [grid][128][kp] row positions
     uint32_t* cand_cnt;    // [grid][128]
@@ -140,34 +141,114 @@ __device__ __forceinline__ bool tile_lockstep(uint32_t* ctr, uint32_t qt, uint32
     return false;
 }
 
-// thread-private candidate list in global memory: unsorted, tracked maximum (the admission bound tau)
-struct TcList {
-    uint32_t cnt, maxpos;
-    float tau;
-};
-// lv[i * vstride] is entry i of this thread's score list (shared memory, transposed: vstride = 128; or global: 1)
-__device__ __noinline__ TcList tc_insert(float v, uint32_t row, float* lv, uint32_t vstride, uint32_t* lr, uint32_t kp, TcList st) {
-    if (st.cnt < kp) {
-        lv[st.cnt * vstride] = v;
-        lr[st.cnt] = row;
-        if (++st.cnt < kp) return st;
-    } else {
-        lv[st.maxpos * vstride] = v;
-        lr[st.maxpos] = row;
+// (float)sqrt((double)s) for an exact non-negative integer s (src/distance/scalar.rs:65).  Below 2^24 the integer is a
+// float, and the correctly rounded float square root equals the double-rounded value (double rounding is innocuous for
+// sqrt when the wide format has >= 2*24+2 bits), so no FP64 instruction is needed; tests/test_oracle_golden.py checks
+// the identity exhaustively on the CPU.
+__device__ __forceinline__ float exact_sqrt_int(int s) {
+    if (s < (1 << 24)) return __fsqrt_rn((float)s);
+    return __double2float_rn(__dsqrt_rn((double)s));
+}
+
+// Integer bound that goes with a key bound: any squared distance s beyond (next float after the key's distance)^2
+// has a strictly larger f32 distance, so it can never beat the key.
+__device__ __forceinline__ int tci_tau_s(uint64_t key) {
+    const float dr = order_bits_inv((uint32_t)(key >> 32));
+    const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
+    const double lim = dn * dn;
+    return lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
+}
+
+// Warp-cooperative compaction of one thread's append buffer (at most 256 keys): the keys are loaded 8 per lane,
+// sorted ascending across the warp with a bitonic network that lives entirely in registers (strides below 8 are
+// register-to-register compare-exchanges, larger strides are lane shuffles; the "flip" form of the network needs no
+// direction flags), and the k smallest are written back to the front of the buffer (and to `out` when given).
+// Returns (to every lane) the k-th smallest key, KEY_NONE when fewer than k keys exist.  ~1.2k instructions per
+// lane: cheap enough that a compaction no longer stalls the accumulator pipeline.
+__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
+
+__device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint32_t k, uint64_t* out, int lane) {
+    __syncwarp();  // the owner lane's appends become visible to the helping lanes
+    uint64_t v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = (uint32_t)lane * 8 + r;
+        v[r] = i < cnt ? buf[i] : KEY_NONE;
     }
-    float best = lv[0];
-    uint32_t bp = 0;
-    for (uint32_t i = 1; i < kp; ++i) {
-        const float x = lv[i * vstride];
-        if (x > best) {
-            best = x;
-            bp = i;
+#pragma unroll
+    for (int size = 2; size <= 256; size <<= 1) {
+        if (size <= 8) {  // element i against i ^ (size - 1), both in this lane
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int pr = r ^ (size - 1);
+                if (pr > r) {
+                    const uint64_t a = v[r], b = v[pr];
+                    v[r] = u64min(a, b);
+                    v[pr] = u64max(a, b);
+                }
+            }
+        } else {          // partner lane = lane ^ (size/8 - 1), partner register = 7 - r
+            const bool keep_min = (lane & (size / 16)) == 0;
+            uint64_t o[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = shfl_xor_u64(v[7 - r], size / 8 - 1);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = keep_min ? u64min(v[r], o[r]) : u64max(v[r], o[r]);
+        }
+#pragma unroll
+        for (int stride = size / 4; stride >= 1; stride >>= 1) {  // element i against i ^ stride
+            if (stride >= 8) {
+                const bool keep_min = (lane & (stride / 8)) == 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint64_t o = shfl_xor_u64(v[r], stride / 8);
+                    v[r] = keep_min ? u64min(v[r], o) : u64max(v[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if ((r & stride) == 0) {
+                        const uint64_t a = v[r], b = v[r ^ stride];
+                        v[r] = u64min(a, b);
+                        v[r ^ stride] = u64max(a, b);
+                    }
+            }
         }
     }
-    st.tau = best;
-    st.maxpos = bp;
-    return st;
+    uint64_t mine = v[0];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = (uint32_t)lane * 8 + r;
+        if (i < k) {
+            buf[i] = v[r];
+            if (out) out[i] = v[r];
+        }
+        if (((k - 1) & 7u) == (uint32_t)r) mine = v[r];
+    }
+    const uint64_t kth = shfl_u64(mine, (int)((k - 1) >> 3));
+    __syncwarp();
+    return kth;
 }
+
+// TMEM -> registers, 32 lanes x 32 columns; the wait names the registers so that no use is scheduled before it
+#define TCI_LD32(v, addr)                                                                                                  \
+    asm volatile(                                                                                                          \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),    \
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),       \
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),       \
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                               \
+        : "r"(addr))
+#define TCI_WAIT32(v)                                                                                                      \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                          \
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),      \
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),           \
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),          \
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])                        \
+                 :                                                                                                         \
+                 : "memory")
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TcParams p) {
@@ -175,12 +256,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries: align by hand (the launch reserves 1 KB of slack)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // layout: [stage][A_raw | A_lo | B_raw | B_lo] ... [colA[2][256] | colB[2][256]] [barriers] [tmem slot]
-    float* s_colA = (float*)(smem + TC_STAGES * TC_STAGE_BYTES);
-    float* s_colB = s_colA + 2 * TC_N;
-    uint64_t* s_bar = (uint64_t*)(s_colB + 2 * TC_N);
+    // layout: [stage][A_raw | A_lo | B_raw | B_lo] ... [colA[4][256] | colB[4][256]] [barriers] [tmem slot] [stage[4][2 KB]]
+    float* s_colA = (float*)(smem + TC_STAGES * TC_STAGE_BYTES);   // [4 epilogue warps][256] per-column scale
+    float* s_colB = s_colA + 4 * TC_N;                             // [4 epilogue warps][256] per-column offset
+    uint64_t* s_bar = (uint64_t*)(s_colB + 4 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
-    float* s_lists = (float*)(s_bar + 32);  // [kp][128] when p.lists_smem
+    uint8_t* s_stage = (uint8_t*)(s_bar + 32);                     // [4 epilogue warps][2 KB] staging of half a chunk (rare path)
     // terms == 3: two 96 KB stages [A_raw | A_lo | B_raw | B_lo]; terms == 1: four 48 KB stages [A | B], no lo-split
     const uint32_t n_stages = p.terms == 1 ? 2 * TC_STAGES : TC_STAGES;
     const uint32_t stage_bytes = p.terms == 1 ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
@@ -340,58 +421,59 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 if (lane == 0) mbar_arrive(bar_full_lo + 8 * s);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===== epilogue warps: thread = query (TMEM lane), columns = slab rows of the tile =====
-        const uint32_t e = threadIdx.x - 128;        // 0..127 == TMEM lane == query within the tile
-        const uint32_t lane_base = (uint32_t)(warp & 3) * 32;
-        const size_t lbase = ((size_t)blockIdx.x * TC_M + e) * p.kp;
-        float* lv = p.lists_smem ? s_lists + e : p.cand_v + lbase;
-        const uint32_t vstride = p.lists_smem ? TC_M : 1u;
-        uint32_t* lr = p.cand_r + lbase;
-        TcList st;
-        st.cnt = 0;
-        st.maxpos = 0;
-        // tile rows past nq hold zero-filled queries: they never admit anything
-        st.tau = (qt * TC_M + e < p.nq) ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);
-        for (uint32_t ti = 0; ti < my_tiles; ++ti) {
-            const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
-            const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
-            // per-column coefficients: v = s * a + b
-            for (uint32_t j = e; j < TC_N; j += 128) {
-                const uint64_t row = row0 + j;
+        // Same scheme as tci8_scan_kernel: a branch-free common path (score + pass mask for 32 columns, the next TMEM chunk
+        // already in flight), a compact rare path (staged chunk, indexed loop) that APPENDS (order_bits(score) << 32 | row)
+        // to the thread's private buffer, and a register bitonic compaction by the whole warp when a buffer fills up
+        // (keeps the kp best, tightens the bound).  The per-column coefficients live in a per-warp copy fetched one tile
+        // ahead, so the four warps never synchronise with each other.
+        const uint32_t ew = (uint32_t)(warp - 4);
+        const uint32_t lane_base = ew * 32;
+        const uint32_t e = lane_base + lane;         // 0..127 == TMEM lane == query within the tile
+        const bool q_ok = qt * TC_M + e < p.nq;      // tile rows past nq hold zero-filled queries: they never admit anything
+        const size_t lidx = (size_t)blockIdx.x * TC_M + e;
+        uint64_t* buf = p.buf_keys + lidx * TC_BUF_CAP;
+        float* my_colA = s_colA + ew * TC_N;
+        float* my_colB = s_colB + ew * TC_N;
+        int* stage = (int*)(s_stage + ew * 2048);    // [16 columns][32 lanes]
+        uint32_t cnt = 0;
+        uint64_t tau_key = KEY_NONE;                 // kp-th best key as of the last compaction
+        float tau_f = q_ok ? __int_as_float(0x7F800000) : __int_as_float(0xFF800000);  // its score: every better key has score <= tau_f
+        float na[TC_N / 32], nb[TC_N / 32];
+        auto fetch_coef = [&](uint32_t ti) {          // per-column coefficients: v = s * a + b
+            const uint64_t r0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+#pragma unroll
+            for (int i = 0; i < (int)TC_N / 32; ++i) {
+                const uint64_t row = r0 + (uint64_t)(i * 32 + lane);
                 bool ok = row < p.n_rows && !(p.skip && p.skip[row]);
                 const float x2 = ok ? p.norms[row] : 0.f;
                 ok = ok && tc_norm_safe(x2);  // unsafe rows are handled by the exact re-rank alone
-                float a, b;
                 if (p.cosine) {
-                    a = (ok && x2 > 0.f) ? -rsqrtf(x2) : 0.f;
-                    b = ok ? 0.f : __int_as_float(0x7F800000);
+                    na[i] = (ok && x2 > 0.f) ? -rsqrtf(x2) : 0.f;
+                    nb[i] = ok ? 0.f : __int_as_float(0x7F800000);
                 } else {
-                    a = -2.f;
-                    b = ok ? x2 : __int_as_float(0x7F800000);
+                    na[i] = -2.f;
+                    nb[i] = ok ? x2 : __int_as_float(0x7F800000);
                 }
-                s_colA[acc * TC_N + j] = a;
-                s_colB[acc * TC_N + j] = b;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+        };
+        if (my_tiles) fetch_coef(0);
+        for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+            const uint64_t row0 = ((uint64_t)g + (uint64_t)ti * p.G) * TC_N;
+#pragma unroll
+            for (int i = 0; i < (int)TC_N / 32; ++i) {
+                my_colA[i * 32 + lane] = na[i];
+                my_colB[i * 32 + lane] = nb[i];
+            }
+            __syncwarp();
+            if (ti + 1 < my_tiles) fetch_coef(ti + 1);
             mbar_wait_b(bar_tfull + 8 * acc, aph);
             tc_fence_after();
-#pragma unroll 1
-            for (uint32_t c = 0; c < ((p.debug & 1) ? 0u : TC_N / 32); ++c) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + (lane_base << 16) + acc * TC_N + c * 32;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // branch-free common case: all 32 scores and a pass mask first, the (rare) inserts afterwards
-                const float4* ca4 = (const float4*)(s_colA + acc * TC_N + c * 32);
-                const float4* cb4 = (const float4*)(s_colB + acc * TC_N + c * 32);
+            auto process = [&](uint32_t (&v)[32], const uint32_t c) {
+                const float4* ca4 = (const float4*)(my_colA + c * 32);
+                const float4* cb4 = (const float4*)(my_colB + c * 32);
                 float sc[32];
                 uint32_t mask = 0;
 #pragma unroll
@@ -402,23 +484,79 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                     sc[4 * j4 + 2] = __fmaf_rn(__uint_as_float(v[4 * j4 + 2]), a.z, b.z);
                     sc[4 * j4 + 3] = __fmaf_rn(__uint_as_float(v[4 * j4 + 3]), a.w, b.w);
                 }
+                // NaN and +inf scores (rows that must not be kept) fail the comparison
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mask |= (sc[j] < st.tau ? 1u : 0u) << j;
-                if (mask) {
+                for (int j = 0; j < 32; ++j) mask |= ((sc[j] <= tau_f && sc[j] < __int_as_float(0x7F800000)) ? 1u : 0u) << j;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (((mask >> j) & 1u) && sc[j] < st.tau)
-                            st = tc_insert(sc[j], (uint32_t)(row0 + c * 32 + j), lv, vstride, lr, p.kp, st);
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t m16 = (mask >> (16 * hh)) & 0xFFFFu;
+                    if (__any_sync(0xffffffffu, m16 != 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) stage[j * 32 + lane] = __float_as_int(sc[16 * hh + j]);
+                        while (m16) {
+                            const int j = __ffs(m16) - 1;
+                            m16 &= m16 - 1;
+                            const uint64_t key = make_key(__int_as_float(stage[j * 32 + lane]), (uint32_t)(row0 + c * 32 + 16 * hh + (uint32_t)j));
+                            if (key < tau_key) buf[cnt++] = key;
+                        }
+                        __syncwarp();
+                    }
+                }
+                // a buffer that could overflow during the next 32 columns is compacted now (warp-uniform loop)
+                unsigned need = __ballot_sync(0xffffffffu, cnt + 32 > TC_BUF_CAP);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const uint64_t bp = shfl_u64((uint64_t)(uintptr_t)buf, src);
+                    const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
+                    const uint64_t kth = warp_compact((uint64_t*)(uintptr_t)bp, bc, p.kp, nullptr, lane);
+                    if (lane == src) {
+                        cnt = min(bc, p.kp);
+                        if (kth != KEY_NONE) {
+                            tau_key = kth;
+                            tau_f = order_bits_inv((uint32_t)(kth >> 32));
+                        }
+                    }
+                }
+            };
+            if (!(p.debug & 1)) {
+                uint32_t va[32], vb[32];
+                const uint32_t tbase = tmem_base + (lane_base << 16) + acc * TC_N;
+                TCI_LD32(va, tbase);
+#pragma unroll 1
+                for (uint32_t c = 0; c < TC_N / 32; c += 2) {
+                    TCI_WAIT32(va);
+                    TCI_LD32(vb, tbase + (c + 1) * 32);
+                    process(va, c);
+                    TCI_WAIT32(vb);
+                    if (c + 2 < TC_N / 32) TCI_LD32(va, tbase + (c + 2) * 32);
+                    process(vb, c + 1);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
-        if (p.lists_smem)
-            for (uint32_t i = 0; i < st.cnt; ++i) p.cand_v[lbase + i] = lv[i * TC_M];
-        p.cand_cnt[(size_t)blockIdx.x * TC_M + e] = st.cnt;
-        p.cand_tau[(size_t)blockIdx.x * TC_M + e] = st.cnt == p.kp ? st.tau : __int_as_float(0x7F800000);
+        // final compaction of every lane's buffer -> the kp best (score, row) of this (CTA, query) in the layout
+        // tc_collect_kernel reads; a list that holds kp entries reports its largest kept score as its drop bound
+        for (int src = 0; src < 32; ++src) {
+            const uint64_t bp = shfl_u64((uint64_t)(uintptr_t)buf, src);
+            const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
+            const size_t li = (size_t)blockIdx.x * TC_M + lane_base + (uint32_t)src;
+            const uint64_t kth = warp_compact((uint64_t*)(uintptr_t)bp, bc, p.kp, nullptr, lane);
+            const uint32_t keep = min(bc, p.kp);
+            const uint64_t* sorted = (const uint64_t*)(uintptr_t)bp;
+            for (uint32_t i = lane; i < keep; i += 32) {
+                const uint64_t key = sorted[i];
+                p.cand_v[li * p.kp + i] = order_bits_inv((uint32_t)(key >> 32));
+                p.cand_r[li * p.kp + i] = (uint32_t)key;
+            }
+            if (lane == 0) {
+                p.cand_cnt[li] = keep;
+                p.cand_tau[li] = kth != KEY_NONE ? order_bits_inv((uint32_t)(kth >> 32)) : __int_as_float(0x7F800000);
+            }
+            __syncwarp();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -574,115 +712,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(TCI_IDESC), "r"(accumulate)
         : "memory");
 }
-
-// (float)sqrt((double)s) for an exact non-negative integer s (src/distance/scalar.rs:65).  Below 2^24 the integer is a
-// float, and the correctly rounded float square root equals the double-rounded value (double rounding is innocuous for
-// sqrt when the wide format has >= 2*24+2 bits), so no FP64 instruction is needed; tests/test_oracle_golden.py checks
-// the identity exhaustively on the CPU.
-__device__ __forceinline__ float exact_sqrt_int(int s) {
-    if (s < (1 << 24)) return __fsqrt_rn((float)s);
-    return __double2float_rn(__dsqrt_rn((double)s));
-}
-
-// Integer bound that goes with a key bound: any squared distance s beyond (next float after the key's distance)^2
-// has a strictly larger f32 distance, so it can never beat the key.
-__device__ __forceinline__ int tci_tau_s(uint64_t key) {
-    const float dr = order_bits_inv((uint32_t)(key >> 32));
-    const double dn = (double)__uint_as_float(__float_as_uint(dr) + 1u);
-    const double lim = dn * dn;
-    return lim < 2147483000.0 ? (int)lim : 0x7FFFFFFE;
-}
-
-// Warp-cooperative compaction of one thread's append buffer (at most 256 keys): the keys are loaded 8 per lane,
-// sorted ascending across the warp with a bitonic network that lives entirely in registers (strides below 8 are
-// register-to-register compare-exchanges, larger strides are lane shuffles; the "flip" form of the network needs no
-// direction flags), and the k smallest are written back to the front of the buffer (and to `out` when given).
-// Returns (to every lane) the k-th smallest key, KEY_NONE when fewer than k keys exist.  ~1.2k instructions per
-// lane: cheap enough that a compaction no longer stalls the accumulator pipeline.
-__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
-__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
-
-__device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint32_t k, uint64_t* out, int lane) {
-    __syncwarp();  // the owner lane's appends become visible to the helping lanes
-    uint64_t v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint32_t i = (uint32_t)lane * 8 + r;
-        v[r] = i < cnt ? buf[i] : KEY_NONE;
-    }
-#pragma unroll
-    for (int size = 2; size <= 256; size <<= 1) {
-        if (size <= 8) {  // element i against i ^ (size - 1), both in this lane
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int pr = r ^ (size - 1);
-                if (pr > r) {
-                    const uint64_t a = v[r], b = v[pr];
-                    v[r] = u64min(a, b);
-                    v[pr] = u64max(a, b);
-                }
-            }
-        } else {          // partner lane = lane ^ (size/8 - 1), partner register = 7 - r
-            const bool keep_min = (lane & (size / 16)) == 0;
-            uint64_t o[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) o[r] = shfl_xor_u64(v[7 - r], size / 8 - 1);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = keep_min ? u64min(v[r], o[r]) : u64max(v[r], o[r]);
-        }
-#pragma unroll
-        for (int stride = size / 4; stride >= 1; stride >>= 1) {  // element i against i ^ stride
-            if (stride >= 8) {
-                const bool keep_min = (lane & (stride / 8)) == 0;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint64_t o = shfl_xor_u64(v[r], stride / 8);
-                    v[r] = keep_min ? u64min(v[r], o) : u64max(v[r], o);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if ((r & stride) == 0) {
-                        const uint64_t a = v[r], b = v[r ^ stride];
-                        v[r] = u64min(a, b);
-                        v[r ^ stride] = u64max(a, b);
-                    }
-            }
-        }
-    }
-    uint64_t mine = v[0];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint32_t i = (uint32_t)lane * 8 + r;
-        if (i < k) {
-            buf[i] = v[r];
-            if (out) out[i] = v[r];
-        }
-        if (((k - 1) & 7u) == (uint32_t)r) mine = v[r];
-    }
-    const uint64_t kth = shfl_u64(mine, (int)((k - 1) >> 3));
-    __syncwarp();
-    return kth;
-}
-
-// TMEM -> registers, 32 lanes x 32 columns; the wait names the registers so that no use is scheduled before it
-#define TCI_LD32(v, addr)                                                                                                  \
-    asm volatile(                                                                                                          \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),    \
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),       \
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),       \
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                               \
-        : "r"(addr))
-#define TCI_WAIT32(v)                                                                                                      \
-    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                          \
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),      \
-                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),           \
-                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),          \
-                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])                        \
-                 :                                                                                                         \
-                 : "memory")
 
 __global__ void __launch_bounds__(TCI_THREADS, 1)
 tci8_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TciParams p) {

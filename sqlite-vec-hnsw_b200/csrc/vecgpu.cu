@@ -103,7 +103,7 @@ struct vecgpu_slab {
 
 enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7,
        WS_TC_CANDV = 8, WS_TC_CANDR = 9, WS_TC_CNT = 10, WS_TC_TAU = 11, WS_TC_PAIRQ = 12, WS_TC_PAIRPOS = 13, WS_TC_DIST = 14,
-       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_COUNT = 20 };
+       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_TC_BUF = 19, WS_COUNT = 20 };
 
 static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
     if (bytes <= s->ws_cap[i]) return 0;
@@ -930,9 +930,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
     int dev = 0;
     CU(cudaGetDevice(&dev));
     const uint32_t kp = ((k + 32 + 7) / 8) * 8;
-    size_t smem = TC_STAGES * TC_STAGE_BYTES + 2 * 2 * TC_N * 4 + 32 * 8 + 1024;  // + alignment slack
-    const bool lists_smem = smem + (size_t)kp * TC_M * 4 <= SMEM_MAX;          // kept scores in shared memory when they fit
-    if (lists_smem) smem += (size_t)kp * TC_M * 4;
+    const size_t smem = TC_STAGES * TC_STAGE_BYTES + 2 * 4 * TC_N * 4 + 32 * 8 + 4 * 2048 + 1024;  // stages, per-warp coefficients, barriers, rare-path staging, alignment slack
     if (cfg_dev != dev) {
         CU(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         CU(cudaFuncSetAttribute(tc_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -984,6 +982,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         const uint32_t cap = std::max(2u, next_pow2(G * kp + TC_MAX_UNSAFE));
         const uint32_t grid = QT * G;
         const size_t lists = (size_t)grid * TC_M;
+        if ((rc = ws_reserve(s, WS_TC_BUF, lists * TC_BUF_CAP * 8))) return rc;
         if ((rc = ws_reserve(s, WS_TC_CANDV, lists * kp * 4))) return rc;
         if ((rc = ws_reserve(s, WS_TC_CANDR, lists * kp * 4))) return rc;
         if ((rc = ws_reserve(s, WS_TC_CNT, lists * 4))) return rc;
@@ -1008,12 +1007,12 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
         tp.kp = kp;
         tp.cosine = metric == VECGPU_COSINE ? 1u : 0u;
         tp.terms = env_u32("VECGPU_TC_TERMS", 1) == 3 ? 3u : 1u;  // 1: one TF32 pass + wider certified bound (default); 3: 3xTF32
-        tp.lists_smem = lists_smem ? 1u : 0u;
         tp.debug = env_u32("VECGPU_TCI_DEBUG", 0);
         tp.QT = QT;
         tp.G = G;
         tp.norms = s->d_norms;
         tp.skip = s->n_skip ? s->d_skip : nullptr;
+        tp.buf_keys = (uint64_t*)s->d_ws[WS_TC_BUF];
         tp.cand_v = (float*)s->d_ws[WS_TC_CANDV];
         tp.cand_r = (uint32_t*)s->d_ws[WS_TC_CANDR];
         tp.cand_cnt = (uint32_t*)s->d_ws[WS_TC_CNT];
