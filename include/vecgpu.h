@@ -85,6 +85,11 @@ int vecgpu_slab_append(vecgpu_slab* slab, const int64_t* rowids, const void* vec
 int vecgpu_slab_upsert(vecgpu_slab* slab, int64_t rowid, const void* vec, uint32_t nbytes);
 int vecgpu_slab_delete(vecgpu_slab* slab, int64_t rowid);
 
+/* Physically drop the skipped rows (tombstones after vecgpu_slab_delete, rows whose blob had the wrong length): SURVEY §8(f)-4,
+ * the compaction that goes with Vec0Tab::delete (src/vtab.rs:1326).  Kept rows keep their order; *removed (optional) = rows
+ * dropped.  Row positions change, so an HNSW index built over the slab must be rebuilt (vecgpu_hnsw_search then fails with
+ * status 4 until vecgpu_hnsw_build is called again).  A dropped rowid can be re-inserted later with vecgpu_slab_upsert. */
+int vecgpu_slab_compact(vecgpu_slab* s, uint64_t* removed);
 /* rows = stored rows including skipped/tombstoned; live = rows scans visit. */
 int vecgpu_slab_count(vecgpu_slab* slab, uint64_t* rows, uint64_t* live);
 /* Copy one row back (debug / tests).  *found = 0 if absent or skipped. */

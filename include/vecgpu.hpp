@@ -236,6 +236,12 @@ public:
         if (rc) return Error::from_status(rc);
         return Unit{};
     }
+    Result<uint64_t> compact() {  // drop the tombstoned rows physically; HNSW indexes over the slab must be rebuilt afterwards
+        uint64_t removed = 0;
+        int rc = vecgpu_slab_compact(h_, &removed);
+        if (rc) return Error::from_status(rc);
+        return removed;
+    }
     uint64_t live_rows() const {
         uint64_t rows = 0, live = 0;
         vecgpu_slab_count(h_, &rows, &live);

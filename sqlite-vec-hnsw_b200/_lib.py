@@ -27,6 +27,7 @@ SIGNATURES = {
     "vecgpu_slab_append": (C.c_int, [_c_slab, _p, _p, C.c_uint64]),
     "vecgpu_slab_upsert": (C.c_int, [_c_slab, C.c_int64, _p, C.c_uint32]),
     "vecgpu_slab_delete": (C.c_int, [_c_slab, C.c_int64]),
+    "vecgpu_slab_compact": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "vecgpu_slab_count": (C.c_int, [_c_slab, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vecgpu_slab_get": (C.c_int, [_c_slab, C.c_int64, _p, C.POINTER(C.c_int)]),
     "vecgpu_knn": (C.c_int, [_c_slab, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),

@@ -105,6 +105,7 @@ struct vecgpu_hnsw {
     std::vector<float> distU;
     std::vector<uint16_t> degU;
     uint64_t scored = 0, rounds = 0;
+    uint64_t slab_gen = 0;  // layout generation of the slab the graph was built over (nodes are row positions)
     std::mutex mu;
     // pinned staging + device buffers for the per-round pair lists
     void* h_pin = nullptr;
@@ -750,6 +751,7 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     h->entry = -1;
     h->entry_level = -1;
     h->scored = h->rounds = 0;
+    h->slab_gen = s->layout_gen;
     h->node_level.assign(n, 0);
     h->upper_base.assign(n, 0);
     uint64_t upper_slots = 0;
@@ -954,6 +956,8 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
     }
     if (out_counts) memset(out_counts, 0, (size_t)nq * 4);
     if (h->entry < 0) return 0;  // empty index: no rows (search.rs:279-281)
+    if (h->slab_gen != s->layout_gen)
+        return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction or out-of-order insert) since this HNSW index was built: rebuild it");
     const uint32_t ef = std::max(ef_search, k);  // search.rs:282
     const size_t qbytes = (size_t)nq * s->row_stride;
     if (qbytes > h->dq_cap) {
@@ -1043,6 +1047,8 @@ extern "C" int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edge
 extern "C" int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* level) {
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->entry >= 0 && h->slab_gen != h->slab->layout_gen)
+        return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction or out-of-order insert) since this HNSW index was built: rebuild it");
     if (rowid) *rowid = h->entry < 0 ? -1 : h_rowid_of(h->slab, (uint32_t)h->entry);
     if (level) *level = h->entry < 0 ? -1 : h->entry_level;
     return 0;
@@ -1066,6 +1072,8 @@ extern "C" int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* f
     if (!h || !n_out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     vecgpu_slab* s = h->slab;
+    if (h->entry >= 0 && h->slab_gen != s->layout_gen)
+        return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction or out-of-order insert) since this HNSW index was built: rebuild it");
     if (h->host_stale) {
         int rc = use_device(s->device);
         if (rc || (rc = hnsw_ensure_host(h))) return rc;

@@ -1026,6 +1026,17 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
     }
 }
 
+// compaction: row j of the new slab = row keep[j] of the old one (one warp per row, 16-byte units)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* src, const uint32_t* keep, uint64_t n, uint32_t units, uint8_t* dst) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t w = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t j = w; j < n; j += nw) {
+        const uint4* a = (const uint4*)(src + (uint64_t)keep[j] * units * 16);
+        uint4* b = (uint4*)(dst + j * units * 16);
+        for (uint32_t u = lane; u < units; u += 32) b[u] = a[u];
+    }
+}
+
 // rowid -> position (binary search over the ascending rowid array, or dense
 // arithmetic) and pair -> query index from the CSR offsets; skipped rows -> -1.
 __global__ void resolve_kernel(const int64_t* cand_rowids, uint64_t n_pairs, const uint32_t* offsets, uint32_t nq,

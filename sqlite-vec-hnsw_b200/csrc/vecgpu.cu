@@ -77,6 +77,7 @@ struct vecgpu_slab {
     // rows, ascending rowid order
     uint8_t* d_vec = nullptr;
     uint64_t cap = 0, rows = 0;
+    uint64_t layout_gen = 0;  // bumped whenever row positions move (out-of-order insert, compaction, reload): position-based indexes go stale
     // rowids: dense (first_rowid + position) until a gap appears, then explicit arrays
     bool dense = true;
     int64_t first_rowid = 1;
@@ -381,6 +382,7 @@ extern "C" int vecgpu_slab_append(vecgpu_slab* s, const int64_t* rowids, const v
 extern "C" int vecgpu_slab_load(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
+    ++s->layout_gen;  // the previous contents (and every row position) are replaced
     int rc = use_device(s->device);
     if (rc) return rc;
     s->rows = 0;
@@ -422,6 +424,7 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
         return 0;
     }
     // out-of-order insert (rare: explicit rowid below MAX): shift the tail by one row
+    ++s->layout_gen;
     slab_materialize_rowids(s);
     slab_find(s, rowid, &ins);
     rc = slab_reserve_rows(s, s->rows + 1);
@@ -461,6 +464,54 @@ extern "C" int vecgpu_slab_delete(vecgpu_slab* s, int64_t rowid) {
     int64_t pos = slab_find(s, rowid, nullptr);
     if (pos < 0) return 0;
     return slab_set_skip(s, (uint64_t)pos, 1);
+}
+
+// Drop the skipped rows (tombstones of vecgpu_slab_delete, wrong-length blobs) physically: the kept rows are gathered, in
+// order, into a fresh allocation that replaces the old one (needs kept_rows * row_stride bytes next to the slab for the
+// duration of the call).  Scans never read skipped rows' flags unless a candidate passes, but they do stream their bytes;
+// after many deletes a compaction gives that bandwidth back.
+extern "C" int vecgpu_slab_compact(vecgpu_slab* s, uint64_t* removed) {
+    if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (removed) *removed = 0;
+    if (s->n_skip == 0) return 0;
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    slab_materialize_rowids(s);
+    std::vector<uint32_t> keep;
+    keep.reserve(s->rows - s->n_skip);
+    for (uint64_t p = 0; p < s->rows; ++p)
+        if (!s->h_skip[p]) keep.push_back((uint32_t)p);
+    const uint64_t kept = keep.size();
+    uint8_t* nvec = nullptr;
+    const uint64_t ncap = std::max<uint64_t>(kept, 1);
+    CU(cudaMalloc((void**)&nvec, (size_t)ncap * s->row_stride));
+    const uint64_t chunk = 1u << 22;  // positions uploaded per gather launch
+    for (uint64_t off = 0; off < kept; off += chunk) {
+        const uint64_t m = std::min(chunk, kept - off);
+        if ((rc = ws_reserve(s, WS_TMP, (size_t)m * 4))) {
+            cudaFree(nvec);
+            return rc;
+        }
+        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], keep.data() + off, (size_t)m * 4, cudaMemcpyHostToDevice, s->stream));
+        gather_rows_kernel<<<(uint32_t)std::min<uint64_t>((m + 7) / 8, (uint64_t)s->num_sms * 16), 256, 0, s->stream>>>(
+            s->d_vec, (const uint32_t*)s->d_ws[WS_TMP], m, s->row_stride / 16, nvec + off * s->row_stride);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    CU(cudaFree(s->d_vec));
+    s->d_vec = nvec;
+    s->cap = ncap;
+    for (uint64_t i = 0; i < kept; ++i) s->h_rowids[i] = s->h_rowids[keep[i]];
+    s->h_rowids.resize(kept);
+    if (removed) *removed = s->rows - kept;
+    s->rows = kept;
+    s->h_skip.assign(kept, 0);
+    s->n_skip = 0;
+    s->norms_valid = false;
+    ++s->layout_gen;
+    if ((rc = slab_sync_rowids(s))) return rc;
+    return slab_sync_skip(s);
 }
 
 extern "C" int vecgpu_slab_count(vecgpu_slab* s, uint64_t* rows, uint64_t* live) {

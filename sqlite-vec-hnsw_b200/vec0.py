@@ -359,6 +359,12 @@ class Slab:
     def delete(self, rowid):
         _check(self._lib.vecgpu_slab_delete(self._h, int(rowid)))
 
+    def compact(self):
+        """Physically drop deleted / unreadable rows; -> number of rows removed.  HNSW indexes over the slab must be rebuilt."""
+        removed = C.c_uint64()
+        _check(self._lib.vecgpu_slab_compact(self._h, C.byref(removed)))
+        return removed.value
+
     def count(self):
         rows, live = C.c_uint64(), C.c_uint64()
         _check(self._lib.vecgpu_slab_count(self._h, C.byref(rows), C.byref(live)))

@@ -109,6 +109,9 @@ int main() {
         auto after = brute_force_search(*slab, blob_f32({1, 2, 3}), 3, DistanceMetric::L2).unwrap();
         CHECK(after.size() == 3 && after[0].first == 3);
         auto sc = slab->score(blob_f32({1, 2, 3}), {3, 1, 99}, DistanceMetric::L2).unwrap();  // src/hnsw/search.rs:501-513
+        CHECK(slab->compact().unwrap() == 2);                                           // rows 1 (deleted) and 2 (empty blob) are gone
+        auto compacted = brute_force_search(*slab, blob_f32({1, 2, 3}), 3, DistanceMetric::L2).unwrap();
+        CHECK(compacted.size() == 3 && compacted[0].first == 3 && compacted[0].second == after[0].second);
         CHECK(std::fabs(sc[0] - std::sqrt(12.0f)) < 1e-6f && std::isnan(sc[1]) && std::isnan(sc[2]));
         delete slab;
     }

@@ -681,6 +681,59 @@ def test_hnsw_empty_and_tiny(vg, gpu):
         idx.close()
 
 
+# ------------------------------------------------------------------ slab maintenance: tombstones + compaction
+@pytest.mark.parametrize("elem,metric,dims", [(F32, COSINE, 48), (I8, L2, 64), (BIT, HAMMING, 96)])
+def test_slab_compact_drops_tombstones_and_keeps_results(vg, orc, gpu, elem, metric, dims):
+    n, k = 20000, 12
+    v = random_rows(elem, n, dims, seed=501)
+    q = random_rows(elem, 20, dims, seed=502)
+    rng = np.random.default_rng(503)
+    dead = np.sort(rng.choice(n, size=n // 3, replace=False))
+    skip = np.zeros(n, dtype="u1")
+    skip[dead] = 1
+    with vg.Slab(elem, dims) as s:
+        s.load(v)                                   # dense rowids 1..n
+        for p in dead:
+            s.delete(int(p) + 1)
+        er, ed, ec = orc.knn(elem, dims, v, q, k, metric, skip=skip)
+        r0, d0, c0 = s.knn(q, k, metric)            # tombstones are skipped by the scan ...
+        assert np.array_equal(r0, er) and same_bits(d0, ed)
+        assert s.count() == (n, n - len(dead))
+        assert s.compact() == len(dead)             # ... and physically gone after the compaction
+        assert s.count() == (n - len(dead), n - len(dead)) and s.compact() == 0
+        r1, d1, c1 = s.knn(q, k, metric)
+        assert np.array_equal(r1, er) and same_bits(d1, ed) and np.array_equal(c1, ec)
+        r2, d2, c2 = s.knn(q[:1], k, metric)        # single-query path too
+        assert np.array_equal(r2, er[:1]) and same_bits(d2, ed[:1])
+        # a dropped rowid can come back (out-of-order insert), and candidate scoring resolves the sparse rowids
+        back = int(dead[5])
+        s.upsert(back + 1, v[back].tobytes())
+        skip[back] = 0
+        er3, ed3, _ = orc.knn(elem, dims, v, q, k, metric, skip=skip)
+        r3, d3, _ = s.knn(q, k, metric)
+        assert np.array_equal(r3, er3) and same_bits(d3, ed3)
+        sc = s.score(q[:1], er3[0], np.array([0, k], dtype="<u4"), metric)
+        assert same_bits(sc, ed3[0])
+
+
+def test_hnsw_index_goes_stale_when_rows_move(vg, gpu):
+    v = random_rows(F32, 4000, 16, seed=511)
+    with vg.Slab(F32, 16) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=8, ef_construction=40)
+        idx.rebuild()
+        idx.search(v[:2], 3)
+        s.delete(7)
+        idx.search(v[:2], 3)                      # a tombstone does not move rows: still fine
+        assert s.compact() == 1
+        with pytest.raises(vg.VecError):          # positions changed: the index must be rebuilt
+            idx.search(v[:2], 3)
+        idx.rebuild()
+        r, d, c = idx.search(v[:2], 3)
+        assert r[0, 0] == 1 and r[1, 0] == 2
+        idx.close()
+
+
 # ------------------------------------------------------------------ K6: whole search_layer on the device (one warp per query)
 class _hnsw_mode:
     """VECGPU_HNSW_DEVICE=0 selects the lockstep driver (one scoring launch per expansion round)."""
