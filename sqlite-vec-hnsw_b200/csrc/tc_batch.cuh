@@ -1,23 +1,28 @@
-// tc_batch.cuh — K2: batched float32 queries as a tensor-core contraction (tcgen05, kind::tf32, 3xTF32).
+// tc_batch.cuh — K2 / K3 batched: many queries against the slab as a tensor-core contraction (tcgen05, TMEM, TMA).
 //
 // Replaces, for nq >> 1 queries, the per-pair simsimd calls of the exact scan
-// (src/vtab.rs:2594-2616 -> src/distance/scalar.rs:17,48) by S = Q * X^T on the 5th-gen tensor cores:
+// (src/vtab.rs:2594-2616 -> src/distance/scalar.rs:17,48,61) by S = Q * X^T on the 5th-gen tensor cores:
 //     ||q - x||^2 = ||q||^2 + ||x||^2 - 2 q.x          cos(q,x) = q.x / (||q|| ||x||)
-// q.x is computed with 3xTF32 error compensation.  The tensor core TRUNCATES fp32 operands to tf32
-// (measured, tools/umma_test.cu), so with hi = x (as the hardware sees it) and lo = x - trunc_tf32(x)
-// (exact in fp32):  q.x ~= hi_q.hi_x + lo_q.hi_x + hi_q.lo_x   (the lo.lo term, ~2^-22, is dropped).
-// The result only SELECTS candidates: every query keeps its k+32 best approximate scores per CTA, a
-// rigorous error bound turns them into a candidate superset of the exact top-k, and the candidates
-// are re-scored by pair_kernel in the canonical fp32 order, so the final rowids and distances are
-// bit-identical to the single-query scan.  Queries whose bound cannot be certified (massive ties)
-// fall back to the exact scan.
 //
+// tc_scan_kernel (float32, kind::tf32).  The product only SELECTS candidates: every query keeps its k+32 best
+// approximate scores per CTA, a rigorous error bound turns them into a candidate superset of the exact top-k
+// (tc_collect_kernel), and the candidates are re-scored by pair_kernel in the canonical fp32 order, so the final rowids
+// and distances are bit-identical to the single-query scan.  Queries whose bound cannot be certified (massive ties)
+// fall back to the exact scan.  Two ways to form q.x (TcParams::terms):
+//   1 (default)  one TF32 pass: the tensor core TRUNCATES fp32 operands to tf32 (measured, tools/umma_test.cu), the
+//                error |q.x - tf32(q).tf32(x)| <= 2^-9 |q||x| (Cauchy-Schwarz) goes into the certified bound;
+//   3            3xTF32: hi = x as the hardware sees it, lo = x - trunc_tf32(x) (exact in fp32),
+//                q.x ~= hi_q.hi_x + lo_q.hi_x + hi_q.lo_x (lo.lo ~ 2^-22 dropped); the lo tiles are made in shared memory.
 // One CTA per SM, 12 warps, warp-specialised:
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) of a 128x32 query chunk + 256x32 row chunk
+//               (optionally multicast to a thread-block cluster), soft lockstep with the CTAs that stream the same rows
 //   warp 1      tcgen05.mma issuer (one lane); owns the TMEM allocation (512 columns = 2 accumulators)
-//   warps 4-7   epilogue: tcgen05.ld of the 128x256 fp32 accumulator, score -> threshold -> candidate list
-//   warps 8-11  transform: lo = x - trunc(x) for both operands, written to the twin "lo" tiles
+//   warps 4-7   epilogue: tcgen05.ld of the 128x256 fp32 accumulator, score -> pass mask -> append buffer -> compaction
+//   warps 8-11  (terms = 3 only) transform: lo = x - trunc(x) for both operands, written to the twin "lo" tiles
 // Pipelines: full_raw/full_lo/empty per smem stage, tmem_full/tmem_empty per accumulator.
+//
+// tci8_scan_kernel (int8 L2, kind::i8): the int32 accumulator is exact, so the epilogue emits the FINAL keys; see the
+// second half of this file.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -673,9 +678,11 @@ __global__ void tc_keys_kernel(const float* dist, const int64_t* pos, uint64_t n
 // K3 (batched): int8 L2 on the tensor cores — tcgen05 kind::i8, exact int32 accumulation.
 //   ||q - x||^2 = |q|^2 + |x|^2 - 2 q.x  is an exact integer, so the epilogue produces the FINAL ranking keys
 //   ((float)sqrt((double)s), row) itself — no re-rank, no error bound.  Same pipeline as tc_scan_kernel minus
-//   the lo-split: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 epilogue; 4 smem stages of 48 KB.
-//   Each epilogue thread (= one query) keeps its k best keys as a binary max-heap in global memory, written
-//   straight into the [query][part][k] layout the final merge reads.
+//   the lo-split: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 and 8-11 epilogue (one 128-column half of every
+//   tile each); 4 smem stages of 48 KB.  Each epilogue thread (= one query, one column half) appends the keys that beat
+//   its bound to a private buffer; full buffers are compacted by the whole warp (register bitonic sort) and the final
+//   k best land in the [query][part][k] layout the final merge reads.  A first launch over a sampled prefix of the slab
+//   provides every query's admission bound for the main launch (TciParams::tau_init).
 // =====================================================================================================
 namespace vg {
 
