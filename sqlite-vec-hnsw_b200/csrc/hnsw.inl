@@ -1,13 +1,18 @@
-// hnsw.inl — batched HNSW build / search driver on top of the gathered scoring kernel (K5).
+// hnsw.inl — host side of the HNSW build / search (BASELINE config 5); the device code is in hnsw_dev.cuh.
 // Included by vecgpu.cu (needs vecgpu_slab, launch_pairs, ws_reserve, pin_reserve, CU, LAUNCHED, fail).
 //
 // What it replaces in the reference: insert_hnsw (src/hnsw/insert.rs:279-532), search_hnsw / search_layer
 // (src/hnsw/search.rs:267-543) and the SQL node/edge fetches behind them (src/hnsw/storage.rs), for the
 // rebuild (src/sql_functions.rs:436-534) and for queries.  The reference walks the graph one query at a
-// time and scores 1-32 neighbours per expansion step through SQLite lookups; here B inserts
-// (or queries) advance in lockstep and every round scores ALL their unvisited neighbours in one launch of
-// pair_kernel over the HBM-resident slab.  Graph state (adjacency + stored edge distances) lives in host
-// memory and can be exported for a bulk write-back into {t}_{c}_hnsw_edges (src/shadow.rs:478-487).
+// time and scores 1-32 neighbours per expansion through SQLite lookups.  Here:
+//   - default: the adjacency lists live in HBM; hnsw_search_kernel walks all layers of a query (or of an
+//     insert of a rebuild batch) with one warp, and a rebuild batch is linked on the device as well
+//     (hnsw_link_*_kernel); the host copy of the lists is refreshed on demand (export, lockstep driver);
+//   - lockstep driver (VECGPU_HNSW_DEVICE=0, and the path that answers a query which overflowed a device
+//     capacity): B inserts / queries advance together and every round scores ALL their unvisited neighbours
+//     in one launch of pair_kernel; heaps, visited sets and linking on the host.
+// Both produce the same graph and the same results; the graph can be exported for a bulk write-back into
+// {t}_{c}_hnsw_edges (src/shadow.rs:478-487).
 //
 // Semantics kept from the reference:
 //   - layer search: entry scored first (search.rs:385-398); pop closest candidate, stop when it is farther
@@ -22,7 +27,7 @@
 //     u comes from a counter-based hash of (seed, position), so builds are reproducible (the reference's
 //     are not: SURVEY F7).
 // Deviation: nodes of one batch do not see each other while searching (they are linked afterwards, in
-// order); batches start small and grow with the graph to keep the effect negligible.  Judged by recall.
+// order); batches start small and grow with the graph (at most a quarter of it).  Judged by recall.
 
 struct HCand {
     float d;
