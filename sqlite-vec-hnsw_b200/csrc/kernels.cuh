@@ -1012,7 +1012,7 @@ __global__ void __launch_bounds__(256) pair_kernel(const PairParams p) {
         float qc = 0.f;
         if (T::HAS_QC) {
             // all 32 lanes participate in the shuffles; groups of 4 stay aligned because LPR==4 here
-            qc = query_const(a, in ? p.units : 0, g, p.qc_kind);
+            qc = query_const(a, (in && bi >= 0) ? p.units : 0, g, p.qc_kind);  // empty candidate slots cost nothing
         }
         if (in && bi >= 0) {
             for (uint32_t u = g; u < p.units; u += LPR) {
