@@ -170,9 +170,6 @@ __device__ __forceinline__ int tci_tau_s(uint64_t key) {
 // direction flags), and the k smallest are written back to the front of the buffer (and to `out` when given).
 // Returns (to every lane) the k-th smallest key, KEY_NONE when fewer than k keys exist.  ~1.2k instructions per
 // lane: cheap enough that a compaction no longer stalls the accumulator pipeline.
-__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
-__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
-
 __device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint32_t k, uint64_t* out, int lane) {
     __syncwarp();  // the owner lane's appends become visible to the helping lanes
     uint64_t v[8];
@@ -181,46 +178,7 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint3
         const uint32_t i = (uint32_t)lane * 8 + r;
         v[r] = i < cnt ? buf[i] : KEY_NONE;
     }
-#pragma unroll
-    for (int size = 2; size <= 256; size <<= 1) {
-        if (size <= 8) {  // element i against i ^ (size - 1), both in this lane
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int pr = r ^ (size - 1);
-                if (pr > r) {
-                    const uint64_t a = v[r], b = v[pr];
-                    v[r] = u64min(a, b);
-                    v[pr] = u64max(a, b);
-                }
-            }
-        } else {          // partner lane = lane ^ (size/8 - 1), partner register = 7 - r
-            const bool keep_min = (lane & (size / 16)) == 0;
-            uint64_t o[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) o[r] = shfl_xor_u64(v[7 - r], size / 8 - 1);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = keep_min ? u64min(v[r], o[r]) : u64max(v[r], o[r]);
-        }
-#pragma unroll
-        for (int stride = size / 4; stride >= 1; stride >>= 1) {  // element i against i ^ stride
-            if (stride >= 8) {
-                const bool keep_min = (lane & (stride / 8)) == 0;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint64_t o = shfl_xor_u64(v[r], stride / 8);
-                    v[r] = keep_min ? u64min(v[r], o) : u64max(v[r], o);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if ((r & stride) == 0) {
-                        const uint64_t a = v[r], b = v[r ^ stride];
-                        v[r] = u64min(a, b);
-                        v[r ^ stride] = u64max(a, b);
-                    }
-            }
-        }
-    }
+    warp_sort256(v, lane);
     uint64_t mine = v[0];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {

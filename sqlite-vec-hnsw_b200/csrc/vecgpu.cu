@@ -666,6 +666,11 @@ static int launch_scan(int elem, int metric, const ScanParams& p, const ScanCfg&
 
 // final selection over the per-CTA partial lists: [nq][n_cand] keys -> k smallest per query, decoded
 static int launch_merge(vecgpu_slab* s, const MergeParams& mp, uint32_t nq, cudaStream_t st) {
+    if (mp.k <= 32 && mp.n_cand <= 2048 && env_u32("VECGPU_MERGE_SMALL", 1)) {
+        merge_small_kernel<<<nq, 256, 0, st>>>(mp);  // two register sorts per query
+        LAUNCHED();
+        return 0;
+    }
     if (mp.n_cand <= 16384) {
         // fits one CTA's shared memory: one bitonic sort per query
         const uint32_t np2 = std::max(2u, next_pow2((uint32_t)mp.n_cand));
