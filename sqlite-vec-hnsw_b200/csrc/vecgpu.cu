@@ -483,24 +483,25 @@ extern "C" int vecgpu_slab_compact(vecgpu_slab* s, uint64_t* removed) {
     for (uint64_t p = 0; p < s->rows; ++p)
         if (!s->h_skip[p]) keep.push_back((uint32_t)p);
     const uint64_t kept = keep.size();
-    uint8_t* nvec = nullptr;
+    struct DevBuf {  // the new allocation is released if anything fails before it replaces the old one
+        uint8_t* p = nullptr;
+        ~DevBuf() { if (p) cudaFree(p); }
+    } nb;
     const uint64_t ncap = std::max<uint64_t>(kept, 1);
-    CU(cudaMalloc((void**)&nvec, (size_t)ncap * s->row_stride));
+    CU(cudaMalloc((void**)&nb.p, (size_t)ncap * s->row_stride));
     const uint64_t chunk = 1u << 22;  // positions uploaded per gather launch
     for (uint64_t off = 0; off < kept; off += chunk) {
         const uint64_t m = std::min(chunk, kept - off);
-        if ((rc = ws_reserve(s, WS_TMP, (size_t)m * 4))) {
-            cudaFree(nvec);
-            return rc;
-        }
+        if ((rc = ws_reserve(s, WS_TMP, (size_t)m * 4))) return rc;
         CU(cudaMemcpyAsync(s->d_ws[WS_TMP], keep.data() + off, (size_t)m * 4, cudaMemcpyHostToDevice, s->stream));
         gather_rows_kernel<<<(uint32_t)std::min<uint64_t>((m + 7) / 8, (uint64_t)s->num_sms * 16), 256, 0, s->stream>>>(
-            s->d_vec, (const uint32_t*)s->d_ws[WS_TMP], m, s->row_stride / 16, nvec + off * s->row_stride);
+            s->d_vec, (const uint32_t*)s->d_ws[WS_TMP], m, s->row_stride / 16, nb.p + off * s->row_stride);
         LAUNCHED();
         CU(cudaStreamSynchronize(s->stream));
     }
     CU(cudaFree(s->d_vec));
-    s->d_vec = nvec;
+    s->d_vec = nb.p;
+    nb.p = nullptr;
     s->cap = ncap;
     for (uint64_t i = 0; i < kept; ++i) s->h_rowids[i] = s->h_rowids[keep[i]];
     s->h_rowids.resize(kept);
