@@ -86,11 +86,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _use_all_host_threads(oracle):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all the host threads it can (it runs on
+    rank 0 only), so the OpenMP team is set explicitly from the CPU affinity of this process."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    oracle.set_threads(max(1, n))
+
+
 def cpu_baseline(seconds_budget=12.0):
     """The oracle port of the reference path on the host cores, bounded prefix of the same corpus."""
     import oracle
 
     oracle.build()
+    _use_all_host_threads(oracle)
     n = CPU_PREFIX_ROWS
     cores = oracle.num_threads()
     vec = oracle.synth_rows(F32, SEED, 1, n, DIMS, GAUSS4)
@@ -120,6 +131,7 @@ def run_reference(args):
     import oracle
 
     oracle.build()
+    _use_all_host_threads(oracle)
     n = CPU_PREFIX_ROWS
     vec = oracle.synth_rows(F32, SEED, 1, n, DIMS, GAUSS4)
     q = oracle.synth_rows(F32, QSEED, 1, BATCH, DIMS, GAUSS4)
