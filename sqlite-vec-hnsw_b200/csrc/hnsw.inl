@@ -996,7 +996,9 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
             if (!qs[i].layers.empty()) emit(which ? which[i] : q0 + i, qs[i].layers[0]);
         return 0;
     };
-    if (hnsw_device_enabled(h)) {
+    // a beam whose sorted array (2 ef keys) does not fit one warp's share of shared memory goes through the lockstep driver
+    const bool ef_fits = ((size_t)2 * ef + 64) * 8 + ((h->max_m0 + 31u) & ~31u) * 4 + s->row_stride <= 200 * 1024;
+    if (hnsw_device_enabled(h) && ef_fits) {
         // K6: the whole layered search on the device, one warp per query
         const uint32_t chunk = 1u << 16;
         std::vector<uint32_t> fb;

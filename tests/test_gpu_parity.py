@@ -898,6 +898,23 @@ def test_hnsw_device_build_overflow_batches_are_exact(vg, orc, gpu):
         idx_h.close()
 
 
+def test_hnsw_huge_ef_uses_the_lockstep_driver(vg, orc, gpu):
+    # ef_search beyond what a warp's shared-memory array can hold: answered by the lockstep driver, same semantics
+    n, dims = 30000, 8
+    v = random_rows(F32, n, dims, seed=441)
+    q = random_rows(F32, 3, dims, seed=442)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=8, ef_construction=40, seed=3)
+        idx.rebuild()
+        before = idx.device_stats()["queries"]
+        r, d, c = idx.search(q, 10, ef_search=20000)
+        assert idx.device_stats()["queries"] == before      # not the device walk
+        er, ed, _ = orc.knn(F32, dims, v, q, 10, L2)
+        assert _recall(r, er) >= 0.9 and np.all(np.diff(d, axis=1) >= 0)
+        idx.close()
+
+
 def test_hnsw_device_large_batch_throughput_path(vg, orc, gpu):
     # many queries in one launch (more than one wave of warps), results independent of the launch shape
     n, dims, nq = 20000, 32, 20000
