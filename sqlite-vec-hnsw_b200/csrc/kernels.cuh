@@ -823,11 +823,6 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
 }
 
 // ---------------------------------------------------------------------------
-// K6: final selection + sort + decode.  One CTA per query reads `n_cand` keys
-// (per-CTA partial lists of the scan), keeps the k smallest, sorts them
-// ascending == (distance_f32, rowid) order, translates positions to rowids.
-// ---------------------------------------------------------------------------
-// ---------------------------------------------------------------------------
 // Warp-wide sort of 256 u64 keys held 8 per lane (element index = lane * 8 + r), ascending: a bitonic network that
 // lives entirely in registers — strides below 8 are register-to-register compare-exchanges, larger strides are lane
 // shuffles; the "flip" form of the network (first stage of every size compares i with i ^ (size - 1)) needs no
@@ -879,6 +874,141 @@ __device__ __forceinline__ void warp_sort256(uint64_t (&v)[8], int lane) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// K4 batched: Hamming for many queries over short bit rows (row_stride <= 128 bytes), lane = query.
+// The multi-query scan (QB = 8) re-reads the query words from shared memory for every row (5.4 instructions per
+// XOR/POPC pair, 9 k instructions of unrolled code, 8 queries per pass over the data).  Here a warp owns 32 queries:
+// each lane keeps ITS query in registers (<= 32 words), every row word is one broadcast LDS for the whole warp, and
+// each lane ranks the rows for its own query in a private k-entry list (unsorted, tracked maximum; entry e of lane l
+// at list[e * 32 + l]: conflict-free).  Rows reach shared memory through the same per-warp self-refilled bulk-copy
+// rings as scan_kernel.  Exact: integer popcounts, keys (order_bits((float)d) << 32 | row) as everywhere else.
+// ---------------------------------------------------------------------------
+struct HamBatchParams {
+    const uint8_t* vectors;
+    const uint8_t* skip;
+    const uint8_t* queries;   // [nq][row_stride], zero padded
+    uint64_t* out_keys;       // [nq][gridDim.x][k]
+    uint64_t n_rows;
+    uint32_t nq, k;
+    uint32_t row_stride;      // multiple of 16, <= 128
+    uint32_t rows_per_tile;   // tile = rows_per_tile * row_stride bytes, one bulk copy
+    uint32_t n_stages;        // ring depth per warp
+    uint32_t n_warps;         // C
+};
+
+template <int W>  // 32-bit words per row
+__global__ void __launch_bounds__(512) ham_batch_kernel(const HamBatchParams p) {
+    extern __shared__ __align__(128) uint8_t hb_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t C = p.n_warps, D = p.n_stages, tile_bytes = p.rows_per_tile * p.row_stride;
+    uint8_t* s_tiles = hb_smem;                                                  // [C][D][tile_bytes]
+    uint64_t* s_list = (uint64_t*)(hb_smem + (size_t)C * D * tile_bytes);        // [C][k][32]
+    uint64_t* s_bar = s_list + (size_t)C * p.k * 32;                             // [C][D]
+    const uint32_t my_bar = smem_u32(s_bar + (size_t)warp * D);
+    uint8_t* my_tiles = s_tiles + (size_t)warp * D * tile_bytes;
+    uint64_t* my_list = s_list + (size_t)warp * p.k * 32;
+    if (lane == 0)
+        for (uint32_t d = 0; d < D; ++d) mbar_init(my_bar + 8 * d, 1);
+    mbar_fence_init();
+    __syncwarp();
+
+    const uint32_t q = blockIdx.y * 32 + lane;
+    const bool q_ok = q < p.nq;
+    uint32_t qw[W];
+    {
+        const uint4* qp = (const uint4*)(p.queries + (size_t)(q_ok ? q : 0) * p.row_stride);
+#pragma unroll
+        for (int w4 = 0; w4 < W / 4; ++w4) {
+            const uint4 v = q_ok ? qp[w4] : make_uint4(0, 0, 0, 0);
+            qw[4 * w4 + 0] = v.x; qw[4 * w4 + 1] = v.y; qw[4 * w4 + 2] = v.z; qw[4 * w4 + 3] = v.w;
+        }
+    }
+    // tiles of this warp: tile t -> CTA t % gridDim.x, the j-th tile of a CTA -> warp j % C
+    const uint64_t n_tiles = (p.n_rows + p.rows_per_tile - 1) / p.rows_per_tile;
+    const uint64_t first = blockIdx.x + (uint64_t)warp * gridDim.x, step = (uint64_t)C * gridDim.x;
+    const uint64_t my_n = first < n_tiles ? (n_tiles - first + step - 1) / step : 0;
+    auto issue = [&](uint64_t j) {  // lane 0: bulk copy of my j-th tile into ring slot j % D
+        const uint64_t row0 = (first + j * step) * p.rows_per_tile;
+        const uint32_t rows = (uint32_t)min((uint64_t)p.rows_per_tile, p.n_rows - row0);
+        const uint32_t bytes = rows * p.row_stride, slot = (uint32_t)(j % D);
+        mbar_expect_tx(my_bar + 8 * slot, bytes);
+        bulk_g2s(smem_u32(my_tiles + (size_t)slot * tile_bytes), p.vectors + row0 * p.row_stride, bytes, my_bar + 8 * slot);
+    };
+    if (lane == 0)
+        for (uint64_t j = 0; j < min((uint64_t)D, my_n); ++j) issue(j);
+
+    uint32_t cnt = 0, maxpos = 0;
+    uint64_t tau_key = q_ok ? KEY_NONE : 0ull;   // a padding lane never admits anything
+    for (uint64_t j = 0; j < my_n; ++j) {
+        const uint32_t slot = (uint32_t)(j % D);
+        mbar_wait(my_bar + 8 * slot, (uint32_t)((j / D) & 1));
+        const uint64_t row0 = (first + j * step) * p.rows_per_tile;
+        const uint32_t rows = (uint32_t)min((uint64_t)p.rows_per_tile, p.n_rows - row0);
+        const uint32_t tb = smem_u32(my_tiles + (size_t)slot * tile_bytes);
+#pragma unroll 2
+        for (uint32_t r = 0; r < rows; ++r) {
+            // (a Harley-Seal carry-save tree that trades 32 POPC for 60 LOP3 + 6 POPC was measured: 10.3 vs 9.8 ms, not kept)
+            int d0 = 0, d1 = 0;
+#pragma unroll
+            for (int w4 = 0; w4 < W / 4; ++w4) {
+                const uint4 x = lds128(tb + r * p.row_stride + w4 * 16);  // same address in every lane: broadcast
+                d0 += __popc(x.x ^ qw[4 * w4 + 0]) + __popc(x.y ^ qw[4 * w4 + 1]);
+                d1 += __popc(x.z ^ qw[4 * w4 + 2]) + __popc(x.w ^ qw[4 * w4 + 3]);
+            }
+            const uint64_t key = make_key((float)(d0 + d1), (uint32_t)(row0 + r));
+            if (key < tau_key && !(p.skip && p.skip[row0 + r])) {   // rare after the first few hundred rows
+                if (cnt < p.k) {
+                    my_list[cnt * 32 + lane] = key;
+                    ++cnt;
+                } else {
+                    my_list[maxpos * 32 + lane] = key;
+                }
+                if (cnt == p.k) {  // full: the bound is the largest kept key
+                    uint64_t m = my_list[lane];
+                    uint32_t mp = 0;
+                    for (uint32_t e = 1; e < p.k; ++e) {
+                        const uint64_t v = my_list[e * 32 + lane];
+                        if (v > m) {
+                            m = v;
+                            mp = e;
+                        }
+                    }
+                    tau_key = m;
+                    maxpos = mp;
+                }
+            }
+        }
+        __syncwarp();         // every lane is done with the slot before it is refilled
+        fence_proxy_async();  // the slot was read through the generic proxy; the copy writes through the async proxy
+        if (lane == 0 && j + D < my_n) issue(j + D);
+    }
+    // blank the unused entries, then one warp per query merges the C lists (C * k <= 256 keys) in registers
+    for (uint32_t e = cnt; e < p.k; ++e) my_list[e * 32 + lane] = KEY_NONE;
+    __syncthreads();
+    for (uint32_t ql = (uint32_t)warp; ql < 32; ql += C) {
+        const uint32_t qq = blockIdx.y * 32 + ql;
+        if (qq >= p.nq) continue;
+        uint64_t v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t i = (uint32_t)lane * 8 + r;   // i -> (warp i / k, entry i % k)
+            v[r] = i < C * p.k ? s_list[((size_t)(i / p.k) * p.k + i % p.k) * 32 + ql] : KEY_NONE;
+        }
+        warp_sort256(v, lane);
+        uint64_t* out = p.out_keys + ((size_t)qq * gridDim.x + blockIdx.x) * p.k;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint32_t i = (uint32_t)lane * 8 + r;
+            if (i < p.k) out[i] = v[r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6: final selection + sort + decode.  One CTA per query reads `n_cand` keys
+// (per-CTA partial lists of the scan), keeps the k smallest, sorts them
+// ascending == (distance_f32, rowid) order, translates positions to rowids.
+// ---------------------------------------------------------------------------
 struct MergeParams {
     const uint64_t* keys;  // [nq][n_cand]
     uint64_t n_cand;

@@ -832,6 +832,53 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         }
         if (rc != 1) return rc;
     }
+    if (s->elem == VECGPU_BIT && nq >= 16 && k <= 32 && s->row_stride <= 128 && s->rows >= 4096 && env_u32("VECGPU_HAM_BATCH", 1)) {
+        // many Hamming queries over short rows: lane = query (ham_batch_kernel), 32 queries per pass over the data
+        HamBatchParams hp{};
+        hp.vectors = s->d_vec;
+        hp.skip = d_skip;
+        hp.queries = d_q;
+        hp.n_rows = s->rows;
+        hp.nq = nq;
+        hp.k = k;
+        hp.row_stride = s->row_stride;
+        hp.n_warps = std::min(16u, 256u / k);       // the CTA merge sorts C * k <= 256 keys per query in registers
+        hp.rows_per_tile = std::max(1u, 2048u / s->row_stride);
+        hp.n_stages = 3;
+        const uint64_t n_tiles = (s->rows + hp.rows_per_tile - 1) / hp.rows_per_tile;
+        const uint32_t gx = (uint32_t)std::min<uint64_t>((n_tiles + hp.n_warps - 1) / hp.n_warps, (uint64_t)s->num_sms);
+        const uint32_t gy = (nq + 31) / 32;
+        rc = ws_reserve(s, WS_PART, (size_t)nq * gx * k * 8);
+        if (rc) return rc;
+        hp.out_keys = (uint64_t*)s->d_ws[WS_PART];
+        const size_t smem = (size_t)hp.n_warps * hp.n_stages * hp.rows_per_tile * s->row_stride + (size_t)hp.n_warps * k * 32 * 8 +
+                            (size_t)hp.n_warps * hp.n_stages * 8;
+        const dim3 grid(gx, gy), block(hp.n_warps * 32);
+        switch (s->row_stride / 4) {
+#define VECGPU_HAM_CASE(W)                                                                                            \
+    case W:                                                                                                           \
+        CU(cudaFuncSetAttribute(ham_batch_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));    \
+        ham_batch_kernel<W><<<grid, block, smem, st>>>(hp);                                                          \
+        break;
+            VECGPU_HAM_CASE(4) VECGPU_HAM_CASE(8) VECGPU_HAM_CASE(12) VECGPU_HAM_CASE(16) VECGPU_HAM_CASE(20) VECGPU_HAM_CASE(24)
+            VECGPU_HAM_CASE(28) VECGPU_HAM_CASE(32)
+#undef VECGPU_HAM_CASE
+            default: return fail(VECGPU_ERR_INVALID_PARAM, "unexpected row stride for the Hamming batch kernel");
+        }
+        LAUNCHED();
+        MergeParams mp{};
+        mp.keys = hp.out_keys;
+        mp.n_cand = (uint64_t)gx * k;
+        mp.k = k;
+        mp.kp2 = next_pow2(k);
+        mp.rowids = d_rowids;
+        mp.first_rowid = s->first_rowid;
+        mp.out_rowids = d_out_rowids;
+        mp.out_dists = d_out_dists;
+        mp.out_counts = d_out_counts;
+        mp.pad_rowid = pad_rowid;
+        return launch_merge(s, mp, nq, st);
+    }
     if (k <= K_FUSED_MAX) {
         ScanCfg c;
         rc = plan_scan(lpr, metric_strict(s->elem, metric), s->row_stride, k, nq, false, c);

@@ -681,6 +681,31 @@ def test_hnsw_empty_and_tiny(vg, gpu):
         idx.close()
 
 
+# ------------------------------------------------------------------ K4 batched: Hamming, lane = query (ham_batch_kernel)
+@pytest.mark.parametrize("dims,nq,k,ties", [(1024, 70, 10, False), (1024, 33, 32, True), (96, 64, 17, False), (1000, 16, 1, True),
+                                            (520, 100, 12, False)])
+def test_hamming_batched_lane_per_query_matches_oracle(vg, orc, gpu, dims, nq, k, ties):
+    n = 60000
+    v = random_rows(BIT, n, dims, seed=601, ties=ties)
+    q = random_rows(BIT, nq, dims, seed=602, ties=ties)
+    rowids = np.arange(n, dtype="<i8") * 4 + 9
+    skip = np.zeros(n, dtype="u1")
+    skip[[0, 1, 31337, n - 1]] = 1
+    with vg.Slab(BIT, dims) as s:
+        s.load(v, rowids)
+        for i in np.flatnonzero(skip):
+            s.delete(int(rowids[i]))
+        r, d, c = s.knn(q, k, HAMMING)
+        os.environ["VECGPU_HAM_BATCH"] = "0"          # the multi-query scan it replaces gives the same answer
+        try:
+            r0, d0, c0 = s.knn(q, k, HAMMING)
+        finally:
+            del os.environ["VECGPU_HAM_BATCH"]
+    er, ed, ec = orc.knn(BIT, dims, v, q, k, HAMMING, rowids=rowids, skip=skip)
+    assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+    assert np.array_equal(r0, er) and same_bits(d0, ed)
+
+
 # ------------------------------------------------------------------ slab maintenance: tombstones + compaction
 @pytest.mark.parametrize("elem,metric,dims", [(F32, COSINE, 48), (I8, L2, 64), (BIT, HAMMING, 96)])
 def test_slab_compact_drops_tombstones_and_keeps_results(vg, orc, gpu, elem, metric, dims):
