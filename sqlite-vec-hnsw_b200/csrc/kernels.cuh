@@ -466,6 +466,58 @@ __device__ __forceinline__ void list_offer(uint64_t* list, ListHdr* hdr, uint32_
     }
 }
 
+// ---------------------------------------------------------------------------
+// Warp-wide sort of 256 u64 keys held 8 per lane (element index = lane * 8 + r), ascending: a bitonic network that
+// lives entirely in registers — strides below 8 are register-to-register compare-exchanges, larger strides are lane
+// shuffles; the "flip" form of the network (first stage of every size compares i with i ^ (size - 1)) needs no
+// direction flags.  ~1.2 k instructions per lane.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
+
+__device__ __forceinline__ void warp_sort256(uint64_t (&v)[8], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 256; size <<= 1) {
+        if (size <= 8) {  // element i against i ^ (size - 1), both in this lane
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int pr = r ^ (size - 1);
+                if (pr > r) {
+                    const uint64_t a = v[r], b = v[pr];
+                    v[r] = u64min(a, b);
+                    v[pr] = u64max(a, b);
+                }
+            }
+        } else {          // partner lane = lane ^ (size/8 - 1), partner register = 7 - r
+            const bool keep_min = (lane & (size / 16)) == 0;
+            uint64_t o[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = shfl_xor_u64(v[7 - r], size / 8 - 1);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = keep_min ? u64min(v[r], o[r]) : u64max(v[r], o[r]);
+        }
+#pragma unroll
+        for (int stride = size / 4; stride >= 1; stride >>= 1) {  // element i against i ^ stride
+            if (stride >= 8) {
+                const bool keep_min = (lane & (stride / 8)) == 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint64_t o = shfl_xor_u64(v[r], stride / 8);
+                    v[r] = keep_min ? u64min(v[r], o) : u64max(v[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if ((r & stride) == 0) {
+                        const uint64_t a = v[r], b = v[r ^ stride];
+                        v[r] = u64min(a, b);
+                        v[r ^ stride] = u64max(a, b);
+                    }
+            }
+        }
+    }
+}
+
 // in-place ascending bitonic sort of n (power of two) u64 keys in shared memory by the whole CTA
 __device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, uint32_t n) {
     for (uint32_t size = 2; size <= n; size <<= 1) {
@@ -809,6 +861,31 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     __syncthreads();
     // ---- CTA merge: the C per-warp lists of a query are contiguous; blank the unused slots, bitonic-sort the
     //      list_stride keys with the whole CTA and emit the k smallest as this CTA's partial result ----
+    if (p.list_stride <= 256) {  // the usual case (C * k <= 256): one warp per query sorts that query's lists in registers,
+                                 // the QB queries of a multi-query pass in parallel instead of QB block-wide sorts in a row
+        for (uint32_t i = (uint32_t)warp; i < nq_here; i += blockDim.x >> 5) {
+            const uint64_t* base = s_list + (size_t)i * p.list_stride;
+            uint64_t v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t j = (uint32_t)lane * 8 + r;
+                uint64_t key = KEY_NONE;
+                if (j < p.list_stride) {
+                    const uint32_t w = j / p.k, e = j - w * p.k;
+                    if (w < C && e < s_hdr[w * QB + i].cnt) key = base[j];
+                }
+                v[r] = key;
+            }
+            warp_sort256(v, lane);
+            uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t j = (uint32_t)lane * 8 + r;
+                if (j < p.k) out[j] = v[r];
+            }
+        }
+        return;
+    }
     for (uint32_t i = 0; i < nq_here; ++i) {
         uint64_t* base = s_list + (size_t)i * p.list_stride;
         for (uint32_t j = threadIdx.x; j < p.list_stride; j += blockDim.x) {
@@ -819,58 +896,6 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
         block_bitonic_sort(base, p.list_stride);
         uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
         for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = base[j];
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Warp-wide sort of 256 u64 keys held 8 per lane (element index = lane * 8 + r), ascending: a bitonic network that
-// lives entirely in registers — strides below 8 are register-to-register compare-exchanges, larger strides are lane
-// shuffles; the "flip" form of the network (first stage of every size compares i with i ^ (size - 1)) needs no
-// direction flags.  ~1.2 k instructions per lane.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
-__device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
-
-__device__ __forceinline__ void warp_sort256(uint64_t (&v)[8], int lane) {
-#pragma unroll
-    for (int size = 2; size <= 256; size <<= 1) {
-        if (size <= 8) {  // element i against i ^ (size - 1), both in this lane
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int pr = r ^ (size - 1);
-                if (pr > r) {
-                    const uint64_t a = v[r], b = v[pr];
-                    v[r] = u64min(a, b);
-                    v[pr] = u64max(a, b);
-                }
-            }
-        } else {          // partner lane = lane ^ (size/8 - 1), partner register = 7 - r
-            const bool keep_min = (lane & (size / 16)) == 0;
-            uint64_t o[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) o[r] = shfl_xor_u64(v[7 - r], size / 8 - 1);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = keep_min ? u64min(v[r], o[r]) : u64max(v[r], o[r]);
-        }
-#pragma unroll
-        for (int stride = size / 4; stride >= 1; stride >>= 1) {  // element i against i ^ stride
-            if (stride >= 8) {
-                const bool keep_min = (lane & (stride / 8)) == 0;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint64_t o = shfl_xor_u64(v[r], stride / 8);
-                    v[r] = keep_min ? u64min(v[r], o) : u64max(v[r], o);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if ((r & stride) == 0) {
-                        const uint64_t a = v[r], b = v[r ^ stride];
-                        v[r] = u64min(a, b);
-                        v[r ^ stride] = u64max(a, b);
-                    }
-            }
-        }
     }
 }
 
