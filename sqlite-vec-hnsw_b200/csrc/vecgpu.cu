@@ -1016,8 +1016,12 @@ static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
 
 static bool tc_eligible(const vecgpu_slab* s, uint32_t nq, uint32_t k, int metric) {
     if (env_u32("VECGPU_TC", 1) == 0) return false;
+    // the tensor-core launch has ~0.3 ms of fixed cost (one compaction per query lane at the end of every CTA): batches of
+    // fewer than 64 queries with less than about 2 M (query, row) pairs are faster through the exact multi-query scan on the
+    // CUDA cores (measured, tools/tc_threshold.py: 32 x 10 k rows 155 vs 365 us, 32 x 100 k rows 830 vs 535 us, 100 x 10 k 440 vs 367 us)
     return s->elem == VECGPU_F32 && (metric == VECGPU_L2 || metric == VECGPU_COSINE) && nq >= env_u32("VECGPU_TC_MIN_NQ", 16) &&
-           s->rows >= 8192 && s->rows < 0x7FFFFFFFull && k <= 96 && s->dims >= 16;
+           s->rows >= 8192 && s->rows < 0x7FFFFFFFull && k <= 96 && s->dims >= 16 &&
+           (nq >= 64 || (uint64_t)nq * s->rows >= env_u32("VECGPU_TC_MIN_WORK", 2000000));
 }
 
 static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,

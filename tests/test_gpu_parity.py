@@ -516,6 +516,30 @@ def test_tc_batched_cluster_multicast_matches_oracle(vg, orc, gpu, tc_terms, clu
         del os.environ["VECGPU_TC_CLUSTER"]
 
 
+def test_small_batches_take_the_cuda_core_route(vg, orc, gpu):
+    # default routing: 32 queries x 20 k rows is below the tensor-core work threshold -> exact multi-query scan, same results
+    n, dims, nq, k = 20000, 64, 32, 10
+    v = random_rows(F32, n, dims, seed=91)
+    q = random_rows(F32, nq, dims, seed=92)
+    old = os.environ.pop("VECGPU_TC_MIN_WORK", None)
+    try:
+        with vg.Slab(F32, dims) as s:
+            s.load(v)
+            before = vg.tc_stats()[0]
+            r, d, c = s.knn(q, k, L2)
+            assert vg.tc_stats()[0] == before, "a small batch must not pay the tensor-core launch"
+            os.environ["VECGPU_TC_MIN_WORK"] = "0"
+            r1, d1, c1 = s.knn(q, k, L2)
+            assert vg.tc_stats()[0] - before == nq
+    finally:
+        if old is not None:
+            os.environ["VECGPU_TC_MIN_WORK"] = old
+        else:
+            os.environ.pop("VECGPU_TC_MIN_WORK", None)
+    er, ed, ec = orc.knn(F32, dims, v, q, k, L2)
+    assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(r1, er) and same_bits(d1, ed)
+
+
 def test_tc_batched_ties_fall_back_to_exact(vg, orc, gpu, tc_terms):
     # a tiny alphabet makes thousands of rows tie at the k-th distance: the candidate bound cannot be
     # certified, the affected queries must be re-run by the exact scan and still match bit for bit
