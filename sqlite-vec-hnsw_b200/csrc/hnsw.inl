@@ -398,7 +398,7 @@ static void hnsw_dev_free_graph(vecgpu_hnsw* h) {
 }
 
 // (re)create the device copy from the host lists
-static int hnsw_dev_upload_all(vecgpu_hnsw* h) {
+static int hnsw_dev_upload_all(vecgpu_hnsw* h, bool empty_graph = false) {
     vecgpu_slab* s = h->slab;
     const size_t n = h->node_level.size(), slots = h->degU.size();
     hnsw_dev_free_graph(h);
@@ -412,16 +412,21 @@ static int hnsw_dev_upload_all(vecgpu_hnsw* h) {
     CU(cudaMalloc(&h->d_distU, std::max<size_t>(1, slots * h->M) * 4));
     h->dn_rows = n;
     h->dn_slots = slots;
-    if (n) {
-        CU(cudaMemcpyAsync(h->d_nbr0, h->nbr0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(h->d_deg0, h->deg0.data(), n * 2, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(h->d_upper_base, h->upper_base.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(h->d_dist0, h->dist0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
-    }
-    if (slots) {
-        CU(cudaMemcpyAsync(h->d_nbrU, h->nbrU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(h->d_degU, h->degU.data(), slots * 2, cudaMemcpyHostToDevice, s->stream));
-        CU(cudaMemcpyAsync(h->d_distU, h->distU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
+    if (n) CU(cudaMemcpyAsync(h->d_upper_base, h->upper_base.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
+    if (empty_graph) {  // start of a rebuild: every list is empty, only the degrees need a defined value
+        CU(cudaMemsetAsync(h->d_deg0, 0, std::max<size_t>(1, n) * 2, s->stream));
+        CU(cudaMemsetAsync(h->d_degU, 0, std::max<size_t>(1, slots) * 2, s->stream));
+    } else {
+        if (n) {
+            CU(cudaMemcpyAsync(h->d_nbr0, h->nbr0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(h->d_deg0, h->deg0.data(), n * 2, cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(h->d_dist0, h->dist0.data(), n * h->max_m0 * 4, cudaMemcpyHostToDevice, s->stream));
+        }
+        if (slots) {
+            CU(cudaMemcpyAsync(h->d_nbrU, h->nbrU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(h->d_degU, h->degU.data(), slots * 2, cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(h->d_distU, h->distU.data(), slots * h->M * 4, cudaMemcpyHostToDevice, s->stream));
+        }
     }
     CU(cudaStreamSynchronize(s->stream));
     h->dirty0.assign(n, 0);
@@ -782,7 +787,7 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     double t_search = 0, t_decode = 0, t_ops = 0, t_link = 0, t_flush = 0;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     if (use_dev) {
-        if ((rc = hnsw_dev_upload_all(h))) return rc;  // empty lists; kept in sync batch by batch
+        if ((rc = hnsw_dev_upload_all(h, true))) return rc;  // empty lists; kept in sync batch by batch
     } else {
         hnsw_dev_free_graph(h);
     }
