@@ -144,6 +144,16 @@ class Vec0Table:
             self.slab.delete(int(rowid))
             self._fingerprint = self._current_fingerprint()
 
+    def compact(self, min_dead_fraction=0.0):
+        """Drop the tombstones left by delete() (and rows with unreadable blobs) from the resident slab when they make up
+        more than `min_dead_fraction` of it; SQLite itself is untouched.  -> rows removed."""
+        if self.slab is None:
+            return 0
+        rows, live = self.slab.count()
+        if rows == live or (rows - live) < min_dead_fraction * rows:
+            return 0
+        return self.slab.compact()
+
     def close(self):
         if self.slab is not None:
             self.slab.close()

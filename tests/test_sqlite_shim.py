@@ -113,6 +113,9 @@ def test_end_to_end_knn_from_sqlite(vg, orc, gpu, tmp_path):
     res = t.knn(nv[0].tobytes(), 4, metric=L2)
     er, ed, _ = orc.knn(F32, dims, v2, nv[0], 4, L2, rowids=rowids2, skip=skip2)
     assert [r for r, _ in res] == list(er[0]) and res[0] == (new_id, 0.0)
+    # compaction of the resident slab keeps every answer (the deleted row and the NULL blob are physically gone)
+    assert t.compact(min_dead_fraction=0.5) == 0 and t.compact() == 2
+    assert t.knn(nv[0].tobytes(), 4, metric=L2) == res and t.slab.count()[0] == t.slab.count()[1]
     # an external writer is noticed and the slab re-staged
     conn.execute('DELETE FROM "items_data" WHERE rowid = ?', (new_id,))
     res = t.knn(nv[0].tobytes(), 1, metric=L2)
