@@ -196,6 +196,9 @@ int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edges, int32_t*
 /* Entry point of the graph (rowid, level) for the {t}_{c}_hnsw_meta row (HnswMetadata.entry_point_rowid / entry_point_level, src/hnsw/mod.rs:97-103); rowid -1 / level -1
  * when the index is empty. */
 int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* level);
+/* Node list for a bulk write-back into {t}_{c}_hnsw_nodes(rowid, level, vector) (src/shadow.rs:464-474): the rows the last
+ * rebuild indexed, ascending rowid, with their level.  cap = 0 only counts. */
+int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* rowids, int32_t* levels, uint64_t* n_out);
 /* Device-search counters: queries (or inserts) answered by the search kernel, how many of those hit a device capacity
  * limit and were re-run by the lockstep driver, and the number of search launches. */
 int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallbacks, uint64_t* launches);

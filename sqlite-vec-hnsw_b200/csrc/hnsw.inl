@@ -101,6 +101,7 @@ struct vecgpu_hnsw {
     int64_t entry = -1;
     int entry_level = -1;
     std::vector<int8_t> node_level;
+    std::vector<uint8_t> in_graph;  // rows that were inserted by the last rebuild (rows skipped at that time are not nodes)
     // level 0 adjacency: [node][max_m0]; upper levels: node with level L owns L consecutive M-wide lists
     std::vector<uint32_t> nbr0;
     std::vector<float> dist0;
@@ -763,6 +764,7 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     h->scored = h->rounds = 0;
     h->slab_gen = s->layout_gen;
     h->node_level.assign(n, 0);
+    h->in_graph.assign(n, 0);
     h->upper_base.assign(n, 0);
     uint64_t upper_slots = 0;
     for (uint64_t pos = 0; pos < n; ++pos) {
@@ -808,7 +810,10 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
         const uint64_t want = std::min<uint64_t>(batch, std::max<uint64_t>(1, h->n_nodes / 4));
         nodes.clear();
         while (pos < n && nodes.size() < want) {
-            if (s->h_skip.empty() || !s->h_skip[pos]) nodes.push_back((uint32_t)pos);
+            if (s->h_skip.empty() || !s->h_skip[pos]) {
+                nodes.push_back((uint32_t)pos);
+                h->in_graph[pos] = 1;
+            }
             ++pos;
         }
         if (nodes.empty()) break;
@@ -1063,6 +1068,30 @@ extern "C" int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* 
         return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction or out-of-order insert) since this HNSW index was built: rebuild it");
     if (rowid) *rowid = h->entry < 0 ? -1 : h_rowid_of(h->slab, (uint32_t)h->entry);
     if (level) *level = h->entry < 0 ? -1 : h->entry_level;
+    return 0;
+}
+
+// Node list for the bulk write-back into {t}_{c}_hnsw_nodes(rowid, level, vector) (src/shadow.rs:464-474): every indexed
+// row with its level.  Call with cap = 0 to get the count in *n_out.
+extern "C" int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* rowids, int32_t* levels, uint64_t* n_out) {
+    if (!h || !n_out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    vecgpu_slab* s = h->slab;
+    if (h->entry >= 0 && h->slab_gen != s->layout_gen)
+        return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction or out-of-order insert) since this HNSW index was built: rebuild it");
+    uint64_t n = 0;
+    if (h->entry >= 0) {
+        const uint64_t rows = h->node_level.size();
+        for (uint64_t pos = 0; pos < rows; ++pos) {
+            if (!h->in_graph[pos]) continue;
+            if (n < cap) {
+                rowids[n] = h_rowid_of(s, (uint32_t)pos);
+                levels[n] = h->node_level[pos];
+            }
+            ++n;
+        }
+    }
+    *n_out = n;
     return 0;
 }
 

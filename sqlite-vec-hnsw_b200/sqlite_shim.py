@@ -44,6 +44,30 @@ def create_shadow_tables(conn, table, n_vector_columns=1, data_columns=()):
     conn.executemany(f'INSERT INTO "main"."{table}_info" (key, value) VALUES (?, ?)', INFO_ROWS)
 
 
+def create_hnsw_shadow_tables(conn, table, column, dims, element_type="float32", distance_metric="l2", m=32, ef_construction=400,
+                              index_quantization="none", rng_seed=12345):
+    """"{t}_{c}_hnsw_meta" (single row), "_hnsw_nodes", "_hnsw_edges" as the reference creates them (src/shadow.rs:407-500,
+    508-600): same columns, defaults and the WITHOUT ROWID primary key (from_rowid, level, to_rowid) of the edge table."""
+    conn.execute(
+        f'CREATE TABLE IF NOT EXISTS "{table}_{column}_hnsw_meta" ('
+        "id INTEGER PRIMARY KEY CHECK (id = 1), m INTEGER NOT NULL DEFAULT 32, max_m0 INTEGER NOT NULL DEFAULT 64, "
+        "ef_construction INTEGER NOT NULL DEFAULT 400, ef_search INTEGER NOT NULL DEFAULT 200, max_level INTEGER NOT NULL DEFAULT 16, "
+        "level_factor REAL NOT NULL DEFAULT 0.28768207245178085, entry_point_rowid INTEGER NOT NULL DEFAULT -1, "
+        "entry_point_level INTEGER NOT NULL DEFAULT -1, num_nodes INTEGER NOT NULL DEFAULT 0, dimensions INTEGER NOT NULL DEFAULT 0, "
+        "element_type TEXT NOT NULL DEFAULT 'float32', distance_metric TEXT NOT NULL DEFAULT 'l2', rng_seed INTEGER NOT NULL DEFAULT 12345, "
+        "hnsw_version INTEGER NOT NULL DEFAULT 1, index_quantization TEXT NOT NULL DEFAULT 'none', normalize_vectors INTEGER NOT NULL DEFAULT 1)")
+    conn.execute(
+        f'INSERT OR IGNORE INTO "{table}_{column}_hnsw_meta" '
+        "(id, m, max_m0, ef_construction, dimensions, element_type, distance_metric, index_quantization, rng_seed, normalize_vectors) "
+        "VALUES (1, ?, ?, ?, ?, ?, ?, ?, ?, ?)",
+        (m, 2 * m, ef_construction, dims, element_type, distance_metric, index_quantization, rng_seed, 1 if distance_metric == "cosine" else 0))
+    conn.execute(f'CREATE TABLE IF NOT EXISTS "{table}_{column}_hnsw_nodes" ('
+                 "rowid INTEGER PRIMARY KEY, level INTEGER NOT NULL, vector BLOB, created_at INTEGER DEFAULT (unixepoch()))")
+    conn.execute(f'CREATE TABLE IF NOT EXISTS "{table}_{column}_hnsw_edges" ('
+                 "from_rowid INTEGER NOT NULL, to_rowid INTEGER NOT NULL, level INTEGER NOT NULL, distance REAL NOT NULL DEFAULT 0.0, "
+                 "PRIMARY KEY (from_rowid, level, to_rowid)) WITHOUT ROWID")
+
+
 def storage_schema(conn, table):
     row = conn.execute(f'SELECT value FROM "main"."{table}_info" WHERE key = \'STORAGE_SCHEMA\'').fetchone()
     return None if row is None else row[0]
@@ -144,6 +168,58 @@ class Vec0Table:
             self.slab.delete(int(rowid))
             self._fingerprint = self._current_fingerprint()
 
+    # ---- vec_rebuild_hnsw (src/sql_functions.rs:436-534) with the graph built on the GPU and written back in bulk
+    def rebuild_hnsw(self, column, new_m=None, new_ef_construction=None):
+        """Rebuild the HNSW index of `column` from the resident slab and replace the contents of the reference's shadow
+        tables "{t}_{c}_hnsw_nodes / _hnsw_edges / _hnsw_meta" (src/shadow.rs:407-500; edges in insert_edges_batch shape,
+        src/hnsw/storage.rs:346-383).  Stored vectors are normalised for cosine columns (src/hnsw/insert.rs:300-322).
+        -> number of indexed vectors."""
+        if self.is_stale():
+            self.stage()
+        meta = f'"{self.table}_{column}_hnsw_meta"'
+        m, efc, seed, metric_s = self.conn.execute(f"SELECT m, ef_construction, rng_seed, distance_metric FROM {meta} WHERE id = 1").fetchone()
+        m = int(new_m) if new_m is not None else m
+        efc = int(new_ef_construction) if new_ef_construction is not None else efc
+        metric = vec0.DistanceMetric.from_str(metric_s)
+        cosine = metric == vec0.DistanceMetric.Cosine and self.vec_type == vec0.VectorType.Float32
+        if getattr(self, "_hnsw", None) is not None:
+            self._hnsw.close()
+            self._hnsw_slab.close() if self._hnsw_slab is not self.slab else None
+        if cosine:  # the graph lives over the STORED representation: unit vectors for cosine columns
+            rowids, vec, skip = read_column(self.conn, self.table, self.column_idx, self.row_bytes)
+            keep = skip == 0
+            stored = vec0.normalize(np.frombuffer(vec[keep].tobytes(), dtype="<f4").reshape(-1, self.dims))
+            self._hnsw_slab = self._slab_factory()
+            self._hnsw_slab.load(stored, rowids[keep])
+        else:
+            self._hnsw_slab = self.slab
+        self._hnsw = vec0.HnswIndex(self._hnsw_slab, metric, M=m, ef_construction=efc, seed=int(seed) & 0x7FFFFFFFFFFFFFFF)
+        self._hnsw.rebuild()
+        rid, lv = self._hnsw.export_nodes()
+        fr, to, elv, dist = self._hnsw.export_edges()
+        entry, entry_level = self._hnsw.entry_point()
+        nodes, edges = f'"{self.table}_{column}_hnsw_nodes"', f'"{self.table}_{column}_hnsw_edges"'
+        self.conn.execute(f"DELETE FROM {edges}")
+        self.conn.execute(f"DELETE FROM {nodes}")
+        blobs = (self._hnsw_slab.get(int(r)) for r in rid)
+        self.conn.executemany(f"INSERT INTO {nodes} (rowid, level, vector) VALUES (?, ?, ?)",
+                              ((int(r), int(l), b) for r, l, b in zip(rid, lv, blobs)))
+        self.conn.executemany(f"INSERT OR REPLACE INTO {edges} (from_rowid, to_rowid, level, distance) VALUES (?, ?, ?, ?)",
+                              zip(fr.tolist(), to.tolist(), elv.tolist(), dist.tolist()))
+        self.conn.execute(f"UPDATE {meta} SET m = ?, max_m0 = ?, ef_construction = ?, entry_point_rowid = ?, entry_point_level = ?, "
+                          "num_nodes = ?, hnsw_version = hnsw_version + 1 WHERE id = 1", (m, 2 * m, efc, entry, entry_level, len(rid)))
+        return len(rid)
+
+    def hnsw_knn(self, query, k, ef_search=200):
+        """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)]."""
+        if getattr(self, "_hnsw", None) is None:
+            raise vec0.InvalidState("no HNSW index: call rebuild_hnsw() first")
+        if isinstance(query, str):
+            query = vec0.Vector.from_json(query, self.vec_type).as_bytes()
+        q = np.frombuffer(query, dtype="u1").reshape(1, -1)
+        r, d, c = self._hnsw.search(q, k, ef_search=ef_search)
+        return [(int(r[0, j]), float(d[0, j])) for j in range(int(c[0]))]
+
     def compact(self, min_dead_fraction=0.0):
         """Drop the tombstones left by delete() (and rows with unreadable blobs) from the resident slab when they make up
         more than `min_dead_fraction` of it; SQLite itself is untouched.  -> rows removed."""
@@ -155,6 +231,11 @@ class Vec0Table:
         return self.slab.compact()
 
     def close(self):
+        if getattr(self, "_hnsw", None) is not None:
+            self._hnsw.close()
+            if self._hnsw_slab is not self.slab:
+                self._hnsw_slab.close()
+            self._hnsw = None
         if self.slab is not None:
             self.slab.close()
             self.slab = None

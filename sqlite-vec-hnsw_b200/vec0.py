@@ -546,6 +546,14 @@ class HnswIndex:
                 dists = ((dists * dists) / np.float32(2.0)).astype("<f4")
         return rowids, dists, counts
 
+    def export_nodes(self):
+        """-> (rowid, level) arrays in the shape of the {t}_{c}_hnsw_nodes table (the vector column is the slab row)."""
+        n = C.c_uint64()
+        _check(self._lib.vecgpu_hnsw_export_nodes(self._h, 0, None, None, C.byref(n)))
+        rid, lv = np.empty(n.value, dtype="<i8"), np.empty(n.value, dtype="<i4")
+        _check(self._lib.vecgpu_hnsw_export_nodes(self._h, n.value, _ptr(rid), _ptr(lv), C.byref(n)))
+        return rid, lv
+
     def export_edges(self):
         """-> (from_rowid, to_rowid, level, distance) arrays in the shape of the {t}_{c}_hnsw_edges table."""
         n = C.c_uint64()

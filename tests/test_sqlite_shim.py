@@ -121,3 +121,50 @@ def test_end_to_end_knn_from_sqlite(vg, orc, gpu, tmp_path):
     res = t.knn(nv[0].tobytes(), 1, metric=L2)
     assert res[0][0] != new_id
     t.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric_s", ["l2", "cosine"])
+def test_rebuild_hnsw_writes_the_reference_shadow_tables(vg, orc, gpu, tmp_path, metric_s):
+    # vec_rebuild_hnsw (src/sql_functions.rs:436-534): graph built on the GPU, written back into the reference's
+    # "{t}_{c}_hnsw_nodes / _hnsw_edges / _hnsw_meta" tables (src/shadow.rs:407-500); a literal restatement of search_hnsw
+    # that reads ONLY those tables (neighbours in primary-key order, as the reference's SELECT returns them) must find
+    # what the resident index finds
+    from oracle import hnsw_ref
+
+    sh = _shim()
+    conn = sqlite3.connect(str(tmp_path / "hnsw.db"))
+    sh.create_shadow_tables(conn, "docs", 1, [])
+    n, dims = 2500, 20
+    v = random_rows(F32, n, dims, seed=7)
+    conn.executemany('INSERT INTO "docs_data" (rowid, vec00) VALUES (?, ?)', [(i + 1, v[i].tobytes()) for i in range(n)])
+    conn.execute('UPDATE "docs_data" SET vec00 = NULL WHERE rowid = 17')
+    sh.create_hnsw_shadow_tables(conn, "docs", "emb", dims, "float32", metric_s, m=12, ef_construction=80)
+    metric = COSINE if metric_s == "cosine" else L2
+    t = sh.Vec0Table(conn, "docs", F32, dims, distance_metric=metric)
+    assert t.rebuild_hnsw("emb") == n - 1
+    m, max_m0, efc, ep, epl, num_nodes = conn.execute(
+        'SELECT m, max_m0, ef_construction, entry_point_rowid, entry_point_level, num_nodes FROM "docs_emb_hnsw_meta"').fetchone()
+    assert (m, max_m0, efc, num_nodes) == (12, 24, 80, n - 1) and ep >= 1 and epl >= 0
+    assert conn.execute('SELECT COUNT(*), MIN(level), COUNT(vector) FROM "docs_emb_hnsw_nodes"').fetchone()[::2] == (n - 1, n - 1)
+    assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_nodes" WHERE rowid = 17').fetchone()[0] == 0
+    assert conn.execute('SELECT level FROM "docs_emb_hnsw_nodes" WHERE rowid = ?', (ep,)).fetchone()[0] == epl
+    deg = conn.execute('SELECT MAX(c) FROM (SELECT COUNT(*) AS c FROM "docs_emb_hnsw_edges" WHERE level = 0 GROUP BY from_rowid)').fetchone()[0]
+    assert deg <= max_m0
+    # stored node vectors: the column's blobs for L2, unit vectors for cosine (src/hnsw/insert.rs:300-322)
+    blob = conn.execute('SELECT vector FROM "docs_emb_hnsw_nodes" WHERE rowid = 5').fetchone()[0]
+    want = vg.normalize(v[4:5])[0] if metric_s == "cosine" else v[4]
+    assert np.array_equal(np.frombuffer(blob, dtype="<f4").view("<u4"), want.view("<u4"))
+    # walk the graph from SQLite alone
+    stored = {r: np.frombuffer(b, dtype="<f4") for r, b in conn.execute('SELECT rowid, vector FROM "docs_emb_hnsw_nodes"')}
+    def nbrs(node, level):
+        return [r[0] for r in conn.execute('SELECT to_rowid FROM "docs_emb_hnsw_edges" WHERE from_rowid = ? AND level = ? ORDER BY to_rowid', (node, level))]
+    q = random_rows(F32, 5, dims, seed=8)
+    for qi in range(len(q)):
+        qs = vg.normalize(q[qi : qi + 1])[0] if metric_s == "cosine" else q[qi]
+        walk = hnsw_ref.search_hnsw(lambda rid: float(orc.distance(F32, qs, stored[rid], L2)), nbrs, ep, epl, 8, 60)
+        got = t.hnsw_knn(q[qi].tobytes(), 8, ef_search=60)
+        assert [r for r, _ in got] == [w[0] for w in walk]
+        want_d = [orc.convert_cosine_output(w[1]) if metric_s == "cosine" else w[1] for w in walk]
+        assert np.allclose([d for _, d in got], want_d, rtol=1e-6, atol=1e-7)
+    t.close()
