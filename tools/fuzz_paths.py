@@ -53,13 +53,21 @@ while time.time() - t0 < budget:
             ok = all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(a, b))
             desc = f"kind={kind} elem={elem} metric={metric} dims={dims} n={n} nq={nq} k={k} ties={ties} sparse={rowids is not None} {fast}"
         else:
-            env(VECGPU_HNSW_DEVICE=1); i1 = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=3); i1.rebuild(batch=int(rng.choice([64, 512, 0])) or 0)
-            bsz = i1  # same batch size for both builds is needed for identical graphs: rebuild the lockstep one with the same value
+            bsz = int(rng.choice([64, 512, 0]))
+            env(VECGPU_HNSW_DEVICE=1); i1 = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=3); i1.rebuild(batch=bsz)
             e1 = i1.export_edges(); r1 = i1.search(q, k, ef_search=ef)
-            env(VECGPU_HNSW_DEVICE=0); r2 = i1.search(q, k, ef_search=ef)
+            env(VECGPU_HNSW_DEVICE=0); r2 = i1.search(q, k, ef_search=ef)       # lockstep walk of the device-built graph
             ok = all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(r1, r2))
-            desc = f"hnsw elem={elem} dims={dims} n={n} M={M} efc={efc} ef={ef} k={k} ties={ties}"
-            i1.close()
+            os.environ["VECGPU_HNSW_DEVICE"] = "1"; os.environ["VECGPU_HNSW_LINK"] = "host"
+            i2 = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=3); i2.rebuild(batch=bsz)   # device walk, host linking
+            os.environ.pop("VECGPU_HNSW_LINK")
+            ok = ok and all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(e1, i2.export_edges()))
+            if rng.integers(0, 3) == 0:
+                env(VECGPU_HNSW_DEVICE=0); i3 = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=3); i3.rebuild(batch=bsz)  # all lockstep
+                ok = ok and all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(e1, i3.export_edges()))
+                i3.close()
+            desc = f"hnsw elem={elem} dims={dims} n={n} M={M} efc={efc} ef={ef} k={k} ties={ties} batch={bsz}"
+            i1.close(); i2.close()
     cases += 1
     if not ok:
         fails += 1
