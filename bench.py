@@ -47,6 +47,28 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(world):
+    """DRAM bytes per launch of the headline scan kernel from the committed `ncu --set full` capture of this very workload
+    (profiles/r1_scan_f32cos_full_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum).  Only meaningful at N = 1, where the
+    per-GPU shard is the captured 10 M-row slab."""
+    if world != 1:
+        return None, "per-GPU shard differs from the captured launch"
+    try:
+        import csv
+
+        with open(os.path.join(ROOT, "profiles", "r1_scan_f32cos_full_raw.csv")) as f:
+            rows = list(csv.reader(f))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            total += float(vals[i]) * scale[units[i]]
+        return total, "ncu --set full capture of this kernel on this workload, profiles/r1_scan_f32cos_full_raw.csv (read + write)"
+    except Exception as e:  # the capture is evidence, not a dependency
+        return None, f"capture not readable: {e}"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region."""
 
@@ -392,6 +414,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        traffic, traffic_src = load_traffic(world)
         qps = args.steps * BATCH / t_dev
         achieved = bytes_local / (scan_ms / 1e3) / 1e9
         line = {
@@ -406,8 +429,8 @@ def run_ours(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": "scan_kernel<F32Cos<1>,1,false> (+ merge_kernel, <1% of the pair)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "scan_kernel<F32Cos<1>,1,false> (+ merge_small_kernel, <1% of the pair)",
                 "algorithmic_bytes_per_launch": bytes_local, "avg_launch_ms": scan_ms,
                 "hbm_aggregate_gbs": achieved * world,
             },
