@@ -13,6 +13,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvecgpu_oracle.so")
+LIB_PATH_AVX512 = os.path.join(_HERE, "libvecgpu_oracle_avx512.so")  # same sources, -march=skylake-avx512 (bit-identical results)
+_SOURCES = ("vecgpu_oracle.c", "simsimd_shapes.c")
 
 F32, I8, BIT = 0, 1, 2
 L2, L1, COSINE, HAMMING = 0, 1, 2, 3
@@ -23,19 +25,33 @@ _lib = None
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc only)."""
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(
-        os.path.join(_HERE, "vecgpu_oracle.c")
-    ):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in _SOURCES)
+    if force or any(not os.path.exists(x) or os.path.getmtime(x) < newest for x in (LIB_PATH, LIB_PATH_AVX512)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return LIB_PATH
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
-        L = C.CDLL(LIB_PATH)
+def _host_has_avx512():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = set(line.split(":", 1)[1].split())
+                    return {"avx512f", "avx512dq", "avx512bw", "avx512vl", "avx512cd", "fma", "avx2"} <= fl
+    except OSError:
+        pass
+    return False
+
+
+def lib_path():
+    """The build this host can run fastest; VECGPU_ORACLE_PORTABLE=1 pins the portable one."""
+    if os.environ.get("VECGPU_ORACLE_PORTABLE", "0") != "1" and os.path.exists(LIB_PATH_AVX512) and _host_has_avx512():
+        return LIB_PATH_AVX512
+    return LIB_PATH
+
+
+def _bind(path):
+        L = C.CDLL(path)
         p = C.c_void_p
         L.orc_row_bytes.restype = C.c_uint32
         L.orc_row_bytes.argtypes = [C.c_int, C.c_uint32]
@@ -52,7 +68,24 @@ def lib():
         L.orc_convert_cosine_output.restype = C.c_float
         L.orc_convert_cosine_output.argtypes = [C.c_float]
         L.orc_synth_rows.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, p]
-        _lib = L
+        L.orc_knn_select.argtypes = L.orc_knn.argtypes
+        L.orc_knn_synth.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint64, C.c_int, p, C.c_uint32, C.c_uint32,
+                                    C.c_int, p, p, p]
+        L.orc_force_plain.argtypes = [C.c_int]
+        L.orc_round_haz.restype = C.c_float
+        L.orc_round_haz.argtypes = [C.c_float]
+        L.orc_shape_supported.argtypes = [C.c_int, C.c_int]
+        L.orc_shape_distances_f32.argtypes = [C.c_int, C.c_int, C.c_uint32, p, C.c_uint64, p, C.c_int, p]
+        L.orc_shape_distances_i8cos.argtypes = [C.c_int, C.c_uint32, p, C.c_uint64, p, p]
+        return L
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = _bind(lib_path())
     return _lib
 
 
@@ -101,6 +134,73 @@ def knn(elem, dims, vectors, queries, k, metric, rowids=None, skip=None):
     if rc:
         raise OracleError(rc)
     return out_r, out_d, out_c
+
+
+def knn_select(elem, dims, vectors, queries, k, metric, rowids=None, skip=None):
+    """Same result as knn() (stable sort + truncate == the k smallest of the (distance, position) order), computed by
+    per-thread selection on all host threads: the form used for big inputs and for bench.py's CPU arm."""
+    rb = row_bytes(elem, dims)
+    v = np.ascontiguousarray(vectors).view(np.uint8).reshape(-1)
+    q = np.ascontiguousarray(queries).view(np.uint8).reshape(-1)
+    n, nq = v.size // rb, q.size // rb
+    r = None if rowids is None else np.ascontiguousarray(rowids, dtype="<i8")
+    s = None if skip is None else np.ascontiguousarray(skip, dtype="u1")
+    out_r = np.empty((nq, k), dtype="<i8")
+    out_d = np.empty((nq, k), dtype="<f4")
+    out_c = np.empty(nq, dtype="<u4")
+    rc = lib().orc_knn_select(
+        elem, dims, None if r is None else _ptr(r), _ptr(v), None if s is None else _ptr(s), n, _ptr(q), nq, k, metric,
+        _ptr(out_r), _ptr(out_d), _ptr(out_c),
+    )
+    if rc:
+        raise OracleError(rc)
+    return out_r, out_d, out_c
+
+
+def knn_synth(elem, dims, seed, first_rowid, n, kind, queries, k, metric):
+    """Exact scan over rows first_rowid..first_rowid+n-1 of the synthetic corpus WITHOUT materialising it (each host
+    thread regenerates a row, scores it against every query and keeps its k best): the CPU side of the parity checks
+    at BASELINE.json's full sizes."""
+    rb = row_bytes(elem, dims)
+    q = np.ascontiguousarray(queries).view(np.uint8).reshape(-1)
+    nq = q.size // rb
+    out_r = np.empty((nq, k), dtype="<i8")
+    out_d = np.empty((nq, k), dtype="<f4")
+    out_c = np.empty(nq, dtype="<u4")
+    rc = lib().orc_knn_synth(elem, dims, seed, first_rowid, n, kind, _ptr(q), nq, k, metric, _ptr(out_r), _ptr(out_d), _ptr(out_c))
+    if rc:
+        raise OracleError(rc)
+    return out_r, out_d, out_c
+
+
+ACC_SHAPES = ["canonical", "serial", "serial_fma", "lanes8_f64red", "lanes16_hadd", "lanes4", "f64"]
+FIN_SHAPES = ["ieee_f64", "ieee_f32", "rsqrt12_nr_f64", "rsqrt14_nr_f64", "rsqrt12_nr_f32"]
+
+
+def shape_supported(acc, fin):
+    return bool(lib().orc_shape_supported(acc, fin))
+
+
+def shape_distances_f32(acc, fin, vectors, query, metric):
+    """f32 L2 / cosine of one query against every row under one of the SimSIMD-shaped accumulation / finish variants
+    (oracle/simsimd_shapes.c)."""
+    v = np.ascontiguousarray(vectors, dtype="<f4")
+    q = np.ascontiguousarray(query, dtype="<f4")
+    out = np.empty(v.shape[0], dtype="<f4")
+    rc = lib().orc_shape_distances_f32(acc, fin, v.shape[1], _ptr(v), v.shape[0], _ptr(q), metric, _ptr(out))
+    if rc:
+        raise OracleError(rc)
+    return out
+
+
+def shape_distances_i8cos(fin, vectors, query):
+    v = np.ascontiguousarray(vectors, dtype="i1")
+    q = np.ascontiguousarray(query, dtype="i1")
+    out = np.empty(v.shape[0], dtype="<f4")
+    rc = lib().orc_shape_distances_i8cos(fin, v.shape[1], _ptr(v), v.shape[0], _ptr(q), _ptr(out))
+    if rc:
+        raise OracleError(rc)
+    return out
 
 
 def distances(elem, dims, vectors, query, metric):
