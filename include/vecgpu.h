@@ -162,16 +162,73 @@ int vecgpu_knn_device(vecgpu_slab* slab, const void* d_queries, uint32_t nq, uin
 int vecgpu_merge_device(int device, const int64_t* d_rowids, const float* d_dists, uint32_t nlists, uint32_t nq,
                         uint32_t k, int64_t* d_out_rowids, float* d_out_dists, void* stream);
 
+/* ---- sharded slabs: one box, several GPUs ---------------------------------------------------
+ * The reference is ONE process calling brute_force_search inline (src/vtab.rs:2286-2305, src/lib.rs:26-34); sharding
+ * is this library's addition and has no reference line to replace.  Rows are cut by contiguous rowid range (every
+ * rowid of shard i is below every rowid of shard i+1, so the global (distance, rowid) order restricted to a shard is
+ * the shard's own order).  Per query: every GPU scans its range and writes its packed top-k (12 bytes per entry +
+ * a count) STRAIGHT INTO THE PEERS' GATHER BUFFERS over NVLink (peer stores + a system-scope release flag), and the
+ * receiving GPU merges as soon as the flags are in: no NCCL call and no pack/unpack kernels on the query path
+ * (csrc/xchg.cuh).  Results are identical to one slab holding all rows.
+ *
+ * (1) ONE-PROCESS form — what the Rust extension would link: a sharded slab handle with the same calls as a slab. */
+typedef struct vecgpu_sharded vecgpu_sharded;
+/* devices NULL / n_devices 0: every visible device.  max_queries / max_k (0: 1024 / 128) size the gather buffers; a
+ * larger batch is exchanged in pieces.  One host worker thread + stream per device. */
+int vecgpu_sharded_create(int elem_type, uint32_t dims, uint64_t capacity_hint_total, const int* devices, uint32_t n_devices,
+                          uint32_t max_queries, uint32_t max_k, vecgpu_sharded** out);
+void vecgpu_sharded_destroy(vecgpu_sharded* g);
+/* As vecgpu_slab_load / _fill_synthetic / _upsert / _delete / _count, over all shards (upserts and deletes are routed
+ * to the shard that owns the rowid's range). */
+int vecgpu_sharded_load(vecgpu_sharded* g, const int64_t* rowids, const void* vectors, uint64_t n);
+int vecgpu_sharded_fill_synthetic(vecgpu_sharded* g, uint64_t seed, int64_t first_rowid, uint64_t n, int kind);
+int vecgpu_sharded_upsert(vecgpu_sharded* g, int64_t rowid, const void* vec, uint32_t nbytes);
+int vecgpu_sharded_delete(vecgpu_sharded* g, int64_t rowid);
+int vecgpu_sharded_count(vecgpu_sharded* g, uint64_t* rows, uint64_t* live);
+uint32_t vecgpu_sharded_num_shards(vecgpu_sharded* g);
+/* The slab (and device) behind shard i, e.g. for vecgpu_slab_compact. */
+int vecgpu_sharded_shard(vecgpu_sharded* g, uint32_t i, vecgpu_slab** slab, int* device);
+/* brute_force_search (src/vtab.rs:2573-2623) over all shards: one call, host buffers, same contract as vecgpu_knn. */
+int vecgpu_sharded_knn(vecgpu_sharded* g, const void* queries, uint32_t nq, uint32_t k, int metric, int64_t* out_rowids,
+                       float* out_dists, uint32_t* out_counts);
+
+/* (2) ONE-PROCESS-PER-GPU form (torchrun / MPI style launchers): each rank owns a slab with its rowid range and an
+ * exchange endpoint; the endpoints are introduced to each other once (same process: _attach_local; other processes:
+ * _export + _attach_ipc, the 128-byte handles travel over whatever channel the launcher has). */
+typedef struct vecgpu_xchg vecgpu_xchg;
+#define VECGPU_XCHG_HANDLE_BYTES 128
+int vecgpu_xchg_create(int device, uint32_t rank, uint32_t world, uint32_t max_queries, uint32_t max_k, vecgpu_xchg** out);
+void vecgpu_xchg_destroy(vecgpu_xchg* x);
+int vecgpu_xchg_export(vecgpu_xchg* x, void* handle /* VECGPU_XCHG_HANDLE_BYTES */);
+int vecgpu_xchg_attach_ipc(vecgpu_xchg* x, const void* handles /* world x VECGPU_XCHG_HANDLE_BYTES, rank order */, uint32_t n_handles);
+int vecgpu_xchg_attach_local(vecgpu_xchg* const* all /* world endpoints, rank order */, uint32_t n);
+/* One rank's part of a sharded query, host buffers in and out (collective: every rank calls it with the same nq, k,
+ * metric, in the same order; rank r's slab must hold rowids below rank r+1's).  Every rank receives the global top-k. */
+int vecgpu_shard_knn(vecgpu_slab* slab, vecgpu_xchg* x, const void* queries, uint32_t nq, uint32_t k, int metric,
+                     int64_t* out_rowids, float* out_dists, uint32_t* out_counts);
+/* Device-resident form: only enqueues on `stream`; outputs padded with INT64_MAX / +inf. */
+int vecgpu_shard_knn_device(vecgpu_slab* slab, vecgpu_xchg* x, const void* d_queries, uint32_t nq, uint32_t k, int metric,
+                            int64_t* d_out_rowids, float* d_out_dists, void* stream);
+/* Exchange + merge of per-rank top-k lists that are already on the device (d_counts NULL: trailing INT64_MAX / +inf
+ * entries are padding).  Collective; enqueues on `stream`. */
+int vecgpu_xchg_merge_device(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts,
+                             uint32_t nq, uint32_t k, int64_t* d_out_rowids, float* d_out_dists, void* stream);
+/* Synchronises `stream` and reports VECGPU_ERR_CUDA if an exchange since the last check timed out waiting for a peer. */
+int vecgpu_xchg_check(vecgpu_xchg* x, void* stream);
+
 /* Number of kernels this library has launched in this process (bench's
  * gpu_launches claim). */
 uint64_t vecgpu_launch_count(void);
-/* Batched float32 queries (nq >= 16, L2 / cosine) run as a tcgen05 3xTF32 contraction that only selects
- * candidates, followed by an exact re-rank; a query whose candidate bound cannot be certified is re-run
- * through the exact scan.  Counters since process start: queries served by that path / of which fell back. */
+/* Batched float32 queries (nq >= 16, L2 / cosine) run as a tcgen05 kind::tf32 contraction that only selects
+ * candidates — ONE TF32 pass by default, with the operand-truncation error inside the certified candidate band
+ * (VECGPU_TC_TERMS=3 selects the 3xTF32 compensated form) — followed by an exact re-rank; a query whose candidate
+ * bound cannot be certified is re-run through the exact scan.  int8 L2 batches run exactly on kind::i8.
+ * Counters since process start: queries served by the tensor-core paths / of which fell back. */
 void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks);
 
 /* ---- HNSW with GPU-batched candidate scoring (BASELINE config 5) -------------------------------------
- * The graph (levels, adjacency, stored edge distances) lives in host memory, with a copy of the adjacency in HBM,
+ * The graph (levels, adjacency, stored edge distances) lives in HBM (the search kernel walks it there and rebuild batches
+ * are linked there); a host copy is refreshed on demand (export, lockstep driver).  It sits
  * next to a slab that holds the STORED node vectors (normalised for cosine columns, int8 when
  * index_quantization=int8: src/hnsw/insert.rs:300-322); `metric` is the INTERNAL metric (src/hnsw/mod.rs:129-137).
  * Searches (queries, and the search half of every insert of a rebuild batch) run wholly on the device, one warp per

@@ -8,6 +8,7 @@ from . import _lib
 from .vec0 import (  # noqa: F401
     DimensionMismatch,
     DistanceMetric,
+    Exchange,
     HnswIndex,
     InvalidDistanceMetric,
     InvalidParameter,
@@ -15,6 +16,7 @@ from .vec0 import (  # noqa: F401
     InvalidVectorFormat,
     InvalidVectorType,
     NotImplementedVec,
+    ShardedSlab,
     Slab,
     VecError,
     Vector,

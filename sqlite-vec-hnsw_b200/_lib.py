@@ -10,6 +10,7 @@ F32, I8, BIT = 0, 1, 2
 L2, L1, COSINE, HAMMING = 0, 1, 2, 3
 OK, ERR_INVALID_PARAM, ERR_DIM_MISMATCH, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3, 4
 SYNTH_UNIFORM, SYNTH_GAUSS4 = 0, 1
+XCHG_HANDLE_BYTES = 128
 
 _c_slab = C.c_void_p
 _p = C.c_void_p
@@ -51,6 +52,25 @@ SIGNATURES = {
     "vecgpu_hnsw_device_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_export_nodes": (C.c_int, [C.c_void_p, C.c_uint64, _p, _p, C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_export_edges": (C.c_int, [C.c_void_p, C.c_uint64, _p, _p, _p, _p, C.POINTER(C.c_uint64)]),
+    "vecgpu_sharded_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, _p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "vecgpu_sharded_destroy": (None, [C.c_void_p]),
+    "vecgpu_sharded_load": (C.c_int, [C.c_void_p, _p, _p, C.c_uint64]),
+    "vecgpu_sharded_fill_synthetic": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_uint64, C.c_int]),
+    "vecgpu_sharded_upsert": (C.c_int, [C.c_void_p, C.c_int64, _p, C.c_uint32]),
+    "vecgpu_sharded_delete": (C.c_int, [C.c_void_p, C.c_int64]),
+    "vecgpu_sharded_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vecgpu_sharded_num_shards": (C.c_uint32, [C.c_void_p]),
+    "vecgpu_sharded_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "vecgpu_sharded_knn": (C.c_int, [C.c_void_p, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
+    "vecgpu_xchg_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "vecgpu_xchg_destroy": (None, [C.c_void_p]),
+    "vecgpu_xchg_export": (C.c_int, [C.c_void_p, _p]),
+    "vecgpu_xchg_attach_ipc": (C.c_int, [C.c_void_p, _p, C.c_uint32]),
+    "vecgpu_xchg_attach_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "vecgpu_shard_knn": (C.c_int, [_c_slab, C.c_void_p, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
+    "vecgpu_shard_knn_device": (C.c_int, [_c_slab, C.c_void_p, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
+    "vecgpu_xchg_merge_device": (C.c_int, [C.c_void_p, _p, _p, _p, C.c_uint32, C.c_uint32, _p, _p, _p]),
+    "vecgpu_xchg_check": (C.c_int, [C.c_void_p, _p]),
     "vecgpu_launch_count": (C.c_uint64, []),
     "vecgpu_tc_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }

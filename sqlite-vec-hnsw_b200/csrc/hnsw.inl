@@ -697,6 +697,7 @@ static int64_t h_rowid_of(const vecgpu_slab* s, uint32_t pos) { return s->dense 
 
 extern "C" int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uint32_t ef_construction, uint64_t seed,
                                   vecgpu_hnsw** out) {
+    VG_TRY
     if (!slab || !out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     *out = nullptr;
     int rc = check_pair(slab->elem, metric);
@@ -715,9 +716,11 @@ extern "C" int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uin
     h->level_factor = 1.0 / std::log((double)M);
     *out = h;
     return 0;
+    VG_CATCH
 }
 
 extern "C" void vecgpu_hnsw_destroy(vecgpu_hnsw* h) {
+    VG_TRY
     if (!h) return;
     if (h->slab) cudaSetDevice(h->slab->device);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -730,6 +733,7 @@ extern "C" void vecgpu_hnsw_destroy(vecgpu_hnsw* h) {
     if (h->h_sw) cudaFreeHost(h->h_sw);
     cudaGetLastError();
     delete h;
+    VG_CATCH_VOID
 }
 
 static void hq_init(vecgpu_hnsw* h, HQuery& q, uint32_t a_index, int node_level, uint32_t ef_wide) {
@@ -749,6 +753,7 @@ static void hq_init(vecgpu_hnsw* h, HQuery& q, uint32_t a_index, int node_level,
 
 // vec_rebuild_hnsw: (re)build the graph over every live row of the slab, `batch` inserts in lockstep
 extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
+    VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
     vecgpu_slab* s = h->slab;
     std::lock_guard<std::mutex> lk(s->mu);
@@ -952,11 +957,13 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
         fprintf(stderr, "[vecgpu hnsw build] search+flush %.3f s  decode %.3f s  ops %.3f s  link %.3f s  (threads %d, %s linking)\n",
                 t_search + t_flush, t_decode, t_ops, t_link, nthreads, dev_link ? "device" : "host");
     return 0;
+    VG_CATCH
 }
 
 // search_hnsw (src/hnsw/search.rs:267-335) for nq queries in lockstep; distances are in the graph's (internal) metric
 extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef_search,
                                   int64_t* out_rowids, float* out_dists, uint32_t* out_counts) {
+    VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
     if (nq == 0 || k == 0) return 0;
     if (!queries || !out_rowids || !out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
@@ -985,11 +992,17 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
     CU(cudaMemcpy2DAsync(h->d_queries, s->row_stride, queries, s->row_bytes, s->row_bytes, nq, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     std::vector<HQuery> qs;
+    // Rows deleted (or emptied) since the build are tombstones in the slab: the walk still passes through their nodes, but
+    // they are never returned (the reference removes the node and its edges, src/vtab.rs:1340-1397; the effect on the result
+    // list is the same: a deleted rowid cannot come back).  The beam holds ef >= k entries, so the list is filtered first.
+    const bool filter = s->n_skip != 0 && !s->h_skip.empty();
     auto emit = [&](uint32_t qi, const std::vector<HCand>& w) {
-        const uint32_t cnt = (uint32_t)std::min<size_t>(k, w.size());
-        for (uint32_t j = 0; j < cnt; ++j) {
-            out_rowids[(size_t)qi * k + j] = h_rowid_of(s, w[j].node);
-            out_dists[(size_t)qi * k + j] = w[j].d;
+        uint32_t cnt = 0;
+        for (size_t j = 0; j < w.size() && cnt < k; ++j) {
+            if (filter && w[j].node < s->h_skip.size() && s->h_skip[w[j].node]) continue;
+            out_rowids[(size_t)qi * k + cnt] = h_rowid_of(s, w[j].node);
+            out_dists[(size_t)qi * k + cnt] = w[j].d;
+            ++cnt;
         }
         if (out_counts) out_counts[qi] = cnt;
     };
@@ -1016,7 +1029,7 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
         for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
             const uint32_t m = std::min(chunk, nq - q0);
             HDevOut o;
-            rc = hnsw_dev_search(h, (const uint8_t*)h->d_queries + (size_t)q0 * s->row_stride, nullptr, nullptr, m, ef, k, nullptr, m, &o);
+            rc = hnsw_dev_search(h, (const uint8_t*)h->d_queries + (size_t)q0 * s->row_stride, nullptr, nullptr, m, ef, filter ? ef : k, nullptr, m, &o);
             if (rc) return rc;
             for (uint32_t i = 0; i < m; ++i) {
                 if (o.status[i]) {
@@ -1038,11 +1051,14 @@ extern "C" int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t 
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk)
         if ((rc = host_loop(nullptr, q0, std::min(chunk, nq - q0)))) return rc;
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edges, int32_t* entry_level, uint64_t* distances_scored,
                                  uint64_t* rounds) {
+    VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lks(h->slab->mu);  // same order as build and search: slab, then index
     std::lock_guard<std::mutex> lk(h->mu);
     if (nodes) *nodes = h->n_nodes;
     if (edges && h->host_stale) {
@@ -1059,22 +1075,28 @@ extern "C" int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edge
     if (distances_scored) *distances_scored = h->scored;
     if (rounds) *rounds = h->rounds;
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* level) {
+    VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lks(h->slab->mu);  // same order as build and search: slab, then index
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->entry >= 0 && h->slab_gen != h->slab->layout_gen)
         return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction or out-of-order insert) since this HNSW index was built: rebuild it");
     if (rowid) *rowid = h->entry < 0 ? -1 : h_rowid_of(h->slab, (uint32_t)h->entry);
     if (level) *level = h->entry < 0 ? -1 : h->entry_level;
     return 0;
+    VG_CATCH
 }
 
 // Node list for the bulk write-back into {t}_{c}_hnsw_nodes(rowid, level, vector) (src/shadow.rs:464-474): every indexed
 // row with its level.  Call with cap = 0 to get the count in *n_out.
 extern "C" int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* rowids, int32_t* levels, uint64_t* n_out) {
+    VG_TRY
     if (!h || !n_out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lks(h->slab->mu);  // same order as build and search: slab, then index
     std::lock_guard<std::mutex> lk(h->mu);
     vecgpu_slab* s = h->slab;
     if (h->entry >= 0 && h->slab_gen != s->layout_gen)
@@ -1093,24 +1115,29 @@ extern "C" int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* r
     }
     *n_out = n;
     return 0;
+    VG_CATCH
 }
 
 // K6 counters: queries answered by the device search kernel, how many of them overflowed a device capacity and were
 // re-run through the lockstep driver, and the number of search launches.
 extern "C" int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallbacks, uint64_t* launches) {
+    VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
     if (queries) *queries = h->dev_queries;
     if (fallbacks) *fallbacks = h->dev_fallbacks;
     if (launches) *launches = h->dev_launches;
     return 0;
+    VG_CATCH
 }
 
 // edge list for a bulk write-back into {t}_{c}_hnsw_edges(from_rowid, to_rowid, level, distance) (src/shadow.rs:478-487).
 // Call with cap = 0 to get the count in *n_out.
 extern "C" int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* from_rowids, int64_t* to_rowids, int32_t* levels,
                                         float* dists, uint64_t* n_out) {
+    VG_TRY
     if (!h || !n_out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lks(h->slab->mu);  // same order as build and search: slab, then index
     std::lock_guard<std::mutex> lk(h->mu);
     vecgpu_slab* s = h->slab;
     if (h->entry >= 0 && h->slab_gen != s->layout_gen)
@@ -1139,4 +1166,5 @@ extern "C" int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* f
     }
     *n_out = n;
     return 0;
+    VG_CATCH
 }

@@ -529,8 +529,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
 // canonical sum of squares of every row (the b2 / a2 of F32Cos), the maximum over the safe rows, and the list
 // of unsafe rows (unsafe[0] = count, unsafe[1..] = positions of the first TC_MAX_UNSAFE)
+// `base` / `norms` point at the first of the n rows; row_base is that row's position in the slab (unsafe[] holds positions)
 __global__ void __launch_bounds__(256) row_norms_kernel(const uint8_t* base, uint32_t stride, uint32_t units, uint64_t n, float* norms,
-                                                        uint32_t* max_bits, uint32_t* unsafe) {
+                                                        uint32_t* max_bits, uint32_t* unsafe, uint32_t row_base) {
     const int g = threadIdx.x & 3;
     const uint64_t n_iter = (n + 63) / 64;
     float mx = 0.f;
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const uint8_t* base, uin
             if (tc_norm_safe(v)) mx = fmaxf(mx, v);
             else if (unsafe) {
                 const uint32_t slot = atomicAdd(unsafe, 1u);
-                if (slot < TC_MAX_UNSAFE) unsafe[1 + slot] = (uint32_t)row;
+                if (slot < TC_MAX_UNSAFE) unsafe[1 + slot] = row_base + (uint32_t)row;
             }
         }
     }

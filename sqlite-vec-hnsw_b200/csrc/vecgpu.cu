@@ -11,14 +11,17 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "../../include/vecgpu.h"
 #include <omp.h>
+#include <unistd.h>
 
 #include "kernels.cuh"
+#include "xchg.cuh"
 #include "tc_batch.cuh"
 #include "hnsw_dev.cuh"
 
@@ -56,6 +59,27 @@ static int fail(int code, const char* fmt, ...) {
                         __LINE__);                                                                               \
     } while (0)
 
+// Nothing may unwind across the C boundary (the header promises it; the caller is Rust, cf. catch_unwind at src/lib.rs:149):
+// every extern "C" entry point that can allocate runs inside VG_TRY / VG_CATCH and turns an exception into status 4.
+static int vg_caught() noexcept {
+    try {
+        throw;
+    } catch (const std::bad_alloc&) {
+        return fail(VECGPU_ERR_CUDA, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(VECGPU_ERR_CUDA, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(VECGPU_ERR_CUDA, "internal error (unknown exception)");
+    }
+}
+#define VG_TRY try {
+#define VG_CATCH \
+    }            \
+    catch (...) { return vg_caught(); }
+#define VG_CATCH_VOID \
+    }                 \
+    catch (...) { vg_caught(); }
+
 static constexpr uint32_t K_FUSED_MAX = 1024;     // above this knn uses emit + radix sort
 static constexpr uint32_t DIMS_MAX = 65536;       // keeps int8 partial sums inside int32
 static constexpr size_t SMEM_MAX = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
@@ -83,11 +107,11 @@ struct vecgpu_slab {
     int64_t first_rowid = 1;
     std::vector<int64_t> h_rowids;
     int64_t* d_rowids = nullptr;
-    uint64_t cap_rowids = 0;
+    uint64_t cap_rowids = 0, rowids_synced = 0;  // d_rowids[0, rowids_synced) == h_rowids[0, rowids_synced)
     // skip flags (tombstones / wrong-length blobs), allocated on first use
     std::vector<uint8_t> h_skip;
     uint8_t* d_skip = nullptr;
-    uint64_t cap_skip = 0, n_skip = 0;
+    uint64_t cap_skip = 0, n_skip = 0, skip_synced = 0;  // d_skip[0, skip_synced) == h_skip[0, skip_synced)
     // canonical |row|^2 cache for the tensor-core batched path (invalidated by any vector write)
     float* d_norms = nullptr;
     uint32_t* d_x2max = nullptr;
@@ -96,15 +120,20 @@ struct vecgpu_slab {
     uint64_t cap_norms = 0;
     bool norms_valid = false;
     // workspaces
-    void* d_ws[20] = {nullptr};
-    size_t ws_cap[20] = {0};
+    void* d_ws[23] = {nullptr};
+    size_t ws_cap[23] = {0};
     void* h_pin[2] = {nullptr};
     size_t pin_cap[2] = {0};
+    // bulk-load staging: two pinned buffers so the host-side copy of chunk i+1 overlaps the DMA of chunk i
+    void* h_stage[2] = {nullptr};
+    size_t stage_cap[2] = {0};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7,
        WS_TC_CANDV = 8, WS_TC_CANDR = 9, WS_TC_CNT = 10, WS_TC_TAU = 11, WS_TC_PAIRQ = 12, WS_TC_PAIRPOS = 13, WS_TC_DIST = 14,
-       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_TC_BUF = 19, WS_COUNT = 20 };
+       WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_TC_BUF = 19, WS_X_ROWID = 20, WS_X_DIST = 21, WS_X_CNT = 22,
+       WS_COUNT = 23 };
 
 static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
     if (bytes <= s->ws_cap[i]) return 0;
@@ -150,35 +179,87 @@ static int slab_reserve_rows(vecgpu_slab* s, uint64_t want) {
     return 0;
 }
 
-static int slab_sync_rowids(vecgpu_slab* s) {  // upload host rowid mirror (non-dense mode)
+// Upload the part of the host rowid mirror the device does not have yet (non-dense mode).  Appends cost O(appended rows):
+// only [rowids_synced, size) travels; the arrays grow geometrically with the slab.  Whoever rewrites entries below
+// rowids_synced (out-of-order insert, compaction, reload) lowers rowids_synced first.
+static int slab_sync_rowids(vecgpu_slab* s) {
     if (s->dense) return 0;
-    if (s->h_rowids.size() > s->cap_rowids) {
-        if (s->d_rowids) CU(cudaFree(s->d_rowids));
-        s->d_rowids = nullptr;
-        s->cap_rowids = std::max<uint64_t>(s->h_rowids.size(), s->cap);
-        CU(cudaMalloc((void**)&s->d_rowids, s->cap_rowids * sizeof(int64_t)));
+    const uint64_t n = s->h_rowids.size();
+    if (n > s->cap_rowids) {
+        const uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(n, s->cap), s->cap_rowids + s->cap_rowids / 2);
+        int64_t* np = nullptr;
+        CU(cudaMalloc((void**)&np, ncap * sizeof(int64_t)));
+        if (s->d_rowids && s->rowids_synced) {
+            cudaError_t e = cudaMemcpy(np, s->d_rowids, s->rowids_synced * sizeof(int64_t), cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess) {
+                cudaFree(np);
+                return fail(VECGPU_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+            }
+        }
+        if (s->d_rowids) cudaFree(s->d_rowids);
+        s->d_rowids = np;
+        s->cap_rowids = ncap;
     }
-    if (!s->h_rowids.empty())
-        CU(cudaMemcpy(s->d_rowids, s->h_rowids.data(), s->h_rowids.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (s->rowids_synced > n) s->rowids_synced = n;
+    if (s->rowids_synced < n) {
+        CU(cudaMemcpy(s->d_rowids + s->rowids_synced, s->h_rowids.data() + s->rowids_synced,
+                      (n - s->rowids_synced) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        s->rowids_synced = n;
+    }
     return 0;
 }
 
-static int slab_sync_skip(vecgpu_slab* s) {  // upload the whole skip mirror
-    if (s->h_skip.empty()) return 0;
-    if (s->h_skip.size() > s->cap_skip) {
-        if (s->d_skip) CU(cudaFree(s->d_skip));
-        s->d_skip = nullptr;
-        s->cap_skip = std::max<uint64_t>(s->h_skip.size(), s->cap);
-        CU(cudaMalloc((void**)&s->d_skip, s->cap_skip));
+// Same for the skip flags.  The device copy is only meaningful below skip_synced: every path that clears or recreates
+// h_skip (load, fill_synthetic, compaction) resets skip_synced to 0, so stale tombstones can never be read by a later
+// scan (they used to survive a reload: the next single-byte update found cap_skip >= rows and uploaded one byte only).
+static int slab_sync_skip(vecgpu_slab* s) {
+    if (s->h_skip.empty()) {
+        s->skip_synced = 0;
+        return 0;
     }
-    CU(cudaMemcpy(s->d_skip, s->h_skip.data(), s->h_skip.size(), cudaMemcpyHostToDevice));
+    const uint64_t n = s->h_skip.size();
+    if (n > s->cap_skip) {
+        const uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(n, s->cap), s->cap_skip + s->cap_skip / 2);
+        uint8_t* np = nullptr;
+        CU(cudaMalloc((void**)&np, ncap));
+        if (s->d_skip && s->skip_synced) {
+            cudaError_t e = cudaMemcpy(np, s->d_skip, s->skip_synced, cudaMemcpyDeviceToDevice);
+            if (e != cudaSuccess) {
+                cudaFree(np);
+                return fail(VECGPU_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+            }
+        }
+        if (s->d_skip) cudaFree(s->d_skip);
+        s->d_skip = np;
+        s->cap_skip = ncap;
+    }
+    if (s->skip_synced > n) s->skip_synced = n;
+    if (s->skip_synced < n) {
+        CU(cudaMemcpy(s->d_skip + s->skip_synced, s->h_skip.data() + s->skip_synced, n - s->skip_synced, cudaMemcpyHostToDevice));
+        s->skip_synced = n;
+    }
     return 0;
+}
+
+// forget every row: host mirrors AND what the device copies are known to hold
+static void slab_reset_rows(vecgpu_slab* s) {
+    s->rows = 0;
+    s->dense = true;
+    s->first_rowid = 1;
+    s->h_rowids.clear();
+    s->rowids_synced = 0;
+    s->h_skip.clear();
+    s->n_skip = 0;
+    s->skip_synced = 0;
+    s->norms_valid = false;
+    ++s->layout_gen;  // every row position is replaced: position-based indexes (HNSW) go stale
 }
 
 static void slab_materialize_rowids(vecgpu_slab* s) {
     if (!s->dense) return;
     s->h_rowids.resize(s->rows);
     for (uint64_t i = 0; i < s->rows; ++i) s->h_rowids[i] = s->first_rowid + (int64_t)i;
+    s->rowids_synced = 0;
     s->dense = false;
 }
 
@@ -203,27 +284,69 @@ static int64_t slab_find(const vecgpu_slab* s, int64_t rowid, uint64_t* ins) {
 
 static int slab_set_skip(vecgpu_slab* s, uint64_t pos, uint8_t v) {
     if (s->h_skip.size() < s->rows) s->h_skip.resize(s->rows, 0);
-    if (s->h_skip[pos] == v) return 0;
+    if (s->h_skip[pos] == v) return slab_sync_skip(s);
     s->h_skip[pos] = v;
     if (v) ++s->n_skip; else --s->n_skip;
-    if (s->cap_skip < s->h_skip.size() || !s->d_skip) return slab_sync_skip(s);
+    if (pos >= s->skip_synced) return slab_sync_skip(s);  // the tail upload carries it
+    int rc = slab_sync_skip(s);
+    if (rc) return rc;
     CU(cudaMemcpy(s->d_skip + pos, &s->h_skip[pos], 1, cudaMemcpyHostToDevice));
     return 0;
 }
 
-// copy n host rows (row_bytes each) into slab rows [pos, pos+n)
+static int slab_update_norms(vecgpu_slab* s, uint64_t pos, uint64_t n);
+
+static constexpr size_t STAGE_BYTES = 16u << 20;  // per staging buffer
+
+// copy n host rows (row_bytes each) into slab rows [pos, pos+n): through two pinned staging buffers, chunk by chunk, with
+// asynchronous copies on the slab's stream (the host-side memcpy of the next chunk runs while the previous one is on the
+// bus); returns after the last byte has landed.  The cached row norms of the tensor-core paths are updated for the written
+// rows only (they used to be thrown away by any write, so a single upsert made the next batched query re-read the slab).
 static int slab_write_rows(vecgpu_slab* s, uint64_t pos, const void* vectors, uint64_t n) {
     if (n == 0) return 0;
-    s->norms_valid = false;
-    uint8_t* dst = s->d_vec + pos * s->row_stride;
-    if (s->row_bytes == s->row_stride) {
-        CU(cudaMemcpy(dst, vectors, (size_t)n * s->row_bytes, cudaMemcpyHostToDevice));
-    } else {
-        CU(cudaMemsetAsync(dst, 0, (size_t)n * s->row_stride, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        CU(cudaMemcpy2D(dst, s->row_stride, vectors, s->row_bytes, s->row_bytes, (size_t)n, cudaMemcpyHostToDevice));
+    const uint64_t chunk_rows = std::max<uint64_t>(1, STAGE_BYTES / s->row_bytes);
+    const size_t want = (size_t)std::min<uint64_t>(n, chunk_rows) * s->row_bytes;
+    const int nbuf = n > chunk_rows ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) {
+        if (s->stage_cap[b] < want) {
+            if (s->h_stage[b]) CU(cudaFreeHost(s->h_stage[b]));
+            s->h_stage[b] = nullptr;
+            s->stage_cap[b] = 0;
+            const size_t cap = n > chunk_rows ? std::max(want, STAGE_BYTES) : std::max(want, (size_t)65536);
+            CU(cudaMallocHost(&s->h_stage[b], cap));
+            s->stage_cap[b] = cap;
+        }
+        if (!s->stage_ev[b]) CU(cudaEventCreateWithFlags(&s->stage_ev[b], cudaEventDisableTiming));
     }
-    return 0;
+    const uint8_t* src = (const uint8_t*)vectors;
+    uint8_t* dst = s->d_vec + pos * s->row_stride;
+    uint64_t i = 0;
+    for (uint64_t off = 0; off < n; off += chunk_rows, ++i) {
+        const int b = (int)(i & 1);
+        const uint64_t m = std::min(chunk_rows, n - off);
+        if (i >= 2) CU(cudaEventSynchronize(s->stage_ev[b]));  // the DMA out of this buffer two chunks ago is done
+        const size_t bytes = (size_t)m * s->row_bytes;
+        if (bytes >= (4u << 20)) {
+            const int parts = 8;
+#pragma omp parallel for schedule(static) num_threads(parts)
+            for (int t = 0; t < parts; ++t) {
+                const size_t lo = bytes * t / parts, hi = bytes * (t + 1) / parts;
+                memcpy((uint8_t*)s->h_stage[b] + lo, src + off * s->row_bytes + lo, hi - lo);
+            }
+        } else {
+            memcpy(s->h_stage[b], src + off * s->row_bytes, bytes);
+        }
+        if (s->row_bytes == s->row_stride) {
+            CU(cudaMemcpyAsync(dst + off * s->row_stride, s->h_stage[b], bytes, cudaMemcpyHostToDevice, s->stream));
+        } else {
+            CU(cudaMemsetAsync(dst + off * s->row_stride, 0, (size_t)m * s->row_stride, s->stream));
+            CU(cudaMemcpy2DAsync(dst + off * s->row_stride, s->row_stride, s->h_stage[b], s->row_bytes, s->row_bytes, (size_t)m,
+                                 cudaMemcpyHostToDevice, s->stream));
+        }
+        CU(cudaEventRecord(s->stage_ev[b], s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return slab_update_norms(s, pos, n);
 }
 
 extern "C" {
@@ -284,6 +407,7 @@ static int use_device(int device) {
 }
 
 extern "C" int vecgpu_slab_create(int elem, uint32_t dims, uint64_t capacity_hint, int device, vecgpu_slab** out) {
+    VG_TRY
     if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "out is NULL");
     *out = nullptr;
     if (elem < 0 || elem > 2) return fail(VECGPU_ERR_UNSUPPORTED, "invalid vector type %d", elem);
@@ -313,9 +437,11 @@ extern "C" int vecgpu_slab_create(int elem, uint32_t dims, uint64_t capacity_hin
     }
     *out = s;
     return 0;
+    VG_CATCH
 }
 
 extern "C" void vecgpu_slab_destroy(vecgpu_slab* s) {
+    VG_TRY
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
@@ -326,11 +452,15 @@ extern "C" void vecgpu_slab_destroy(vecgpu_slab* s) {
     cudaFree(s->d_norms);
     cudaFree(s->d_x2max);
     cudaFree(s->d_unsafe);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
         if (s->h_pin[i]) cudaFreeHost(s->h_pin[i]);
+        if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
+        if (s->stage_ev[i]) cudaEventDestroy(s->stage_ev[i]);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
+    VG_CATCH_VOID
 }
 
 static int slab_append_locked(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
@@ -347,12 +477,19 @@ static int slab_append_locked(vecgpu_slab* s, const int64_t* rowids, const void*
     }
     int rc = slab_reserve_rows(s, s->rows + n);
     if (rc) return rc;
+    // the device write comes first: a failure leaves rows / rowids / skip flags exactly as they were
+    rc = slab_write_rows(s, s->rows, vectors, n);
+    if (rc) return rc;
     // still dense?
     bool stays_dense = s->dense;
     if (s->dense && rowids) {
         const int64_t expect0 = s->rows ? last + 1 : rowids[0];
         for (uint64_t i = 0; i < n && stays_dense; ++i) stays_dense = rowids[i] == expect0 + (int64_t)i;
     }
+    const uint64_t old_rows = s->rows;
+    const bool was_dense = s->dense;
+    const int64_t old_first = s->first_rowid;
+    const size_t old_skip = s->h_skip.size();
     if (s->dense && !stays_dense) slab_materialize_rowids(s);
     if (s->dense) {
         if (s->rows == 0) s->first_rowid = rowids ? rowids[0] : 1;
@@ -360,41 +497,51 @@ static int slab_append_locked(vecgpu_slab* s, const int64_t* rowids, const void*
         const int64_t start = s->rows ? last + 1 : 1;
         for (uint64_t i = 0; i < n; ++i) s->h_rowids.push_back(rowids ? rowids[i] : start + (int64_t)i);
     }
-    rc = slab_write_rows(s, s->rows, vectors, n);
-    if (rc) return rc;
     s->rows += n;
-    if (!s->h_skip.empty()) {
-        s->h_skip.resize(s->rows, 0);
-        rc = slab_sync_skip(s);
-        if (rc) return rc;
+    if (!s->h_skip.empty()) s->h_skip.resize(s->rows, 0);
+    rc = slab_sync_skip(s);
+    if (!rc) rc = slab_sync_rowids(s);
+    if (rc) {  // roll the host state back to what the device arrays still describe
+        s->rows = old_rows;
+        s->h_skip.resize(old_skip);
+        s->skip_synced = std::min<uint64_t>(s->skip_synced, old_skip);
+        if (was_dense) {
+            s->dense = true;
+            s->first_rowid = old_first;
+            s->h_rowids.clear();
+            s->rowids_synced = 0;
+        } else {
+            s->h_rowids.resize(old_rows);
+            s->rowids_synced = std::min<uint64_t>(s->rowids_synced, old_rows);
+        }
+        return rc;
     }
-    return slab_sync_rowids(s);
+    return 0;
 }
 
 extern "C" int vecgpu_slab_append(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     int rc = use_device(s->device);
     if (rc) return rc;
     return slab_append_locked(s, rowids, vectors, n);
+    VG_CATCH
 }
 
 extern "C" int vecgpu_slab_load(vecgpu_slab* s, const int64_t* rowids, const void* vectors, uint64_t n) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
-    ++s->layout_gen;  // the previous contents (and every row position) are replaced
     int rc = use_device(s->device);
     if (rc) return rc;
-    s->rows = 0;
-    s->dense = true;
-    s->first_rowid = 1;
-    s->h_rowids.clear();
-    s->h_skip.clear();
-    s->n_skip = 0;
+    slab_reset_rows(s);  // the previous contents (and every row position) are replaced
     return slab_append_locked(s, rowids, vectors, n);
+    VG_CATCH
 }
 
 extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec, uint32_t nbytes) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     int rc = use_device(s->device);
@@ -423,40 +570,60 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
         if (!good) return slab_set_skip(s, s->rows - 1, 1);
         return 0;
     }
-    // out-of-order insert (rare: explicit rowid below MAX): shift the tail by one row
-    ++s->layout_gen;
+    // out-of-order insert (rare: explicit rowid below MAX): the tail moves up by one row ON THE DEVICE — vectors, rowids and
+    // skip flags alike — and only the new element is uploaded (it used to re-upload both whole mirrors: 90 MB per insert at
+    // 10 M rows).  The host mirrors shift with one memmove each.
     slab_materialize_rowids(s);
+    if ((rc = slab_sync_rowids(s))) return rc;
+    if ((rc = slab_sync_skip(s))) return rc;
     slab_find(s, rowid, &ins);
     rc = slab_reserve_rows(s, s->rows + 1);
     if (rc) return rc;
     const uint64_t tail = s->rows - ins;
+    const bool has_skip = !s->h_skip.empty();
+    // make room for one more element in the device mirrors (both are fully synced here; growing preserves the contents)
+    s->h_rowids.push_back(0);
+    if (has_skip) s->h_skip.push_back(0);
+    rc = slab_sync_rowids(s);
+    if (!rc && has_skip) rc = slab_sync_skip(s);
+    s->h_rowids.pop_back();
+    if (has_skip) s->h_skip.pop_back();
+    s->rowids_synced = std::min<uint64_t>(s->rowids_synced, s->rows);
+    s->skip_synced = std::min<uint64_t>(s->skip_synced, has_skip ? s->rows : 0);
+    if (rc) return rc;
     if (tail) {
-        rc = ws_reserve(s, WS_TMP, (size_t)tail * s->row_stride);
+        const size_t vb = (size_t)tail * s->row_stride;
+        rc = ws_reserve(s, WS_TMP, std::max(vb, (size_t)tail * 8));
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_vec + ins * s->row_stride, (size_t)tail * s->row_stride,
-                           cudaMemcpyDeviceToDevice, s->stream));
-        CU(cudaMemcpyAsync(s->d_vec + (ins + 1) * s->row_stride, s->d_ws[WS_TMP], (size_t)tail * s->row_stride,
-                           cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_vec + ins * s->row_stride, vb, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_vec + (ins + 1) * s->row_stride, s->d_ws[WS_TMP], vb, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_rowids + ins, tail * 8, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_rowids + ins + 1, s->d_ws[WS_TMP], tail * 8, cudaMemcpyDeviceToDevice, s->stream));
+        if (has_skip) {
+            CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_skip + ins, tail, cudaMemcpyDeviceToDevice, s->stream));
+            CU(cudaMemcpyAsync(s->d_skip + ins + 1, s->d_ws[WS_TMP], tail, cudaMemcpyDeviceToDevice, s->stream));
+        }
         CU(cudaStreamSynchronize(s->stream));
     }
-    s->norms_valid = false;
+    ++s->layout_gen;
+    s->norms_valid = false;  // cached norms are position-indexed
     s->h_rowids.insert(s->h_rowids.begin() + (ptrdiff_t)ins, rowid);
-    if (!s->h_skip.empty()) {
-        s->h_skip.resize(s->rows, 0);
-        s->h_skip.insert(s->h_skip.begin() + (ptrdiff_t)ins, 0);
-    }
+    if (has_skip) s->h_skip.insert(s->h_skip.begin() + (ptrdiff_t)ins, 0);
     s->rows += 1;
+    const uint8_t zero_flag = 0;
+    CU(cudaMemcpy(s->d_rowids + ins, &rowid, 8, cudaMemcpyHostToDevice));
+    if (has_skip) CU(cudaMemcpy(s->d_skip + ins, &zero_flag, 1, cudaMemcpyHostToDevice));
+    s->rowids_synced = s->rows;
+    if (has_skip) s->skip_synced = s->rows;
     rc = slab_write_rows(s, ins, src, 1);
-    if (rc) return rc;
-    rc = slab_sync_rowids(s);
-    if (rc) return rc;
-    rc = slab_sync_skip(s);
     if (rc) return rc;
     if (!good) return slab_set_skip(s, ins, 1);
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_slab_delete(vecgpu_slab* s, int64_t rowid) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     int rc = use_device(s->device);
@@ -464,6 +631,7 @@ extern "C" int vecgpu_slab_delete(vecgpu_slab* s, int64_t rowid) {
     int64_t pos = slab_find(s, rowid, nullptr);
     if (pos < 0) return 0;
     return slab_set_skip(s, (uint64_t)pos, 1);
+    VG_CATCH
 }
 
 // Drop the skipped rows (tombstones of vecgpu_slab_delete, wrong-length blobs) physically: the kept rows are gathered, in
@@ -471,6 +639,7 @@ extern "C" int vecgpu_slab_delete(vecgpu_slab* s, int64_t rowid) {
 // duration of the call).  Scans never read skipped rows' flags unless a candidate passes, but they do stream their bytes;
 // after many deletes a compaction gives that bandwidth back.
 extern "C" int vecgpu_slab_compact(vecgpu_slab* s, uint64_t* removed) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     if (removed) *removed = 0;
@@ -511,19 +680,25 @@ extern "C" int vecgpu_slab_compact(vecgpu_slab* s, uint64_t* removed) {
     s->n_skip = 0;
     s->norms_valid = false;
     ++s->layout_gen;
+    s->rowids_synced = 0;
+    s->skip_synced = 0;
     if ((rc = slab_sync_rowids(s))) return rc;
     return slab_sync_skip(s);
+    VG_CATCH
 }
 
 extern "C" int vecgpu_slab_count(vecgpu_slab* s, uint64_t* rows, uint64_t* live) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     if (rows) *rows = s->rows;
     if (live) *live = s->rows - s->n_skip;
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_slab_get(vecgpu_slab* s, int64_t rowid, void* out_vec, int* found) {
+    VG_TRY
     if (!s || !found) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     std::lock_guard<std::mutex> lk(s->mu);
     int rc = use_device(s->device);
@@ -534,6 +709,7 @@ extern "C" int vecgpu_slab_get(vecgpu_slab* s, int64_t rowid, void* out_vec, int
     if (out_vec) CU(cudaMemcpy(out_vec, s->d_vec + (uint64_t)pos * s->row_stride, s->row_bytes, cudaMemcpyDeviceToHost));
     *found = 1;
     return 0;
+    VG_CATCH
 }
 
 // ---------------------------------------------------------------------------
@@ -1006,11 +1182,36 @@ static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
     CU(cudaMemsetAsync(s->d_x2max, 0, 4, st));
     CU(cudaMemsetAsync(s->d_unsafe, 0, (1 + TC_MAX_UNSAFE) * 4, st));
     row_norms_kernel<<<(uint32_t)s->num_sms * 8, 256, 0, st>>>(s->d_vec, s->row_stride, s->row_stride / 16, s->rows, s->d_norms,
-                                                               s->d_x2max, s->d_unsafe);
+                                                               s->d_x2max, s->d_unsafe, 0u);
     LAUNCHED();
     CU(cudaMemcpyAsync(&s->n_unsafe, s->d_unsafe, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     s->norms_valid = true;
+    return 0;
+}
+
+// Rows [pos, pos+n) were just (re)written: refresh their cached norms in place instead of invalidating the cache (an upsert
+// used to make the next batched query recompute all of them — a full pass over the slab).  The maximum only ever grows and a
+// row that was unusable stays on the always-re-ranked list: both remain valid (conservative) bounds.
+static int slab_update_norms(vecgpu_slab* s, uint64_t pos, uint64_t n) {
+    if (!s->norms_valid || n == 0) return 0;
+    if (pos + n > s->cap_norms || s->elem == VECGPU_BIT) {
+        s->norms_valid = false;
+        return 0;
+    }
+    const uint8_t* base = s->d_vec + pos * s->row_stride;
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 63) / 64, (uint64_t)s->num_sms * 8));
+    if (s->elem == VECGPU_I8) {
+        row_norms_i8_kernel<<<blocks, 256, 0, s->stream>>>(base, s->row_stride, s->row_stride / 16, n, (int*)s->d_norms + pos);
+        LAUNCHED();
+        CU(cudaStreamSynchronize(s->stream));
+        return 0;
+    }
+    row_norms_kernel<<<blocks, 256, 0, s->stream>>>(base, s->row_stride, s->row_stride / 16, n, s->d_norms + pos, s->d_x2max, s->d_unsafe,
+                                                    (uint32_t)pos);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(&s->n_unsafe, s->d_unsafe, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return 0;
 }
 
@@ -1104,7 +1305,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
 
         // |q|^2 in the canonical order
         row_norms_kernel<<<std::max(1u, std::min((nq + 63) / 64, 1024u)), 256, 0, st>>>(dq, s->row_stride, s->row_stride / 16, nq,
-                                                                                        (float*)s->d_ws[WS_TC_QNORM], nullptr, nullptr);
+                                                                                        (float*)s->d_ws[WS_TC_QNORM], nullptr, nullptr, 0u);
         LAUNCHED();
         CUtensorMap mapQ;
         if ((rc = make_f32_map(&mapQ, dq, s->dims, nq, s->row_stride, TC_M))) return rc;
@@ -1350,6 +1551,7 @@ static int stage_queries(vecgpu_slab* s, const void* queries, uint32_t nq) {
 
 extern "C" int vecgpu_knn(vecgpu_slab* s, const void* queries, uint32_t nq, uint32_t k, int metric, int64_t* out_rowids,
                           float* out_dists, uint32_t* out_counts) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     int rc = check_pair(s->elem, metric);
     if (rc) return rc;
@@ -1383,10 +1585,12 @@ extern "C" int vecgpu_knn(vecgpu_slab* s, const void* queries, uint32_t nq, uint
     memcpy(out_dists, h + n_out * 8, n_out * 4);
     if (out_counts) memcpy(out_counts, h + n_out * 12, (size_t)nq * 4);
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_knn_device(vecgpu_slab* s, const void* d_queries, uint32_t nq, uint32_t k, int metric,
                                  int64_t* d_out_rowids, float* d_out_dists, void* stream) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     int rc = check_pair(s->elem, metric);
     if (rc) return rc;
@@ -1406,10 +1610,12 @@ extern "C" int vecgpu_knn_device(vecgpu_slab* s, const void* d_queries, uint32_t
         dq = (const uint8_t*)s->d_ws[WS_QUERY];
     }
     return knn_core(s, dq, nq, k, metric, d_out_rowids, d_out_dists, nullptr, INT64_MAX, st);
+    VG_CATCH
 }
 
 extern "C" int vecgpu_merge_device(int device, const int64_t* d_rowids, const float* d_dists, uint32_t nlists, uint32_t nq,
                                    uint32_t k, int64_t* d_out_rowids, float* d_out_dists, void* stream) {
+    VG_TRY
     if (!d_rowids || !d_dists || !d_out_rowids || !d_out_dists) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     if (nq == 0 || k == 0 || nlists == 0) return 0;
     int rc = use_device(device);
@@ -1429,6 +1635,7 @@ extern "C" int vecgpu_merge_device(int device, const int64_t* d_rowids, const fl
     xmerge_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(p);
     LAUNCHED();
     return 0;
+    VG_CATCH
 }
 
 // ---------------------------------------------------------------------------
@@ -1458,6 +1665,7 @@ static int launch_pairs(int elem, int metric, const PairParams& p, int num_sms, 
 
 extern "C" int vecgpu_score(vecgpu_slab* s, const void* queries, uint32_t nq, const int64_t* cand_rowids,
                             const uint32_t* cand_offsets, int metric, float* out_dists) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     int rc = check_pair(s->elem, metric);
     if (rc) return rc;
@@ -1508,6 +1716,7 @@ extern "C" int vecgpu_score(vecgpu_slab* s, const void* queries, uint32_t nq, co
     CU(cudaStreamSynchronize(s->stream));
     memcpy(out_dists, h, np * 4);
     return 0;
+    VG_CATCH
 }
 
 struct DevBuf {
@@ -1517,6 +1726,7 @@ struct DevBuf {
 
 extern "C" int vecgpu_distance_pairs(int elem, uint32_t dims_a, uint32_t dims_b, const void* a, const void* b, uint64_t n,
                                      int metric, int device, float* out) {
+    VG_TRY
     if (elem < 0 || elem > 2) return fail(VECGPU_ERR_UNSUPPORTED, "invalid vector type %d", elem);
     // order of checks follows src/distance/mod.rs:57-83: dimensions, (types), then the metric match
     if (dims_a != dims_b) return fail(VECGPU_ERR_DIM_MISMATCH, "Dimension mismatch: expected %u, got %u", dims_a, dims_b);
@@ -1553,6 +1763,7 @@ extern "C" int vecgpu_distance_pairs(int elem, uint32_t dims_a, uint32_t dims_b,
     if (rc) return rc;
     CU(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
     return 0;
+    VG_CATCH
 }
 
 // ---------------------------------------------------------------------------
@@ -1570,6 +1781,7 @@ static int producer_common(const float* in, uint64_t n, uint32_t dims, int devic
 static uint32_t blocks_for(uint64_t threads) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((threads + 255) / 256, 148 * 16)); }
 
 extern "C" int vecgpu_normalize_f32(const float* in, uint64_t n, uint32_t dims, int device, float* out) {
+    VG_TRY
     if (n == 0) return 0;
     if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     DevBuf din, dout, dflag;
@@ -1585,9 +1797,11 @@ extern "C" int vecgpu_normalize_f32(const float* in, uint64_t n, uint32_t dims, 
     CU(cudaMemcpy(out, dout.p, n * dims * 4, cudaMemcpyDeviceToHost));
     if (flag) return fail(VECGPU_ERR_INVALID_PARAM, "Cannot normalize zero vector");  // src/vector.rs:451-455
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_quantize_int8(const float* in, uint64_t n, uint32_t dims, int device, int8_t* out) {
+    VG_TRY
     if (n == 0) return 0;
     if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     DevBuf din, dout;
@@ -1598,9 +1812,11 @@ extern "C" int vecgpu_quantize_int8(const float* in, uint64_t n, uint32_t dims, 
     LAUNCHED();
     CU(cudaMemcpy(out, dout.p, n * dims, cudaMemcpyDeviceToHost));
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_quantize_int8_for_index(const float* in, uint64_t n, uint32_t dims, int device, int8_t* out) {
+    VG_TRY
     if (n == 0) return 0;
     if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     DevBuf din, dout;
@@ -1611,9 +1827,11 @@ extern "C" int vecgpu_quantize_int8_for_index(const float* in, uint64_t n, uint3
     LAUNCHED();
     CU(cudaMemcpy(out, dout.p, n * dims, cudaMemcpyDeviceToHost));
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_quantize_binary(const float* in, uint64_t n, uint32_t dims, int device, uint8_t* out) {
+    VG_TRY
     if (n == 0) return 0;
     if (!out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
     DevBuf din, dout;
@@ -1625,28 +1843,25 @@ extern "C" int vecgpu_quantize_binary(const float* in, uint64_t n, uint32_t dims
     LAUNCHED();
     CU(cudaMemcpy(out, dout.p, n * nb, cudaMemcpyDeviceToHost));
     return 0;
+    VG_CATCH
 }
 
 // ---------------------------------------------------------------------------
 // synthetic fill + device view
 // ---------------------------------------------------------------------------
 extern "C" int vecgpu_slab_fill_synthetic(vecgpu_slab* s, uint64_t seed, int64_t first_rowid, uint64_t n, int kind) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     if (kind != VECGPU_SYNTH_UNIFORM && !(kind == VECGPU_SYNTH_GAUSS4 && s->elem == VECGPU_F32))
         return fail(VECGPU_ERR_INVALID_PARAM, "unsupported synthetic kind %d for this element type", kind);
     std::lock_guard<std::mutex> lk(s->mu);
     int rc = use_device(s->device);
     if (rc) return rc;
-    s->rows = 0;
-    s->dense = true;
-    s->h_rowids.clear();
-    s->h_skip.clear();
-    s->n_skip = 0;
+    slab_reset_rows(s);  // bumps layout_gen: an HNSW index built over the old rows fails loudly until rebuilt
     rc = slab_reserve_rows(s, n);
     if (rc) return rc;
     s->first_rowid = first_rowid;
     s->rows = n;
-    s->norms_valid = false;
     if (n == 0) return 0;
     const uint32_t grid = (uint32_t)s->num_sms * 16;
     if (s->elem == VECGPU_F32)
@@ -1658,18 +1873,26 @@ extern "C" int vecgpu_slab_fill_synthetic(vecgpu_slab* s, uint64_t seed, int64_t
     LAUNCHED();
     CU(cudaStreamSynchronize(s->stream));
     return 0;
+    VG_CATCH
 }
 
 extern "C" int vecgpu_slab_device_view(vecgpu_slab* s, void** d_vectors, uint32_t* row_stride, uint64_t* rows) {
+    VG_TRY
     if (!s) return fail(VECGPU_ERR_INVALID_PARAM, "slab is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     if (d_vectors) *d_vectors = s->d_vec;
     if (row_stride) *row_stride = s->row_stride;
     if (rows) *rows = s->rows;
     return 0;
+    VG_CATCH
 }
 
 // ---------------------------------------------------------------------------
 // batched HNSW driver (config 5)
 // ---------------------------------------------------------------------------
 #include "hnsw.inl"
+
+// ---------------------------------------------------------------------------
+// sharded slabs: exchange endpoints, per-rank and one-process entry points
+// ---------------------------------------------------------------------------
+#include "xchg_host.inl"

@@ -454,6 +454,142 @@ def merge_device(d_rowids, d_dists, stream=None):
     return out_r, out_d
 
 
+# ---------------------------------------------------------------- sharded slabs, C entry points of csrc/xchg_host.inl
+class Exchange:
+    """One rank's exchange endpoint (vecgpu_xchg): gather buffer in this GPU's HBM that the peers write their local top-k
+    into over NVLink.  One per (rank, GPU); introduce the endpoints with attach_local (same process) or
+    export_handle + attach_ipc (one process per GPU)."""
+
+    def __init__(self, device, rank, world, max_queries=1024, max_k=128):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device, self.rank, self.world = device, rank, world
+        _check(self._lib.vecgpu_xchg_create(device, rank, world, max_queries, max_k, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.vecgpu_xchg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def export_handle(self):
+        buf = np.zeros(_lib.XCHG_HANDLE_BYTES, dtype="u1")
+        _check(self._lib.vecgpu_xchg_export(self._h, _ptr(buf)))
+        return buf
+
+    def attach_ipc(self, handles):
+        """handles: [world, 128] u8, row p = rank p's export_handle()."""
+        h = np.ascontiguousarray(handles, dtype="u1").reshape(self.world, _lib.XCHG_HANDLE_BYTES)
+        _check(self._lib.vecgpu_xchg_attach_ipc(self._h, _ptr(h), self.world))
+
+    @staticmethod
+    def attach_local(endpoints):
+        arr = (C.c_void_p * len(endpoints))(*[e._h.value for e in endpoints])
+        _check(_lib.load().vecgpu_xchg_attach_local(arr, len(endpoints)))
+
+    def shard_knn(self, slab, queries, k, metric):
+        """vecgpu_shard_knn: this rank's part of a sharded query, host buffers; -> global (rowids, dists, counts)."""
+        q, nq = slab._queries(queries)
+        k = int(k)
+        rowids = np.full((nq, k), -1, dtype="<i8")
+        dists = np.full((nq, k), np.inf, dtype="<f4")
+        counts = np.zeros(nq, dtype="<u4")
+        _check(self._lib.vecgpu_shard_knn(slab._h, self._h, _ptr(q), nq, k, int(DistanceMetric(metric)), _ptr(rowids), _ptr(dists),
+                                          _ptr(counts)))
+        return rowids, dists, counts
+
+    def shard_knn_device(self, slab, d_queries, k, metric, stream=None):
+        import torch
+
+        nq = d_queries.numel() * d_queries.element_size() // slab.row_bytes
+        rowids = torch.empty((nq, k), dtype=torch.int64, device=d_queries.device)
+        dists = torch.empty((nq, k), dtype=torch.float32, device=d_queries.device)
+        st = torch.cuda.current_stream(d_queries.device).cuda_stream if stream is None else stream
+        _check(self._lib.vecgpu_shard_knn_device(slab._h, self._h, d_queries.data_ptr(), nq, int(k), int(DistanceMetric(metric)),
+                                                 rowids.data_ptr(), dists.data_ptr(), C.c_void_p(st)))
+        return rowids, dists
+
+    def merge_device(self, d_rowids, d_dists, stream=None):
+        """Exchange + merge of this rank's [nq, k] device results with every peer's (collective)."""
+        import torch
+
+        nq, k = d_rowids.shape
+        out_r = torch.empty((nq, k), dtype=torch.int64, device=d_rowids.device)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=d_rowids.device)
+        st = torch.cuda.current_stream(d_rowids.device).cuda_stream if stream is None else stream
+        _check(self._lib.vecgpu_xchg_merge_device(self._h, d_rowids.contiguous().data_ptr(), d_dists.contiguous().data_ptr(), None, nq, k,
+                                                  out_r.data_ptr(), out_d.data_ptr(), C.c_void_p(st)))
+        return out_r, out_d
+
+    def check(self, stream=None):
+        _check(self._lib.vecgpu_xchg_check(self._h, C.c_void_p(stream or 0)))
+
+
+class ShardedSlab:
+    """vecgpu_sharded: one slab cut by rowid range over several GPUs of THIS process (the form the Rust extension links)."""
+
+    def __init__(self, vec_type, dims, devices=None, capacity_hint=0, max_queries=1024, max_k=128):
+        self.vec_type = VectorType(vec_type)
+        self.dims = int(dims)
+        self.row_bytes = self.vec_type.row_bytes(self.dims)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        if devices is None:
+            arr, n = None, 0
+        else:
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+        _check(self._lib.vecgpu_sharded_create(int(self.vec_type), self.dims, capacity_hint, arr, n, max_queries, max_k, C.byref(self._h)))
+        self.n_shards = int(self._lib.vecgpu_sharded_num_shards(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.vecgpu_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def load(self, vectors, rowids=None):
+        v = _as_raw(vectors, self.vec_type).reshape(-1)
+        n = v.size * v.itemsize // self.row_bytes
+        r = None if rowids is None else np.ascontiguousarray(rowids, dtype="<i8")
+        _check(self._lib.vecgpu_sharded_load(self._h, None if r is None else _ptr(r), _ptr(v), n))
+        return n
+
+    def fill_synthetic(self, seed, n, first_rowid=1, kind=_lib.SYNTH_UNIFORM):
+        _check(self._lib.vecgpu_sharded_fill_synthetic(self._h, seed, first_rowid, n, kind))
+
+    def upsert(self, rowid, blob):
+        b = bytes(blob) if blob is not None else b""
+        buf = np.frombuffer(b, dtype="u1") if b else np.zeros(1, dtype="u1")
+        _check(self._lib.vecgpu_sharded_upsert(self._h, int(rowid), _ptr(buf), len(b)))
+
+    def delete(self, rowid):
+        _check(self._lib.vecgpu_sharded_delete(self._h, int(rowid)))
+
+    def count(self):
+        rows, live = C.c_uint64(), C.c_uint64()
+        _check(self._lib.vecgpu_sharded_count(self._h, C.byref(rows), C.byref(live)))
+        return rows.value, live.value
+
+    _queries = Slab._queries
+
+    def knn(self, queries, k, metric):
+        q, nq = self._queries(queries)
+        k = int(k)
+        rowids = np.full((nq, k), -1, dtype="<i8")
+        dists = np.full((nq, k), np.inf, dtype="<f4")
+        counts = np.zeros(nq, dtype="<u4")
+        _check(self._lib.vecgpu_sharded_knn(self._h, _ptr(q), nq, k, int(DistanceMetric(metric)), _ptr(rowids), _ptr(dists), _ptr(counts)))
+        return rowids, dists, counts
+
+
 # ---------------------------------------------------------------- brute_force_search (src/vtab.rs:2573-2623)
 def brute_force_search(slab, query_vector, k, distance_metric):
     """Exact k-NN: every live row scored, stable order by (distance, rowid), first k.

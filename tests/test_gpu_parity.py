@@ -1118,3 +1118,121 @@ def test_full_size_properties_int8_and_bit(vg, orc, gpu, elem, dims, metric, k, 
             rows = np.concatenate([orc.synth_rows(elem, 4 + elem, int(x), 1, dims, 0) for x in r[qi]])
             want = orc.distances(elem, dims, rows, q[qi], metric)
             assert np.array_equal(bits(d[qi]), bits(want))
+
+
+# ------------------------------------------------------------------ round-2 regressions: slab maintenance
+def test_reload_does_not_resurrect_tombstones(vg, orc, gpu):
+    """Delete row A, load() new data, delete row B: the device copy of the skip flags must not keep A's old tombstone
+    (it used to: the reload cleared the host mirror only and the next delete uploaded a single byte)."""
+    dims, n = 16, 500
+    v1 = random_rows(F32, n, dims, seed=1)
+    v2 = random_rows(F32, n, dims, seed=2)
+    with vg.Slab(F32, dims) as s:
+        s.load(v1)
+        s.delete(7)
+        s.delete(300)
+        s.load(v2)                      # every position now holds a live row again
+        s.delete(450)                   # rowid B
+        skip = np.zeros(n, dtype="u1")
+        skip[449] = 1
+        for q in (v2[6], v2[299], v2[449]):
+            r, d, c = s.knn(q, 3, L2)
+            er, ed, ec = orc.knn(F32, dims, v2, q, 3, L2, skip=skip)
+            assert np.array_equal(r, er) and same_bits(d, ed)
+        assert s.knn(v2[6], 1, L2)[0][0, 0] == 7 and s.knn(v2[299], 1, L2)[0][0, 0] == 300
+        # same through fill_synthetic and through a compaction down to zero rows
+        s.fill_synthetic(seed=5, n=n, kind=1)
+        s.delete(2)
+        cpu = orc.synth_rows(F32, 5, 1, n, dims, 1)
+        assert s.knn(cpu[6], 1, L2)[0][0, 0] == 7 and s.knn(cpu[299], 1, L2)[0][0, 0] == 300 and s.knn(cpu[449], 1, L2)[0][0, 0] == 450
+
+
+@pytest.mark.parametrize("elem,metric,dims", [(F32, COSINE, 96), (F32, L2, 64), (I8, L2, 128)])
+def test_norm_cache_is_updated_by_upserts_not_discarded(vg, orc, gpu, elem, metric, dims):
+    """Batched (tensor-core) queries cache |row|^2; upserts, appends and out-of-order inserts must leave it correct."""
+    n, nq, k = 20_000, 32, 10
+    v = random_rows(elem, n, dims, seed=41)
+    q = random_rows(elem, nq, dims, seed=42)
+    rowids = np.arange(10, 10 + 2 * n, 2, dtype="<i8")  # gaps, so out-of-order inserts are possible
+    with vg.Slab(elem, dims) as s:
+        s.load(v, rowids)
+        tc0 = vg.tc_stats()[0]
+        s.knn(q, k, metric)
+        assert vg.tc_stats()[0] - tc0 == nq  # the cache exists now
+        vv, rr = v.copy(), rowids.copy()
+        # in-place update: make row 1234 the exact match of query 0
+        vv[1234] = q[0]
+        s.upsert(int(rr[1234]), vv[1234].tobytes())
+        # append: exact match of query 1 at the end
+        s.upsert(int(rr[-1] + 7), q[1].tobytes())
+        vv = np.concatenate([vv, q[1:2]])
+        rr = np.concatenate([rr, [rr[-1] + 7]])
+        # out-of-order insert: exact match of query 2 in the middle (positions shift)
+        new_id = int(rr[5000] + 1)
+        s.upsert(new_id, q[2].tobytes())
+        vv = np.concatenate([vv[:5001], q[2:3], vv[5001:]])
+        rr = np.concatenate([rr[:5001], [new_id], rr[5001:]])
+        r, d, c = s.knn(q, k, metric)
+        er, ed, ec = orc.knn(elem, dims, vv, q, k, metric, rowids=rr)
+        assert np.array_equal(r, er) and same_bits(d, ed)
+        assert r[0, 0] == rr[1234] and r[1, 0] == rr[-1] and r[2, 0] == new_id
+
+
+def test_out_of_order_inserts_with_tombstones(vg, orc, gpu):
+    dims = 12
+    rng = np.random.default_rng(9)
+    v = random_rows(I8, 300, dims, seed=3, ties=True)
+    ids = rng.permutation(np.arange(1, 1201, 4))[:300].astype("<i8")  # arbitrary insertion order
+    q = random_rows(I8, 3, dims, seed=4, ties=True)
+    with vg.Slab(I8, dims) as s:
+        live = {}
+        for i, (rid, row) in enumerate(zip(ids, v)):
+            s.upsert(int(rid), row.tobytes())
+            live[int(rid)] = row
+            if i % 7 == 3:  # tombstone something already present, sometimes re-insert it
+                victim = int(ids[rng.integers(0, i + 1)])
+                s.delete(victim)
+                live.pop(victim, None)
+            if i % 50 == 49:
+                rr = np.array(sorted(live), dtype="<i8")
+                vv = np.stack([live[int(x)] for x in rr])
+                r, d, c = s.knn(q, 8, L2)
+                er, ed, ec = orc.knn(I8, dims, vv, q, 8, L2, rowids=rr)
+                assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+
+
+@pytest.mark.parametrize("dims,n", [(768, 30_000), (5, 1_200_000)])
+def test_bulk_load_through_the_staging_buffers(vg, orc, gpu, dims, n):
+    """Loads larger than one 16 MB staging buffer (packed rows and rows padded to the 16-byte stride)."""
+    v = np.random.default_rng(dims).standard_normal((n, dims)).astype("<f4")
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        for rid in (1, 2, n // 3, n - 1, n):
+            assert s.get(rid) == v[rid - 1].tobytes()
+        q = v[[n // 2]]
+        r, d, c = s.knn(q, 5, L2)
+        er, ed, ec = orc.knn_select(F32, dims, v, q, 5, L2)
+        assert np.array_equal(r, er) and same_bits(d, ed)
+
+
+def test_hnsw_never_returns_deleted_rows_and_goes_stale_on_refill(vg, orc, gpu):
+    dims, n = 32, 4000
+    v = random_rows(F32, n, dims, seed=51)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=16, ef_construction=100, seed=1)
+        idx.rebuild()
+        q = v[[100, 200, 300]]
+        r, d, c = idx.search(q, 5, ef_search=64)
+        assert list(r[:, 0]) == [101, 201, 301]
+        for rid in (101, 201):
+            s.delete(rid)
+        r, d, c = idx.search(q, 5, ef_search=64)
+        assert 101 not in r and 201 not in r and r[2, 0] == 301 and np.all(c == 5)
+        # what comes back is the exact order of the live rows among the beam
+        er, ed, _ = s.knn(q, 5, L2)
+        assert np.array_equal(r[2], er[2])
+        s.fill_synthetic(seed=2, n=n, kind=1)  # every row replaced: the index must fail loudly, not walk stale positions
+        with pytest.raises(vg.InvalidState):
+            idx.search(q, 5, ef_search=64)
+        idx.close()
