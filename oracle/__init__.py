@@ -43,6 +43,28 @@ def _host_has_avx512():
     return False
 
 
+LIB_PATH_NATIVE = os.path.join(_HERE, "libvecgpu_oracle_native.so")
+
+
+def build_native():
+    """-march=native build made ON THE MACHINE THAT RUNS IT (bench.py's CPU arm calls this on the GPU box, so the CPU
+    number is not held back by a portable build).  Same sources, same flags otherwise: bit-identical results.
+    Returns the path, or None when it cannot be built here."""
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _bind(LIB_PATH_NATIVE)  # must load and resolve every symbol on this CPU
+        return LIB_PATH_NATIVE
+    except Exception:
+        return None
+
+
+def use_library(path):
+    """Switch the bound library (e.g. to the native build)."""
+    global _lib
+    _lib = _bind(path)
+    return _lib
+
+
 def lib_path():
     """The build this host can run fastest; VECGPU_ORACLE_PORTABLE=1 pins the portable one."""
     if os.environ.get("VECGPU_ORACLE_PORTABLE", "0") != "1" and os.path.exists(LIB_PATH_AVX512) and _host_has_avx512():

@@ -6,6 +6,9 @@
 //                      src/lib.rs:26-34, src/vtab.rs:2286-2305): a slab cut by contiguous rowid range over several
 //                      devices, one host worker thread + stream per device, a single call returns the global top-k.
 // Device code: xchg.cuh.
+#include <condition_variable>
+#include <functional>
+#include <thread>
 
 struct vecgpu_xchg {
     int device = 0;
@@ -188,16 +191,18 @@ extern "C" int vecgpu_xchg_attach_local(vecgpu_xchg* const* all, uint32_t n) {
     VG_CATCH
 }
 
-// push the local top-k (device arrays) and merge: the exchange of ONE batch.  Enqueues on `st`.
-static int xchg_exchange(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts, uint32_t nq, uint32_t k,
-                         int64_t pad_rowid, int64_t* d_out_rowids, float* d_out_dists, uint32_t* d_out_counts, int root, cudaStream_t st) {
+// The exchange of ONE batch = xchg_push (local top-k -> the peers' gather buffers, flags published) followed on the receiving
+// ranks by xchg_merge (flag wait + k-way merge).  Both only enqueue on `st`.
+static int xchg_push(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts, uint32_t nq, uint32_t k,
+                     int root, uint32_t* epoch_out, cudaStream_t st) {
     if (!x->attached) return fail(VECGPU_ERR_INVALID_PARAM, "exchange endpoint is not attached to its peers yet");
     if (nq > x->cap_q || (uint64_t)nq * k > x->lay.cap_entries)
         return fail(VECGPU_ERR_INVALID_PARAM, "exchange of %u queries x k=%u exceeds the endpoint's capacity (%u queries, %llu entries)", nq, k,
                     x->cap_q, (unsigned long long)x->lay.cap_entries);
     if ((uint64_t)x->world * k > 16384) return fail(VECGPU_ERR_INVALID_PARAM, "world*k must be <= 16384");
     const uint32_t epoch = ++x->epoch;
-    const uint32_t all = x->world >= 32 ? 0xFFFFFFFFu : ((1u << x->world) - 1u);
+    *epoch_out = epoch;
+    const uint32_t all = (1u << x->world) - 1u;
     XPushParams pp{};
     pp.tab = x->d_tab;
     pp.lay = x->lay;
@@ -213,7 +218,11 @@ static int xchg_exchange(vecgpu_xchg* x, const int64_t* d_rowids, const float* d
     const uint32_t pgrid = std::min<uint32_t>(nq, 296);
     xpush_kernel<<<pgrid, 128, 0, st>>>(pp);
     LAUNCHED();
-    if (root >= 0 && (uint32_t)root != x->rank) return 0;  // gather-to-root: only the root merges
+    return 0;
+}
+
+static int xchg_merge(vecgpu_xchg* x, uint32_t epoch, uint32_t nq, uint32_t k, int64_t pad_rowid, int64_t* d_out_rowids, float* d_out_dists,
+                      uint32_t* d_out_counts, cudaStream_t st) {
     XWaitMergeParams wp{};
     wp.tab = x->d_tab;
     wp.lay = x->lay;
@@ -221,7 +230,7 @@ static int xchg_exchange(vecgpu_xchg* x, const int64_t* d_rowids, const float* d
     wp.k = k;
     wp.rank = x->rank;
     wp.epoch = epoch;
-    wp.src_mask = all;
+    wp.src_mask = (1u << x->world) - 1u;
     wp.np2 = std::max(2u, next_pow2(x->world * k));
     wp.pad_rowid = pad_rowid;
     wp.out_rowids = d_out_rowids;
@@ -244,6 +253,27 @@ static int xchg_exchange(vecgpu_xchg* x, const int64_t* d_rowids, const float* d
     LAUNCHED();
     return 0;
 }
+
+static int xchg_exchange(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts, uint32_t nq, uint32_t k,
+                         int64_t pad_rowid, int64_t* d_out_rowids, float* d_out_dists, uint32_t* d_out_counts, int root, cudaStream_t st) {
+    uint32_t epoch = 0;
+    int rc = xchg_push(x, d_rowids, d_dists, d_counts, nq, k, root, &epoch, st);
+    if (rc) return rc;
+    if (root >= 0 && (uint32_t)root != x->rank) return 0;  // gather-to-root: only the root merges
+    return xchg_merge(x, epoch, nq, k, pad_rowid, d_out_rowids, d_out_dists, d_out_counts, st);
+}
+
+// In ONE process the shards' host threads can order the streams with CUDA events instead of letting the merge kernel poll:
+// every worker records an event after its push and counts itself in; a worker that is about to merge waits (on the host,
+// microseconds) until all pushes of this piece are ENQUEUED, then makes its stream wait for those events.  The flags are
+// then already published when xwait_merge_kernel starts, so it never spins — which matters when several shards share one
+// device (tests on a 1-GPU box): a polling kernel there can deadlock against a peer whose next kernel is held back by an
+// implicit device-wide serialisation point (cudaMalloc / cudaFree of a growing workspace).
+struct ShardSync {
+    std::atomic<uint32_t>* pushes;  // total pushes enqueued in this call, all workers
+    cudaEvent_t* events;            // [n] one per worker
+    uint32_t n, me;
+};
 
 static int xchg_check_err(vecgpu_xchg* x, cudaStream_t st) {  // after the stream has been synchronised up to an exchange
     CU(cudaMemcpyAsync(x->h_err, x->d_err, 4, cudaMemcpyDeviceToHost, st));
@@ -289,32 +319,55 @@ enum { XWS_ROWID = 0, XWS_DIST = 1, XWS_CNT = 2 };
 // anybody but the root); a batch that needs several exchanges is all-gathered so that the merges pace every rank (a rank
 // that only pushed could overwrite a buffer half the root has not merged yet).
 static int shard_knn_locked(vecgpu_slab* s, vecgpu_xchg* x, const void* queries, uint32_t nq, uint32_t k, int metric, int root,
-                            int64_t* out_rowids, float* out_dists, uint32_t* out_counts) {
-    int rc = use_device(s->device);
-    if (rc) return rc;
+                            int64_t* out_rowids, float* out_dists, uint32_t* out_counts, const ShardSync* sync = nullptr) {
     const bool receives = root < 0 || (uint32_t)root == x->rank;
     const uint32_t chunk = std::max(1u, std::min(x->cap_q, (uint32_t)std::min<uint64_t>(x->lay.cap_entries / k, 0xFFFFFFFFull)));
     if (nq > chunk) root = -1;
+    const bool merges = root < 0 || (uint32_t)root == x->rank;
     const size_t n_out = (size_t)nq * k;
-    rc = stage_queries(s, queries, nq);
-    if (rc) return rc;
-    if ((rc = ws_reserve(s, WS_OUT_ROWID, n_out * 8))) return rc;
-    if ((rc = ws_reserve(s, WS_OUT_DIST, n_out * 4))) return rc;
-    if ((rc = ws_reserve(s, WS_OUT_CNT, (size_t)nq * 4))) return rc;
-    if ((rc = ws_reserve(s, WS_X_ROWID, n_out * 8))) return rc;
-    if ((rc = ws_reserve(s, WS_X_DIST, n_out * 4))) return rc;
-    if ((rc = ws_reserve(s, WS_X_CNT, (size_t)nq * 4))) return rc;
+    // a worker that fails before its pushes still counts them in, so that no peer waits for it forever
+    auto bail = [&](int code) {
+        if (sync) sync->pushes->fetch_add((nq + chunk - 1) / chunk, std::memory_order_release);
+        return code;
+    };
+    int rc = use_device(s->device);
+    if (rc) return bail(rc);
+    if ((rc = stage_queries(s, queries, nq))) return bail(rc);
+    if ((rc = ws_reserve(s, WS_OUT_ROWID, n_out * 8))) return bail(rc);
+    if ((rc = ws_reserve(s, WS_OUT_DIST, n_out * 4))) return bail(rc);
+    if ((rc = ws_reserve(s, WS_OUT_CNT, (size_t)nq * 4))) return bail(rc);
+    if ((rc = ws_reserve(s, WS_X_ROWID, n_out * 8))) return bail(rc);
+    if ((rc = ws_reserve(s, WS_X_DIST, n_out * 4))) return bail(rc);
+    if ((rc = ws_reserve(s, WS_X_CNT, (size_t)nq * 4))) return bail(rc);
     int64_t* lr = (int64_t*)s->d_ws[WS_X_ROWID];
     float* ld = (float*)s->d_ws[WS_X_DIST];
     uint32_t* lc = (uint32_t*)s->d_ws[WS_X_CNT];
-    // local scan of every query first (one launch sequence), then the exchanges chunk by chunk
+    // local scan of every query first (one launch sequence), then the exchanges piece by piece
     rc = knn_core(s, (const uint8_t*)s->d_ws[WS_QUERY], nq, k, metric, lr, ld, lc, -1, s->stream);
-    if (rc) return rc;
-    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+    uint32_t piece = 0;
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk, ++piece) {
         const uint32_t m = std::min(chunk, nq - q0);
-        rc = xchg_exchange(x, lr + (size_t)q0 * k, ld + (size_t)q0 * k, lc + q0, m, k, -1, (int64_t*)s->d_ws[WS_OUT_ROWID] + (size_t)q0 * k,
-                           (float*)s->d_ws[WS_OUT_DIST] + (size_t)q0 * k, (uint32_t*)s->d_ws[WS_OUT_CNT] + q0, root, s->stream);
-        if (rc) return rc;
+        uint32_t epoch = 0;
+        if (!rc) rc = xchg_push(x, lr + (size_t)q0 * k, ld + (size_t)q0 * k, lc + q0, m, k, root, &epoch, s->stream);
+        if (sync) {
+            // count in even after a failure: the peers must not wait for this worker forever
+            if (!rc && cudaEventRecord(sync->events[sync->me], s->stream) != cudaSuccess) rc = fail(VECGPU_ERR_CUDA, "cudaEventRecord failed");
+            sync->pushes->fetch_add(1, std::memory_order_release);
+            if (merges) {
+                const uint32_t want = (piece + 1) * sync->n;
+                while (sync->pushes->load(std::memory_order_acquire) < want) std::this_thread::yield();
+                for (uint32_t p = 0; p < sync->n && !rc; ++p)
+                    if (p != sync->me && cudaStreamWaitEvent(s->stream, sync->events[p], 0) != cudaSuccess)
+                        rc = fail(VECGPU_ERR_CUDA, "cudaStreamWaitEvent failed");
+            }
+        }
+        if (!rc && merges)
+            rc = xchg_merge(x, epoch, m, k, -1, (int64_t*)s->d_ws[WS_OUT_ROWID] + (size_t)q0 * k, (float*)s->d_ws[WS_OUT_DIST] + (size_t)q0 * k,
+                            (uint32_t*)s->d_ws[WS_OUT_CNT] + q0, s->stream);
+    }
+    if (rc) {
+        cudaStreamSynchronize(s->stream);
+        return rc;
     }
     if (!receives) {
         CU(cudaStreamSynchronize(s->stream));
@@ -397,9 +450,6 @@ extern "C" int vecgpu_shard_knn_device(vecgpu_slab* s, vecgpu_xchg* x, const voi
 // =====================================================================================================
 // ONE-PROCESS sharded slab: the form the Rust extension would use on an 8-GPU box.
 // =====================================================================================================
-#include <condition_variable>
-#include <functional>
-#include <thread>
 
 struct ShardWorker {
     std::thread th;
@@ -420,6 +470,8 @@ struct vecgpu_sharded {
     std::vector<vecgpu_xchg*> xs;
     std::vector<ShardWorker*> workers;
     std::vector<int64_t> lo_rowid;  // first rowid of shard i (INT64_MAX while empty); routes upserts / deletes
+    std::vector<cudaEvent_t> events;  // one per shard: "my push of this piece is enqueued up to here"
+    std::atomic<uint32_t> pushes{0};
     uint32_t cap_q = 0, cap_k = 0;
     std::mutex mu;
 };
@@ -484,8 +536,13 @@ extern "C" void vecgpu_sharded_destroy(vecgpu_sharded* g) {
         if (w->th.joinable()) w->th.join();
         delete w;
     }
+    for (size_t i = 0; i < g->events.size(); ++i) {
+        cudaSetDevice(g->devices[i]);
+        cudaEventDestroy(g->events[i]);
+    }
     for (vecgpu_xchg* x : g->xs) vecgpu_xchg_destroy(x);
     for (vecgpu_slab* s : g->slabs) vecgpu_slab_destroy(s);
+    cudaGetLastError();
     delete g;
     VG_CATCH_VOID
 }
@@ -520,6 +577,12 @@ extern "C" int vecgpu_sharded_create(int elem, uint32_t dims, uint64_t capacity_
         if (rc) break;
         g->xs.push_back(x);
         g->lo_rowid.push_back(INT64_MAX);
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            rc = fail(VECGPU_ERR_CUDA, "cudaEventCreate failed");
+            break;
+        }
+        g->events.push_back(ev);
     }
     if (!rc && n_devices > 1) rc = vecgpu_xchg_attach_local(g->xs.data(), n_devices);
     if (rc) {
@@ -672,12 +735,14 @@ extern "C" int vecgpu_sharded_knn(vecgpu_sharded* g, const void* queries, uint32
         if ((uint64_t)k > g->xs[0]->lay.cap_entries || (uint64_t)g->n * k > 16384)
             return fail(VECGPU_ERR_INVALID_PARAM, "k=%u exceeds the sharded slab's exchange capacity (create it with a larger max_k)", k);
     }
+    g->pushes.store(0, std::memory_order_release);
     return sharded_run(g, [&](uint32_t i) {
         vecgpu_slab* s = g->slabs[i];
         vecgpu_xchg* x = g->xs[i];
         std::lock_guard<std::mutex> l1(s->mu);
         std::lock_guard<std::mutex> l2(x->mu);
-        return shard_knn_locked(s, x, queries, nq, k, metric, /*root=*/0, out_rowids, out_dists, out_counts);
+        ShardSync sync{&g->pushes, g->events.data(), g->n, i};
+        return shard_knn_locked(s, x, queries, nq, k, metric, /*root=*/0, out_rowids, out_dists, out_counts, &sync);
     });
     VG_CATCH
 }
