@@ -10,6 +10,7 @@
 // mbarriers, scores QB queries per pass in a fixed ("canonical") accumulation
 // order and keeps a fused per-warp top-k, so no distance array is written.
 #pragma once
+#include "xpush.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -562,6 +563,100 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, uint32_t n) {
 // with copies completing out of order a warp could observe the parity of an
 // older, still incomplete phase (mbarrier parity waits alias every two phases).
 // ---------------------------------------------------------------------------
+struct MergeParams {
+    const uint64_t* keys;  // [nq][n_cand]
+    uint64_t n_cand;
+    uint32_t k;
+    uint32_t kp2;             // next power of two >= k
+    const int64_t* rowids;    // position -> rowid, or nullptr when dense
+    int64_t first_rowid;      // dense: rowid = first_rowid + position
+    int64_t* out_rowids;      // [nq][k]
+    float* out_dists;         // [nq][k]
+    uint32_t* out_counts;     // [nq] or nullptr
+    int64_t pad_rowid;        // value for unused slots (-1 host API, INT64_MAX device API)
+};
+
+
+// one result slot: key -> (rowid, distance) or padding; returns 1 for a real entry
+__device__ __forceinline__ uint32_t merge_emit(const MergeParams& p, uint32_t q, uint32_t j, uint64_t key) {
+    const size_t o = (size_t)q * p.k + j;
+    if (key == KEY_NONE) {
+        p.out_rowids[o] = p.pad_rowid;
+        p.out_dists[o] = __int_as_float(0x7F800000);
+        return 0;
+    }
+    const uint32_t pos = (uint32_t)key;
+    p.out_rowids[o] = p.rowids ? p.rowids[pos] : p.first_rowid + (int64_t)pos;
+    p.out_dists[o] = order_bits_inv((uint32_t)(key >> 32));
+    return 1;
+}
+
+// Final selection for query q by ONE CTA (any block size that is a multiple of 32): the n_cand partial keys -> k smallest,
+// ascending, decoded.  `scratch` is shared memory: 256 keys are enough for the register path (k <= 32 and at most 2048
+// candidates: eight 256-key register sorts, then one more over their 8 x 32 survivors), np2 keys for the bitonic path.
+// Used by the merge kernels and by the fused tail of scan_kernel (last CTA done).  Ends with a __syncthreads().
+__device__ __forceinline__ void final_merge_cta(const MergeParams& p, uint32_t q, uint64_t* scratch, uint32_t np2, bool allow_small) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint64_t* src = p.keys + (size_t)q * p.n_cand;
+    if (allow_small && p.k <= 32 && p.n_cand <= 2048) {
+        for (int w = warp; w < 8; w += nwarps) {
+            uint64_t v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t j = (uint32_t)w * 256 + (uint32_t)lane * 8 + r;
+                v[r] = j < p.n_cand ? __ldcg(src + j) : KEY_NONE;
+            }
+            warp_sort256(v, lane);
+            if (lane < 4) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) scratch[w * 32 + lane * 8 + r] = v[r];
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = scratch[lane * 8 + r];
+            warp_sort256(v, lane);
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t j = (uint32_t)lane * 8 + r;
+                if (j < p.k) cnt += merge_emit(p, q, j, v[r]);
+            }
+            if (p.out_counts) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+                if (lane == 0) p.out_counts[q] = cnt;
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    for (uint32_t j = threadIdx.x; j < np2; j += blockDim.x) scratch[j] = j < p.n_cand ? __ldcg(src + j) : KEY_NONE;
+    __syncthreads();
+    block_bitonic_sort(scratch, np2);
+    __shared__ uint32_t fm_total;
+    if (threadIdx.x == 0) fm_total = 0;
+    __syncthreads();
+    uint32_t cnt = 0;
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) cnt += merge_emit(p, q, j, j < np2 ? scratch[j] : KEY_NONE);
+    if (cnt) atomicAdd(&fm_total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && p.out_counts) p.out_counts[q] = fm_total;
+    __syncthreads();
+}
+
+// Fused tail of the streaming scan: when `counter` is set, the CTA that finishes LAST (atomic ticket per query pass) runs
+// the final merge of its pass's queries itself — no second launch — and, for a sharded slab, pushes the result into the
+// peers' gather buffers (xpush.cuh).  The counter re-arms itself.
+struct ScanTail {
+    uint32_t* counter;   // [gridDim.y] zero-initialised tickets, nullptr = separate merge launch
+    uint32_t np2;        // bitonic size for the shared-memory path
+    MergeParams mp;
+    XPushParams push;    // push.tab == nullptr: nothing to push
+};
+
 struct ScanParams {
     const uint8_t* vectors;  // slab rows, row_stride bytes apart, zero padded
     const uint8_t* skip;     // per-row flags (non-zero = skipped by scans) or nullptr
@@ -580,6 +675,7 @@ struct ScanParams {
     uint32_t n_consumers;      // C warps per CTA (blockDim = 32*C)
     uint32_t qc_kind;          // 0 f32 sum of squares, 1 int8
     uint32_t list_stride;      // keys reserved per query for the C per-warp lists: pow2 >= C*k
+    ScanTail tail;
 };
 
 // physical unit read by a lane for logical unit u (see "rotating" above)
@@ -884,18 +980,37 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
                 if (j < p.k) out[j] = v[r];
             }
         }
-        return;
-    }
-    for (uint32_t i = 0; i < nq_here; ++i) {
-        uint64_t* base = s_list + (size_t)i * p.list_stride;
-        for (uint32_t j = threadIdx.x; j < p.list_stride; j += blockDim.x) {
-            const uint32_t w = j / p.k, e = j - w * p.k;
-            if (w >= C || e >= s_hdr[w * QB + i].cnt) base[j] = KEY_NONE;
+    } else {
+        for (uint32_t i = 0; i < nq_here; ++i) {
+            uint64_t* base = s_list + (size_t)i * p.list_stride;
+            for (uint32_t j = threadIdx.x; j < p.list_stride; j += blockDim.x) {
+                const uint32_t w = j / p.k, e = j - w * p.k;
+                if (w >= C || e >= s_hdr[w * QB + i].cnt) base[j] = KEY_NONE;
+            }
+            __syncthreads();
+            block_bitonic_sort(base, p.list_stride);
+            uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
+            for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = base[j];
         }
-        __syncthreads();
-        block_bitonic_sort(base, p.list_stride);
-        uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
-        for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = base[j];
+    }
+    // ---- fused tail: the last CTA of this query pass merges the gridDim.x partial lists (and pushes to the peers) ----
+    if (p.tail.counter == nullptr) return;
+    __shared__ uint32_t s_last;
+    __threadfence();  // this CTA's partial lists are visible device-wide before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(p.tail.counter + blockIdx.y, 1u);
+        s_last = prev + 1 == gridDim.x ? 1u : 0u;
+        if (s_last) p.tail.counter[blockIdx.y] = 0;  // re-armed for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    uint64_t* scratch = (uint64_t*)s_stage;  // every bulk copy into the stages has been consumed
+    for (uint32_t i = 0; i < nq_here; ++i) final_merge_cta(p.tail.mp, q0 + i, scratch, p.tail.np2, true);
+    if (p.tail.push.tab != nullptr) {
+        for (uint32_t i = 0; i < nq_here; ++i) xpush_query(p.tail.push, q0 + i);
+        xpush_publish(p.tail.push, gridDim.y);
     }
 }
 
@@ -1034,49 +1149,10 @@ __global__ void __launch_bounds__(512) ham_batch_kernel(const HamBatchParams p) 
 // (per-CTA partial lists of the scan), keeps the k smallest, sorts them
 // ascending == (distance_f32, rowid) order, translates positions to rowids.
 // ---------------------------------------------------------------------------
-struct MergeParams {
-    const uint64_t* keys;  // [nq][n_cand]
-    uint64_t n_cand;
-    uint32_t k;
-    uint32_t kp2;             // next power of two >= k
-    const int64_t* rowids;    // position -> rowid, or nullptr when dense
-    int64_t first_rowid;      // dense: rowid = first_rowid + position
-    int64_t* out_rowids;      // [nq][k]
-    float* out_dists;         // [nq][k]
-    uint32_t* out_counts;     // [nq] or nullptr
-    int64_t pad_rowid;        // value for unused slots (-1 host API, INT64_MAX device API)
-};
-
 // small candidate sets (n_cand <= 16384, e.g. 148 lists x k<=110): load everything, bitonic-sort, keep the first k.
 __global__ void __launch_bounds__(1024) merge_sort_kernel(const MergeParams p, uint32_t np2) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* keys = (uint64_t*)smem;
-    const uint64_t* src = p.keys + (size_t)blockIdx.x * p.n_cand;
-    for (uint32_t j = threadIdx.x; j < np2; j += blockDim.x) keys[j] = j < p.n_cand ? src[j] : KEY_NONE;
-    __syncthreads();
-    block_bitonic_sort(keys, np2);
-    uint32_t cnt = 0;
-    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
-        const uint64_t key = j < np2 ? keys[j] : KEY_NONE;
-        const size_t o = (size_t)blockIdx.x * p.k + j;
-        if (key == KEY_NONE) {
-            p.out_rowids[o] = p.pad_rowid;
-            p.out_dists[o] = __int_as_float(0x7F800000);
-        } else {
-            const uint32_t pos = (uint32_t)key;
-            p.out_rowids[o] = p.rowids ? p.rowids[pos] : p.first_rowid + (int64_t)pos;
-            p.out_dists[o] = order_bits_inv((uint32_t)(key >> 32));
-            ++cnt;
-        }
-    }
-    if (p.out_counts) {
-        __shared__ uint32_t total;
-        if (threadIdx.x == 0) total = 0;
-        __syncthreads();
-        if (cnt) atomicAdd(&total, cnt);
-        __syncthreads();
-        if (threadIdx.x == 0) p.out_counts[blockIdx.x] = total;
-    }
+    final_merge_cta(p, blockIdx.x, (uint64_t*)smem, np2, false);
 }
 
 // Small-table fast path of the final merge (k <= 32, at most 2048 candidates per query: e.g. 148 CTAs x k = 10):
@@ -1085,47 +1161,7 @@ __global__ void __launch_bounds__(1024) merge_sort_kernel(const MergeParams p, u
 // is most of a single query's latency on a 10 k-row table).
 __global__ void __launch_bounds__(256) merge_small_kernel(const MergeParams p) {
     __shared__ uint64_t part[256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t* src = p.keys + (size_t)blockIdx.x * p.n_cand;
-    uint64_t v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint32_t j = (uint32_t)warp * 256 + (uint32_t)lane * 8 + r;
-        v[r] = j < p.n_cand ? src[j] : KEY_NONE;
-    }
-    warp_sort256(v, lane);
-    if (lane < 4) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) part[warp * 32 + lane * 8 + r] = v[r];
-    }
-    __syncthreads();
-    if (warp != 0) return;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = part[lane * 8 + r];
-    warp_sort256(v, lane);
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint32_t j = (uint32_t)lane * 8 + r;
-        if (j < p.k) {
-            const uint64_t key = v[r];
-            const size_t o = (size_t)blockIdx.x * p.k + j;
-            if (key == KEY_NONE) {
-                p.out_rowids[o] = p.pad_rowid;
-                p.out_dists[o] = __int_as_float(0x7F800000);
-            } else {
-                const uint32_t pos = (uint32_t)key;
-                p.out_rowids[o] = p.rowids ? p.rowids[pos] : p.first_rowid + (int64_t)pos;
-                p.out_dists[o] = order_bits_inv((uint32_t)(key >> 32));
-                ++cnt;
-            }
-        }
-    }
-    if (p.out_counts) {
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
-        if (lane == 0) p.out_counts[blockIdx.x] = cnt;
-    }
+    final_merge_cta(p, blockIdx.x, part, 0, true);
 }
 
 // large candidate sets: after a segmented radix sort of [nq][n_cand] keys, decode the first k of each segment

@@ -81,6 +81,7 @@ static int vg_caught() noexcept {
     catch (...) { vg_caught(); }
 
 static constexpr uint32_t K_FUSED_MAX = 1024;     // above this knn uses emit + radix sort
+static constexpr size_t DIRECT_OUT_MAX = 4096;    // result entries (nq*k) up to which kernels write straight into mapped pinned memory
 static constexpr uint32_t DIMS_MAX = 65536;       // keeps int8 partial sums inside int32
 static constexpr size_t SMEM_MAX = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
 
@@ -120,20 +121,23 @@ struct vecgpu_slab {
     uint64_t cap_norms = 0;
     bool norms_valid = false;
     // workspaces
-    void* d_ws[23] = {nullptr};
-    size_t ws_cap[23] = {0};
+    void* d_ws[24] = {nullptr};
+    size_t ws_cap[24] = {0};
     void* h_pin[2] = {nullptr};
     size_t pin_cap[2] = {0};
     // bulk-load staging: two pinned buffers so the host-side copy of chunk i+1 overlaps the DMA of chunk i
     void* h_stage[2] = {nullptr};
     size_t stage_cap[2] = {0};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    // sharded queries: a push the next fused scan tail should carry (set by shard_knn_locked around knn_core)
+    const XPushParams* fuse_push = nullptr;
+    bool fuse_push_done = false;
 };
 
 enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7,
        WS_TC_CANDV = 8, WS_TC_CANDR = 9, WS_TC_CNT = 10, WS_TC_TAU = 11, WS_TC_PAIRQ = 12, WS_TC_PAIRPOS = 13, WS_TC_DIST = 14,
        WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_TC_BUF = 19, WS_X_ROWID = 20, WS_X_DIST = 21, WS_X_CNT = 22,
-       WS_COUNT = 23 };
+       WS_TICKET = 23, WS_COUNT = 24 };
 
 static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
     if (bytes <= s->ws_cap[i]) return 0;
@@ -1074,8 +1078,6 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         p.contig = c.contig;
         p.n_consumers = c.C;
         p.list_stride = list_stride_for(c.C, k);
-        rc = launch_scan(s->elem, metric, p, c, false, dim3(gx, gy), st);
-        if (rc) return rc;
         MergeParams mp{};
         mp.keys = p.out_keys;
         mp.n_cand = (uint64_t)gx * k;
@@ -1087,6 +1089,27 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         mp.out_dists = d_out_dists;
         mp.out_counts = d_out_counts;
         mp.pad_rowid = pad_rowid;
+        // One query pass (nq <= QB): the last CTA to finish merges the gx partial lists itself (and carries a sharded query's
+        // push), so a query is ONE launch instead of scan + merge (+ push).
+        const uint32_t np2 = std::max(2u, next_pow2((uint32_t)mp.n_cand));
+        const bool fuse = gy == 1 && env_u32("VECGPU_FUSE_MERGE", 1) && mp.n_cand <= 16384 &&
+                          (size_t)np2 * 8 <= (size_t)c.S * c.C * c.R * c.srs;
+        if (fuse) {
+            if (!s->d_ws[WS_TICKET]) {
+                if ((rc = ws_reserve(s, WS_TICKET, 256))) return rc;
+                CU(cudaMemsetAsync(s->d_ws[WS_TICKET], 0, 256, st));
+            }
+            p.tail.counter = (uint32_t*)s->d_ws[WS_TICKET];
+            p.tail.np2 = np2;
+            p.tail.mp = mp;
+            if (s->fuse_push) {
+                p.tail.push = *s->fuse_push;
+                s->fuse_push_done = true;
+            }
+        }
+        rc = launch_scan(s->elem, metric, p, c, false, dim3(gx, gy), st);
+        if (rc) return rc;
+        if (fuse) return 0;
         return launch_merge(s, mp, nq, st);
     }
 
@@ -1567,20 +1590,28 @@ extern "C" int vecgpu_knn(vecgpu_slab* s, const void* queries, uint32_t nq, uint
     const size_t n_out = (size_t)nq * k;
     rc = stage_queries(s, queries, nq);
     if (rc) return rc;
-    if ((rc = ws_reserve(s, WS_OUT_ROWID, n_out * 8))) return rc;
-    if ((rc = ws_reserve(s, WS_OUT_DIST, n_out * 4))) return rc;
-    if ((rc = ws_reserve(s, WS_OUT_CNT, (size_t)nq * 4))) return rc;
-    rc = knn_core(s, (const uint8_t*)s->d_ws[WS_QUERY], nq, k, metric, (int64_t*)s->d_ws[WS_OUT_ROWID],
-                  (float*)s->d_ws[WS_OUT_DIST], (uint32_t*)s->d_ws[WS_OUT_CNT], -1, s->stream);
-    if (rc) return rc;
-    // results come back through pinned memory, then into the caller's buffers
     const size_t pin_bytes = n_out * 12 + (size_t)nq * 4;
     if ((rc = pin_reserve(s, 1, pin_bytes))) return rc;
     uint8_t* h = (uint8_t*)s->h_pin[1];
-    CU(cudaMemcpyAsync(h, s->d_ws[WS_OUT_ROWID], n_out * 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + n_out * 8, s->d_ws[WS_OUT_DIST], n_out * 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + n_out * 12, s->d_ws[WS_OUT_CNT], (size_t)nq * 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    if (n_out <= DIRECT_OUT_MAX && k <= K_FUSED_MAX) {
+        // small results: the merge writes them straight into this pinned (device-mapped) buffer over PCIe — no device->host
+        // copies in the stream, the host only waits for the stream (was three dependent cudaMemcpyAsync, ~25 us)
+        rc = knn_core(s, (const uint8_t*)s->d_ws[WS_QUERY], nq, k, metric, (int64_t*)h, (float*)(h + n_out * 8), (uint32_t*)(h + n_out * 12), -1,
+                      s->stream);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(s->stream));
+    } else {
+        if ((rc = ws_reserve(s, WS_OUT_ROWID, n_out * 8))) return rc;
+        if ((rc = ws_reserve(s, WS_OUT_DIST, n_out * 4))) return rc;
+        if ((rc = ws_reserve(s, WS_OUT_CNT, (size_t)nq * 4))) return rc;
+        rc = knn_core(s, (const uint8_t*)s->d_ws[WS_QUERY], nq, k, metric, (int64_t*)s->d_ws[WS_OUT_ROWID],
+                      (float*)s->d_ws[WS_OUT_DIST], (uint32_t*)s->d_ws[WS_OUT_CNT], -1, s->stream);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h, s->d_ws[WS_OUT_ROWID], n_out * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h + n_out * 8, s->d_ws[WS_OUT_DIST], n_out * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h + n_out * 12, s->d_ws[WS_OUT_CNT], (size_t)nq * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
     memcpy(out_rowids, h, n_out * 8);
     memcpy(out_dists, h + n_out * 8, n_out * 4);
     if (out_counts) memcpy(out_counts, h + n_out * 12, (size_t)nq * 4);

@@ -66,9 +66,9 @@ extern "C" int vecgpu_xchg_create(int device, uint32_t rank, uint32_t world, uin
     if (cudaMalloc((void**)&x->d_tab, sizeof(XPeerTable)) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMalloc((void**)&x->d_done, 8) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMemset(x->d_done, 0, 8) != cudaSuccess) return bail("cudaMemset");
-    x->d_err = x->d_done + 1;
-    if (cudaMallocHost((void**)&x->h_err, 4) != cudaSuccess) return bail("cudaMallocHost");
+    if (cudaMallocHost((void**)&x->h_err, 64) != cudaSuccess) return bail("cudaMallocHost");
     *x->h_err = 0;
+    x->d_err = x->h_err;  // pinned + device-mapped (UVA): the merge kernel stores into it directly, the host reads it after a sync
     x->peer_base[rank] = x->d_buf;
     if (world == 1) {
         XPeerTable t{};
@@ -193,15 +193,13 @@ extern "C" int vecgpu_xchg_attach_local(vecgpu_xchg* const* all, uint32_t n) {
 
 // The exchange of ONE batch = xchg_push (local top-k -> the peers' gather buffers, flags published) followed on the receiving
 // ranks by xchg_merge (flag wait + k-way merge).  Both only enqueue on `st`.
-static int xchg_push(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts, uint32_t nq, uint32_t k,
-                     int root, uint32_t* epoch_out, cudaStream_t st) {
+static int xchg_push_prepare(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts, uint32_t nq, uint32_t k,
+                             int root, XPushParams* pp_out) {
     if (!x->attached) return fail(VECGPU_ERR_INVALID_PARAM, "exchange endpoint is not attached to its peers yet");
     if (nq > x->cap_q || (uint64_t)nq * k > x->lay.cap_entries)
         return fail(VECGPU_ERR_INVALID_PARAM, "exchange of %u queries x k=%u exceeds the endpoint's capacity (%u queries, %llu entries)", nq, k,
                     x->cap_q, (unsigned long long)x->lay.cap_entries);
     if ((uint64_t)x->world * k > 16384) return fail(VECGPU_ERR_INVALID_PARAM, "world*k must be <= 16384");
-    const uint32_t epoch = ++x->epoch;
-    *epoch_out = epoch;
     const uint32_t all = (1u << x->world) - 1u;
     XPushParams pp{};
     pp.tab = x->d_tab;
@@ -212,13 +210,24 @@ static int xchg_push(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dis
     pp.nq = nq;
     pp.k = k;
     pp.rank = x->rank;
-    pp.epoch = epoch;
+    pp.epoch = ++x->epoch;
     pp.peer_mask = root < 0 ? all : (1u << root);
     pp.done = x->d_done;
-    const uint32_t pgrid = std::min<uint32_t>(nq, 296);
-    xpush_kernel<<<pgrid, 128, 0, st>>>(pp);
+    *pp_out = pp;
+    return 0;
+}
+static int xchg_push_launch(const XPushParams& pp, cudaStream_t st) {
+    xpush_kernel<<<std::min<uint32_t>(pp.nq, 296), 128, 0, st>>>(pp);
     LAUNCHED();
     return 0;
+}
+static int xchg_push(vecgpu_xchg* x, const int64_t* d_rowids, const float* d_dists, const uint32_t* d_counts, uint32_t nq, uint32_t k,
+                     int root, uint32_t* epoch_out, cudaStream_t st) {
+    XPushParams pp{};
+    int rc = xchg_push_prepare(x, d_rowids, d_dists, d_counts, nq, k, root, &pp);
+    if (rc) return rc;
+    *epoch_out = pp.epoch;
+    return xchg_push_launch(pp, st);
 }
 
 static int xchg_merge(vecgpu_xchg* x, uint32_t epoch, uint32_t nq, uint32_t k, int64_t pad_rowid, int64_t* d_out_rowids, float* d_out_dists,
@@ -275,13 +284,10 @@ struct ShardSync {
     uint32_t n, me;
 };
 
-static int xchg_check_err(vecgpu_xchg* x, cudaStream_t st) {  // after the stream has been synchronised up to an exchange
-    CU(cudaMemcpyAsync(x->h_err, x->d_err, 4, cudaMemcpyDeviceToHost, st));
+static int xchg_check_err(vecgpu_xchg* x, cudaStream_t st) {  // synchronises the stream, then reads the (host-resident) error word
     CU(cudaStreamSynchronize(st));
-    if (*x->h_err) {
+    if (*(volatile uint32_t*)x->h_err) {
         *x->h_err = 0;
-        cudaMemsetAsync(x->d_err, 0, 4, st);
-        cudaStreamSynchronize(st);
         return fail(VECGPU_ERR_CUDA, "exchange timed out: a peer rank never delivered its top-k (did every rank issue the same call?)");
     }
     return 0;
@@ -342,13 +348,37 @@ static int shard_knn_locked(vecgpu_slab* s, vecgpu_xchg* x, const void* queries,
     int64_t* lr = (int64_t*)s->d_ws[WS_X_ROWID];
     float* ld = (float*)s->d_ws[WS_X_DIST];
     uint32_t* lc = (uint32_t*)s->d_ws[WS_X_CNT];
-    // local scan of every query first (one launch sequence), then the exchanges piece by piece
+    // final results: small ones are written by the merge kernel straight into mapped pinned memory (no D2H copies)
+    const size_t pin_bytes = n_out * 12 + (size_t)nq * 4;
+    if ((rc = pin_reserve(s, 1, pin_bytes))) return bail(rc);
+    uint8_t* h = (uint8_t*)s->h_pin[1];
+    const bool direct = n_out <= DIRECT_OUT_MAX;
+    int64_t* fr = direct ? (int64_t*)h : (int64_t*)s->d_ws[WS_OUT_ROWID];
+    float* fd = direct ? (float*)(h + n_out * 8) : (float*)s->d_ws[WS_OUT_DIST];
+    uint32_t* fc = direct ? (uint32_t*)(h + n_out * 12) : (uint32_t*)s->d_ws[WS_OUT_CNT];
+    // local scan of every query first (one launch sequence), then the exchanges piece by piece.  A batch that is ONE piece and
+    // ONE query pass lets the scan's last CTA carry the push (scan_kernel's fused tail): no separate merge / push launches.
+    XPushParams pp0{};
+    const bool one_piece = nq <= chunk;
+    if (one_piece) {
+        if ((rc = xchg_push_prepare(x, lr, ld, lc, nq, k, root, &pp0))) return bail(rc);
+        s->fuse_push = &pp0;
+        s->fuse_push_done = false;
+    }
     rc = knn_core(s, (const uint8_t*)s->d_ws[WS_QUERY], nq, k, metric, lr, ld, lc, -1, s->stream);
+    const bool pushed_by_scan = s->fuse_push_done;
+    s->fuse_push = nullptr;
+    s->fuse_push_done = false;
     uint32_t piece = 0;
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk, ++piece) {
         const uint32_t m = std::min(chunk, nq - q0);
         uint32_t epoch = 0;
-        if (!rc) rc = xchg_push(x, lr + (size_t)q0 * k, ld + (size_t)q0 * k, lc + q0, m, k, root, &epoch, s->stream);
+        if (one_piece) {
+            epoch = pp0.epoch;
+            if (!rc && !pushed_by_scan) rc = xchg_push_launch(pp0, s->stream);
+        } else if (!rc) {
+            rc = xchg_push(x, lr + (size_t)q0 * k, ld + (size_t)q0 * k, lc + q0, m, k, root, &epoch, s->stream);
+        }
         if (sync) {
             // count in even after a failure: the peers must not wait for this worker forever
             if (!rc && cudaEventRecord(sync->events[sync->me], s->stream) != cudaSuccess) rc = fail(VECGPU_ERR_CUDA, "cudaEventRecord failed");
@@ -361,33 +391,19 @@ static int shard_knn_locked(vecgpu_slab* s, vecgpu_xchg* x, const void* queries,
                         rc = fail(VECGPU_ERR_CUDA, "cudaStreamWaitEvent failed");
             }
         }
-        if (!rc && merges)
-            rc = xchg_merge(x, epoch, m, k, -1, (int64_t*)s->d_ws[WS_OUT_ROWID] + (size_t)q0 * k, (float*)s->d_ws[WS_OUT_DIST] + (size_t)q0 * k,
-                            (uint32_t*)s->d_ws[WS_OUT_CNT] + q0, s->stream);
+        if (!rc && merges) rc = xchg_merge(x, epoch, m, k, -1, fr + (size_t)q0 * k, fd + (size_t)q0 * k, fc + q0, s->stream);
     }
     if (rc) {
         cudaStreamSynchronize(s->stream);
         return rc;
     }
-    if (!receives) {
-        CU(cudaStreamSynchronize(s->stream));
-        return root < 0 ? xchg_check_err(x, s->stream) : 0;
+    if (!receives) return xchg_check_err(x, s->stream);
+    if (!direct) {
+        CU(cudaMemcpyAsync(h, s->d_ws[WS_OUT_ROWID], n_out * 8, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h + n_out * 8, s->d_ws[WS_OUT_DIST], n_out * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(h + n_out * 12, s->d_ws[WS_OUT_CNT], (size_t)nq * 4, cudaMemcpyDeviceToHost, s->stream));
     }
-    const size_t pin_bytes = n_out * 12 + (size_t)nq * 4 + 4;
-    if ((rc = pin_reserve(s, 1, pin_bytes))) return rc;
-    uint8_t* h = (uint8_t*)s->h_pin[1];
-    CU(cudaMemcpyAsync(h, s->d_ws[WS_OUT_ROWID], n_out * 8, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + n_out * 8, s->d_ws[WS_OUT_DIST], n_out * 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + n_out * 12, s->d_ws[WS_OUT_CNT], (size_t)nq * 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(h + n_out * 12 + (size_t)nq * 4, x->d_err, 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    uint32_t err = 0;
-    memcpy(&err, h + n_out * 12 + (size_t)nq * 4, 4);
-    if (err) {
-        cudaMemsetAsync(x->d_err, 0, 4, s->stream);
-        cudaStreamSynchronize(s->stream);
-        return fail(VECGPU_ERR_CUDA, "exchange timed out: a peer rank never delivered its top-k (did every rank issue the same call?)");
-    }
+    if ((rc = xchg_check_err(x, s->stream))) return rc;
     memcpy(out_rowids, h, n_out * 8);
     memcpy(out_dists, h + n_out * 8, n_out * 4);
     if (out_counts) memcpy(out_counts, h + n_out * 12, (size_t)nq * 4);

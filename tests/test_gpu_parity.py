@@ -1236,3 +1236,32 @@ def test_hnsw_never_returns_deleted_rows_and_goes_stale_on_refill(vg, orc, gpu):
         with pytest.raises(vg.InvalidState):
             idx.search(q, 5, ef_search=64)
         idx.close()
+
+
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+def test_fused_scan_tail_equals_separate_merge_launch(vg, orc, gpu, elem, metric, monkeypatch):
+    """nq <= 8 runs scan + final merge in ONE launch (last CTA done); VECGPU_FUSE_MERGE=0 restores the two-launch form."""
+    dims = 200 if elem != BIT else 520
+    v = random_rows(elem, 60_000, dims, seed=81, ties=(elem != F32))
+    q = random_rows(elem, 8, dims, seed=82, ties=(elem != F32))
+    with vg.Slab(elem, dims) as s:
+        s.load(v)
+        for nq, k in ((1, 10), (3, 1), (8, 33), (1, 100), (2, 700)):
+            er, ed, ec = orc.knn_select(elem, dims, v, q[:nq], k, metric)
+            l0 = vg.launch_count()
+            r, d, c = s.knn(q[:nq], k, metric)
+            fused_launches = vg.launch_count() - l0
+            monkeypatch.setenv("VECGPU_FUSE_MERGE", "0")
+            l0 = vg.launch_count()
+            r2, d2, c2 = s.knn(q[:nq], k, metric)
+            split_launches = vg.launch_count() - l0
+            monkeypatch.delenv("VECGPU_FUSE_MERGE")
+            assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+            assert np.array_equal(r2, er) and same_bits(d2, ed) and np.array_equal(c2, ec)
+            if not (elem == F32 and metric == L1):  # f32 L1 has its own TMA kernel (always two launches)
+                assert fused_launches < split_launches
+        # many back-to-back fused launches: the ticket counter must re-arm itself every time
+        for _ in range(200):
+            r3, d3, _ = s.knn(q[:1], 10, metric)
+        er, ed, _ = orc.knn_select(elem, dims, v, q[:1], 10, metric)
+        assert np.array_equal(r3, er) and same_bits(d3, ed)
