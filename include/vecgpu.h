@@ -216,6 +216,10 @@ int vecgpu_xchg_merge_device(vecgpu_xchg* x, const int64_t* d_rowids, const floa
 /* Synchronises `stream` and reports VECGPU_ERR_CUDA if an exchange since the last check timed out waiting for a peer. */
 int vecgpu_xchg_check(vecgpu_xchg* x, void* stream);
 
+/* Developer hook: d_buf (device, (SMs * 4 + 1) x u64) receives per-CTA globaltimer stamps of the following single-query
+ * scans (CTA start, pipeline primed, rows done, CTA end, end of the fused merge); NULL switches it off.  Process-wide. */
+void vecgpu_debug_scan_timeline(void* d_buf);
+
 /* Number of kernels this library has launched in this process (bench's
  * gpu_launches claim). */
 uint64_t vecgpu_launch_count(void);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "vecgpu_shard_knn_device": (C.c_int, [_c_slab, C.c_void_p, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
     "vecgpu_xchg_merge_device": (C.c_int, [C.c_void_p, _p, _p, _p, C.c_uint32, C.c_uint32, _p, _p, _p]),
     "vecgpu_xchg_check": (C.c_int, [C.c_void_p, _p]),
+    "vecgpu_debug_scan_timeline": (None, [_p]),
     "vecgpu_launch_count": (C.c_uint64, []),
     "vecgpu_tc_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }

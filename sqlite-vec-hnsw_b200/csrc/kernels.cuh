@@ -520,6 +520,20 @@ __device__ __forceinline__ void warp_sort256(uint64_t (&v)[8], int lane) {
 }
 
 // in-place ascending bitonic sort of n (power of two) u64 keys in shared memory by the whole CTA
+// ONE out-of-line copy of the register sorter for the scan's tails (per-CTA list merge, fused final merge, merge kernels):
+// every CTA runs it on its own lists just before the last CTA needs it for the final merge, so its ~1.2 k instructions are
+// already in the instruction caches there.  (Measured with the globaltimer stamps of tools/scan_timeline.py: with a
+// separately inlined copy the final merge took ~35 us after a 3.8 GB scan — cold code fetched behind a thrashed L2 —
+// against ~12 us on a table that fits L2.)
+__device__ __noinline__ void warp_sort256_shared(uint64_t* v, int lane) {
+    uint64_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = v[i];
+    warp_sort256(r, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = r[i];
+}
+
 __device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, uint32_t n) {
     for (uint32_t size = 2; size <= n; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -606,7 +620,7 @@ __device__ __forceinline__ void final_merge_cta(const MergeParams& p, uint32_t q
                 const uint32_t j = (uint32_t)w * 256 + (uint32_t)lane * 8 + r;
                 v[r] = j < p.n_cand ? __ldcg(src + j) : KEY_NONE;
             }
-            warp_sort256(v, lane);
+            warp_sort256_shared(v, lane);
             if (lane < 4) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) scratch[w * 32 + lane * 8 + r] = v[r];
@@ -617,7 +631,7 @@ __device__ __forceinline__ void final_merge_cta(const MergeParams& p, uint32_t q
             uint64_t v[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) v[r] = scratch[lane * 8 + r];
-            warp_sort256(v, lane);
+            warp_sort256_shared(v, lane);
             uint32_t cnt = 0;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -651,7 +665,9 @@ __device__ __forceinline__ void final_merge_cta(const MergeParams& p, uint32_t q
 // the final merge of its pass's queries itself — no second launch — and, for a sharded slab, pushes the result into the
 // peers' gather buffers (xpush.cuh).  The counter re-arms itself.
 struct ScanTail {
-    uint32_t* counter;   // [gridDim.y] zero-initialised tickets, nullptr = separate merge launch
+    uint32_t* counter;   // [gridDim.y] zero-initialised tickets (nullptr: no tail at all); the last CTA of a pass re-arms them
+    uint32_t* dyn;       // [gridDim.y] zero-initialised tile counters: tiles are handed out dynamically (nullptr: static round robin)
+    uint32_t do_merge;   // 1: the last CTA runs the final merge (no separate merge launch)
     uint32_t np2;        // bitonic size for the shared-memory path
     MergeParams mp;
     XPushParams push;    // push.tab == nullptr: nothing to push
@@ -676,7 +692,14 @@ struct ScanParams {
     uint32_t qc_kind;          // 0 f32 sum of squares, 1 int8
     uint32_t list_stride;      // keys reserved per query for the C per-warp lists: pow2 >= C*k
     ScanTail tail;
+    unsigned long long* dbg;   // optional [gridDim.x][4] globaltimer stamps: CTA start, pipeline primed, rows done, CTA end (tools/scan_timeline.py)
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // physical unit read by a lane for logical unit u (see "rotating" above)
 template <class T>
@@ -703,9 +726,11 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     uint64_t* s_list = (uint64_t*)(s_hdr + C * QB);
     uint64_t* s_bar = s_list + (EMIT ? 0 : (size_t)QB * p.list_stride);  // lists are query-major: [QB][list_stride]
     const uint32_t bar_full = smem_u32(s_bar);
+    uint32_t* s_tile = (uint32_t*)(s_bar + S);  // [S] tile held by each ring slot (dynamic tile scheduling)
 
     const uint32_t q0 = blockIdx.y * QB;  // first query of this pass
     const uint32_t nq_here = min((uint32_t)QB, p.nq_total - q0);
+    if (p.dbg && threadIdx.x == 0 && blockIdx.y == 0) p.dbg[blockIdx.x * 4 + 0] = globaltimer_ns();
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) mbar_init(bar_full + 8 * s, 1);
@@ -755,13 +780,40 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
         const uint32_t my_tiles = first_tile < n_tiles ? (uint32_t)((n_tiles - first_tile + tile_step - 1) / tile_step) : 0u;
         const uint32_t my_iters = my_tiles * p.n_chunks;
 
+        // Dynamic tile scheduling (single-chunk rows): instead of the fixed round robin, a warp takes the NEXT tile of the
+        // slab from a global counter whenever it refills a ring slot.  Tiles are still handed out in address order (the
+        // CTAs keep reading neighbouring memory), but a CTA that streams a little slower simply takes fewer tiles: with the
+        // static split the first CTA was done after 508 us and the last after 551 us on a 3.84 GB shard
+        // (tools/scan_timeline.py) — 8 % of the launch spent waiting for stragglers.
+        const bool dyn = !EMIT && p.tail.dyn != nullptr;
+        uint32_t* my_tile_slots = s_tile + warp * D;
+        // ring depth in use: the prologue must not let the first warps hoard a small table (each warp starts with its fair
+        // share of tiles at most), so a table with fewer tiles than D per warp runs with a shallower ring
+        const uint32_t Dr = dyn ? (uint32_t)max((uint64_t)1, min((uint64_t)D, (n_tiles + (uint64_t)C * gridDim.x - 1) / ((uint64_t)C * gridDim.x))) : D;
         // issue the copies of ring iteration `lit` (tile lit / n_chunks, chunk lit % n_chunks) into slot lit % D
         auto issue = [&](uint32_t lit) {
-            if (lit >= my_iters) return;
-            const uint32_t jl = lit / p.n_chunks, c = lit - jl * p.n_chunks;
-            const uint64_t row0 = (first_tile + (uint64_t)jl * tile_step) * RS;
+            uint32_t jl, c;
+            uint64_t row0;
+            if (dyn) {
+                uint32_t t = 0;
+                if (lane == 0) {
+                    t = atomicAdd(p.tail.dyn + blockIdx.y, 1u);
+                    my_tile_slots[lit % Dr] = (uint64_t)t < n_tiles ? t : 0xFFFFFFFFu;
+                }
+                t = __shfl_sync(0xffffffffu, t, 0);
+                __syncwarp();
+                if ((uint64_t)t >= n_tiles) return;
+                jl = lit;
+                c = 0;
+                row0 = (uint64_t)t * RS;
+            } else {
+                if (lit >= my_iters) return;
+                jl = lit / p.n_chunks;
+                c = lit - jl * p.n_chunks;
+                row0 = (first_tile + (uint64_t)jl * tile_step) * RS;
+            }
             const uint32_t valid = (uint32_t)min((uint64_t)RS, p.n_rows - row0);
-            const uint32_t slot = lit % D;
+            const uint32_t slot = lit % Dr;
             const uint32_t bar = my_bar + 8 * slot;
             const uint32_t dst0 = smem_u32(my_stage + (size_t)slot * stage_bytes);
             fence_proxy_async();  // the stage was read through the generic proxy; the copy writes through the async proxy
@@ -781,7 +833,8 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
             }
             __syncwarp();
         };
-        for (uint32_t lit = 0; lit < D; ++lit) issue(lit);  // prologue: fill the ring
+        for (uint32_t lit = 0; lit < Dr; ++lit) issue(lit);  // prologue: fill the ring
+        if (p.dbg && threadIdx.x == 0 && blockIdx.y == 0) p.dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
 
         // thread-per-row integer path (Hamming): byte offsets of the 8 units of a 128-byte segment in this
         // lane's rotated order, and the query in registers when a row is exactly one segment (bit[1024])
@@ -795,8 +848,13 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
             for (int t = 0; t < 8; ++t) qreg[t] = lds128(q_base + offs[t]);
         }
 
-        for (uint32_t jl = 0; jl < my_tiles; ++jl) {
-            const uint64_t row0 = (first_tile + (uint64_t)jl * tile_step) * RS;
+        for (uint32_t jl = 0; dyn || jl < my_tiles; ++jl) {
+            uint64_t row0 = (first_tile + (uint64_t)jl * tile_step) * RS;
+            if (dyn) {
+                const uint32_t t = my_tile_slots[jl % Dr];  // written by lane 0 in issue(), __syncwarp()ed there
+                if (t == 0xFFFFFFFFu) break;               // tiles are handed out in order: nothing is left for this warp
+                row0 = (uint64_t)t * RS;
+            }
             const uint32_t it0 = jl * p.n_chunks;
             for (uint32_t ms = 0; ms < m_steps; ++ms) {
                 const uint32_t r_in_stage = ms * RPW + rl;
@@ -804,7 +862,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
                 T::init(acc);
                 for (uint32_t c = 0; c < p.n_chunks; ++c) {
                     const uint32_t lit = it0 + c;
-                    const uint32_t s = lit % D, ph = (lit / D) & 1;
+                    const uint32_t s = lit % Dr, ph = (lit / Dr) & 1;
                     if (ms == 0) mbar_wait(my_bar + 8 * s, ph);
                     const uint32_t off = p.contig ? 0 : c * p.chunk_bytes;
                     const uint32_t len = p.contig ? p.row_stride : min(p.chunk_bytes, p.row_stride - off);
@@ -923,7 +981,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
                     }
                     if (ms == m_steps - 1) {
                         __syncwarp();     // every lane has consumed its loads of this stage
-                        issue(lit + D);   // refill it with the tile D steps ahead
+                        issue(lit + Dr);  // refill it with the tile Dr steps ahead
                     }
                 }
                 // ---- distance -> key -> fused top-k (or emit) ----
@@ -955,6 +1013,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     }
     if (EMIT) return;
     __syncthreads();
+    if (p.dbg && threadIdx.x == 0 && blockIdx.y == 0) p.dbg[blockIdx.x * 4 + 2] = globaltimer_ns();
     // ---- CTA merge: the C per-warp lists of a query are contiguous; blank the unused slots, bitonic-sort the
     //      list_stride keys with the whole CTA and emit the k smallest as this CTA's partial result ----
     if (p.list_stride <= 256) {  // the usual case (C * k <= 256): one warp per query sorts that query's lists in registers,
@@ -972,7 +1031,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
                 }
                 v[r] = key;
             }
-            warp_sort256(v, lane);
+            warp_sort256_shared(v, lane);
             uint64_t* out = p.out_keys + ((size_t)(q0 + i) * gridDim.x + blockIdx.x) * p.k;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -994,6 +1053,10 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
         }
     }
     // ---- fused tail: the last CTA of this query pass merges the gridDim.x partial lists (and pushes to the peers) ----
+    if (p.dbg && blockIdx.y == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 3] = globaltimer_ns();
+    }
     if (p.tail.counter == nullptr) return;
     __shared__ uint32_t s_last;
     __threadfence();  // this CTA's partial lists are visible device-wide before its ticket is
@@ -1001,10 +1064,13 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     if (threadIdx.x == 0) {
         const uint32_t prev = atomicAdd(p.tail.counter + blockIdx.y, 1u);
         s_last = prev + 1 == gridDim.x ? 1u : 0u;
-        if (s_last) p.tail.counter[blockIdx.y] = 0;  // re-armed for the next launch
+        if (s_last) {  // re-arm for the next launch
+            p.tail.counter[blockIdx.y] = 0;
+            if (p.tail.dyn) p.tail.dyn[blockIdx.y] = 0;
+        }
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last || !p.tail.do_merge) return;
     __threadfence();
     uint64_t* scratch = (uint64_t*)s_stage;  // every bulk copy into the stages has been consumed
     for (uint32_t i = 0; i < nq_here; ++i) final_merge_cta(p.tail.mp, q0 + i, scratch, p.tail.np2, true);
@@ -1012,6 +1078,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
         for (uint32_t i = 0; i < nq_here; ++i) xpush_query(p.tail.push, q0 + i);
         xpush_publish(p.tail.push, gridDim.y);
     }
+    if (p.dbg && threadIdx.x == 0 && blockIdx.y == 0) p.dbg[gridDim.x * 4] = globaltimer_ns();  // end of the fused merge
 }
 
 // ---------------------------------------------------------------------------

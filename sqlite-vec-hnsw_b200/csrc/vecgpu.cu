@@ -84,6 +84,7 @@ static constexpr uint32_t K_FUSED_MAX = 1024;     // above this knn uses emit + 
 static constexpr size_t DIRECT_OUT_MAX = 4096;    // result entries (nq*k) up to which kernels write straight into mapped pinned memory
 static constexpr uint32_t DIMS_MAX = 65536;       // keeps int8 partial sums inside int32
 static constexpr size_t SMEM_MAX = 227 * 1024;    // opt-in dynamic shared memory per CTA on sm_100
+static constexpr size_t SCAN_SMEM_MAX = SMEM_MAX - 1024;  // scan_kernel also has a few static __shared__ words (fused tail)
 
 static uint32_t env_u32(const char* name, uint32_t dflt) {
     const char* v = getenv(name);
@@ -389,6 +390,11 @@ int vecgpu_metric_supported(int elem, int metric) {
 }
 
 }  // extern "C"
+
+// Developer hook (not part of the reference surface): a device buffer of (num_sms * 4 + 1) u64 that the next single-query
+// scans fill with globaltimer stamps per CTA; NULL switches it off.  tools/scan_timeline.py reads it.
+static unsigned long long* g_scan_dbg = nullptr;
+extern "C" void vecgpu_debug_scan_timeline(void* d_buf) { g_scan_dbg = (unsigned long long*)d_buf; }
 
 static int check_pair(int elem, int metric) {
     if (elem < 0 || elem > 2) return fail(VECGPU_ERR_UNSUPPORTED, "invalid vector type %d", elem);
@@ -735,7 +741,7 @@ static uint32_t list_stride_for(uint32_t C, uint32_t k) { return std::max(2u, ne
 
 static size_t scan_fixed_smem(uint32_t C, uint32_t QB, uint32_t row_stride, uint32_t k, bool emit) {
     return (size_t)QB * row_stride + 64 + (size_t)C * QB * sizeof(ListHdr) +
-           (emit ? 0 : (size_t)QB * list_stride_for(C, k) * 8) + 2 * 32 * 8 + 128;
+           (emit ? 0 : (size_t)QB * list_stride_for(C, k) * 8) + 2 * 32 * 8 + 64 * 4 + 128;  // ... barriers (S <= 64), tile slots, slack
 }
 
 static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint32_t nq, bool emit, ScanCfg& c) {
@@ -745,11 +751,11 @@ static int plan_scan(int lpr, bool strict, uint32_t row_stride, uint32_t k, uint
     const uint32_t qb_cap = env_u32("VECGPU_SCAN_QB", 8);
     while (c.QB > 1 && c.QB > qb_cap) c.QB >>= 1;
     // keep lists + queries under ~1/3 of shared memory
-    while (c.QB > 1 && scan_fixed_smem(c.C, c.QB, row_stride, k, emit) > SMEM_MAX / 3) c.QB >>= 1;
-    while (c.C > 1 && scan_fixed_smem(c.C, c.QB, row_stride, k, emit) > SMEM_MAX / 2) c.C >>= 1;
+    while (c.QB > 1 && scan_fixed_smem(c.C, c.QB, row_stride, k, emit) > SCAN_SMEM_MAX / 3) c.QB >>= 1;
+    while (c.C > 1 && scan_fixed_smem(c.C, c.QB, row_stride, k, emit) > SCAN_SMEM_MAX / 2) c.C >>= 1;
     const size_t fixed = scan_fixed_smem(c.C, c.QB, row_stride, k, emit);
-    if (fixed + 2 * 16 * RPW > SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "row too wide for the scan kernel");
-    const size_t avail = SMEM_MAX - fixed;
+    if (fixed + 2 * 16 * RPW > SCAN_SMEM_MAX) return fail(VECGPU_ERR_INVALID_PARAM, "row too wide for the scan kernel");
+    const size_t avail = SCAN_SMEM_MAX - fixed;
     const uint32_t stage_target = std::max(1u, env_u32("VECGPU_SCAN_STAGE_KB", 8)) * 1024;
     const bool force_rows = env_u32("VECGPU_SCAN_PERROW", 0) != 0;
 
@@ -805,7 +811,7 @@ static int launch_scan_inst(const ScanParams& p, const ScanCfg& c, dim3 grid, cu
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (configured_for_device != dev) {
-        CU(cudaFuncSetAttribute(scan_kernel<T, QB, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        CU(cudaFuncSetAttribute(scan_kernel<T, QB, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_MAX));
         configured_for_device = dev;
     }
     scan_kernel<T, QB, EMIT><<<grid, 32 * c.C, c.smem, st>>>(p);
@@ -1094,12 +1100,19 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         const uint32_t np2 = std::max(2u, next_pow2((uint32_t)mp.n_cand));
         const bool fuse = gy == 1 && env_u32("VECGPU_FUSE_MERGE", 1) && mp.n_cand <= 16384 &&
                           (size_t)np2 * 8 <= (size_t)c.S * c.C * c.R * c.srs;
-        if (fuse) {
-            if (!s->d_ws[WS_TICKET]) {
-                if ((rc = ws_reserve(s, WS_TICKET, 256))) return rc;
-                CU(cudaMemsetAsync(s->d_ws[WS_TICKET], 0, 256, st));
+        const bool dynamic = c.n_chunks == 1 && env_u32("VECGPU_SCAN_DYNAMIC", 1) != 0;
+        if (fuse || dynamic) {
+            // tickets + tile counters, one pair per query pass; zeroed when (re)allocated, re-armed by the last CTA of every pass
+            const size_t need = std::max<size_t>(256, (size_t)gy * 8);
+            if (need > s->ws_cap[WS_TICKET]) {
+                if ((rc = ws_reserve(s, WS_TICKET, need))) return rc;
+                CU(cudaMemsetAsync(s->d_ws[WS_TICKET], 0, s->ws_cap[WS_TICKET], st));
             }
             p.tail.counter = (uint32_t*)s->d_ws[WS_TICKET];
+            p.tail.dyn = dynamic ? (uint32_t*)s->d_ws[WS_TICKET] + gy : nullptr;
+            p.tail.do_merge = fuse ? 1u : 0u;
+        }
+        if (fuse) {
             p.tail.np2 = np2;
             p.tail.mp = mp;
             if (s->fuse_push) {
@@ -1107,6 +1120,7 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
                 s->fuse_push_done = true;
             }
         }
+        p.dbg = g_scan_dbg;  // developer timeline (vecgpu_debug_scan_timeline), normally NULL
         rc = launch_scan(s->elem, metric, p, c, false, dim3(gx, gy), st);
         if (rc) return rc;
         if (fuse) return 0;

@@ -1258,7 +1258,7 @@ def test_fused_scan_tail_equals_separate_merge_launch(vg, orc, gpu, elem, metric
             monkeypatch.delenv("VECGPU_FUSE_MERGE")
             assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
             assert np.array_equal(r2, er) and same_bits(d2, ed) and np.array_equal(c2, ec)
-            if not (elem == F32 and metric == L1):  # f32 L1 has its own TMA kernel (always two launches)
+            if k <= 33 and not (elem == F32 and metric == L1):  # f32 L1 has its own TMA kernel (always two launches)
                 assert fused_launches < split_launches
         # many back-to-back fused launches: the ticket counter must re-arm itself every time
         for _ in range(200):

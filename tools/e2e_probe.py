@@ -24,7 +24,7 @@ for name, elem, dims, metric, k, n in [("cfg1 10k x f32[384] L2", 0, 384, 0, 10,
     if elem == 0:
         qh = np.random.default_rng(1).standard_normal((64, dims)).astype("<f4").view(np.uint8).reshape(64, rb)
     qd = torch.from_numpy(qh).to(dev)
-    for fuse in ("1", "0"):
+    for fuse in ("0", "1", "0", "1", "0", "1"):
         os.environ["VECGPU_FUSE_MERGE"] = fuse
         iters = 200 if n <= 2_000_000 else 30
         for _ in range(5):
