@@ -667,6 +667,7 @@ __device__ __forceinline__ void final_merge_cta(const MergeParams& p, uint32_t q
 struct ScanTail {
     uint32_t* counter;   // [gridDim.y] zero-initialised tickets (nullptr: no tail at all); the last CTA of a pass re-arms them
     uint32_t* dyn;       // [gridDim.y] zero-initialised tile counters: tiles are handed out dynamically (nullptr: static round robin)
+    uint32_t static_rounds;  // with dyn: every warp first takes this many tiles of the static round robin, the rest is dynamic
     uint32_t do_merge;   // 1: the last CTA runs the final merge (no separate merge launch)
     uint32_t np2;        // bitonic size for the shared-memory path
     MergeParams mp;
@@ -732,9 +733,22 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     const uint32_t nq_here = min((uint32_t)QB, p.nq_total - q0);
     if (p.dbg && threadIdx.x == 0 && blockIdx.y == 0) p.dbg[blockIdx.x * 4 + 0] = globaltimer_ns();
 
+    // Dynamic tile scheduling state (see the comment at `dyn` below): the CTA draws BLOCKS of 16 consecutive tiles from the
+    // global counter (one global atomic per 16 tiles: per-tile global atomics on one address saturate at ~350 M/s and cost
+    // 14 % of the bandwidth), its warps take single tiles out of the current block with a shared-memory ticket.
+    __shared__ uint32_t s_dynL, s_dynProd, s_dynDone, s_dynBase[8];
+    const bool dyn = !EMIT && p.tail.dyn != nullptr;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) mbar_init(bar_full + 8 * s, 1);
         mbar_fence_init();
+        if (dyn) {
+            const uint32_t r = atomicAdd(p.tail.dyn + blockIdx.y, 32u);  // blocks 0 and 1 of this CTA
+            s_dynBase[0] = r;
+            s_dynBase[1] = r + 16;
+            s_dynProd = 2;
+            s_dynL = 0;
+            s_dynDone = 0;
+        }
     }
     // stage queries (zero-fill the slots past nq_here so the arithmetic stays finite)
     {
@@ -781,28 +795,71 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
         const uint32_t my_iters = my_tiles * p.n_chunks;
 
         // Dynamic tile scheduling (single-chunk rows): instead of the fixed round robin, a warp takes the NEXT tile of the
-        // slab from a global counter whenever it refills a ring slot.  Tiles are still handed out in address order (the
-        // CTAs keep reading neighbouring memory), but a CTA that streams a little slower simply takes fewer tiles: with the
-        // static split the first CTA was done after 508 us and the last after 551 us on a 3.84 GB shard
-        // (tools/scan_timeline.py) — 8 % of the launch spent waiting for stragglers.
-        const bool dyn = !EMIT && p.tail.dyn != nullptr;
+        // CTA's current 16-tile block whenever it refills a ring slot, and the CTA draws the next block from a global
+        // counter.  Tiles are still handed out in address order (the CTAs keep reading neighbouring memory), but a CTA that
+        // streams a little slower simply takes fewer blocks: with the static split the first CTA was done after 508 us
+        // and the last after 551 us on a 3.84 GB shard (tools/scan_timeline.py) — 8 % of the launch spent waiting for
+        // stragglers.
         uint32_t* my_tile_slots = s_tile + warp * D;
         // ring depth in use: the prologue must not let the first warps hoard a small table (each warp starts with its fair
         // share of tiles at most), so a table with fewer tiles than D per warp runs with a shallower ring
         const uint32_t Dr = dyn ? (uint32_t)max((uint64_t)1, min((uint64_t)D, (n_tiles + (uint64_t)C * gridDim.x - 1) / ((uint64_t)C * gridDim.x))) : D;
+        bool reserve_next = false;
+        // Two phases: the first `sr` tiles of every warp come from the static round robin (tile -> SM affinity as before: a
+        // fully dynamic hand-out, per tile or per 16-tile block, streamed 13 % SLOWER in steady state — measured three ways,
+        // profiles/README.md), the remaining ~10 % of the slab is handed out dynamically and absorbs the stragglers.
+        const uint32_t sr = dyn ? p.tail.static_rounds : 0u;
+        const uint32_t n_static = sr * C * gridDim.x;
+        uint32_t my_ticket = 0;  // lane 0: this warp's shared-memory ticket for its NEXT dynamic refill (drawn one refill ahead)
+        if (dyn && sr == 0 && lane == 0) my_ticket = atomicAdd(&s_dynL, 1u);
+        // ticket -> tile: block = ticket / 16 (its base was published by warp 0 at least one block ago), offset = ticket % 16
+        auto resolve_ticket = [&]() -> uint32_t {
+            const uint32_t b = my_ticket >> 4, o = my_ticket & 15u;
+            while (*(volatile uint32_t*)&s_dynProd <= b) {
+                if (*(volatile uint32_t*)&s_dynDone) return 0xFFFFFFFFu;  // the slab is exhausted: later blocks are never published
+                __nanosleep(32);
+            }
+            const uint32_t base = *(volatile uint32_t*)&s_dynBase[b & 7u];
+            return base >= 0xFFFFFFF0u ? 0xFFFFFFFFu : base + o;
+        };
+        // warp 0 keeps the block ring one block ahead of the CTA's consumption
+        auto top_up = [&]() {
+            uint32_t prod = *(volatile uint32_t*)&s_dynProd;
+            const uint32_t cons = (*(volatile uint32_t*)&s_dynL) >> 4;
+            while ((int32_t)(prod - cons) < 2) {
+                const uint32_t r = atomicAdd(p.tail.dyn + blockIdx.y, 16u);
+                *(volatile uint32_t*)&s_dynBase[prod & 7u] = r;
+                __threadfence_block();
+                *(volatile uint32_t*)&s_dynProd = ++prod;
+                if ((uint64_t)r + n_static >= n_tiles) {
+                    *(volatile uint32_t*)&s_dynDone = 1u;
+                    break;
+                }
+            }
+        };
         // issue the copies of ring iteration `lit` (tile lit / n_chunks, chunk lit % n_chunks) into slot lit % D
         auto issue = [&](uint32_t lit) {
             uint32_t jl, c;
             uint64_t row0;
             if (dyn) {
-                uint32_t t = 0;
+                uint32_t t = 0xFFFFFFFFu;
                 if (lane == 0) {
-                    t = atomicAdd(p.tail.dyn + blockIdx.y, 1u);
-                    my_tile_slots[lit % Dr] = (uint64_t)t < n_tiles ? t : 0xFFFFFFFFu;
+                    if (lit < sr) {
+                        t = (uint32_t)(first_tile + (uint64_t)lit * tile_step);  // static phase: the fixed round robin
+                    } else {
+                        t = resolve_ticket();
+                        if (t != 0xFFFFFFFFu) t += n_static;
+                        if ((uint64_t)t >= n_tiles) {
+                            t = 0xFFFFFFFFu;
+                            if (warp == 0) *(volatile uint32_t*)&s_dynDone = 1u;  // warp 0 stops topping up: nobody may wait for it
+                        }
+                    }
+                    my_tile_slots[lit % Dr] = t;
                 }
                 t = __shfl_sync(0xffffffffu, t, 0);
                 __syncwarp();
-                if ((uint64_t)t >= n_tiles) return;
+                if (t == 0xFFFFFFFFu) return;
+                reserve_next = lit + 1 >= sr;  // the next refill is a dynamic one: draw its ticket now
                 jl = lit;
                 c = 0;
                 row0 = (uint64_t)t * RS;
@@ -830,6 +887,13 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
                 __syncwarp();
                 for (uint32_t r = lane; r < valid; r += 32)
                     bulk_g2s(dst0 + r * p.smem_row_stride, p.vectors + (row0 + r) * p.row_stride + off, len, bar);
+            }
+            if (reserve_next) {
+                if (lane == 0) {
+                    my_ticket = atomicAdd(&s_dynL, 1u);  // consumed by the NEXT refill: the latency overlaps a tile of work
+                    if (warp == 0) top_up();
+                }
+                reserve_next = false;
             }
             __syncwarp();
         };

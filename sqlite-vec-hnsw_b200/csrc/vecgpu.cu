@@ -1100,7 +1100,20 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         const uint32_t np2 = std::max(2u, next_pow2((uint32_t)mp.n_cand));
         const bool fuse = gy == 1 && env_u32("VECGPU_FUSE_MERGE", 1) && mp.n_cand <= 16384 &&
                           (size_t)np2 * 8 <= (size_t)c.S * c.C * c.R * c.srs;
-        const bool dynamic = c.n_chunks == 1 && env_u32("VECGPU_SCAN_DYNAMIC", 1) != 0;
+        // Dynamic tile hand-out (experimental, OFF by default).  The static round robin leaves the CTAs finishing 4-8 % apart
+        // (tools/scan_timeline.py: first CTA done after 534 us, last after 557 us on a 3.84 GB shard), but every dynamic form
+        // tried was slower overall: with 4 warps x 2 stages of 24 KB per SM each warp's refill is latency-critical, the
+        // bookkeeping alone (ticket -> tile through shared memory) costs 9 % and handing tiles out in arrival order another
+        // 6 % (profiles/r2_scan_timeline5.txt).  VECGPU_SCAN_DYNAMIC: 0 = static (default), 1 = 90 % static then dynamic,
+        // 2 = all dynamic (16-tile blocks per CTA), 3 = static order through the dynamic code path.
+        const uint32_t dyn_mode = env_u32("VECGPU_SCAN_DYNAMIC", 0);
+        const uint64_t per_round = (uint64_t)gx * c.C;
+        const bool dynamic = c.n_chunks == 1 && dyn_mode != 0 && n_tiles >= 16 * per_round && n_tiles < 0xFFFFFF00ull;
+        if (dynamic) {
+            const uint64_t rounds = n_tiles / per_round;
+            p.tail.static_rounds = dyn_mode == 2 ? 0u : dyn_mode == 3 ? (uint32_t)rounds
+                                   : (uint32_t)(rounds * env_u32("VECGPU_SCAN_STATIC_PCT", 90) / 100);
+        }
         if (fuse || dynamic) {
             // tickets + tile counters, one pair per query pass; zeroed when (re)allocated, re-armed by the last CTA of every pass
             const size_t need = std::max<size_t>(256, (size_t)gy * 8);

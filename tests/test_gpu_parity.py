@@ -1258,8 +1258,8 @@ def test_fused_scan_tail_equals_separate_merge_launch(vg, orc, gpu, elem, metric
             monkeypatch.delenv("VECGPU_FUSE_MERGE")
             assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
             assert np.array_equal(r2, er) and same_bits(d2, ed) and np.array_equal(c2, ec)
-            if k <= 33 and not (elem == F32 and metric == L1):  # f32 L1 has its own TMA kernel (always two launches)
-                assert fused_launches < split_launches
+            if nq in (1, 8) and k <= 33 and not (elem == F32 and metric == L1):  # one query pass; f32 L1 has its own TMA kernel
+                assert fused_launches < split_launches, (nq, k, fused_launches, split_launches)
         # many back-to-back fused launches: the ticket counter must re-arm itself every time
         for _ in range(200):
             r3, d3, _ = s.knn(q[:1], 10, metric)
