@@ -20,8 +20,8 @@ for n, dims, metric in cases:
     sl = vg.Slab(0, dims)
     sl.fill_synthetic(seed=3, n=n, kind=1)
     q = torch.randn(dims, device="cuda")
-    buf = torch.zeros(148 * 4 + 1, dtype=torch.int64, device="cuda")
-    for fuse, dynmode in [(f, d) for d in os.environ.get("TIMELINE_DYN_MODES", "1").split(",") for f in os.environ.get("TIMELINE_FUSE", "1,0").split(",")]:
+    buf = torch.zeros(148 * 4 + 8, dtype=torch.int64, device="cuda")
+    for fuse, dynmode in [(f, d) for d in os.environ.get("TIMELINE_DYN_MODES", "0").split(",") for f in os.environ.get("TIMELINE_FUSE", "1,0").split(",")]:
         os.environ["VECGPU_FUSE_MERGE"] = fuse
         os.environ["VECGPU_SCAN_DYNAMIC"] = dynmode
         for _ in range(3):
@@ -42,7 +42,8 @@ for n, dims, metric in cases:
             st = st[st[:, 0] > 0]
             t0 = st[:, 0].min()
             rows.append([a.elapsed_time(b) * 1e3, (st[:, 0].max() - t0) / 1e3, (st[:, 1].max() - t0) / 1e3, (st[:, 2].min() - t0) / 1e3,
-                         (st[:, 2].max() - t0) / 1e3, (st[:, 3].max() - t0) / 1e3, (t[148 * 4] - t0) / 1e3 if t[148 * 4] else float("nan")])
+                         (st[:, 2].max() - t0) / 1e3, (st[:, 3].max() - t0) / 1e3, (t[148 * 4] - t0) / 1e3 if t[148 * 4] else float("nan")]
+                        + [(t[148 * 4 + i] - t0) / 1e3 if t[148 * 4 + i] else float("nan") for i in (1, 2, 3, 4)])
         r = np.median(np.array(rows), axis=0)
         print(f"{n} x f32[{dims}] fuse={fuse} dyn={dynmode}: event {r[0]:8.1f} us | last CTA start +{r[1]:5.1f} | all primed +{r[2]:5.1f} | first CTA rows done +{r[3]:7.1f} | "
               f"last CTA rows done +{r[4]:7.1f} | last CTA end +{r[5]:7.1f} | fused merge end +{r[6]:7.1f}", flush=True)
