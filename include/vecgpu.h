@@ -138,9 +138,11 @@ int vecgpu_quantize_binary(const float* in, uint64_t n, uint32_t dims, int devic
 /* ---- device-resident variants (bench `value`, multi-GPU shards) ---------
  * Pointers prefixed d_ are device pointers on the slab's device; `stream` is a
  * cudaStream_t passed as void* (NULL = the CUDA default stream).  These calls
- * only enqueue work on that stream; the caller synchronises, and must not run
- * them concurrently with other calls on the same slab (they share the slab's
- * scratch buffers in stream order). */
+ * only enqueue work on that stream; the caller synchronises.  Calls on the same
+ * slab share its scratch buffers in stream order; the streaming-scan path keeps
+ * TWO scratch sets, so independent queries may be pipelined on two streams (the
+ * tail of one scan then overlaps the start of the next); other paths, and a
+ * third stream, are serialised against the earlier work with events. */
 
 /* Make the slab hold n rows with dense rowids first_rowid.. generated on the
  * device by the counter-based generator value(seed, rowid, j) that

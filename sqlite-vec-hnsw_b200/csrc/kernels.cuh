@@ -674,6 +674,7 @@ struct ScanTail {
     XPushParams push;    // push.tab == nullptr: nothing to push
 };
 
+static constexpr uint32_t SCAN_INLINE_Q_MAX = 3328;  // bytes of one padded query row carried in the parameters (f32[768] = 3072)
 struct ScanParams {
     const uint8_t* vectors;  // slab rows, row_stride bytes apart, zero padded
     const uint8_t* skip;     // per-row flags (non-zero = skipped by scans) or nullptr
@@ -694,7 +695,12 @@ struct ScanParams {
     uint32_t list_stride;      // keys reserved per query for the C per-warp lists: pow2 >= C*k
     ScanTail tail;
     unsigned long long* dbg;   // optional [gridDim.x][4] globaltimer stamps: CTA start, pipeline primed, rows done, CTA end (tools/scan_timeline.py)
+    // A single host query travels INSIDE the launch (kernel parameter space) instead of through a host->device copy that the
+    // kernel would have to wait for: one stream operation less per query (~6 us of a 600 us sharded query).
+    uint32_t inline_q_bytes;   // 0: queries are at `queries` (device memory)
+    alignas(16) uint8_t inline_q[SCAN_INLINE_Q_MAX];
 };
+static_assert(sizeof(ScanParams) <= 4096, "kernel parameters are limited to 4 KB");
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -711,7 +717,7 @@ __device__ __forceinline__ uint32_t phys_unit(uint32_t u, uint32_t units8, uint3
 }
 
 template <class T, int QB, bool EMIT>
-__global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ ScanParams p) {
     constexpr int LPR = T::LPR;
     constexpr int RPW = 32 / LPR;  // rows a warp scores at once
     extern __shared__ __align__(128) uint8_t smem[];
@@ -753,7 +759,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanParams p) {
     // stage queries (zero-fill the slots past nq_here so the arithmetic stays finite)
     {
         const uint32_t qunits = p.row_stride / 16;
-        const uint4* gq = (const uint4*)(p.queries + (size_t)q0 * p.row_stride);
+        const uint4* gq = p.inline_q_bytes ? (const uint4*)p.inline_q : (const uint4*)(p.queries + (size_t)q0 * p.row_stride);
         uint4* sq = (uint4*)s_query;
         for (uint32_t i = threadIdx.x; i < QB * qunits; i += blockDim.x)
             sq[i] = (i / qunits) < nq_here ? gq[i] : make_uint4(0, 0, 0, 0);

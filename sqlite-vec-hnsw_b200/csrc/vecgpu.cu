@@ -122,8 +122,8 @@ struct vecgpu_slab {
     uint64_t cap_norms = 0;
     bool norms_valid = false;
     // workspaces
-    void* d_ws[24] = {nullptr};
-    size_t ws_cap[24] = {0};
+    void* d_ws[27] = {nullptr};
+    size_t ws_cap[27] = {0};
     void* h_pin[2] = {nullptr};
     size_t pin_cap[2] = {0};
     // bulk-load staging: two pinned buffers so the host-side copy of chunk i+1 overlaps the DMA of chunk i
@@ -133,12 +133,23 @@ struct vecgpu_slab {
     // sharded queries: a push the next fused scan tail should carry (set by shard_knn_locked around knn_core)
     const XPushParams* fuse_push = nullptr;
     bool fuse_push_done = false;
+    // host-API queries: staged in pinned memory, uploaded only if the chosen path needs them in device memory (a single
+    // query for the streaming scan rides in the kernel parameters instead)
+    const uint8_t* h_q_staged = nullptr;
+    size_t h_q_bytes = 0;
+    bool q_uploaded = true;
+    // Device-API callers may pipeline independent single-query scans on TWO streams (the tail of one scan — stragglers,
+    // list merges — then overlaps the start of the next): the streaming-scan path has a second set of scratch buffers.
+    // slot_stream[i] = the stream that currently owns scratch set i.
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    cudaEvent_t slot_ev = nullptr;
 };
 
 enum { WS_QUERY = 0, WS_PART = 1, WS_OUT_ROWID = 2, WS_OUT_DIST = 3, WS_OUT_CNT = 4, WS_TMP = 5, WS_TMP2 = 6, WS_TMP3 = 7,
        WS_TC_CANDV = 8, WS_TC_CANDR = 9, WS_TC_CNT = 10, WS_TC_TAU = 11, WS_TC_PAIRQ = 12, WS_TC_PAIRPOS = 13, WS_TC_DIST = 14,
        WS_TC_KEYS = 15, WS_TC_QNORM = 16, WS_TC_FLAGS = 17, WS_TC_LOCK = 18, WS_TC_BUF = 19, WS_X_ROWID = 20, WS_X_DIST = 21, WS_X_CNT = 22,
-       WS_TICKET = 23, WS_COUNT = 24 };
+       WS_TICKET = 23, WS_PART1 = 24, WS_TICKET1 = 25, WS_QUERY1 = 26, WS_COUNT = 27 };
 
 static int ws_reserve(vecgpu_slab* s, int i, size_t bytes) {
     if (bytes <= s->ws_cap[i]) return 0;
@@ -300,6 +311,8 @@ static int slab_set_skip(vecgpu_slab* s, uint64_t pos, uint8_t v) {
 }
 
 static int slab_update_norms(vecgpu_slab* s, uint64_t pos, uint64_t n);
+
+static int query_upload_if_needed(vecgpu_slab* s, cudaStream_t st);
 
 static constexpr size_t STAGE_BYTES = 16u << 20;  // per staging buffer
 
@@ -467,6 +480,7 @@ extern "C" void vecgpu_slab_destroy(vecgpu_slab* s) {
         if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]);
         if (s->stage_ev[i]) cudaEventDestroy(s->stage_ev[i]);
     }
+    if (s->slot_ev) cudaEventDestroy(s->slot_ev);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -892,6 +906,47 @@ static int launch_merge(vecgpu_slab* s, const MergeParams& mp, uint32_t nq, cuda
     return 0;
 }
 
+// Which scratch set a call on stream `st` uses (see vecgpu_slab::slot_stream).  A third stream takes over set 0 after waiting
+// for its previous owner.
+static int slab_pick_slot(vecgpu_slab* s, cudaStream_t st, int* slot) {
+    for (int i = 0; i < 2; ++i)
+        if (s->slot_used[i] && s->slot_stream[i] == st) {
+            *slot = i;
+            return 0;
+        }
+    for (int i = 0; i < 2; ++i)
+        if (!s->slot_used[i]) {
+            s->slot_used[i] = true;
+            s->slot_stream[i] = st;
+            *slot = i;
+            return 0;
+        }
+    if (!s->slot_ev) CU(cudaEventCreateWithFlags(&s->slot_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(s->slot_ev, s->slot_stream[0]));
+    CU(cudaStreamWaitEvent(st, s->slot_ev, 0));
+    s->slot_stream[0] = st;
+    *slot = 0;
+    return 0;
+}
+// Paths that only have ONE set of scratch buffers run exclusively: a call from the second stream first waits for the first
+// stream's work (and the first stream for this call afterwards: slab_exclusive_end).
+static int slab_exclusive_begin(vecgpu_slab* s, cudaStream_t st, int slot) {
+    if (slot == 0 && !s->slot_used[1]) return 0;
+    const int other = 1 - slot;
+    if (!s->slot_used[other] || s->slot_stream[other] == st) return 0;
+    if (!s->slot_ev) CU(cudaEventCreateWithFlags(&s->slot_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(s->slot_ev, s->slot_stream[other]));
+    CU(cudaStreamWaitEvent(st, s->slot_ev, 0));
+    return 0;
+}
+static int slab_exclusive_end(vecgpu_slab* s, cudaStream_t st, int slot) {
+    const int other = 1 - slot;
+    if (!s->slot_used[other] || s->slot_stream[other] == st) return 0;
+    CU(cudaEventRecord(s->slot_ev, st));
+    CU(cudaStreamWaitEvent(s->slot_stream[other], s->slot_ev, 0));
+    return 0;
+}
+
 // f32 L1 single/batched scan through swizzled TMA boxes (scan_l1_tma_kernel); returns 1 if not applicable
 static int make_tile_map(CUtensorMap* m, CUtensorMapDataType dtype, uint32_t inner_elems_total, uint32_t box_inner, const void* base,
                          uint64_t rows, uint32_t stride_bytes, uint32_t box_rows, CUtensorMapSwizzle swz);
@@ -954,7 +1009,7 @@ static int knn_l1_tma(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t 
 
 // queries already on the device, padded to row_stride.  Results to device arrays.
 static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
-                    float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
+                    float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st, int slot = 0) {
     int rc;
     if (k == 0 || nq == 0) return 0;
     const uint8_t* d_skip = s->n_skip ? s->d_skip : nullptr;
@@ -1072,9 +1127,10 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         const uint64_t n_tiles = (s->rows + c.R - 1) / c.R;
         const uint32_t gx = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)s->num_sms);
         const uint32_t gy = (nq + c.QB - 1) / c.QB;
-        rc = ws_reserve(s, WS_PART, (size_t)nq * gx * k * 8);
+        const int ws_part = slot ? WS_PART1 : WS_PART, ws_ticket = slot ? WS_TICKET1 : WS_TICKET;  // per-stream scratch set
+        rc = ws_reserve(s, ws_part, (size_t)nq * gx * k * 8);
         if (rc) return rc;
-        p.out_keys = (uint64_t*)s->d_ws[WS_PART];
+        p.out_keys = (uint64_t*)s->d_ws[ws_part];
         p.k = k;
         p.chunk_bytes = c.CB;
         p.n_chunks = c.n_chunks;
@@ -1117,12 +1173,12 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         if (fuse || dynamic) {
             // tickets + tile counters, one pair per query pass; zeroed when (re)allocated, re-armed by the last CTA of every pass
             const size_t need = std::max<size_t>(256, (size_t)gy * 8);
-            if (need > s->ws_cap[WS_TICKET]) {
-                if ((rc = ws_reserve(s, WS_TICKET, need))) return rc;
-                CU(cudaMemsetAsync(s->d_ws[WS_TICKET], 0, s->ws_cap[WS_TICKET], st));
+            if (need > s->ws_cap[ws_ticket]) {
+                if ((rc = ws_reserve(s, ws_ticket, need))) return rc;
+                CU(cudaMemsetAsync(s->d_ws[ws_ticket], 0, s->ws_cap[ws_ticket], st));
             }
-            p.tail.counter = (uint32_t*)s->d_ws[WS_TICKET];
-            p.tail.dyn = dynamic ? (uint32_t*)s->d_ws[WS_TICKET] + gy : nullptr;
+            p.tail.counter = (uint32_t*)s->d_ws[ws_ticket];
+            p.tail.dyn = dynamic ? (uint32_t*)s->d_ws[ws_ticket] + gy : nullptr;
             p.tail.do_merge = fuse ? 1u : 0u;
         }
         if (fuse) {
@@ -1132,6 +1188,12 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
                 p.tail.push = *s->fuse_push;
                 s->fuse_push_done = true;
             }
+        }
+        if (!s->q_uploaded && s->h_q_staged && nq == 1 && s->row_stride <= SCAN_INLINE_Q_MAX) {
+            p.inline_q_bytes = s->row_stride;
+            memcpy(p.inline_q, s->h_q_staged, s->row_stride);
+        } else if ((rc = query_upload_if_needed(s, st))) {
+            return rc;
         }
         p.dbg = g_scan_dbg;  // developer timeline (vecgpu_debug_scan_timeline), normally NULL
         rc = launch_scan(s->elem, metric, p, c, false, dim3(gx, gy), st);
@@ -1276,7 +1338,7 @@ static bool tc_eligible(const vecgpu_slab* s, uint32_t nq, uint32_t k, int metri
 }
 
 static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
-                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st);
+                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st, int slot);
 static int launch_pairs(int elem, int metric, const PairParams& p, int num_sms, cudaStream_t st);
 
 static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t k, int metric, int64_t* d_out_rowids,
@@ -1284,7 +1346,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
     int rc = slab_ensure_norms(s, st);
     if (rc) return rc;
     if (s->n_unsafe > TC_MAX_UNSAFE)  // too many rows with unusable norms: the whole batch goes through the exact scan
-        return knn_exact(s, d_q, nq_all, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
+        return knn_exact(s, d_q, nq_all, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st, 0);
     static int cfg_dev = -1;
     int dev = 0;
     CU(cudaGetDevice(&dev));
@@ -1458,7 +1520,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             if (flags[q]) {
                 g_tc_fallbacks.fetch_add(1, std::memory_order_relaxed);
                 rc = knn_exact(s, dq + (size_t)q * s->row_stride, 1, k, metric, d_out_rowids + (size_t)(qoff + q) * k,
-                               d_out_dists + (size_t)(qoff + q) * k, d_out_counts ? d_out_counts + qoff + q : nullptr, pad_rowid, st);
+                               d_out_dists + (size_t)(qoff + q) * k, d_out_counts ? d_out_counts + qoff + q : nullptr, pad_rowid, st, 0);
                 if (rc) return rc;
             }
     }
@@ -1573,15 +1635,35 @@ static int knn_tci8(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_
 
 static int knn_core(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k, int metric, int64_t* d_out_rowids,
                     float* d_out_dists, uint32_t* d_out_counts, int64_t pad_rowid, cudaStream_t st) {
-    if (nq && k && tci8_eligible(s, nq, k, metric))
-        return knn_tci8(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
-    if (nq && k && tc_eligible(s, nq, k, metric))
-        return knn_tc(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
-    return knn_exact(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
+    int rc;
+    // a staged host query that the streaming scan can carry in its parameters is not uploaded at all
+    const bool inline_q = !s->q_uploaded && nq == 1 && s->row_stride <= SCAN_INLINE_Q_MAX && k != 0 && k <= K_FUSED_MAX && s->rows != 0 &&
+                          !(metric_strict(s->elem, metric) && s->row_stride >= 128 && k <= 256) /* f32 L1 has its own TMA kernel */ &&
+                          env_u32("VECGPU_INLINE_QUERY", 1) != 0;
+    if (!inline_q && (rc = query_upload_if_needed(s, st))) return rc;
+    int slot = 0;
+    if ((rc = slab_pick_slot(s, st, &slot))) return rc;
+    const bool tci8 = nq && k && tci8_eligible(s, nq, k, metric), tc = !tci8 && nq && k && tc_eligible(s, nq, k, metric);
+    // the plain streaming scan has a scratch set per stream; everything else runs exclusively
+    const bool plain = !tci8 && !tc && k <= K_FUSED_MAX && s->rows != 0 &&
+                       !(metric_strict(s->elem, metric) && s->row_stride >= 128 && k <= 256) &&
+                       !(s->elem == VECGPU_BIT && nq >= 16 && k <= 32 && s->row_stride <= 128 && s->rows >= 4096);
+    if (!plain && (rc = slab_exclusive_begin(s, st, slot))) return rc;
+    if (tci8)
+        rc = knn_tci8(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
+    else if (tc)
+        rc = knn_tc(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st);
+    else
+        rc = knn_exact(s, d_q, nq, k, metric, d_out_rowids, d_out_dists, d_out_counts, pad_rowid, st, plain ? slot : 0);
+    if (!plain && !rc) rc = slab_exclusive_end(s, st, slot);
+    s->q_uploaded = true;  // whatever was staged has been consumed
+    s->h_q_staged = nullptr;
+    return rc;
 }
 
-// stage nq host queries (row_bytes each) into the slab's padded device query buffer
-static int stage_queries(vecgpu_slab* s, const void* queries, uint32_t nq) {
+// stage nq host queries (row_bytes each), padded to row_stride, in pinned memory; upload = also copy them into the slab's
+// device query buffer now (otherwise query_upload_if_needed does it when a path asks for device-resident queries)
+static int stage_queries(vecgpu_slab* s, const void* queries, uint32_t nq, bool upload = true) {
     const size_t bytes = (size_t)nq * s->row_stride;
     int rc = pin_reserve(s, 0, bytes);
     if (rc) return rc;
@@ -1595,7 +1677,19 @@ static int stage_queries(vecgpu_slab* s, const void* queries, uint32_t nq) {
         for (uint32_t q = 0; q < nq; ++q)
             memcpy(h + (size_t)q * s->row_stride, (const uint8_t*)queries + (size_t)q * s->row_bytes, s->row_bytes);
     }
-    CU(cudaMemcpyAsync(s->d_ws[WS_QUERY], h, bytes, cudaMemcpyHostToDevice, s->stream));
+    s->h_q_staged = h;
+    s->h_q_bytes = bytes;
+    s->q_uploaded = false;
+    if (upload) {
+        CU(cudaMemcpyAsync(s->d_ws[WS_QUERY], h, bytes, cudaMemcpyHostToDevice, s->stream));
+        s->q_uploaded = true;
+    }
+    return 0;
+}
+static int query_upload_if_needed(vecgpu_slab* s, cudaStream_t st) {
+    if (s->q_uploaded) return 0;
+    CU(cudaMemcpyAsync(s->d_ws[WS_QUERY], s->h_q_staged, s->h_q_bytes, cudaMemcpyHostToDevice, st));
+    s->q_uploaded = true;
     return 0;
 }
 
@@ -1615,7 +1709,7 @@ extern "C" int vecgpu_knn(vecgpu_slab* s, const void* queries, uint32_t nq, uint
     rc = use_device(s->device);
     if (rc) return rc;
     const size_t n_out = (size_t)nq * k;
-    rc = stage_queries(s, queries, nq);
+    rc = stage_queries(s, queries, nq, /*upload=*/false);
     if (rc) return rc;
     const size_t pin_bytes = n_out * 12 + (size_t)nq * 4;
     if ((rc = pin_reserve(s, 1, pin_bytes))) return rc;
@@ -1660,12 +1754,15 @@ extern "C" int vecgpu_knn_device(vecgpu_slab* s, const void* d_queries, uint32_t
     cudaStream_t st = (cudaStream_t)stream;  // NULL == the CUDA default stream, as everywhere in CUDA
     const uint8_t* dq = (const uint8_t*)d_queries;
     if (s->row_bytes != s->row_stride) {
-        rc = ws_reserve(s, WS_QUERY, (size_t)nq * s->row_stride);
+        int slot = 0;
+        if ((rc = slab_pick_slot(s, st, &slot))) return rc;
+        const int ws_q = slot ? WS_QUERY1 : WS_QUERY;
+        rc = ws_reserve(s, ws_q, (size_t)nq * s->row_stride);
         if (rc) return rc;
         pad_rows_kernel<<<std::min<uint32_t>(1024, (nq * s->row_stride + 255) / 256), 256, 0, st>>>(
-            dq, s->row_bytes, (uint8_t*)s->d_ws[WS_QUERY], s->row_stride, nq);
+            dq, s->row_bytes, (uint8_t*)s->d_ws[ws_q], s->row_stride, nq);
         LAUNCHED();
-        dq = (const uint8_t*)s->d_ws[WS_QUERY];
+        dq = (const uint8_t*)s->d_ws[ws_q];
     }
     return knn_core(s, dq, nq, k, metric, d_out_rowids, d_out_dists, nullptr, INT64_MAX, st);
     VG_CATCH

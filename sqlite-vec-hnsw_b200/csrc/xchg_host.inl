@@ -338,7 +338,7 @@ static int shard_knn_locked(vecgpu_slab* s, vecgpu_xchg* x, const void* queries,
     };
     int rc = use_device(s->device);
     if (rc) return bail(rc);
-    if ((rc = stage_queries(s, queries, nq))) return bail(rc);
+    if ((rc = stage_queries(s, queries, nq, /*upload=*/false))) return bail(rc);
     if ((rc = ws_reserve(s, WS_OUT_ROWID, n_out * 8))) return bail(rc);
     if ((rc = ws_reserve(s, WS_OUT_DIST, n_out * 4))) return bail(rc);
     if ((rc = ws_reserve(s, WS_OUT_CNT, (size_t)nq * 4))) return bail(rc);

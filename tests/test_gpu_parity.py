@@ -1265,3 +1265,35 @@ def test_fused_scan_tail_equals_separate_merge_launch(vg, orc, gpu, elem, metric
             r3, d3, _ = s.knn(q[:1], 10, metric)
         er, ed, _ = orc.knn_select(elem, dims, v, q[:1], 10, metric)
         assert np.array_equal(r3, er) and same_bits(d3, ed)
+
+
+def test_two_stream_pipelining_of_single_query_scans(vg, orc, gpu):
+    """Independent queries issued alternately on two streams (per-stream scratch sets) and a third stream that has to take
+    over a set: same answers as one stream; a tensor-core batch in the middle runs exclusively."""
+    import torch
+
+    dims, n, k = 128, 400_000, 10
+    with vg.Slab(F32, dims) as s:
+        s.fill_synthetic(seed=12, n=n, kind=1)
+        q = orc.synth_rows(F32, 13, 1, 40, dims, 1)
+        er, ed, _ = orc.knn_synth(F32, dims, 12, 1, n, 1, q, k, COSINE)
+        dq = torch.from_numpy(q).cuda()
+        s0, s1, s2 = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        s1.wait_stream(s0)
+        s2.wait_stream(s0)
+        outs = []
+        for j in range(32):
+            st = (s0, s1)[j % 2]
+            with torch.cuda.stream(st):
+                outs.append(s.knn_device(dq[j], k, COSINE, stream=st.cuda_stream))
+            if j == 15:  # a batched (tensor-core) call in between, on the second stream
+                with torch.cuda.stream(s1):
+                    big = s.knn_device(dq[:32], k, COSINE, stream=s1.cuda_stream)
+        with torch.cuda.stream(s2):  # a third stream
+            late = [s.knn_device(dq[32 + j], k, COSINE, stream=s2.cuda_stream) for j in range(8)]
+        torch.cuda.synchronize()
+        for j in range(32):
+            assert np.array_equal(outs[j][0].cpu().numpy()[0], er[j]) and np.array_equal(bits(outs[j][1].cpu().numpy()[0]), bits(ed[j]))
+        assert np.array_equal(big[0].cpu().numpy(), er[:32]) and np.array_equal(bits(big[1].cpu().numpy()), bits(ed[:32]))
+        for j in range(8):
+            assert np.array_equal(late[j][0].cpu().numpy()[0], er[32 + j])
