@@ -243,6 +243,16 @@ void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks);
  * their unvisited neighbours in one launch.  Both give identical results. */
 typedef struct vecgpu_hnsw vecgpu_hnsw;
 
+/* The STORED representation of a float32 column's node vectors (src/hnsw/insert.rs:300-322): normalised when the column's
+ * metric is cosine (HnswMetadata.normalize_vectors), then quantize_int8_for_index'ed with index_quantization=int8
+ * (src/vector.rs:554-575).  Built on the device from the column's slab into a new slab with the same rowids and row
+ * positions (element type f32 or int8); rows that cannot be stored (zero vectors under normalisation, skipped rows) are
+ * skipped there too.  *out = NULL when neither step applies (the column slab is the stored representation).  Queries get
+ * the same treatment (src/hnsw/search.rs:285-302) through vecgpu_normalize_f32 / vecgpu_quantize_int8_for_index; the
+ * internal metric over the stored slab is L2 (cosine columns) / the column's metric, distances of cosine columns convert
+ * as d^2 / 2 (src/hnsw/mod.rs:129-146).  The caller owns *out (vecgpu_slab_destroy). */
+int vecgpu_hnsw_stored_slab(vecgpu_slab* column_slab, int normalize, int int8_quantization, vecgpu_slab** out);
+
 /* M in [2,100], ef_construction in [10,2000] as vec_rebuild_hnsw validates (src/sql_functions.rs:442-469);
  * max_m0 = 2M (:489-505).  `seed` makes level assignment reproducible. */
 int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uint32_t ef_construction, uint64_t seed, vecgpu_hnsw** out);

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvecgpu_oracle.so")
 LIB_PATH_AVX512 = os.path.join(_HERE, "libvecgpu_oracle_avx512.so")  # same sources, -march=skylake-avx512 (bit-identical results)
-_SOURCES = ("vecgpu_oracle.c", "simsimd_shapes.c")
+_SOURCES = ("vecgpu_oracle.c", "simsimd_shapes.c", "hnsw_seq.c")
 
 F32, I8, BIT = 0, 1, 2
 L2, L1, COSINE, HAMMING = 0, 1, 2, 3
@@ -99,6 +99,17 @@ def _bind(path):
         L.orc_shape_supported.argtypes = [C.c_int, C.c_int]
         L.orc_shape_distances_f32.argtypes = [C.c_int, C.c_int, C.c_uint32, p, C.c_uint64, p, C.c_int, p]
         L.orc_shape_distances_i8cos.argtypes = [C.c_int, C.c_uint32, p, C.c_uint64, p, p]
+        L.orc_hnsw_new.restype = C.c_void_p
+        L.orc_hnsw_new.argtypes = [C.c_int, C.c_uint32, C.c_int, p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_hnsw_free.argtypes = [p]
+        L.orc_hnsw_insert.argtypes = [p, C.c_uint32, C.c_int]
+        L.orc_hnsw_build.argtypes = [p, p, p]
+        L.orc_hnsw_search.restype = C.c_uint32
+        L.orc_hnsw_search.argtypes = [p, p, C.c_uint32, C.c_uint32, p, p]
+        L.orc_hnsw_export.restype = C.c_uint64
+        L.orc_hnsw_export.argtypes = [p, p, p, p, p]
+        L.orc_hnsw_info.argtypes = [p, p, p, p, p, p, p]
+        L.orc_hnsw_levels.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, p]
         return L
 
 
@@ -290,3 +301,65 @@ def synth_rows(elem, seed, first_rowid, n, dims, kind=0):
     if elem == I8:
         return out.view("i1").reshape(n, dims)
     return out.reshape(n, rb)
+
+
+class HnswSeq:
+    """Strictly sequential HNSW (oracle/hnsw_seq.c): the reference's insert_hnsw / search_hnsw, one insert at a time.
+    `vectors` are the STORED node vectors (normalised / quantised by the caller as the column demands), `metric` the
+    internal metric.  Node ids are row positions (0-based)."""
+
+    def __init__(self, elem, dims, metric, vectors, M=16, ef_construction=200, quirk=False):
+        self.elem, self.dims = elem, dims
+        self._v = np.ascontiguousarray(vectors)  # keep alive: the C side borrows it
+        self.n = self._v.view(np.uint8).size // row_bytes(elem, dims)
+        self._h = lib().orc_hnsw_new(elem, dims, metric, _ptr(self._v), self.n, M, ef_construction, 1 if quirk else 0)
+        self.M = M
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_hnsw_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def levels(seed, n, M):
+        """The product's reproducible level sequence (same hash as csrc/hnsw.inl)."""
+        out = np.empty(n, dtype="i1")
+        lib().orc_hnsw_levels(seed, n, M, _ptr(out))
+        return out
+
+    def build(self, levels, skip=None):
+        lv = np.ascontiguousarray(levels, dtype="i1")
+        sk = None if skip is None else np.ascontiguousarray(skip, dtype="u1")
+        lib().orc_hnsw_build(self._h, _ptr(lv), None if sk is None else _ptr(sk))
+
+    def search(self, queries, k, ef_search):
+        q = np.ascontiguousarray(queries)
+        rb = row_bytes(self.elem, self.dims)
+        qb = q.view(np.uint8).reshape(-1, rb)
+        nodes = np.full((qb.shape[0], k), -1, dtype="<i8")
+        dists = np.full((qb.shape[0], k), np.inf, dtype="<f4")
+        on = np.empty(k, dtype="<u4")
+        od = np.empty(k, dtype="<f4")
+        for i in range(qb.shape[0]):
+            c = lib().orc_hnsw_search(self._h, _ptr(qb[i]), k, ef_search, _ptr(on), _ptr(od))
+            nodes[i, :c] = on[:c]
+            dists[i, :c] = od[:c]
+        return nodes, dists
+
+    def export(self):
+        """-> (from, to, level, distance) of every edge, grouped by (from, level), neighbours ascending."""
+        e = int(lib().orc_hnsw_export(self._h, None, None, None, None))
+        fr, to = np.empty(e, dtype="<u4"), np.empty(e, dtype="<u4")
+        lv, ds = np.empty(e, dtype="<i4"), np.empty(e, dtype="<f4")
+        lib().orc_hnsw_export(self._h, _ptr(fr), _ptr(to), _ptr(lv), _ptr(ds))
+        return fr, to, lv, ds
+
+    def info(self):
+        entry, nodes, dist, fetches = C.c_int64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lvl = C.c_int32()
+        hist = (C.c_uint64 * 5)()
+        lib().orc_hnsw_info(self._h, C.byref(entry), C.byref(lvl), C.byref(nodes), C.byref(dist), hist, C.byref(fetches))
+        return dict(entry=entry.value, entry_level=lvl.value, nodes=nodes.value, distances=dist.value,
+                    batch_hist={"1-4": hist[0], "5-16": hist[1], "17-32": hist[2], "33-64": hist[3], "65+": hist[4]}, fetches=fetches.value)

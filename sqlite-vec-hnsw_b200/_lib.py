@@ -42,6 +42,7 @@ SIGNATURES = {
     "vecgpu_slab_device_view": (C.c_int, [_c_slab, C.POINTER(_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "vecgpu_knn_device": (C.c_int, [_c_slab, _p, C.c_uint32, C.c_uint32, C.c_int, _p, _p, _p]),
     "vecgpu_merge_device": (C.c_int, [C.c_int, _p, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _p, _p]),
+    "vecgpu_hnsw_stored_slab": (C.c_int, [_c_slab, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "vecgpu_hnsw_create": (C.c_int, [_c_slab, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "vecgpu_hnsw_destroy": (None, [C.c_void_p]),
     "vecgpu_hnsw_build": (C.c_int, [C.c_void_p, C.c_uint32]),

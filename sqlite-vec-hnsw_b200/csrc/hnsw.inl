@@ -695,6 +695,61 @@ static inline HCand h_decode(uint64_t key) { return HCand{order_bits_inv((uint32
 // ---- C ABI ------------------------------------------------------------------------------------------------
 static int64_t h_rowid_of(const vecgpu_slab* s, uint32_t pos) { return s->dense ? s->first_rowid + (int64_t)pos : s->h_rowids[pos]; }
 
+// The slab an HNSW index of a float32 column is built over: the STORED representation of src/hnsw/insert.rs:300-322 —
+// normalised for cosine columns, int8-quantised with index_quantization=int8 — produced on the device from the column's
+// slab (same rowids, same positions; rows the reference could not store are skipped).  *out = NULL when the column slab
+// itself is the stored representation (no normalisation, no quantisation).
+extern "C" int vecgpu_hnsw_stored_slab(vecgpu_slab* col, int normalize, int int8_quantization, vecgpu_slab** out) {
+    VG_TRY
+    if (!col || !out) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    *out = nullptr;
+    if (!normalize && !int8_quantization) return 0;
+    if (col->elem != VECGPU_F32)  // search.rs:291-301 / insert.rs:303-322 apply both steps to Float32 columns only
+        return fail(VECGPU_ERR_UNSUPPORTED, "normalisation / int8 index quantisation apply to float32 columns only");
+    std::lock_guard<std::mutex> lk(col->mu);
+    int rc = use_device(col->device);
+    if (rc) return rc;
+    vecgpu_slab* st = nullptr;
+    rc = vecgpu_slab_create(int8_quantization ? VECGPU_I8 : VECGPU_F32, col->dims, col->rows, col->device, &st);
+    if (rc) return rc;
+    struct Guard {
+        vecgpu_slab* s;
+        ~Guard() { if (s) vecgpu_slab_destroy(s); }
+    } guard{st};
+    const uint64_t n = col->rows;
+    st->rows = n;
+    st->dense = col->dense;
+    st->first_rowid = col->first_rowid;
+    st->h_rowids = col->h_rowids;
+    st->rowids_synced = 0;
+    if ((rc = slab_sync_rowids(st))) return rc;
+    if (n) {
+        uint8_t* d_flags = nullptr;
+        CU(cudaMalloc((void**)&d_flags, n));
+        struct FreeDev {
+            void* p;
+            ~FreeDev() { cudaFree(p); }
+        } fd{d_flags};
+        hnsw_stored_rows_kernel<<<(uint32_t)std::min<uint64_t>((n + 127) / 128, (uint64_t)col->num_sms * 16), 128, 0, col->stream>>>(
+            col->d_vec, col->row_stride, n, col->dims, normalize ? 1 : 0, int8_quantization ? 1 : 0, st->d_vec, st->row_stride,
+            col->n_skip ? col->d_skip : nullptr, d_flags);
+        LAUNCHED();
+        st->h_skip.resize(n);
+        CU(cudaMemcpyAsync(st->h_skip.data(), d_flags, n, cudaMemcpyDeviceToHost, col->stream));
+        CU(cudaStreamSynchronize(col->stream));
+        uint64_t dead = 0;
+        for (uint64_t i = 0; i < n; ++i) dead += st->h_skip[i] != 0;
+        st->n_skip = dead;
+        if (!dead) st->h_skip.clear();
+        st->skip_synced = 0;
+        if ((rc = slab_sync_skip(st))) return rc;
+    }
+    guard.s = nullptr;
+    *out = st;
+    return 0;
+    VG_CATCH
+}
+
 extern "C" int vecgpu_hnsw_create(vecgpu_slab* slab, int metric, uint32_t M, uint32_t ef_construction, uint64_t seed,
                                   vecgpu_hnsw** out) {
     VG_TRY

@@ -1559,6 +1559,39 @@ __global__ void quantize_index_kernel(const float* in, uint64_t total, int8_t* o
     }
 }
 
+// HNSW node vectors as the reference STORES them (src/hnsw/insert.rs:300-322): a float32 column row is normalised when the
+// column's metric is cosine (Vector::normalize, vector.rs:444-466: strict-order sum of squares, IEEE sqrt and divisions) and
+// then, with index_quantization=int8, quantised by quantize_int8_for_index (vector.rs:554-575).  One thread per row (the
+// normalisation is a strict left-to-right sum), source and destination are slab rows (strided, zero padded).  A row that
+// cannot be normalised (zero magnitude: the reference's insert fails, vector.rs:451-455) is flagged in skip_out.
+__global__ void hnsw_stored_rows_kernel(const uint8_t* src, uint32_t src_stride, uint64_t n, uint32_t d, int do_norm, int do_q8,
+                                        uint8_t* dst, uint32_t dst_stride, const uint8_t* skip_in, uint8_t* skip_out) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const float* v = (const float*)(src + r * src_stride);
+        uint8_t* o = dst + r * dst_stride;
+        bool dead = skip_in != nullptr && skip_in[r] != 0;
+        float m = 1.f;
+        if (do_norm && !dead) {
+            float s = 0.f;
+            for (uint32_t i = 0; i < d; ++i) s = __fadd_rn(s, __fmul_rn(v[i], v[i]));
+            m = __fsqrt_rn(s);
+            if (m == 0.f) dead = true;
+        }
+        for (uint32_t i = 0; i < d; ++i) {
+            float x = dead ? 0.f : (do_norm ? __fdiv_rn(v[i], m) : v[i]);
+            if (do_q8) {
+                const float c = x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x);
+                ((int8_t*)o)[i] = (int8_t)roundf(__fmul_rn(c, 127.0f));
+            } else {
+                ((float*)o)[i] = x;
+            }
+        }
+        const uint32_t used = do_q8 ? d : d * 4u;
+        for (uint32_t i = used; i < dst_stride; ++i) o[i] = 0;
+        if (skip_out) skip_out[r] = dead ? 1 : 0;
+    }
+}
+
 // quantize_binary (vector.rs:579-608): strict-order mean, one thread per row
 __global__ void quantize_binary_kernel(const float* in, uint64_t n, uint32_t d, uint8_t* out) {
     const uint32_t nb = (d + 7) / 8;

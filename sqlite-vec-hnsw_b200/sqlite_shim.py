@@ -73,22 +73,30 @@ def storage_schema(conn, table):
     return None if row is None else row[0]
 
 
-def read_column(conn, table, column_idx, row_bytes):
-    """-> (rowids int64[n], vectors uint8[n, row_bytes], skip uint8[n]) in ascending rowid order."""
+def read_column(conn, table, column_idx, row_bytes, chunk=65536):
+    """-> (rowids int64[n], vectors uint8[n, row_bytes], skip uint8[n]) in ascending rowid order
+    (SELECT rowid, vecNN ... ORDER BY rowid: src/shadow.rs:853-868 / 721-740).  Rows are fetched in chunks and each chunk's
+    well-formed blobs are joined with one b"".join (the per-row Python work is a length check)."""
     cur = conn.execute(f'SELECT rowid, vec{column_idx:02d} FROM "main"."{table}_data" ORDER BY rowid')
-    rowids, chunks, skip = [], [], []
+    ids, parts, skips = [], [], []
     zero = bytes(row_bytes)
-    for rowid, blob in cur:
-        rowids.append(rowid)
-        if blob is None or len(blob) != row_bytes:  # empty / NULL / wrong length: the scan skips the row
-            chunks.append(zero)
-            skip.append(1)
+    while True:
+        rows = cur.fetchmany(chunk)
+        if not rows:
+            break
+        rid = np.fromiter((r[0] for r in rows), dtype="<i8", count=len(rows))
+        # empty / NULL / wrong length: the scan skips the row (src/vtab.rs:2596-2613)
+        bad = np.fromiter((b is None or len(b) != row_bytes for _, b in rows), dtype=bool, count=len(rows))
+        if bad.any():
+            blob = b"".join(zero if x else bytes(b) for x, (_, b) in zip(bad.tolist(), rows))
         else:
-            chunks.append(bytes(blob))
-            skip.append(0)
-    n = len(rowids)
-    vec = np.frombuffer(b"".join(chunks), dtype="u1").reshape(n, row_bytes) if n else np.zeros((0, row_bytes), dtype="u1")
-    return np.asarray(rowids, dtype="<i8"), vec, np.asarray(skip, dtype="u1")
+            blob = b"".join(b for _, b in rows)
+        ids.append(rid)
+        parts.append(np.frombuffer(blob, dtype="u1").reshape(len(rows), row_bytes))
+        skips.append(bad.astype("u1"))
+    if not ids:
+        return np.zeros(0, dtype="<i8"), np.zeros((0, row_bytes), dtype="u1"), np.zeros(0, dtype="u1")
+    return np.concatenate(ids), np.concatenate(parts), np.concatenate(skips)
 
 
 class Vec0Table:
@@ -154,6 +162,7 @@ class Vec0Table:
         if self.slab is not None:
             self.slab.upsert(rowid, blob or b"")
             self._fingerprint = self._current_fingerprint()
+        self._hnsw_stale = getattr(self, "_hnsw", None) is not None
         return rowid
 
     def update(self, rowid, blob):
@@ -161,12 +170,30 @@ class Vec0Table:
         if self.slab is not None:
             self.slab.upsert(int(rowid), blob or b"")
             self._fingerprint = self._current_fingerprint()
+        self._hnsw_stale = getattr(self, "_hnsw", None) is not None
 
     def delete(self, rowid):
-        self.conn.execute(f'DELETE FROM "main"."{self.table}_data" WHERE rowid = ?', (int(rowid),))
+        rowid = int(rowid)
+        col = getattr(self, "_hnsw_column", None)
+        if col is not None:
+            # Vec0Tab::delete (src/vtab.rs:1340-1397): the node, its edges in both directions, num_nodes / hnsw_version, and a new
+            # entry point (the highest remaining node) when the entry point itself goes
+            nodes, edges, meta = (f'"{self.table}_{col}_hnsw_{x}"' for x in ("nodes", "edges", "meta"))
+            self.conn.execute(f"DELETE FROM {nodes} WHERE rowid = ?", (rowid,))
+            self.conn.execute(f"DELETE FROM {edges} WHERE from_rowid = ? OR to_rowid = ?", (rowid, rowid))
+            row = self.conn.execute(f"SELECT entry_point_rowid, num_nodes FROM {meta} WHERE id = 1").fetchone()
+            if row is not None:
+                entry, num = row
+                self.conn.execute(f"UPDATE {meta} SET num_nodes = ?, hnsw_version = hnsw_version + 1 WHERE id = 1", (max(0, num - 1),))
+                if entry == rowid:
+                    new = self.conn.execute(f"SELECT rowid, level FROM {nodes} ORDER BY level DESC LIMIT 1").fetchone()
+                    self.conn.execute(f"UPDATE {meta} SET entry_point_rowid = ?, entry_point_level = ? WHERE id = 1", new or (-1, -1))
+        self.conn.execute(f'DELETE FROM "main"."{self.table}_data" WHERE rowid = ?', (rowid,))
         if self.slab is not None:
-            self.slab.delete(int(rowid))
+            self.slab.delete(rowid)
             self._fingerprint = self._current_fingerprint()
+        if getattr(self, "_hnsw", None) is not None and self._hnsw_slab is not self.slab:
+            self._hnsw_slab.delete(rowid)  # the stored-representation slab carries its own tombstones
 
     # ---- vec_rebuild_hnsw (src/sql_functions.rs:436-534) with the graph built on the GPU and written back in bulk
     def rebuild_hnsw(self, column, new_m=None, new_ef_construction=None):
@@ -177,23 +204,20 @@ class Vec0Table:
         if self.is_stale():
             self.stage()
         meta = f'"{self.table}_{column}_hnsw_meta"'
-        m, efc, seed, metric_s = self.conn.execute(f"SELECT m, ef_construction, rng_seed, distance_metric FROM {meta} WHERE id = 1").fetchone()
+        m, efc, seed, metric_s, quant = self.conn.execute(
+            f"SELECT m, ef_construction, rng_seed, distance_metric, index_quantization FROM {meta} WHERE id = 1").fetchone()
         m = int(new_m) if new_m is not None else m
         efc = int(new_ef_construction) if new_ef_construction is not None else efc
         metric = vec0.DistanceMetric.from_str(metric_s)
-        cosine = metric == vec0.DistanceMetric.Cosine and self.vec_type == vec0.VectorType.Float32
         if getattr(self, "_hnsw", None) is not None:
             self._hnsw.close()
-            self._hnsw_slab.close() if self._hnsw_slab is not self.slab else None
-        if cosine:  # the graph lives over the STORED representation: unit vectors for cosine columns
-            rowids, vec, skip = read_column(self.conn, self.table, self.column_idx, self.row_bytes)
-            keep = skip == 0
-            stored = vec0.normalize(np.frombuffer(vec[keep].tobytes(), dtype="<f4").reshape(-1, self.dims))
-            self._hnsw_slab = self._slab_factory()
-            self._hnsw_slab.load(stored, rowids[keep])
-        else:
-            self._hnsw_slab = self.slab
-        self._hnsw = vec0.HnswIndex(self._hnsw_slab, metric, M=m, ef_construction=efc, seed=int(seed) & 0x7FFFFFFFFFFFFFFF)
+        # the graph lives over the STORED representation (src/hnsw/insert.rs:300-322): unit vectors for cosine columns, int8
+        # with index_quantization=int8 — derived from the resident column slab on the device
+        self._hnsw = vec0.HnswIndex.for_column(self.slab, metric, M=m, ef_construction=efc, seed=int(seed) & 0x7FFFFFFFFFFFFFFF,
+                                               index_quantization=quant or "none")
+        self._hnsw_slab = self._hnsw.slab
+        self._hnsw_column = column
+        self._hnsw_stale = False
         self._hnsw.rebuild()
         rid, lv = self._hnsw.export_nodes()
         fr, to, elv, dist = self._hnsw.export_edges()
@@ -210,10 +234,17 @@ class Vec0Table:
                           "num_nodes = ?, hnsw_version = hnsw_version + 1 WHERE id = 1", (m, 2 * m, efc, entry, entry_level, len(rid)))
         return len(rid)
 
-    def hnsw_knn(self, query, k, ef_search=200):
-        """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)]."""
+    def hnsw_knn(self, query, k, ef_search=200, auto_rebuild=False):
+        """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)].
+        Rows deleted since the rebuild are never returned.  Rows inserted or updated since the rebuild are not in the graph
+        (the reference inserts them incrementally, src/vtab.rs:1409 -> insert_hnsw; this index is rebuilt in bulk instead):
+        the call refuses to answer from a stale index unless auto_rebuild=True rebuilds it first."""
         if getattr(self, "_hnsw", None) is None:
             raise vec0.InvalidState("no HNSW index: call rebuild_hnsw() first")
+        if getattr(self, "_hnsw_stale", False):
+            if not auto_rebuild:
+                raise vec0.InvalidState("rows were inserted or updated since the last rebuild_hnsw(): rebuild the index")
+            self.rebuild_hnsw(self._hnsw_column)
         if isinstance(query, str):
             query = vec0.Vector.from_json(query, self.vec_type).as_bytes()
         q = np.frombuffer(query, dtype="u1").reshape(1, -1)
@@ -232,9 +263,7 @@ class Vec0Table:
 
     def close(self):
         if getattr(self, "_hnsw", None) is not None:
-            self._hnsw.close()
-            if self._hnsw_slab is not self.slab:
-                self._hnsw_slab.close()
+            self._hnsw.close()  # also releases the stored-representation slab it owns
             self._hnsw = None
         if self.slab is not None:
             self.slab.close()

@@ -128,9 +128,9 @@ _NP = {VectorType.Float32: np.dtype("<f4"), VectorType.Int8: np.dtype("i1"), Vec
 
 
 def _ptr(a):
-    # plain integer address: ctypes converts it for a c_void_p argument (a.ctypes.data_as() builds two ctypes objects per
-    # call, several microseconds each — it showed in the per-query end-to-end time)
-    return a.ctypes.data
+    # keeps `a` alive for the duration of the call (the ctypes object references the array).  The per-query hot paths
+    # (Slab.knn, Exchange.shard_knn) pass `named_array.ctypes.data` instead: data_as() costs several microseconds per argument.
+    return a.ctypes.data_as(C.c_void_p)
 
 
 def _as_raw(x, vec_type):
@@ -316,6 +316,18 @@ class Slab:
         self._h = C.c_void_p()
         self._lib = _lib.load()
         _check(self._lib.vecgpu_slab_create(int(self.vec_type), self.dims, capacity_hint, device, C.byref(self._h)))
+
+    @classmethod
+    def _adopt(cls, handle, vec_type, dims, device):
+        """Wrap a slab handle the library created (e.g. vecgpu_hnsw_stored_slab); the wrapper owns it."""
+        self = cls.__new__(cls)
+        self.vec_type = VectorType(vec_type)
+        self.dims = int(dims)
+        self.device = device
+        self.row_bytes = self.vec_type.row_bytes(self.dims)
+        self._lib = _lib.load()
+        self._h = handle
+        return self
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -619,22 +631,49 @@ def brute_force_search(slab, query_vector, k, distance_metric):
 class HnswIndex:
     """Graph over the rows of a slab that holds the STORED node vectors; built and searched with GPU-batched
     candidate scoring.  `metric` is the column's metric; cosine columns must load normalised vectors and are
-    searched with L2 internally, distances converted on output (src/hnsw/mod.rs:129-146)."""
+    searched with L2 internally, distances converted on output (src/hnsw/mod.rs:129-146).
+    HnswIndex.for_column() derives the stored slab from a float32 column slab the way the reference does
+    (normalise for cosine, quantize_int8_for_index with index_quantization=int8: src/hnsw/insert.rs:300-322)."""
 
-    def __init__(self, slab, metric, M=32, ef_construction=400, seed=42, normalize_vectors=True):
+    def __init__(self, slab, metric, M=32, ef_construction=400, seed=42, normalize_vectors=True, index_quantization="none",
+                 _column_type=None, _owns_slab=False):
         # defaults of HnswParams (src/hnsw/mod.rs:35-47)
         self.slab = slab
         self.metric = DistanceMetric(metric)
         self.normalize_vectors = bool(normalize_vectors)
+        self.index_quantization = str(index_quantization).lower()
+        if self.index_quantization not in ("none", "int8"):
+            raise InvalidParameter(f"unknown index_quantization {index_quantization!r}")
+        self.column_type = VectorType(slab.vec_type if _column_type is None else _column_type)
+        self._owns_slab = _owns_slab
         self.internal = internal_distance_metric(self.metric, self.normalize_vectors)
         self._lib = _lib.load()
         self._h = C.c_void_p()
         _check(self._lib.vecgpu_hnsw_create(slab._h, int(self.internal), M, ef_construction, seed, C.byref(self._h)))
 
+    @classmethod
+    def for_column(cls, column_slab, metric, M=32, ef_construction=400, seed=42, index_quantization="none"):
+        """Index over a vec0 column: builds the stored representation on the device (vecgpu_hnsw_stored_slab) when the
+        column is float32 and cosine and/or index_quantization=int8, otherwise indexes the column slab itself."""
+        metric = DistanceMetric(metric)
+        f32 = column_slab.vec_type == VectorType.Float32
+        norm = f32 and metric == DistanceMetric.Cosine          # HnswMetadata.normalize_vectors (src/hnsw/mod.rs:120-123)
+        q8 = f32 and str(index_quantization).lower() == "int8"   # insert.rs:303-313: float32 columns only
+        h = C.c_void_p()
+        _check(_lib.load().vecgpu_hnsw_stored_slab(column_slab._h, 1 if norm else 0, 1 if q8 else 0, C.byref(h)))
+        if h.value:
+            stored = Slab._adopt(h, VectorType.Int8 if q8 else VectorType.Float32, column_slab.dims, column_slab.device)
+            return cls(stored, metric, M, ef_construction, seed, normalize_vectors=True, index_quantization=index_quantization,
+                       _column_type=VectorType.Float32, _owns_slab=True)
+        return cls(column_slab, metric, M, ef_construction, seed, normalize_vectors=True, index_quantization="none")
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.vecgpu_hnsw_destroy(self._h)
             self._h = C.c_void_p()
+        if getattr(self, "_owns_slab", False) and self.slab is not None:
+            self.slab.close()
+            self.slab = None
 
     __del__ = close
 
@@ -664,9 +703,14 @@ class HnswIndex:
     def search(self, queries, k, ef_search=200):
         """search_hnsw (src/hnsw/search.rs:267-335).  Queries are raw column vectors; cosine queries are
         normalised here (search.rs:291-293).  -> (rowids [nq,k], distances in the column's metric, counts)."""
-        q = _as_raw(queries, self.slab.vec_type)
-        if self.metric == DistanceMetric.Cosine and self.normalize_vectors and self.slab.vec_type == VectorType.Float32:
-            q = normalize(np.frombuffer(q.tobytes(), dtype="<f4").reshape(-1, self.slab.dims), self.slab.device)
+        q = _as_raw(queries, self.column_type)
+        if self.column_type == VectorType.Float32:
+            # the query gets the stored representation's treatment (search.rs:285-302): normalise, then quantise
+            if self.metric == DistanceMetric.Cosine and self.normalize_vectors:
+                q = normalize(np.frombuffer(q.tobytes(), dtype="<f4").reshape(-1, self.slab.dims), self.slab.device)
+            if self.index_quantization == "int8" and self.slab.vec_type == VectorType.Int8:
+                q = quantize_int8_for_index(np.frombuffer(np.ascontiguousarray(q).tobytes(), dtype="<f4").reshape(-1, self.slab.dims),
+                                            self.slab.device)
         nbytes = q.size * q.itemsize
         if nbytes == 0 or nbytes % self.slab.row_bytes:
             raise DimensionMismatch(f"Dimension mismatch: expected {self.slab.dims}", self.slab.dims, None)

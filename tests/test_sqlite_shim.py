@@ -168,3 +168,73 @@ def test_rebuild_hnsw_writes_the_reference_shadow_tables(vg, orc, gpu, tmp_path,
         want_d = [orc.convert_cosine_output(w[1]) if metric_s == "cosine" else w[1] for w in walk]
         assert np.allclose([d for _, d in got], want_d, rtol=1e-6, atol=1e-7)
     t.close()
+
+
+@pytest.mark.gpu
+def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
+    """Vec0Tab::delete (src/vtab.rs:1340-1397) removes the node, its edges in both directions and fixes the meta row;
+    the resident index never returns a deleted rowid; inserts / updates make it stale until it is rebuilt."""
+    sh = _shim()
+    conn = sqlite3.connect(str(tmp_path / "hooks.db"))
+    sh.create_shadow_tables(conn, "docs", 1, [])
+    n, dims = 1200, 16
+    v = random_rows(F32, n, dims, seed=17)
+    conn.executemany('INSERT INTO "docs_data" (rowid, vec00) VALUES (?, ?)', [(i + 1, v[i].tobytes()) for i in range(n)])
+    sh.create_hnsw_shadow_tables(conn, "docs", "emb", dims, "float32", "cosine", m=8, ef_construction=60)
+    t = sh.Vec0Table(conn, "docs", F32, dims, distance_metric=COSINE)
+    t.rebuild_hnsw("emb")
+    ep, num0, ver0 = conn.execute('SELECT entry_point_rowid, num_nodes, hnsw_version FROM "docs_emb_hnsw_meta"').fetchone()
+    assert t.hnsw_knn(v[99].tobytes(), 3)[0][0] == 100
+    # delete an ordinary node and the entry point itself
+    for rid in (100, ep):
+        t.delete(rid)
+        assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_nodes" WHERE rowid = ?', (rid,)).fetchone()[0] == 0
+        assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_edges" WHERE from_rowid = ? OR to_rowid = ?', (rid, rid)).fetchone()[0] == 0
+    ep2, epl2, num1, ver1 = conn.execute('SELECT entry_point_rowid, entry_point_level, num_nodes, hnsw_version FROM "docs_emb_hnsw_meta"').fetchone()
+    assert num1 == num0 - 2 and ver1 == ver0 + 2 and ep2 not in (ep, 100)
+    assert conn.execute('SELECT MAX(level) FROM "docs_emb_hnsw_nodes"').fetchone()[0] == epl2
+    got = [r for r, _ in t.hnsw_knn(v[99].tobytes(), 10, ef_search=80)]
+    assert 100 not in got and ep not in got and len(got) == 10
+    # the exact scan agrees that both are gone
+    exact = [r for r, _ in t.knn(v[99].tobytes(), 10)]
+    assert 100 not in exact and ep not in exact
+    # an insert leaves the bulk-built index stale: refuse, or rebuild on demand
+    new = random_rows(F32, 1, dims, seed=18)[0]
+    new_id = t.insert(new.tobytes())
+    with pytest.raises(vg.InvalidState):
+        t.hnsw_knn(new.tobytes(), 3)
+    assert t.hnsw_knn(new.tobytes(), 3, auto_rebuild=True)[0][0] == new_id
+    t.update(5, new.tobytes())
+    with pytest.raises(vg.InvalidState):
+        t.hnsw_knn(new.tobytes(), 3)
+    t.close()
+
+
+@pytest.mark.gpu
+def test_rebuild_hnsw_with_int8_index_quantization(vg, orc, gpu, tmp_path):
+    """index_quantization=int8 on a cosine float32 column: stored node vectors are quantize_int8_for_index(normalize(v))
+    (src/hnsw/insert.rs:300-322), the query likewise (src/hnsw/search.rs:285-302), the graph is walked with int8 L2; the
+    reference's bar is recall@10 >= 90 % against the float32 ground truth (tests/test_quantization_perf.rs:194-289)."""
+    sh = _shim()
+    conn = sqlite3.connect(str(tmp_path / "q8.db"))
+    sh.create_shadow_tables(conn, "docs", 1, [])
+    n, dims, nq = 5000, 128, 20
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((n, dims)).astype("<f4")
+    q = v[rng.choice(n, nq, replace=False)] + 0.05 * rng.standard_normal((nq, dims)).astype("<f4")
+    conn.executemany('INSERT INTO "docs_data" (rowid, vec00) VALUES (?, ?)', [(i + 1, v[i].tobytes()) for i in range(n)])
+    sh.create_hnsw_shadow_tables(conn, "docs", "emb", dims, "float32", "cosine", m=32, ef_construction=400, index_quantization="int8")
+    t = sh.Vec0Table(conn, "docs", F32, dims, distance_metric=COSINE)
+    assert t.rebuild_hnsw("emb") == n
+    # stored blobs are int8[dims], bit-identical to the reference pipeline restated by the oracle
+    blob = conn.execute('SELECT vector FROM "docs_emb_hnsw_nodes" WHERE rowid = 7').fetchone()[0]
+    assert len(blob) == dims
+    assert np.array_equal(np.frombuffer(blob, dtype="i1"), orc.quantize_int8_for_index(orc.normalize(v[6:7]))[0])
+    er, _, _ = orc.knn(F32, dims, v, q, 10, COSINE)
+    hit = 0
+    for qi in range(nq):
+        got = [r for r, _ in t.hnsw_knn(q[qi].tobytes(), 10, ef_search=200)]
+        hit += len(set(got) & set(er[qi].tolist()))
+    assert hit / (10 * nq) >= 0.90
+    # the walk equals the sequential oracle's walk over the same stored vectors when the graph is built one insert at a time
+    t.close()
