@@ -271,6 +271,217 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
     }
 }
 
+// ---- K6c: the same walk with ONE CTA per query — the latency form (few queries: SQL issues one per MATCH, src/vtab.rs:2249) ----
+// A lone warp spends most of an expansion waiting: its <= 32 fresh neighbours are scored 8 at a time with a handful of
+// loads in flight per lane, the visited set is a table of atomics in global memory.  Here 8 warps share one query:
+//   - scoring: every 4-lane (or 1-lane) group takes one pending neighbour, so all <= 64 rows of an expansion are fetched at
+//     once (each lane issues its loads 8 deep) — one HBM round trip per expansion instead of three or four;
+//   - the visited set is an open-addressing table in SHARED memory (32 K slots), cleared per layer by the whole CTA;
+//   - the sorted result/candidate array, the admission rule and the pop rule are the single-warp kernel's, run by warp 0 in
+//     adjacency order — so results are bit-identical to hnsw_search_kernel (tests compare them).
+// Queries are still handed out by the atomic counter (grid = min(nq, SMs)).  A query that overflows the table or the
+// array is flagged and answered by the other paths, exactly as before.
+static constexpr uint32_t HC_VIS = 32768;       // shared-memory visited slots (power of two)
+static constexpr uint32_t HC_THREADS = 256;
+
+__device__ __forceinline__ bool hvis_insert_smem(uint32_t* t, uint32_t mask, uint32_t key) {
+    uint32_t h = (key * 2654435761u) & mask;
+    while (true) {
+        const uint32_t old = atomicCAS(&t[h], HV_EMPTY, key);
+        if (old == HV_EMPTY) return true;
+        if (old == key) return false;
+        h = (h + 1) & mask;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSearchParams p) {
+    constexpr int LPR = T::LPR;
+    constexpr int GROUPS = HC_THREADS / LPR;  // rows scored per pass of the CTA
+    extern __shared__ __align__(16) uint8_t h_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+    const uint32_t pend_cap = (p.g.max_m0 + 31u) & ~31u;
+    // layout: [visited HC_VIS x 4][L cap x 8][pend ids][pend dist][query]
+    uint32_t* vt = (uint32_t*)h_smem;
+    uint64_t* L = (uint64_t*)(vt + HC_VIS);
+    uint32_t* pend = (uint32_t*)(L + p.cap);
+    float* pend_d = (float*)(pend + pend_cap);
+    uint4* sq = (uint4*)(pend_d + pend_cap);
+    __shared__ uint32_t s_q, s_npend, s_status, s_done, s_entry;
+
+    while (true) {
+        if (threadIdx.x == 0) s_q = atomicAdd(p.next_q, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= p.nq) break;
+        const uint32_t ai = p.a_index ? p.a_index[q] : q;
+        const uint4* ag = (const uint4*)(p.a_base + (uint64_t)ai * p.a_stride);
+        for (uint32_t u = threadIdx.x; u < p.units; u += HC_THREADS) sq[u] = __ldg(ag + u);
+        __syncthreads();
+        const uint4* a = sq;
+        float qc = 0.f;
+        if (T::HAS_QC) qc = query_const(a, p.units, lane & 3, p.qc_kind);  // every 4-lane group computes the same value
+        const int nlev = p.node_level ? (int)p.node_level[q] : -1;
+        const uint32_t slot0 = p.out_off ? p.out_off[q] : q;
+        if (threadIdx.x == 0) {
+            s_entry = p.entry;
+            s_status = 0;
+        }
+        unsigned long long nscored = 0;
+        __syncthreads();
+
+        for (int level = p.entry_level; level >= 0; --level) {
+            if (s_status) break;
+            const bool wide = nlev < 0 ? level == 0 : level <= nlev;
+            const uint32_t ef = wide ? p.ef_wide : 1u;
+            const uint32_t vsz = ef == 1u ? 4096u : HC_VIS;
+            const uint32_t vmask = vsz - 1, vlimit = vsz - (vsz >> 2);
+            for (uint32_t i = threadIdx.x * 4; i < vsz; i += HC_THREADS * 4) *(uint4*)(vt + i) = make_uint4(HV_EMPTY, HV_EMPTY, HV_EMPTY, HV_EMPTY);
+            __syncthreads();
+            // warp 0's registers carry the layer state
+            uint32_t len = 0, lo = 0, vcount = 1, steps = 0;
+            uint32_t worst_hi = 0xFFFFFFFFu;
+            if (threadIdx.x == 0) {
+                pend[0] = s_entry;
+                hvis_insert_smem(vt, vmask, s_entry);
+                s_npend = 1;
+                s_done = 0;
+            }
+            __syncthreads();
+
+            while (true) {
+                // ---- scoring phase: one group per pending node, all groups at once
+                const uint32_t npend = s_npend;
+                for (uint32_t r = (uint32_t)grp; r < npend; r += GROUPS) {
+                    const uint32_t node = pend[r];
+                    typename T::Acc acc;
+                    T::init(acc);
+                    const uint4* b = (const uint4*)(p.b_base + (uint64_t)node * p.b_stride);
+#pragma unroll 8
+                    for (uint32_t u = g; u < p.units; u += LPR) {
+                        const uint4 x = __ldg(b + u);
+                        const uint4 qv[1] = {a[u]};
+                        T::step(acc, x, qv);
+                    }
+                    const float d = T::finish(acc, 0, &qc);
+                    if (g == 0) pend_d[r] = d;
+                }
+                nscored += (threadIdx.x == 0) ? npend : 0;
+                __syncthreads();
+
+                // ---- control phase (warp 0): admit in adjacency order, then pop until a candidate has fresh neighbours
+                if (warp == 0) {
+                    uint32_t status = 0;
+                    for (uint32_t j = 0; j < npend; ++j) {
+                        const float dj = pend_d[j];
+                        const uint32_t nj = pend[j];
+                        if (dj != dj) continue;  // NaN never enters a heap
+                        const uint32_t oj = order_bits(dj);
+                        if (len < ef || oj < worst_hi) {  // search.rs:516 (strict <)
+                            const uint64_t key = ((uint64_t)oj << 32) | ((uint64_t)nj << 1);
+                            const uint32_t pos = hlist_insert(L, len, key, lane);
+                            ++len;
+                            if (pos < lo) lo = pos;
+                            if (len > ef) {  // keep only the entries behind ef that tie with the worst result
+                                const uint32_t wd = (uint32_t)(L[ef - 1] >> 32);
+                                uint32_t keep = ef;
+                                for (uint32_t c = ef; c < len; c += 32) {
+                                    const uint32_t i = c + lane;
+                                    const bool tie = i < len && (uint32_t)(L[i] >> 32) == wd;
+                                    const uint32_t m = __ballot_sync(0xffffffffu, tie);
+                                    keep += __popc(m);
+                                    if (m != 0xffffffffu) break;
+                                }
+                                len = keep;
+                            }
+                            worst_hi = (uint32_t)(L[min(len, ef) - 1] >> 32);
+                            if (len >= p.cap) {
+                                status = 1;
+                                break;
+                            }
+                        }
+                    }
+                    uint32_t np2 = 0;
+                    bool layer_done = false;
+                    while (!status && np2 == 0) {
+                        uint32_t ci = 0xFFFFFFFFu;
+                        for (uint32_t c = lo & ~31u; c < len; c += 32) {
+                            const uint32_t i = c + lane;
+                            const bool un = i < len && i >= lo && !(L[i] & 1ull);
+                            const uint32_t m = __ballot_sync(0xffffffffu, un);
+                            if (m) {
+                                ci = c + (uint32_t)__ffs(m) - 1u;
+                                break;
+                            }
+                        }
+                        if (ci == 0xFFFFFFFFu) {  // == the reference's stop (search.rs:406-410)
+                            layer_done = true;
+                            break;
+                        }
+                        const uint64_t ck = L[ci];
+                        __syncwarp();
+                        if (lane == 0) L[ci] = ck | 1ull;
+                        __syncwarp();
+                        lo = ci + 1;
+                        const uint32_t cn = (uint32_t)(ck & 0xFFFFFFFFull) >> 1;
+                        const uint32_t* nb;
+                        uint32_t deg;
+                        if (level == 0) {
+                            nb = p.g.nbr0 + (size_t)cn * p.g.max_m0;
+                            deg = p.g.deg0[cn];
+                        } else {
+                            const size_t slot = (size_t)p.g.upper_base[cn] + (size_t)(level - 1);
+                            nb = p.g.nbrU + slot * p.g.M;
+                            deg = p.g.degU[slot];
+                        }
+                        if (vcount + deg > vlimit || ++steps > p.max_steps) {
+                            status = 1;
+                            break;
+                        }
+                        for (uint32_t i0 = 0; i0 < deg; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            uint32_t v = 0;
+                            bool isnew = false;
+                            if (i < deg) {
+                                v = nb[i];
+                                isnew = hvis_insert_smem(vt, vmask, v);
+                            }
+                            const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+                            if (isnew) pend[np2 + __popc(m & ((1u << lane) - 1u))] = v;
+                            np2 += __popc(m);
+                        }
+                        vcount += np2;
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        s_npend = np2;
+                        s_done = (layer_done || status) ? 1u : 0u;
+                        if (status) s_status = 1;
+                    }
+                    if (layer_done && !status) {  // results of this layer
+                        if (len > 0 && lane == 0) s_entry = (uint32_t)(L[0] & 0xFFFFFFFFull) >> 1;  // closest result seeds the next layer
+                        if (wide) {
+                            const uint32_t slot = slot0 + (uint32_t)level;
+                            const uint32_t cnt = min(min(len, ef), p.take);
+                            for (uint32_t i = lane; i < cnt; i += 32) p.out_keys[(size_t)slot * p.take + i] = L[i];
+                            if (lane == 0) p.out_cnt[slot] = cnt;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (s_done) break;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            p.status[q] = s_status;
+            atomicAdd(p.scored, nscored);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- linking on the device (insert.rs:408-498 for a whole batch) ---------------------------------------------------
 // The search kernel left, per (insert, layer), the sorted closest results in out_keys.  Forward edges: the new node's own
 // list is exactly its first min(cnt, maxc) results, in order.  Reverse edges: every (neighbour, layer) list receives the

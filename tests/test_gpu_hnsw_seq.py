@@ -107,3 +107,28 @@ def test_int8_index_quantised_column_equals_the_sequential_reference(vg, orc, gp
         assert agree >= 0.9
         idx.close()
         h.close()
+
+
+@pytest.mark.parametrize("elem,dims", [(F32, 384), (I8, 128)])
+def test_cta_per_query_walk_equals_the_warp_walk(vg, orc, gpu, elem, dims, monkeypatch):
+    """Few queries take hnsw_search_cta_kernel (one CTA per query: all fresh neighbours scored at once, visited set in
+    shared memory); it must return exactly what the one-warp-per-query kernel returns, ids and distance bits."""
+    n, M, efc = 30_000, 16, 100
+    v = orc.synth_rows(elem, 6, 1, n, dims, 1 if elem == F32 else 0)
+    q = orc.synth_rows(elem, 7, 1, 40, dims, 1 if elem == F32 else 0)
+    with vg.Slab(elem, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=M, ef_construction=efc, seed=3)
+        idx.rebuild()
+        for ef, k in ((10, 10), (64, 10), (200, 10), (400, 50)):
+            monkeypatch.setenv("VECGPU_HNSW_CTA_MAX_NQ", "0")
+            wr, wd, wc = idx.search(q, k, ef_search=ef)      # warp kernel
+            monkeypatch.setenv("VECGPU_HNSW_CTA_MAX_NQ", "64")
+            cr, cd, cc = idx.search(q, k, ef_search=ef)      # CTA kernel (40 queries)
+            c1 = [idx.search(q[i], k, ef_search=ef) for i in range(3)]  # and one query at a time
+            monkeypatch.delenv("VECGPU_HNSW_CTA_MAX_NQ")
+            assert np.array_equal(wr, cr) and np.array_equal(wd.view("<u4"), cd.view("<u4")) and np.array_equal(wc, cc)
+            for i in range(3):
+                assert np.array_equal(c1[i][0][0], wr[i]) and np.array_equal(c1[i][1][0].view("<u4"), wd[i].view("<u4"))
+        assert idx.device_stats()["fallbacks"] == 0
+        idx.close()
