@@ -543,13 +543,13 @@ static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) 
     // Few queries (the SQL case is ONE per MATCH): one CTA per query scores all fresh neighbours of an expansion at once and
     // keeps the visited set in shared memory (hnsw_search_cta_kernel).  Only for walks whose beam fits its tables.
     const uint32_t cta_max = env_u32("VECGPU_HNSW_CTA_MAX_NQ", 64);
-    const size_t cta_smem = (size_t)HC_VIS * 4 + (size_t)p.cap * 8 + (size_t)((h->max_m0 + 31u) & ~31u) * 8 + (size_t)s->row_stride + 64;
-    if (p.nq <= cta_max && p.node_level == nullptr && p.q_smem && cta_smem <= 200 * 1024 && p.ef_wide <= 512) {
+    const size_t cta_smem = (size_t)HC_VIS * 4 + (size_t)p.cap * 8 + (size_t)((h->max_m0 + 31u) & ~31u) * 8 + (size_t)s->row_stride * (1 + HC_ROWS) + 64;
+    if (p.nq <= cta_max && p.node_level == nullptr && p.q_smem && cta_smem <= 220 * 1024 && p.ef_wide <= 512) {
         static int cfg_dev_cta = -1;
         int dev2 = 0;
         CU(cudaGetDevice(&dev2));
         if (cfg_dev_cta != dev2) {
-            CU(cudaFuncSetAttribute(hnsw_search_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CU(cudaFuncSetAttribute(hnsw_search_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             cfg_dev_cta = dev2;
         }
         hnsw_search_cta_kernel<T><<<std::min<uint32_t>(p.nq, (uint32_t)s->num_sms), HC_THREADS, cta_smem, s->stream>>>(p);

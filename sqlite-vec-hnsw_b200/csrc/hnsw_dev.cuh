@@ -73,13 +73,17 @@ __device__ __forceinline__ bool hvis_insert(uint32_t* t, uint32_t mask, uint32_t
 // Warp-uniform arguments; returns the position.
 __device__ __forceinline__ uint32_t hlist_insert(uint64_t* L, uint32_t len, uint64_t x, int lane) {
     const uint64_t xk = x | 1ull;
-    uint32_t pos = 0;
-    for (uint32_t c = 0; c < len; c += 32) {
-        const uint32_t i = c + lane;
-        const bool lt = i < len && (L[i] | 1ull) < xk;
-        const uint32_t m = __ballot_sync(0xffffffffu, lt);
-        pos += __popc(m);
-        if (m != 0xffffffffu) break;
+    // The position is searched from the TAIL: an admitted neighbour almost always lands just ahead of the worst result, so
+    // one or two 32-entry chunks are looked at (and shifted) instead of the whole array from the front — the sorted insert
+    // was most of a single query's latency (~0.7 us each at ef = 200, thousands per query).
+    uint32_t pos = len;
+    for (int c = len ? (int)((len - 1) >> 5) : -1; c >= 0; --c) {
+        const uint32_t i = ((uint32_t)c << 5) + lane;
+        const bool gt = i < len && (L[i] | 1ull) > xk;
+        const uint32_t m = __ballot_sync(0xffffffffu, gt);
+        const uint32_t n_gt = __popc(m), valid = min(32u, len - ((uint32_t)c << 5));
+        pos -= n_gt;
+        if (n_gt < valid) break;  // this chunk holds an entry below x: everything further down is below x too
     }
     if (len > 0) {  // shift [pos, len) up by one, highest chunk first
         for (int c = (int)((len - 1) >> 5); c >= (int)(pos >> 5); --c) {
@@ -283,6 +287,12 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
 // array is flagged and answered by the other paths, exactly as before.
 static constexpr uint32_t HC_VIS = 32768;       // shared-memory visited slots (power of two)
 static constexpr uint32_t HC_THREADS = 256;
+static constexpr uint32_t HC_ROWS = 32;         // neighbour rows staged in shared memory per scoring pass
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ bool hvis_insert_smem(uint32_t* t, uint32_t mask, uint32_t key) {
     uint32_t h = (key * 2654435761u) & mask;
@@ -302,12 +312,13 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = threadIdx.x % LPR, grp = threadIdx.x / LPR;
     const uint32_t pend_cap = (p.g.max_m0 + 31u) & ~31u;
-    // layout: [visited HC_VIS x 4][L cap x 8][pend ids][pend dist][query]
+    // layout: [visited HC_VIS x 4][L cap x 8][pend ids][pend dist][query][staged rows HC_ROWS x units x 16]
     uint32_t* vt = (uint32_t*)h_smem;
     uint64_t* L = (uint64_t*)(vt + HC_VIS);
     uint32_t* pend = (uint32_t*)(L + p.cap);
     float* pend_d = (float*)(pend + pend_cap);
     uint4* sq = (uint4*)(pend_d + pend_cap);
+    uint4* srow = sq + p.units;
     __shared__ uint32_t s_q, s_npend, s_status, s_done, s_entry;
 
     while (true) {
@@ -353,19 +364,33 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
             while (true) {
                 // ---- scoring phase: one group per pending node, all groups at once
                 const uint32_t npend = s_npend;
-                for (uint32_t r = (uint32_t)grp; r < npend; r += GROUPS) {
-                    const uint32_t node = pend[r];
-                    typename T::Acc acc;
-                    T::init(acc);
-                    const uint4* b = (const uint4*)(p.b_base + (uint64_t)node * p.b_stride);
-#pragma unroll 8
-                    for (uint32_t u = g; u < p.units; u += LPR) {
-                        const uint4 x = __ldg(b + u);
-                        const uint4 qv[1] = {a[u]};
-                        T::step(acc, x, qv);
+                for (uint32_t base = 0; base < npend; base += HC_ROWS) {
+                    // every thread fires its 16-byte pieces of the <= 32 rows at once (cp.async: no registers, no waiting in
+                    // between): the whole expansion costs ONE memory round trip, not units / 4 dependent ones per lane
+                    const uint32_t nr = min(HC_ROWS, npend - base), total = nr * p.units;
+                    for (uint32_t idx = threadIdx.x; idx < total; idx += HC_THREADS) {
+                        const uint32_t r = idx / p.units, u = idx - r * p.units;
+                        cp_async16(srow + idx, (const uint4*)(p.b_base + (uint64_t)pend[base + r] * p.b_stride) + u);
                     }
-                    const float d = T::finish(acc, 0, &qc);
-                    if (g == 0) pend_d[r] = d;
+                    cp_async_wait_all();
+                    __syncthreads();
+                    for (uint32_t r0 = 0; r0 < nr; r0 += GROUPS) {  // uniform trip count: T::finish shuffles across the warp
+                        const uint32_t r = r0 + (uint32_t)grp;
+                        const bool valid = r < nr;
+                        typename T::Acc acc;
+                        T::init(acc);
+                        if (valid) {
+                            const uint4* b = srow + (size_t)r * p.units;
+#pragma unroll 4
+                            for (uint32_t u = g; u < p.units; u += LPR) {
+                                const uint4 qv[1] = {a[u]};
+                                T::step(acc, b[u], qv);
+                            }
+                        }
+                        const float d = T::finish(acc, 0, &qc);
+                        if (valid && g == 0) pend_d[base + r] = d;
+                    }
+                    __syncthreads();
                 }
                 nscored += (threadIdx.x == 0) ? npend : 0;
                 __syncthreads();
@@ -373,32 +398,42 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                 // ---- control phase (warp 0): admit in adjacency order, then pop until a candidate has fresh neighbours
                 if (warp == 0) {
                     uint32_t status = 0;
-                    for (uint32_t j = 0; j < npend; ++j) {
-                        const float dj = pend_d[j];
-                        const uint32_t nj = pend[j];
-                        if (dj != dj) continue;  // NaN never enters a heap
-                        const uint32_t oj = order_bits(dj);
-                        if (len < ef || oj < worst_hi) {  // search.rs:516 (strict <)
-                            const uint64_t key = ((uint64_t)oj << 32) | ((uint64_t)nj << 1);
-                            const uint32_t pos = hlist_insert(L, len, key, lane);
-                            ++len;
-                            if (pos < lo) lo = pos;
-                            if (len > ef) {  // keep only the entries behind ef that tie with the worst result
-                                const uint32_t wd = (uint32_t)(L[ef - 1] >> 32);
-                                uint32_t keep = ef;
-                                for (uint32_t c = ef; c < len; c += 32) {
-                                    const uint32_t i = c + lane;
-                                    const bool tie = i < len && (uint32_t)(L[i] >> 32) == wd;
-                                    const uint32_t m = __ballot_sync(0xffffffffu, tie);
-                                    keep += __popc(m);
-                                    if (m != 0xffffffffu) break;
+                    for (uint32_t j0 = 0; j0 < npend && !status; j0 += 32) {
+                        // The worst result only ever gets better, so a neighbour that fails `d < worst` NOW (with the set
+                        // full) fails when its turn comes too: those are discarded 32 at a time; the survivors are admitted
+                        // one by one, in adjacency order, re-checked against the then-current worst (search.rs:516).
+                        const uint32_t jj = j0 + lane;
+                        const float dl = jj < npend ? pend_d[jj] : __int_as_float(0x7FC00000);
+                        const uint32_t ol = order_bits(dl);
+                        const bool maybe = jj < npend && dl == dl && (len < ef || ol < worst_hi);
+                        uint32_t todo = __ballot_sync(0xffffffffu, maybe);
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const uint32_t oj = __shfl_sync(0xffffffffu, ol, src);
+                            const uint32_t nj = pend[j0 + src];
+                            if (len < ef || oj < worst_hi) {  // search.rs:516 (strict <)
+                                const uint64_t key = ((uint64_t)oj << 32) | ((uint64_t)nj << 1);
+                                const uint32_t pos = hlist_insert(L, len, key, lane);
+                                ++len;
+                                if (pos < lo) lo = pos;
+                                if (len > ef) {  // keep only the entries behind ef that tie with the worst result
+                                    const uint32_t wd = (uint32_t)(L[ef - 1] >> 32);
+                                    uint32_t keep = ef;
+                                    for (uint32_t c = ef; c < len; c += 32) {
+                                        const uint32_t i = c + lane;
+                                        const bool tie = i < len && (uint32_t)(L[i] >> 32) == wd;
+                                        const uint32_t m = __ballot_sync(0xffffffffu, tie);
+                                        keep += __popc(m);
+                                        if (m != 0xffffffffu) break;
+                                    }
+                                    len = keep;
                                 }
-                                len = keep;
-                            }
-                            worst_hi = (uint32_t)(L[min(len, ef) - 1] >> 32);
-                            if (len >= p.cap) {
-                                status = 1;
-                                break;
+                                worst_hi = (uint32_t)(L[min(len, ef) - 1] >> 32);
+                                if (len >= p.cap) {
+                                    status = 1;
+                                    break;
+                                }
                             }
                         }
                     }
@@ -426,13 +461,18 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                         lo = ci + 1;
                         const uint32_t cn = (uint32_t)(ck & 0xFFFFFFFFull) >> 1;
                         const uint32_t* nb;
-                        uint32_t deg;
+                        uint32_t deg, maxd;
+                        uint32_t first = 0;  // the first 32 neighbour ids are fetched together with the degree: one round trip
                         if (level == 0) {
                             nb = p.g.nbr0 + (size_t)cn * p.g.max_m0;
+                            maxd = p.g.max_m0;
+                            if ((uint32_t)lane < maxd) first = __ldg(nb + lane);
                             deg = p.g.deg0[cn];
                         } else {
                             const size_t slot = (size_t)p.g.upper_base[cn] + (size_t)(level - 1);
                             nb = p.g.nbrU + slot * p.g.M;
+                            maxd = p.g.M;
+                            if ((uint32_t)lane < maxd) first = nb[lane];
                             deg = p.g.degU[slot];
                         }
                         if (vcount + deg > vlimit || ++steps > p.max_steps) {
@@ -444,7 +484,7 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                             uint32_t v = 0;
                             bool isnew = false;
                             if (i < deg) {
-                                v = nb[i];
+                                v = i0 == 0 ? first : nb[i];
                                 isnew = hvis_insert_smem(vt, vmask, v);
                             }
                             const uint32_t m = __ballot_sync(0xffffffffu, isnew);
