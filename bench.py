@@ -406,7 +406,7 @@ def run_ours(args):
             sl = vg.Slab(elem, dims)
             sl.fill_synthetic(seed=4 + elem, n=n, kind=kind)
             q1 = torch.from_numpy(oracle.synth_rows(elem, 77, 1, 100, dims, kind).copy()).to(dev)
-            ms1 = timed(lambda: sl.knn_device(q1[0], k, metric, stream=stream.cuda_stream), 10)
+            ms1 = timed(lambda: sl.knn_device(q1[0], k, metric, stream=stream.cuda_stream), 30)
             gbs = n * sl.row_bytes / (ms1 / 1e3) / 1e9
             ent = {"rows": n, "single_query_ms": ms1, "single_query_qps": 1e3 / ms1, "achieved_gbs": gbs,
                    "frac_of_measured_hbm": gbs / load_peaks()[0]}
@@ -440,20 +440,26 @@ def run_ours(args):
         r5, _, _ = idx.search(q5, 10, ef_search=200)
         t_search = time.perf_counter() - t0
         sc5 = idx.stats()["distances_scored"] - sc0
-        t0 = time.perf_counter()
         idx.search(q5[:1], 10, ef_search=200)
-        t_one = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for j in range(20):
+            idx.search(q5[j + 1:j + 2], 10, ef_search=200)
+        t_one = (time.perf_counter() - t0) / 20
         er5, _, _ = sl.knn(q5[:500], 10, L2)
         rec = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(r5[:500], er5)) / er5.size
         extras["cfg5_hnsw_1m_384_l2_m16_efc200"] = {
             "rows": n5, "rebuild_s": t_build, "rebuild_vec_per_s": n5 / t_build, "distances_scored_build": st5["distances_scored"],
             "edges": st5["edges"], "search_launches_build": idx.device_stats()["launches"],
             "search20000_ef200_qps": 20000 / t_search, "search_gathered_gbs": sc5 * 384 * 4 / t_search / 1e9,
-            "single_query_ms": t_one * 1e3, "device_fallbacks": idx.device_stats()["fallbacks"],
+            "single_query_ms": t_one * 1e3, "single_query_kernel": "hnsw_search_cta_kernel (one CTA per query; mean of 20 calls of vecgpu_hnsw_search, host in / host out)",
+            "device_fallbacks": idx.device_stats()["fallbacks"],
             "recall_at_10_vs_exact_scan": rec,
-            "note": "host wall clock around vecgpu_hnsw_build / vecgpu_hnsw_search (host buffers in and out); recall on i.i.d. "
-                    "N(0,1) data with the reference's keep-closest pruning is inherently low (DESIGN.md), identical for sequential insertion",
-            "kernel": "hnsw_search_kernel (whole layered walk on the device, one warp per query)",
+            "recall_of_the_reference_procedure": "0.339 at ef=200 for a strictly sequential build of the same 1 M rows on the CPU (oracle/hnsw_seq.c, "
+                                                 "profiles/r2_hnsw_recall_cpu_sequential_1m.txt): the low recall on i.i.d. 384-d data is the algorithm's "
+                                                 "(M=16, keep-closest pruning), not the batching's; batch 1 on the GPU reproduces that graph edge for edge",
+            "expansion_batch_histogram": idx.batch_histogram(),
+            "note": "host wall clock around vecgpu_hnsw_build / vecgpu_hnsw_search (host buffers in and out)",
+            "kernel": "hnsw_search_kernel (whole layered walk on the device, one warp per query) for batches; hnsw_search_cta_kernel for <= 64 queries",
         }
         idx.close()
         sl.close()

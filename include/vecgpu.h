@@ -275,6 +275,10 @@ int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* rowids, int3
 /* Device-search counters: queries (or inserts) answered by the search kernel, how many of those hit a device capacity
  * limit and were re-run by the lockstep driver, and the number of search launches. */
 int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallbacks, uint64_t* launches);
+/* Expansion batch-size histogram of the device walks since the last rebuild started — the reference's BATCH_SIZE_1_4,
+ * _5_16, _17_32, _33_64, _65_PLUS counters (src/hnsw/search.rs:73-85, 443-455): expansions by the number of unvisited
+ * neighbours they scored. */
+int vecgpu_hnsw_batch_histogram(vecgpu_hnsw* h, uint64_t out5[5]);
 /* Edge list for a bulk write-back into {t}_{c}_hnsw_edges (src/shadow.rs:478-487; insert_edges_batch shape,
  * src/hnsw/storage.rs:346-383).  cap = 0 only counts. */
 int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* from_rowids, int64_t* to_rowids, int32_t* levels,

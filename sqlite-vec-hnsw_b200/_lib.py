@@ -51,6 +51,7 @@ SIGNATURES = {
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_entry_point": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "vecgpu_hnsw_device_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vecgpu_hnsw_batch_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_export_nodes": (C.c_int, [C.c_void_p, C.c_uint64, _p, _p, C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_export_edges": (C.c_int, [C.c_void_p, C.c_uint64, _p, _p, _p, _p, C.POINTER(C.c_uint64)]),
     "vecgpu_sharded_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, _p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),

@@ -111,6 +111,7 @@ struct vecgpu_hnsw {
     std::vector<float> distU;
     std::vector<uint16_t> degU;
     uint64_t scored = 0, rounds = 0;
+    uint64_t batch_hist[5] = {0, 0, 0, 0, 0};  // device walks: expansions by unvisited-neighbour count (search.rs:443-455 buckets)
     uint64_t slab_gen = 0;  // layout generation of the slab the graph was built over (nodes are row positions)
     std::mutex mu;
     // pinned staging + device buffers for the per-round pair lists
@@ -581,7 +582,7 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     // upload block: [a_index][out_off][node_level]   download block: [cnt][status][scored][keys]
     const size_t o_ai = 0, o_off = al(o_ai + (size_t)nq * 4), o_lvl = al(o_off + (size_t)nq * 4), up_end = al(o_lvl + nq);
     const size_t o_cnt = up_end, o_status = al(o_cnt + (size_t)n_slots * 4), o_scored = al(o_status + (size_t)nq * 4),
-                 o_next = o_scored + 8, o_keys = al(o_scored + 16), total = o_keys + (size_t)n_slots * take * 8;
+                 o_next = o_scored + 8, o_hist = o_scored + 16, o_keys = al(o_scored + 16 + 40), total = o_keys + (size_t)n_slots * take * 8;
     if ((rc = hnsw_sw_reserve(h, total))) return rc;
     uint8_t* hp = h->h_sw;
     uint8_t* dp = h->d_sw;
@@ -619,6 +620,7 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     p.out_cnt = (uint32_t*)(dp + o_cnt);
     p.status = (uint32_t*)(dp + o_status);
     p.scored = (unsigned long long*)(dp + o_scored);
+    p.hist = (unsigned long long*)(dp + o_hist);
     p.next_q = (unsigned int*)(dp + o_next);
     p.out_keys = (uint64_t*)(dp + o_keys);
     p.max_steps = 1u << 20;
@@ -640,6 +642,7 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     CU(cudaMemcpyAsync(hp + o_cnt, dp + o_cnt, (fetch_keys ? total : o_keys) - o_cnt, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     h->scored += *(const unsigned long long*)(hp + o_scored);
+    for (int b = 0; b < 5; ++b) h->batch_hist[b] += ((const unsigned long long*)(hp + o_hist))[b];
     h->rounds += 1;
     h->dev_launches += 1;
     h->dev_queries += nq;
@@ -838,6 +841,7 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     h->entry = -1;
     h->entry_level = -1;
     h->scored = h->rounds = 0;
+    for (int b = 0; b < 5; ++b) h->batch_hist[b] = 0;
     h->slab_gen = s->layout_gen;
     h->node_level.assign(n, 0);
     h->in_graph.assign(n, 0);
@@ -1191,6 +1195,17 @@ extern "C" int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* r
 
 // K6 counters: queries answered by the device search kernel, how many of them overflowed a device capacity and were
 // re-run through the lockstep driver, and the number of search launches.
+// The reference's expansion batch-size histogram (BATCH_SIZE_1_4 ... BATCH_SIZE_65_PLUS, src/hnsw/search.rs:73-85, 443-455):
+// expansions of the device walks (build and queries) by the number of unvisited neighbours they scored.
+extern "C" int vecgpu_hnsw_batch_histogram(vecgpu_hnsw* h, uint64_t out5[5]) {
+    VG_TRY
+    if (!h || !out5) return fail(VECGPU_ERR_INVALID_PARAM, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (int b = 0; b < 5; ++b) out5[b] = h->batch_hist[b];
+    return 0;
+    VG_CATCH
+}
+
 extern "C" int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallbacks, uint64_t* launches) {
     VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");

@@ -53,6 +53,8 @@ struct HSearchParams {
     uint32_t* status;            // [q]
     unsigned int* next_q;        // work counter
     unsigned long long* scored;  // distances computed
+    unsigned long long* hist;    // [5] expansions by number of unvisited neighbours scored: 1-4, 5-16, 17-32, 33-64, 65+
+                                 // (the reference's BATCH_SIZE_* counters, src/hnsw/search.rs:443-455)
     uint32_t max_steps;
     uint32_t q_smem;             // 1: each warp stages its query in shared memory (units * 16 bytes per warp)
 };
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
         uint32_t entry = p.entry;
         uint32_t status = 0;
         unsigned long long nscored = 0;
+        uint32_t hb[5] = {0, 0, 0, 0, 0};
 
         for (int level = p.entry_level; level >= 0 && !status; --level) {
             const bool wide = nlev < 0 ? level == 0 : level <= nlev;
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
                     __syncwarp();
                 }
                 if (layer_done || status) break;
+                hb[npend <= 4 ? 0 : npend <= 16 ? 1 : npend <= 32 ? 2 : npend <= 64 ? 3 : 4]++;
             }
             if (status) break;
             if (len > 0) entry = (uint32_t)(L[0] & 0xFFFFFFFFull) >> 1;  // closest result seeds the next layer
@@ -271,6 +275,9 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
         if (lane == 0) {
             p.status[q] = status;
             atomicAdd(p.scored, nscored);
+            if (p.hist)
+                for (int b = 0; b < 5; ++b)
+                    if (hb[b]) atomicAdd(p.hist + b, (unsigned long long)hb[b]);
         }
     }
 }
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
             s_status = 0;
         }
         unsigned long long nscored = 0;
+        uint32_t hb[5] = {0, 0, 0, 0, 0};  // thread 0 counts
         __syncthreads();
 
         for (int level = p.entry_level; level >= 0; --level) {
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                         s_npend = np2;
                         s_done = (layer_done || status) ? 1u : 0u;
                         if (status) s_status = 1;
+                        if (!layer_done && !status) hb[np2 <= 4 ? 0 : np2 <= 16 ? 1 : np2 <= 32 ? 2 : np2 <= 64 ? 3 : 4]++;
                     }
                     if (layer_done && !status) {  // results of this layer
                         if (len > 0 && lane == 0) s_entry = (uint32_t)(L[0] & 0xFFFFFFFFull) >> 1;  // closest result seeds the next layer
@@ -517,6 +526,9 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
         if (threadIdx.x == 0) {
             p.status[q] = s_status;
             atomicAdd(p.scored, nscored);
+            if (p.hist)
+                for (int b = 0; b < 5; ++b)
+                    if (hb[b]) atomicAdd(p.hist + b, (unsigned long long)hb[b]);
         }
         __syncthreads();
     }

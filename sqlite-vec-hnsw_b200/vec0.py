@@ -700,6 +700,13 @@ class HnswIndex:
         _check(self._lib.vecgpu_hnsw_device_stats(self._h, C.byref(q), C.byref(f), C.byref(l)))
         return dict(queries=q.value, fallbacks=f.value, launches=l.value)
 
+    def batch_histogram(self):
+        """Expansions of the device walks by number of unvisited neighbours scored (the reference's BATCH_SIZE_* buckets,
+        src/hnsw/search.rs:443-455)."""
+        h = (C.c_uint64 * 5)()
+        _check(self._lib.vecgpu_hnsw_batch_histogram(self._h, h))
+        return {"1-4": h[0], "5-16": h[1], "17-32": h[2], "33-64": h[3], "65+": h[4]}
+
     def search(self, queries, k, ef_search=200):
         """search_hnsw (src/hnsw/search.rs:267-335).  Queries are raw column vectors; cosine queries are
         normalised here (search.rs:291-293).  -> (rowids [nq,k], distances in the column's metric, counts)."""

@@ -42,6 +42,10 @@ def test_batch_of_one_build_equals_the_sequential_reference_graph(vg, orc, gpu, 
             assert got[key] == want[key], f"adjacency of node {key[0]} at level {key[1]} differs from the sequential build"
         info = h.info()
         assert idx.entry_point() == (info["entry"] + 1, info["entry_level"])
+        # the same walk step for step: the expansion batch-size histogram (search.rs:443-455 buckets) and the number of
+        # distances computed by the build are identical too
+        assert idx.batch_histogram() == info["batch_hist"]
+        assert idx.stats()["distances_scored"] == info["distances"]
         # same walk results (ids and distance bits) on the two graphs
         r, d, c = idx.search(q, 10, ef_search=64)
         orr, od = h.search(q, 10, 64)
