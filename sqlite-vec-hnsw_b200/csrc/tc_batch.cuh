@@ -66,6 +66,8 @@ struct TcParams {
     uint32_t* lockstep;    // [G][32] tile counters of the query-tile CTAs of each row group (zeroed before the launch), or NULL
     uint32_t lock_slack;   // how many tiles a peer may be behind
     uint32_t cs;           // cluster size (1, 2, 4, 8; divides QT): the CTAs of a cluster share every row tile through TMA multicast
+    uint32_t pair;         // 1 (with cs == 2, terms == 1): the two CTAs of a cluster form a tcgen05 cta_group::2 PAIR — M = 256
+                           // queries x N = 256 rows per instruction, each CTA stages its own 128 queries and HALF of the row tile
     const float* norms;    // [rows] canonical sum of squares of each slab row
     const uint8_t* skip;   // per-row skip flags or nullptr
     uint64_t* buf_keys;    // [grid][128][TC_BUF_CAP] per-thread append buffers
@@ -108,6 +110,33 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
 }
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+// ---- cta_group::2 (CTA pair) forms, validated by tools/umma2_test.cu ----
+// Both CTAs issue their own TMA loads; the bytes complete on the LEADER's mbarrier (same offset, peer bit of the
+// shared::cluster address cleared), whose owner then issues one M = 256 MMA for the pair.
+static constexpr uint32_t TC_PEER_BIT_MASK = 0xFEFFFFFFu;
+static constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((256u >> 4) << 24);  // M = 256
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(leader_bar & TC_PEER_BIT_MASK)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(TC_IDESC_PAIR), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar),
+                 "r"(rank)
                  : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -225,26 +254,34 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     uint64_t* s_bar = (uint64_t*)(s_colB + 4 * TC_N);
     uint32_t* s_tmem = (uint32_t*)(s_bar + 16);
     uint8_t* s_stage = (uint8_t*)(s_bar + 32);                     // [4 epilogue warps][2 KB] staging of half a chunk (rare path)
-    // terms == 3: two 96 KB stages [A_raw | A_lo | B_raw | B_lo]; terms == 1: four 48 KB stages [A | B], no lo-split
-    const uint32_t n_stages = p.terms == 1 ? 2 * TC_STAGES : TC_STAGES;
-    const uint32_t stage_bytes = p.terms == 1 ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
+    // terms == 3: two 96 KB stages [A_raw | A_lo | B_raw | B_lo]; terms == 1: four 48 KB stages [A | B], no lo-split;
+    // pair: six 32 KB stages [A (this CTA's 128 queries) | B half (this CTA's 128 rows of the tile)]
+    const bool pair = p.pair != 0;
+    const uint32_t n_stages = pair ? 6u : (p.terms == 1 ? 2 * TC_STAGES : TC_STAGES);
+    const uint32_t stage_bytes = pair ? TC_A_BYTES + TC_B_BYTES / 2 : (p.terms == 1 ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES);
     const uint32_t b_off = p.terms == 1 ? TC_A_BYTES : 2 * TC_A_BYTES;
-    const uint32_t bar_full_raw = smem_u32(s_bar), bar_full_lo = smem_u32(s_bar + n_stages), bar_empty = smem_u32(s_bar + 2 * n_stages),
-                   bar_tfull = smem_u32(s_bar + 3 * n_stages), bar_tempty = smem_u32(s_bar + 3 * n_stages + 2);
+    // 16 barrier slots: full_raw[n] empty[n] tfull[2] tempty[2] full_lo[n] (full_lo only exists for terms == 3, n = 2)
+    const uint32_t bar_full_raw = smem_u32(s_bar), bar_empty = smem_u32(s_bar + n_stages), bar_tfull = smem_u32(s_bar + 2 * n_stages),
+                   bar_tempty = smem_u32(s_bar + 2 * n_stages + 2), bar_full_lo = smem_u32(s_bar + 2 * n_stages + 4);
 
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (pair) {  // both CTAs of the pair allocate, same warp, same slot address
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < n_stages; ++s) {
             mbar_init(bar_full_raw + 8 * s, 1);
-            mbar_init(bar_full_lo + 8 * s, TC_XFORM_THREADS / 32);   // one arrival per transform warp
-            mbar_init(bar_empty + 8 * s, p.cs);  // tcgen05.commit of every CTA that receives the multicast row tiles
+            if (p.terms != 1) mbar_init(bar_full_lo + 8 * s, TC_XFORM_THREADS / 32);   // one arrival per transform warp
+            mbar_init(bar_empty + 8 * s, pair ? 1u : p.cs);  // tcgen05.commit of every CTA that receives the multicast row tiles (pair: ONE multicast commit)
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);     // tcgen05.commit
-            mbar_init(bar_tempty + 8 * a, 4);    // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * a, pair ? 8u : 4u);    // one arrival per epilogue warp (pair: of BOTH CTAs, on the leader's barrier)
         }
         mbar_fence_init();
     }
@@ -253,7 +290,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tc_fence_after();
     if (p.cs > 1) cluster_sync_all();  // every CTA's barriers exist before the first multicast can land
     const uint32_t tmem_base = *s_tmem;
-    const uint32_t crank = blockIdx.x % p.cs;                    // rank in the cluster (consecutive query tiles of one row group)
+    uint32_t crank = blockIdx.x % p.cs;                          // rank in the cluster (consecutive query tiles of one row group)
+    if (p.cs > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
     const uint32_t slice_rows = TC_N / p.cs;                     // rows of every tile this CTA fetches for the whole cluster
 
@@ -273,6 +311,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                     mbar_wait_b(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t base = smem_u32(smem + s * stage_bytes);
+                    if (pair) {
+                        // this CTA's 128 queries and its half of the row tile; all four loads of the pair complete on the
+                        // leader's barrier, which expects the 64 KB
+                        if (crank == 0) mbar_expect_tx(bar_full_raw + 8 * s, 2 * (TC_A_BYTES + TC_B_BYTES / 2));
+                        tma_load_2d_pair(base, &mapQ, (int)(kc * TC_KC), (int)(qt * TC_M), bar_full_raw + 8 * s);
+                        tma_load_2d_pair(base + b_off, &mapX, (int)(kc * TC_KC), row0 + (int)(crank * (TC_N / 2)), bar_full_raw + 8 * s);
+                        continue;
+                    }
                     mbar_expect_tx(bar_full_raw + 8 * s, TC_A_BYTES + TC_B_BYTES);
                     tma_load_2d(base, &mapQ, (int)(kc * TC_KC), (int)(qt * TC_M), bar_full_raw + 8 * s);
                     if (p.cs > 1)
@@ -289,7 +335,30 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         // The hi.hi MMAs of a chunk only need the TMA data, the two lo terms also need the lo-split.  While the issuer
         // waits for the lo-split of chunk `it` it opportunistically issues hi.hi of chunk it+1 as soon as that chunk's
         // data has landed (non-blocking probes), so the tensor pipe has work during the transform.
-        if (lane == 0 && p.terms == 1) {
+        if (pair) {
+            // CTA pair: only the leader issues; one instruction covers the pair's 256 queries x the tile's 256 rows, reading
+            // each CTA's A tile and B half from that CTA's shared memory — per SM and K-step 8 KB are written by TMA and 8 KB
+            // read by the tensor core instead of 12 + 12 (the single-CTA form is bound by exactly that shared-memory traffic)
+            if (lane == 0 && crank == 0) {
+                uint32_t it = 0;
+                for (uint32_t ti = 0; ti < my_tiles; ++ti) {
+                    const uint32_t acc = ti & 1, aph = (ti >> 1) & 1;
+                    mbar_wait_b(bar_tempty + 8 * acc, aph ^ 1);  // the epilogue warps of BOTH CTAs have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TC_N;
+                    for (uint32_t kc = 0; kc < p.nk; ++kc, ++it) {
+                        const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
+                        const uint32_t a = smem_u32(smem + s * stage_bytes), b = a + b_off;
+                        mbar_wait_b(bar_full_raw + 8 * s, ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t k = 0; k < TC_KSTEPS; ++k) umma2_tf32(d_tmem, umma_desc(a + k * 32), umma_desc(b + k * 32), (kc | k) != 0);
+                        umma2_commit_mc(bar_empty + 8 * s, 0b11);  // both producers may refill the stage
+                    }
+                    umma2_commit_mc(bar_tfull + 8 * acc, 0b11);   // both CTAs' epilogues may read their half of the accumulator
+                }
+            }
+        } else if (lane == 0 && p.terms == 1) {
             // single TF32 pass: the operands are used as they are (the tensor core truncates them to TF32); the wider
             // error bound is paid for by a slightly larger certified candidate set, not by two more MMAs
             uint32_t it = 0;
@@ -498,7 +567,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (lane == 0) {
+                if (pair && crank != 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);  // the leader's MMA warp owns the pair's accumulators
+                else mbar_arrive(bar_tempty + 8 * acc);
+            }
         }
         // final compaction of every lane's buffer -> the kp best (score, row) of this (CTA, query) in the layout
         // tc_collect_kernel reads; a list that holds kp entries reports its largest kept score as its drop bound
@@ -524,7 +596,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (p.cs > 1) cluster_sync_all();  // peers may still arrive on this CTA's barriers until they are done too
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (warp == 1) {
+        if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
 }
 
 // canonical sum of squares of every row (the b2 / a2 of F32Cos), the maximum over the safe rows, and the list

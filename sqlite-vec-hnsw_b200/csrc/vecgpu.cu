@@ -1379,6 +1379,11 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             const uint32_t want = std::min(8u, env_u32("VECGPU_TC_CLUSTER", 1));
             while (cs * 2 <= want && QT % (cs * 2) == 0) cs *= 2;
         }
+        // CTA PAIRS (tcgen05 cta_group::2): two consecutive query tiles of a row group share every row tile — M = 256 per
+        // instruction, each SM stages its own 128 queries and half of the rows.  The single-CTA form is bound by shared-memory
+        // traffic (TMA writes + tensor-core reads of 12 KB each per K-step against ~128 B/clk); the pair moves 8 + 8 KB.
+        const bool pair = env_u32("VECGPU_TC_TERMS", 1) != 3 && QT % 2 == 0 && env_u32("VECGPU_TC_PAIR", 1) != 0 && cs == 1;
+        if (pair) cs = 2;
         if (cs > 1) {
             cudaLaunchConfig_t occ{};
             occ.gridDim = dim3(QT * G);
@@ -1446,6 +1451,7 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             tp.lock_slack = env_u32("VECGPU_TC_LOCKSLACK", 0);
         }
         tp.cs = cs;
+        tp.pair = pair ? 1u : 0u;
         if (cs > 1) {
             CUtensorMap mapXs;  // row-tile slices of TC_N / cs rows
             if ((rc = make_f32_map(&mapXs, s->d_vec, s->dims, s->rows, s->row_stride, TC_N / cs))) return rc;
