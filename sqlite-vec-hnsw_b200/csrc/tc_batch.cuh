@@ -242,6 +242,9 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* buf, uint32_t cnt, uint3
                  :                                                                                                         \
                  : "memory")
 
+// PAIR = true is the cta_group::2 instantiation: it must be launched with a cluster of exactly two CTAs (a kernel that contains
+// cta_group::2 instructions cannot be launched without a cluster at all, so the two forms are separate kernels).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapX, const TcParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -256,7 +259,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     uint8_t* s_stage = (uint8_t*)(s_bar + 32);                     // [4 epilogue warps][2 KB] staging of half a chunk (rare path)
     // terms == 3: two 96 KB stages [A_raw | A_lo | B_raw | B_lo]; terms == 1: four 48 KB stages [A | B], no lo-split;
     // pair: six 32 KB stages [A (this CTA's 128 queries) | B half (this CTA's 128 rows of the tile)]
-    const bool pair = p.pair != 0;
+    constexpr bool pair = PAIR;
     const uint32_t n_stages = pair ? 6u : (p.terms == 1 ? 2 * TC_STAGES : TC_STAGES);
     const uint32_t stage_bytes = pair ? TC_A_BYTES + TC_B_BYTES / 2 : (p.terms == 1 ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES);
     const uint32_t b_off = p.terms == 1 ? TC_A_BYTES : 2 * TC_A_BYTES;
@@ -265,7 +268,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                    bar_tempty = smem_u32(s_bar + 2 * n_stages + 2), bar_full_lo = smem_u32(s_bar + 2 * n_stages + 4);
 
     if (warp == 1) {
-        if (pair) {  // both CTAs of the pair allocate, same warp, same slot address
+        if constexpr (pair) {  // both CTAs of the pair allocate, same warp, same slot address
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
@@ -311,7 +314,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1;
                     mbar_wait_b(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t base = smem_u32(smem + s * stage_bytes);
-                    if (pair) {
+                    if constexpr (pair) {
                         // this CTA's 128 queries and its half of the row tile; all four loads of the pair complete on the
                         // leader's barrier, which expects the 64 KB
                         if (crank == 0) mbar_expect_tx(bar_full_raw + 8 * s, 2 * (TC_A_BYTES + TC_B_BYTES / 2));
@@ -335,7 +338,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         // The hi.hi MMAs of a chunk only need the TMA data, the two lo terms also need the lo-split.  While the issuer
         // waits for the lo-split of chunk `it` it opportunistically issues hi.hi of chunk it+1 as soon as that chunk's
         // data has landed (non-blocking probes), so the tensor pipe has work during the transform.
-        if (pair) {
+        if constexpr (pair) {
             // CTA pair: only the leader issues; one instruction covers the pair's 256 queries x the tile's 256 rows, reading
             // each CTA's A tile and B half from that CTA's shared memory — per SM and K-step 8 KB are written by TMA and 8 KB
             // read by the tensor core instead of 12 + 12 (the single-CTA form is bound by exactly that shared-memory traffic)
@@ -568,8 +571,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (pair && crank != 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);  // the leader's MMA warp owns the pair's accumulators
-                else mbar_arrive(bar_tempty + 8 * acc);
+                if constexpr (pair) {
+                    if (crank != 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);  // the leader's MMA warp owns the pair's accumulators
+                    else mbar_arrive(bar_tempty + 8 * acc);
+                } else {
+                    mbar_arrive(bar_tempty + 8 * acc);
+                }
             }
         }
         // final compaction of every lane's buffer -> the kp best (score, row) of this (CTA, query) in the layout
@@ -597,7 +604,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     __syncthreads();
     if (p.cs > 1) cluster_sync_all();  // peers may still arrive on this CTA's barriers until they are done too
     if (warp == 1) {
-        if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }

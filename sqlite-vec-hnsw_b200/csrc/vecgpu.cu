@@ -1353,7 +1353,8 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
     const uint32_t kp = ((k + 32 + 7) / 8) * 8;
     const size_t smem = TC_STAGES * TC_STAGE_BYTES + 2 * 4 * TC_N * 4 + 32 * 8 + 4 * 2048 + 1024;  // stages, per-warp coefficients, barriers, rare-path staging, alignment slack
     if (cfg_dev != dev) {
-        CU(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        CU(cudaFuncSetAttribute(tc_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+        CU(cudaFuncSetAttribute(tc_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         CU(cudaFuncSetAttribute(tc_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CU(cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         cfg_dev = dev;
@@ -1379,10 +1380,13 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             const uint32_t want = std::min(8u, env_u32("VECGPU_TC_CLUSTER", 1));
             while (cs * 2 <= want && QT % (cs * 2) == 0) cs *= 2;
         }
-        // CTA PAIRS (tcgen05 cta_group::2): two consecutive query tiles of a row group share every row tile — M = 256 per
-        // instruction, each SM stages its own 128 queries and half of the rows.  The single-CTA form is bound by shared-memory
-        // traffic (TMA writes + tensor-core reads of 12 KB each per K-step against ~128 B/clk); the pair moves 8 + 8 KB.
-        const bool pair = env_u32("VECGPU_TC_TERMS", 1) != 3 && QT % 2 == 0 && env_u32("VECGPU_TC_PAIR", 1) != 0 && cs == 1;
+        // CTA PAIRS (tcgen05 cta_group::2, VECGPU_TC_PAIR=1): two consecutive query tiles of a row group share every row tile —
+        // M = 256 per instruction, each SM stages its own 128 queries and half of the rows (8 + 8 KB of shared-memory traffic
+        // per K-step instead of 12 + 12).  Implemented, exact and tested, but measured NO faster on 1024 x 10 M x 768
+        // (25.7 vs 25.6 ms, profiles/r2_tc_pair_perf.txt): the batch runs under the 1 kW power cap — even a pure MMA loop over
+        // resident operands drops from 1117 to ~1050 TFLOP/s within half a second as the SM clock falls from 1965 to
+        // 1665 MHz (profiles/r2_mma_peak_long.txt) — so halving the operand traffic does not buy throughput.  Off by default.
+        bool pair = env_u32("VECGPU_TC_TERMS", 1) != 3 && QT % 2 == 0 && env_u32("VECGPU_TC_PAIR", 0) != 0 && cs == 1;
         if (pair) cs = 2;
         if (cs > 1) {
             cudaLaunchConfig_t occ{};
@@ -1396,9 +1400,10 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             occ.attrs = &oa;
             occ.numAttrs = 1;
             int max_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_scan_kernel, &occ) != cudaSuccess || max_clusters < 1) {
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, pair ? tc_scan_kernel<true> : tc_scan_kernel<false>, &occ) != cudaSuccess || max_clusters < 1) {
                 cudaGetLastError();
                 cs = 1;
+                pair = false;
             } else {
                 // all clusters must be co-resident (one wave): fewer row groups when the GPCs cannot hold QT*G/cs clusters
                 G = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(G, (uint64_t)max_clusters * cs / QT));
@@ -1467,9 +1472,10 @@ static int knn_tc(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq_all, uint32_t 
             la.val.clusterDim.y = la.val.clusterDim.z = 1;
             lc.attrs = &la;
             lc.numAttrs = 1;
-            CU(cudaLaunchKernelEx(&lc, tc_scan_kernel, mapQ, mapXs, tp));
+            if (pair) CU(cudaLaunchKernelEx(&lc, tc_scan_kernel<true>, mapQ, mapXs, tp));
+            else CU(cudaLaunchKernelEx(&lc, tc_scan_kernel<false>, mapQ, mapXs, tp));
         } else {
-            tc_scan_kernel<<<grid, TC_THREADS, smem, st>>>(mapQ, mapX, tp);
+            tc_scan_kernel<false><<<grid, TC_THREADS, smem, st>>>(mapQ, mapX, tp);
         }
         LAUNCHED();
 

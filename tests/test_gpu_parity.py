@@ -516,6 +516,26 @@ def test_tc_batched_cluster_multicast_matches_oracle(vg, orc, gpu, tc_terms, clu
         del os.environ["VECGPU_TC_CLUSTER"]
 
 
+@pytest.mark.parametrize("metric", [L2, COSINE], ids=["l2", "cos"])
+@pytest.mark.parametrize("dims,nq,k", [(768, 130, 10), (100, 256, 5), (384, 1000, 32), (64, 300, 96)])
+def test_tc_batched_cta_pairs_match_oracle(vg, orc, gpu, metric, dims, nq, k, monkeypatch):
+    """VECGPU_TC_PAIR=1: tcgen05 cta_group::2 — two CTAs share one M = 256 MMA, each staging its own 128 queries and half of
+    the row tile (pair TMA loads completing on the leader's mbarrier, multicast commits, remote accumulator release).  Same
+    exact results; an odd number of query tiles (nq = 300 -> 3 tiles) falls back to single CTAs."""
+    monkeypatch.setenv("VECGPU_TC_PAIR", "1")
+    n = 20_000
+    v = random_rows(F32, n, dims, seed=101)
+    q = random_rows(F32, nq, dims, seed=102)
+    with vg.Slab(F32, dims) as s:
+        s.load(v)
+        tc0 = vg.tc_stats()
+        r, d, c = s.knn(q, k, metric)
+        tc1 = vg.tc_stats()
+        assert tc1[0] - tc0[0] == nq and tc1[1] == tc0[1]
+    er, ed, ec = orc.knn_select(F32, dims, v, q, k, metric)
+    assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+
+
 def test_small_batches_take_the_cuda_core_route(vg, orc, gpu):
     # default routing: 32 queries x 20 k rows is below the tensor-core work threshold -> exact multi-query scan, same results
     n, dims, nq, k = 20000, 64, 32, 10

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int iters, unsigned lo
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+extern int g_iters;
 template <int KIND>
 static void run(const char* name, double ops_per_mma, const char* unit) {
     int* d_err;
@@ -94,7 +95,7 @@ static void run(const char* name, double ops_per_mma, const char* unit) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaFuncSetAttribute(mma_peak_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     for (int rep = 0; rep < 4; ++rep) {
-        const int iters = rep == 0 ? 64 : 4096;
+        const int iters = rep == 0 ? 64 : g_iters;
         cudaEvent_t a, b;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
@@ -112,7 +113,9 @@ static void run(const char* name, double ops_per_mma, const char* unit) {
     }
 }
 
-int main() {
+int g_iters = 4096;
+int main(int argc, char** argv) {
+    if (argc > 1) g_iters = atoi(argv[1]);  // e.g. 200000 for a ~0.5 s launch: shows the rate under the power cap
     run<0>("kind::tf32 K=8 ", 2.0 * 128 * 256 * 8, "TFLOP/s");
     run<1>("kind::i8   K=32", 2.0 * 128 * 256 * 32, "TOP/s");
     return 0;
