@@ -21,6 +21,7 @@
 #include <string>
 #include <utility>
 #include <variant>
+#include <array>
 #include <vector>
 
 #include "vecgpu.h"
@@ -221,6 +222,17 @@ public:
     }
     vecgpu_slab* raw() { return h_; }
     size_t row_bytes() const { return vecgpu::row_bytes(vec_type, dims); }
+    // The STORED representation of this column for an HNSW index (src/hnsw/insert.rs:300-322): normalised for cosine
+    // columns, quantize_int8_for_index'ed with index_quantization=int8.  nullptr when neither applies (this slab is it).
+    Result<std::unique_ptr<Slab>> stored_for_hnsw(bool normalize_vectors, bool int8_quantization) {
+        vecgpu_slab* out = nullptr;
+        int rc = vecgpu_hnsw_stored_slab(h_, normalize_vectors ? 1 : 0, int8_quantization ? 1 : 0, &out);
+        if (rc) return Error::from_status(rc);
+        if (!out) return std::unique_ptr<Slab>();
+        auto s = std::make_unique<Slab>(int8_quantization ? VectorType::Int8 : VectorType::Float32, dims);
+        s->h_ = out;
+        return s;
+    }
     Result<Unit> load(const int64_t* rowids, const void* vectors, uint64_t n) {
         int rc = vecgpu_slab_load(h_, rowids, vectors, n);
         if (rc) return Error::from_status(rc);
@@ -276,6 +288,65 @@ inline Result<std::vector<std::pair<int64_t, float>>> brute_force_search(Slab& s
     return out;
 }
 
+// ---- ShardedSlab: one column split by contiguous rowid range over the GPUs of the box (one process) ------------
+// Same calls as Slab; a query scans every shard and the shards exchange + merge their top-k over NVLink peer memory.
+class ShardedSlab {
+    vecgpu_sharded* h_ = nullptr;
+
+public:
+    VectorType vec_type;
+    size_t dims;
+    ShardedSlab(VectorType t, size_t d) : vec_type(t), dims(d) {}
+    ShardedSlab(const ShardedSlab&) = delete;
+    ShardedSlab& operator=(const ShardedSlab&) = delete;
+    ~ShardedSlab() { if (h_) vecgpu_sharded_destroy(h_); }
+    // devices empty: every visible device; a device may appear more than once (several shards on one GPU)
+    static Result<std::unique_ptr<ShardedSlab>> create(VectorType t, size_t dims, const std::vector<int>& devices = {},
+                                                       uint64_t capacity_hint_total = 0, uint32_t max_queries = 0, uint32_t max_k = 0) {
+        auto s = std::make_unique<ShardedSlab>(t, dims);
+        int rc = vecgpu_sharded_create((int)t, (uint32_t)dims, capacity_hint_total, devices.empty() ? nullptr : devices.data(),
+                                       (uint32_t)devices.size(), max_queries, max_k, &s->h_);
+        if (rc) return Error::from_status(rc);
+        return s;
+    }
+    size_t row_bytes() const { return vecgpu::row_bytes(vec_type, dims); }
+    uint32_t num_shards() const { return vecgpu_sharded_num_shards(h_); }
+    Result<Unit> load(const int64_t* rowids, const void* vectors, uint64_t n) {
+        int rc = vecgpu_sharded_load(h_, rowids, vectors, n);
+        if (rc) return Error::from_status(rc);
+        return Unit{};
+    }
+    Result<Unit> upsert(int64_t rowid, const std::vector<uint8_t>& blob) {
+        int rc = vecgpu_sharded_upsert(h_, rowid, blob.empty() ? (const void*)"" : blob.data(), (uint32_t)blob.size());
+        if (rc) return Error::from_status(rc);
+        return Unit{};
+    }
+    Result<Unit> remove(int64_t rowid) {
+        int rc = vecgpu_sharded_delete(h_, rowid);
+        if (rc) return Error::from_status(rc);
+        return Unit{};
+    }
+    uint64_t live_rows() const {
+        uint64_t rows = 0, live = 0;
+        vecgpu_sharded_count(h_, &rows, &live);
+        return live;
+    }
+    // brute_force_search (src/vtab.rs:2573-2623) over all shards
+    Result<std::vector<std::pair<int64_t, float>>> brute_force_search(const std::vector<uint8_t>& query_vector, size_t k, DistanceMetric distance_metric) {
+        std::vector<std::pair<int64_t, float>> out;
+        if (query_vector.size() != row_bytes()) return out;
+        const uint32_t kk = (uint32_t)std::min<uint64_t>(k, live_rows());
+        if (!vecgpu_metric_supported((int)vec_type, (int)distance_metric) || kk == 0) return out;
+        std::vector<int64_t> rowids(kk);
+        std::vector<float> dists(kk);
+        uint32_t count = 0;
+        int rc = vecgpu_sharded_knn(h_, query_vector.data(), 1, kk, (int)distance_metric, rowids.data(), dists.data(), &count);
+        if (rc) return Error::from_status(rc);
+        for (uint32_t i = 0; i < count; ++i) out.emplace_back(rowids[i], dists[i]);
+        return out;
+    }
+};
+
 // ---- HnswIndex ------------------------------------------------------------------------------------------------
 class HnswIndex {
     vecgpu_hnsw* h_ = nullptr;
@@ -309,6 +380,13 @@ public:
         std::vector<std::pair<int64_t, float>> out;
         for (uint32_t i = 0; i < count; ++i) out.emplace_back(rowids[i], convert_distance_for_output(metric_, normalize_, dists[i]));
         return out;
+    }
+    // BATCH_SIZE_1_4 / _5_16 / _17_32 / _33_64 / _65_PLUS (src/hnsw/search.rs:73-85): expansions by neighbours scored
+    Result<std::array<uint64_t, 5>> batch_histogram() {
+        std::array<uint64_t, 5> h{};
+        int rc = vecgpu_hnsw_batch_histogram(h_, h.data());
+        if (rc) return Error::from_status(rc);
+        return h;
     }
     // HnswMetadata.entry_point_rowid / entry_point_level (src/hnsw/mod.rs:97-103); (-1, -1) when empty
     Result<std::pair<int64_t, int32_t>> entry_point() {

@@ -544,16 +544,26 @@ static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) 
     // Few queries (the SQL case is ONE per MATCH): one CTA per query scores all fresh neighbours of an expansion at once and
     // keeps the visited set in shared memory (hnsw_search_cta_kernel).  Only for walks whose beam fits its tables.
     const uint32_t cta_max = env_u32("VECGPU_HNSW_CTA_MAX_NQ", 64);
-    const size_t cta_smem = (size_t)HC_VIS * 4 + (size_t)p.cap * 8 + (size_t)((h->max_m0 + 31u) & ~31u) * 8 + (size_t)s->row_stride * (1 + HC_ROWS) + 64;
+    // visited slots: a walk touches ~ef x 30 nodes; 16 K slots (at most 3/4 used) cover ef <= 256 and leave room for the second row buffer
+    p.cta_vis = p.ef_wide <= 256 ? 16384u : HC_VIS;
+    size_t cta_smem = (size_t)p.cta_vis * 4 + (size_t)p.cap * 16 + (size_t)((h->max_m0 + 31u) & ~31u) * 12 + (size_t)s->row_stride * (1 + HC_ROWS) + 64;
+    p.spec_rows = 0;
+    if (p.prefetch && env_u32("VECGPU_HNSW_SPEC_ROWS", 1) && cta_smem + (size_t)s->row_stride * HC_ROWS <= 220 * 1024) {
+        p.spec_rows = 1;
+        cta_smem += (size_t)s->row_stride * HC_ROWS;
+    }
     if (p.nq <= cta_max && p.node_level == nullptr && p.q_smem && cta_smem <= 220 * 1024 && p.ef_wide <= 512) {
         static int cfg_dev_cta = -1;
         int dev2 = 0;
         CU(cudaGetDevice(&dev2));
         if (cfg_dev_cta != dev2) {
-            CU(cudaFuncSetAttribute(hnsw_search_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            CU(cudaFuncSetAttribute(hnsw_search_cta_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            CU(cudaFuncSetAttribute(hnsw_search_cta_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             cfg_dev_cta = dev2;
         }
-        hnsw_search_cta_kernel<T><<<std::min<uint32_t>(p.nq, (uint32_t)s->num_sms), HC_THREADS, cta_smem, s->stream>>>(p);
+        const uint32_t cta_grid = std::min<uint32_t>(p.nq, (uint32_t)s->num_sms);
+        if (p.prof) hnsw_search_cta_kernel<T, true><<<cta_grid, HC_THREADS, cta_smem, s->stream>>>(p);
+        else hnsw_search_cta_kernel<T, false><<<cta_grid, HC_THREADS, cta_smem, s->stream>>>(p);
         LAUNCHED();
         return 0;
     }
@@ -582,7 +592,7 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     // upload block: [a_index][out_off][node_level]   download block: [cnt][status][scored][keys]
     const size_t o_ai = 0, o_off = al(o_ai + (size_t)nq * 4), o_lvl = al(o_off + (size_t)nq * 4), up_end = al(o_lvl + nq);
     const size_t o_cnt = up_end, o_status = al(o_cnt + (size_t)n_slots * 4), o_scored = al(o_status + (size_t)nq * 4),
-                 o_next = o_scored + 8, o_hist = o_scored + 16, o_keys = al(o_scored + 16 + 40), total = o_keys + (size_t)n_slots * take * 8;
+                 o_next = o_scored + 8, o_hist = o_scored + 16, o_prof = o_hist + 40, o_keys = al(o_prof + 160), total = o_keys + (size_t)n_slots * take * 8;
     if ((rc = hnsw_sw_reserve(h, total))) return rc;
     uint8_t* hp = h->h_sw;
     uint8_t* dp = h->d_sw;
@@ -621,6 +631,10 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     p.status = (uint32_t*)(dp + o_status);
     p.scored = (unsigned long long*)(dp + o_scored);
     p.hist = (unsigned long long*)(dp + o_hist);
+    p.batch_admit = env_u32("VECGPU_HNSW_BATCH_ADMIT", 1);
+    p.prefetch = env_u32("VECGPU_HNSW_PREFETCH", 1);
+    const bool prof = getenv("VECGPU_HNSW_TIMING") != nullptr;
+    p.prof = prof ? (unsigned long long*)(dp + o_prof) : nullptr;
     p.next_q = (unsigned int*)(dp + o_next);
     p.out_keys = (uint64_t*)(dp + o_keys);
     p.max_steps = 1u << 20;
@@ -643,6 +657,13 @@ static int hnsw_dev_search(vecgpu_hnsw* h, const uint8_t* a_base, const uint32_t
     CU(cudaStreamSynchronize(s->stream));
     h->scored += *(const unsigned long long*)(hp + o_scored);
     for (int b = 0; b < 5; ++b) h->batch_hist[b] += ((const unsigned long long*)(hp + o_hist))[b];
+    if (prof) {
+        const unsigned long long* pf = (const unsigned long long*)(hp + o_prof);
+        if (pf[0] | pf[1] | pf[2] | pf[3])
+            fprintf(stderr, "[vecgpu] hnsw CTA walk, %u queries, cycles: row fetch %llu, scoring %llu, admission %llu, pop+adjacency+visited %llu; admission batches merged %llu, one by one %llu; expansions with rows staged ahead %llu of %llu; admission split: prediction %llu, ranks %llu, placement %llu, finish %llu; since the end of scoring (summed): helper released %llu, "
+                    "helper list ready %llu, helper copies issued %llu, warp 0 at the end barrier %llu, barrier passed %llu, rows landed %llu\n",
+                    nq, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], pf[8], pf[9], pf[10], pf[11], pf[12], pf[13], pf[14], pf[15], pf[16], pf[17]);
+    }
     h->rounds += 1;
     h->dev_launches += 1;
     h->dev_queries += nq;

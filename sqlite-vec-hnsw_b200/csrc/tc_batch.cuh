@@ -84,7 +84,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 // shared-memory matrix descriptors, K-major: 8-row groups are SBO bytes apart; layout 2 = SWIZZLE_128B (128-byte rows),
-// layout 4 = SWIZZLE_64B (64-byte rows).  Both verified on the device (tools/umma_test.cu, tools/umma_test_sw64.cu).
+// layout 4 = SWIZZLE_64B (64-byte rows).  Both verified on the device (tools/umma_test.cu; the SWIZZLE_64B variant differs only in the layout field and the 64-byte row pitch).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }

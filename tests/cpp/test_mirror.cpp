@@ -131,6 +131,49 @@ int main() {
         delete idx;
         delete slab;
     }
+    // ---- stored representation (src/hnsw/insert.rs:300-322) + index_quantization=int8 (src/vector.rs:554-575)
+    {
+        auto col = Slab::create(VectorType::Float32, 3).unwrap().release();
+        const float rows[12] = {2, 0, 0, 4, 3, 0, 0, 0, 5, 0, 0, 0};  // raw column values; row 4 is a zero vector
+        CHECK(col->load(nullptr, rows, 4).is_ok());
+        auto none = col->stored_for_hnsw(false, false);
+        CHECK(none.is_ok() && none.unwrap() == nullptr);
+        auto st = col->stored_for_hnsw(true, false).unwrap().release();  // normalised; the zero vector cannot be stored
+        CHECK(st && st->vec_type == VectorType::Float32 && st->live_rows() == 3);
+        auto idx = HnswIndex::create(*st, DistanceMetric::Cosine).unwrap().release();
+        CHECK(idx->rebuild().is_ok());
+        auto res = idx->search(blob_f32({1, 0, 0}), 2).unwrap();
+        CHECK(res.size() == 2 && res[0].first == 1 && res[1].first == 2 && std::fabs(res[1].second - 0.2f) < 1e-5f);
+        auto hist = idx->batch_histogram().unwrap();
+        CHECK(hist[0] + hist[1] + hist[2] + hist[3] + hist[4] > 0 && hist[4] == 0);
+        auto q8 = col->stored_for_hnsw(true, true).unwrap().release();
+        CHECK(q8 && q8->vec_type == VectorType::Int8 && q8->row_bytes() == 3);
+        auto sc = q8->score({127, 0, 0}, {1, 2}, DistanceMetric::L2).unwrap();       // (127,0,0) and round((.8,.6,0)*127) = (102,76,0)
+        CHECK(sc[0] == 0.0f && std::fabs(sc[1] - std::sqrt(25.0f * 25.0f + 76.0f * 76.0f)) < 1e-4f);
+        delete idx;
+        delete q8;
+        delete st;
+        delete col;
+    }
+    // ---- a column sharded by rowid range (two shards on device 0): same answers as one slab
+    {
+        auto sh = ShardedSlab::create(VectorType::Float32, 3, {0, 0}).unwrap().release();
+        auto one = Slab::create(VectorType::Float32, 3).unwrap().release();
+        std::vector<float> rows;
+        for (int i = 1; i <= 40; ++i) { rows.push_back((float)(i % 7)); rows.push_back((float)(i % 5) + 1); rows.push_back((float)i * 0.25f); }
+        CHECK(sh->load(nullptr, rows.data(), 40).is_ok() && one->load(nullptr, rows.data(), 40).is_ok());
+        CHECK(sh->num_shards() == 2 && sh->live_rows() == 40);
+        CHECK(sh->remove(7).is_ok() && one->remove(7).is_ok());
+        CHECK(sh->upsert(33, blob_f32({1, 2, 3})).is_ok() && one->upsert(33, blob_f32({1, 2, 3})).is_ok());
+        for (auto m : {DistanceMetric::L2, DistanceMetric::Cosine, DistanceMetric::L1}) {
+            auto a = sh->brute_force_search(blob_f32({1, 2, 3}), 12, m).unwrap();
+            auto b = brute_force_search(*one, blob_f32({1, 2, 3}), 12, m).unwrap();
+            CHECK(a.size() == 12 && a == b);
+        }
+        CHECK(sh->brute_force_search(blob_f32({1, 2}), 5, DistanceMetric::L2).unwrap().empty());
+        delete one;
+        delete sh;
+    }
     if (g_fail) std::printf("FAILED %d checks (%d passed)\n", g_fail, g_pass);
     else std::printf("ALL_PASSED %d checks\n", g_pass);
     return g_fail ? 1 : 0;
