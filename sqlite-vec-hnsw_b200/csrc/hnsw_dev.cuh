@@ -65,6 +65,7 @@ struct HSearchParams {
 };
 
 static constexpr uint32_t HV_EMPTY = 0xFFFFFFFFu;
+static constexpr uint32_t HV_TOMB = 0xFFFFFFFEu;  // a slot given back (never matches a node id, never reused)
 
 __device__ __forceinline__ bool hvis_insert(uint32_t* t, uint32_t mask, uint32_t key) {  // true if newly inserted
     uint32_t h = (key * 2654435761u) & mask;
@@ -105,54 +106,6 @@ __device__ __forceinline__ uint32_t hlist_insert(uint64_t* L, uint32_t len, uint
     if (lane == 0) L[pos] = x;
     __syncwarp();
     return pos;
-}
-
-// Batch admission: merge up to 32 new keys (one per lane; `has` false = none) into the sorted array in ONE pass, writing
-// the merged array to the spare buffer L2 (then the two swap).  The reference admits neighbours one by one against a worst
-// result that moves (search.rs:516); when no two distances tie at the cut after ef entries the outcome is simply the first
-// ef entries of the merge, whatever the order — that is what this computes.  With a tie AT THE CUT the outcome depends on
-// the order of admission, so nothing is changed and false is returned: the caller replays the batch one by one
-// (hlist_insert).  Every key's final position is its rank: new key = (entries of L below it) + (new keys below it), old
-// entries take the remaining positions in order.
-__device__ __forceinline__ bool hlist_merge32(uint64_t*& L, uint64_t*& L2, uint32_t& len, uint32_t& lo, uint32_t ef, uint64_t key, bool has,
-                                              int lane) {
-    const uint32_t m = __ballot_sync(0xffffffffu, has);
-    const uint32_t n = __popc(m);
-    const uint64_t xk = key | 1ull;
-    uint32_t r_new = 0;
-    for (uint32_t t = m; t; t &= t - 1) {
-        const uint64_t kb = __shfl_sync(0xffffffffu, key, __ffs(t) - 1);
-        r_new += kb < key ? 1u : 0u;  // nodes are unique: no equal keys
-    }
-    uint32_t r_old = 0;
-    if (has) {  // lower bound of the key in L
-        uint32_t a = 0, b = len;
-        while (a < b) {
-            const uint32_t mid = (a + b) >> 1;
-            if ((L[mid] | 1ull) < xk) a = mid + 1;
-            else b = mid;
-        }
-        r_old = a;
-    }
-    const uint32_t pos = r_old + r_new;  // final position of this lane's key (distinct over the lanes)
-    const uint32_t total = len + n, out_n = min(total, ef + 1u);  // entries [0, ef] are all that can matter
-    if (has && pos < out_n) L2[pos] = key;
-    // old entries fill the remaining output positions in order: output t takes L[t - (new keys placed below t)]
-    for (uint32_t bo = 0; bo < out_n; bo += 32) {
-        const uint32_t rel = pos - bo;
-        const uint32_t mask_new = __reduce_or_sync(0xffffffffu, (has && rel < 32u) ? (1u << rel) : 0u);
-        const uint32_t below = __popc(__ballot_sync(0xffffffffu, has && pos < bo));
-        const uint32_t t = bo + lane;
-        if (!((mask_new >> lane) & 1u) && t < out_n) L2[t] = L[t - below - __popc(mask_new & ((1u << lane) - 1u))];
-    }
-    __syncwarp();
-    if (total > ef && (uint32_t)(L2[ef - 1] >> 32) == (uint32_t)(L2[ef] >> 32)) return false;  // tie at the cut: order matters
-    len = min(total, ef);
-    lo = min(lo, __reduce_min_sync(0xffffffffu, has ? pos : 0xFFFFFFFFu));
-    uint64_t* t = L;
-    L = L2;
-    L2 = t;
-    return true;
 }
 
 template <class T>
@@ -336,15 +289,32 @@ __global__ void __launch_bounds__(256) hnsw_search_kernel(const HSearchParams p)
 }
 
 // ---- K6c: the same walk with ONE CTA per query — the latency form (few queries: SQL issues one per MATCH, src/vtab.rs:2249) ----
-// A lone warp spends most of an expansion waiting: its <= 32 fresh neighbours are scored 8 at a time with a handful of
-// loads in flight per lane, the visited set is a table of atomics in global memory.  Here 8 warps share one query:
-//   - scoring: every 4-lane (or 1-lane) group takes one pending neighbour, so all <= 64 rows of an expansion are fetched at
-//     once (each lane issues its loads 8 deep) — one HBM round trip per expansion instead of three or four;
-//   - the visited set is an open-addressing table in SHARED memory (32 K slots), cleared per layer by the whole CTA;
-//   - the sorted result/candidate array, the admission rule and the pop rule are the single-warp kernel's, run by warp 0 in
-//     adjacency order — so results are bit-identical to hnsw_search_kernel (tests compare them).
+// A lone warp spends most of an expansion waiting: its <= 32 fresh neighbours are scored 8 at a time, every admitted one is
+// a sorted insert, the visited set is a table of atomics in global memory — ~24 us per expansion.  A single query is a chain
+// of ~ef dependent expansions, so what counts is the length of that chain in (mostly dependent) instructions of one warp:
+// about 6-9 cycles each.  Here 8 warps share one query and the chain is cut three ways:
+//   - SCORING (warps 0..3): every 4-lane (or 1-lane) group takes one pending neighbour; the rows are in shared memory (one
+//     bulk copy per row, all in flight at once) and each lane requests 8 pieces of row and query before using the first.
+//   - ADMISSION (warps 0..3): the <= 32 scored neighbours that can still beat the worst result are merged into the sorted
+//     result/candidate array in ONE pass — every key's place is its rank (new keys below it: warps 0..2, a third each;
+//     entries of the array below it: warp 3, binary search), the old entries take the remaining places in order (32 places
+//     per warp at a time), written into a second array that then becomes the current one.  Without distance ties at the cut
+//     after ef entries this equals the reference's one-by-one admission (search.rs:516) whatever the order; with a tie AT
+//     THE CUT the order matters, and the batch is replayed one by one (hlist_admit_one_by_one), exactly as the one-warp kernel.
+//   - LOOK-AHEAD (warps 4..7, led by HC_LEAD_WARP): while the others score, the lead finds the closest entry not expanded yet
+//     and asks for the adjacency lists of every node that can be popped next into L2; when the scores are known it names the
+//     candidate the pop WILL return (the closer of that entry and the best admissible new neighbour — provably the next pop
+//     unless a tie at the cut intervenes) and expands it already, while warps 0..3 are busy with the array: neighbours read,
+//     the unvisited ones entered into the visited set and listed, their rows copied into the second row buffer (all four
+//     helper warps issue; a lone warp would serialise 23 copies).  Warp 0's pop compares: same candidate -> list and rows ARE
+//     the next expansion (no adjacency read, no inserts, no fetch on the critical path: ~97 % of the expansions of a
+//     1 M-row walk); different candidate -> the helper's visited entries are taken back (tombstones) and the step is done
+//     the plain way.  Every path yields the one-warp kernel's results bit for bit (tests compare them, ties included).
+//   - the visited set is an open-addressing table in SHARED memory (16 K slots for ef <= 256 — which leaves room for the
+//     second row buffer — else 32 K), cleared per layer by the whole CTA.
 // Queries are still handed out by the atomic counter (grid = min(nq, SMs)).  A query that overflows the table or the
-// array is flagged and answered by the other paths, exactly as before.
+// array is flagged and answered by the other paths, exactly as before.  Measured (profiles/r2_hnsw_latency4.txt): 0.63 ms
+// per single query at ef = 200 on 1 M x 384 (one-warp kernel: 3.4-5.5 ms), 0.23 ms at ef = 50.
 static constexpr uint32_t HC_VIS = 32768;       // shared-memory visited slots (power of two)
 static constexpr uint32_t HC_THREADS = 256;
 static constexpr uint32_t HC_ROWS = 32;         // neighbour rows staged in shared memory per scoring pass
@@ -352,13 +322,9 @@ static constexpr uint32_t HC_MERGE_WARPS = 4;   // warps 0..3 update the result 
 static constexpr uint32_t HC_LEAD_WARP = 5;     // ... led by this one (not on warp 0's scheduler: warp w issues on sub-partition w % 4)
 
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ void l2_prefetch_bulk(const void* gmem, uint32_t bytes) {  // bytes: multiple of 16
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ bool hvis_insert_smem(uint32_t* t, uint32_t mask, uint32_t key) {
     uint32_t h = (key * 2654435761u) & mask;
@@ -435,7 +401,7 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
     uint4* srow = sq + p.units;                          // rows being scored
     uint4* srow_next = srow + (size_t)HC_ROWS * p.units;  // rows of the predicted next expansion (spec_rows)
     __shared__ uint32_t s_q, s_npend, s_status, s_done, s_entry, s_pred, s_pnp, s_hb[5];
-    __shared__ uint32_t s_len, s_worst, s_cur, s_mstatus, s_rank[4][32], s_lenlo[2], s_lo;  // the admission's state, shared by warps 0..3
+    __shared__ uint32_t s_len, s_worst, s_cur, s_mstatus, s_rank[4][32], s_lenlo[2], s_lo, s_vcount, s_pred_cn, s_accepted;  // the admission's state, shared by warps 0..3
     __shared__ __align__(8) uint64_t s_bar[2];  // mbarriers of the row copies: [0] rows fetched ahead by the helper warp, [1] rows fetched on demand
     __shared__ unsigned long long s_pf[20];
     __shared__ long long s_t0;
@@ -505,6 +471,9 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
             if (threadIdx.x == 0) {
                 s_len = 0;
                 s_lo = 0;
+                s_vcount = 1;
+                s_pred_cn = 0xFFFFFFFFu;
+                s_accepted = 0;
                 s_worst = 0xFFFFFFFFu;
                 s_cur = 0;
                 s_mstatus = 0;
@@ -520,11 +489,13 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                 // ---- scoring phase: one group per pending node, all groups at once
                 const uint32_t npend = s_npend;
                 const uint32_t pnp = s_pnp;
-                const bool ahead = p.spec_rows && pnp >= 1u && pnp <= HC_ROWS;  // the helper warp has copies in flight into srow_next
-                bool staged = false;  // ... of exactly these rows, in this order?
-                if (ahead && pnp == npend) {
-                    const bool same = (uint32_t)lane >= npend || pend[lane] == ppend[lane];
-                    staged = __all_sync(0xffffffffu, same);  // every warp reads the same lists: uniform over the CTA
+                const bool ahead = p.spec_rows && pnp >= 1u && pnp <= HC_ROWS;  // the helper warps have copies in flight into srow_next
+                const bool accepted = s_accepted != 0;  // warp 0 took the helper's list of fresh neighbours as this expansion
+                const bool staged = ahead && accepted;  // ... so those copies are this expansion's rows
+                if (accepted) {
+                    uint32_t* t = pend;
+                    pend = ppend;
+                    ppend = t;
                 }
                 if (ahead) {  // wait for them either way: the buffer and the barrier are used again
                     mbar_wait(bar_ahead, par_ahead);
@@ -556,6 +527,19 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                             break;
                         }
                     }
+                    // ... and asks for the adjacency lists of everyone who can be next (that entry and the nodes being
+                    // scored), so that the winner's list comes from L2 instead of HBM
+                    if (level == 0) {
+#pragma unroll 1
+                        for (uint32_t j = lane; j <= npend; j += 32) {
+                            const uint32_t node = j < npend ? pend[j] : (pred_key == ~0ull ? 0xFFFFFFFFu : (uint32_t)(pred_key & 0xFFFFFFFFull) >> 1);
+                            if (node != 0xFFFFFFFFu) {
+                                const uint8_t* row = (const uint8_t*)(p.g.nbr0 + (size_t)node * p.g.max_m0);
+                                for (uint32_t o = 0; o < p.g.max_m0 * 4u; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.g.deg0 + node));
+                            }
+                        }
+                    }
                 }
                 for (uint32_t base = 0; base < npend; base += HC_ROWS) {
                     // every warp fires the 16-byte pieces of its rows at once (cp.async: no registers, no waiting in
@@ -579,11 +563,28 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                         typename T::Acc acc;
                         T::init(acc);
                         if (valid) {
-                            const uint4* b = srow + (size_t)r * p.units;
-#pragma unroll 8
-                            for (uint32_t u = g; u < p.units; u += LPR) {
-                                const uint4 qv[1] = {a[u]};
-                                T::step(acc, b[u], qv);
+                            // eight 16-byte pieces of the row and of the query are requested before the first is used
+                            // (left to itself the compiler loads a pair, waits ~30 cycles, uses it, loads the next pair)
+                            const uint32_t bs = smem_u32(srow + (size_t)r * p.units), as = smem_u32(a);
+#pragma unroll 1
+                            for (uint32_t u0 = g; u0 < p.units; u0 += LPR * 8) {
+                                uint4 bv[8], av[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint32_t u = u0 + (uint32_t)j * LPR;
+                                    if (u < p.units) {
+                                        bv[j] = lds128(bs + u * 16u);
+                                        av[j] = lds128(as + u * 16u);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint32_t u = u0 + (uint32_t)j * LPR;
+                                    if (u < p.units) {
+                                        const uint4 qv[1] = {av[j]};
+                                        T::step(acc, bv[j], qv);
+                                    }
+                                }
                             }
                         }
                         const float d = T::finish(acc, 0, &qc);
@@ -691,7 +692,13 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                 if (warp == 0) {
                     lap(2);
                     uint32_t np2 = 0;
-                    bool layer_done = false;
+                    bool layer_done = false, accept = false;
+                    uint32_t spec_cn = 0xFFFFFFFFu, spec_np = 0;
+                    if (p.prefetch) {  // the helper warp's speculative expansion (its list is complete behind this barrier)
+                        asm volatile("bar.sync 1, 64;" ::: "memory");
+                        spec_cn = *(volatile uint32_t*)&s_pred_cn;
+                        spec_np = *(volatile uint32_t*)&s_pnp;
+                    }
 #pragma unroll 1
                     while (!status && np2 == 0) {
                         uint32_t ci = 0xFFFFFFFFu;
@@ -715,6 +722,33 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                         __syncwarp();
                         lo = ci + 1;
                         const uint32_t cn = (uint32_t)(ck & 0xFFFFFFFFull) >> 1;
+                        accept = false;
+                        if (spec_cn != 0xFFFFFFFFu) {
+                            // The helper warp has already expanded the candidate it predicted: neighbours read, the fresh
+                            // ones entered into the visited set and listed (ppend), their rows on the way.  If that is
+                            // the candidate popped here, its work IS this expansion; if not, its entries are taken back.
+                            const bool hit = cn == spec_cn;
+                            spec_cn = 0xFFFFFFFFu;
+                            if (hit) {
+                                if (++steps > p.max_steps) {
+                                    status = 1;
+                                    break;
+                                }
+                                np2 = spec_np;
+                                vcount += np2;
+                                accept = true;
+                                continue;
+                            }
+#pragma unroll 1
+                            for (uint32_t j = lane; j < spec_np; j += 32) {
+                                const uint32_t v = ppend[j];
+                                uint32_t h = (v * 2654435761u) & vmask;
+                                while (vt[h] != v) h = (h + 1) & vmask;
+                                vt[h] = HV_TOMB;
+                            }
+                            vcount += spec_np;  // the slots stay occupied
+                            __syncwarp();
+                        }
                         const uint32_t* nb;
                         const uint16_t* dg;
                         uint32_t maxd;
@@ -754,6 +788,8 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                     if (lane == 0) {
                         s_npend = np2;
                         s_lo = lo;
+                        s_vcount = vcount;
+                        s_accepted = (accept && np2 > 0) ? 1u : 0u;
                         s_done = (layer_done || status) ? 1u : 0u;
                         if (status) s_status = 1;
                         if (!layer_done && !status) s_hb[np2 <= 4 ? 0 : np2 <= 16 ? 1 : np2 <= 32 ? 2 : np2 <= 64 ? 3 : 4] += 1;
@@ -805,39 +841,35 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
                             }
                             const uint32_t first = (uint32_t)lane < maxd ? __ldg(nb + lane) : 0u;  // with the degree: one round trip
                             const uint32_t deg = *dg;
-                            np = 0;
-                            const uint32_t vt_s = smem_u32(vt);
+                            if (s_vcount + deg <= vlimit) {  // (else warp 0 meets the full table itself)
+                                // exactly warp 0's expansion step (below): the visited set is this warp's alone until warp 0
+                                // has finished the array
+                                np = 0;
 #pragma unroll 1
-                            for (uint32_t i0 = 0; i0 < deg; i0 += 32) {
-                                const uint32_t i = i0 + lane;
-                                uint32_t v = 0;
-                                bool fresh = false;
-                                if (i < deg) {
-                                    v = i0 == 0 ? first : __ldg(nb + i);
-                                    fresh = true;  // read-only probe (warp 0 inserts later: a stale answer only costs the fetch)
-#pragma unroll 1
-                                    for (uint32_t h = (v * 2654435761u) & vmask, n = 0; n < 64; h = (h + 1) & vmask, ++n) {
-                                        uint32_t x;
-                                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x) : "r"(vt_s + h * 4u));
-                                        if (x == HV_EMPTY) break;
-                                        if (x == v) {
-                                            fresh = false;
-                                            break;
-                                        }
+                                for (uint32_t i0 = 0; i0 < deg; i0 += 32) {
+                                    const uint32_t i = i0 + lane;
+                                    uint32_t v = 0;
+                                    bool fresh = false;
+                                    if (i < deg) {
+                                        v = i0 == 0 ? first : __ldg(nb + i);
+                                        fresh = hvis_insert_smem(vt, vmask, v);
                                     }
+                                    const uint32_t m = __ballot_sync(0xffffffffu, fresh);
+                                    if (fresh) {
+                                        ppend[np + __popc(m & ((1u << lane) - 1u))] = v;
+                                        if (!p.spec_rows) l2_prefetch_bulk(p.b_base + (uint64_t)v * p.b_stride, row_bytes);
+                                    }
+                                    np += __popc(m);
                                 }
-                                const uint32_t m = __ballot_sync(0xffffffffu, fresh);
-                                if (fresh) {
-                                    ppend[np + __popc(m & ((1u << lane) - 1u))] = v;
-                                    if (!p.spec_rows) l2_prefetch_bulk(p.b_base + (uint64_t)v * p.b_stride, row_bytes);
-                                }
-                                np += __popc(m);
                             }
                         }
                         if (lane == 0) {
                             s_pnp = np;
+                            s_pred_cn = np == 0xFFFFFFFFu ? 0xFFFFFFFFu : cn;
                             if (p.spec_rows && np >= 1u && np <= HC_ROWS) mbar_expect_tx(bar_ahead, np * row_bytes);
                         }
+                        __syncwarp();
+                        asm volatile("bar.arrive 1, 64;" ::: "memory");  // warp 0 may take the list from here on
                         hs(13);
                     }
                     if (p.spec_rows) {  // all four helper warps issue the copies (one per row; a lone warp would serialise them)

@@ -118,7 +118,8 @@ def test_cta_per_query_walk_equals_the_warp_walk(vg, orc, gpu, elem, dims, monke
     """Few queries take hnsw_search_cta_kernel (one CTA per query: all fresh neighbours scored at once, visited set in
     shared memory, the neighbours of an expansion admitted in one merge); it must return exactly what the
     one-warp-per-query kernel returns, ids and distance bits — also where distances tie constantly (int8[16]: the merge
-    hands a batch whose cut falls inside a tie back to the one-by-one admission) and with VECGPU_HNSW_BATCH_ADMIT=0."""
+    hands a batch whose cut falls inside a tie back to the one-by-one admission, and the helper warps' look-ahead
+    mispredicts there, so its visited entries are taken back) and with each of the three mechanisms switched off."""
     n, M, efc = 30_000, 16, 100
     v = orc.synth_rows(elem, 6, 1, n, dims, 1 if elem == F32 else 0)
     q = orc.synth_rows(elem, 7, 1, 40, dims, 1 if elem == F32 else 0)
@@ -132,12 +133,16 @@ def test_cta_per_query_walk_equals_the_warp_walk(vg, orc, gpu, elem, dims, monke
             monkeypatch.setenv("VECGPU_HNSW_CTA_MAX_NQ", "64")
             cr, cd, cc = idx.search(q, k, ef_search=ef)      # CTA kernel (40 queries)
             c1 = [idx.search(q[i], k, ef_search=ef) for i in range(3)]  # and one query at a time
-            monkeypatch.setenv("VECGPU_HNSW_BATCH_ADMIT", "0")
-            sr, sd, sc = idx.search(q, k, ef_search=ef)      # CTA kernel, one sorted insert per admitted neighbour
-            monkeypatch.delenv("VECGPU_HNSW_BATCH_ADMIT")
+            variants = []
+            for knob in ("VECGPU_HNSW_BATCH_ADMIT", "VECGPU_HNSW_PREFETCH", "VECGPU_HNSW_SPEC_ROWS"):
+                # one sorted insert per admitted neighbour / no look-ahead by the helper warps / look-ahead into L2 only
+                monkeypatch.setenv(knob, "0")
+                variants.append((knob, idx.search(q, k, ef_search=ef)))
+                monkeypatch.delenv(knob)
             monkeypatch.delenv("VECGPU_HNSW_CTA_MAX_NQ")
             assert np.array_equal(wr, cr) and np.array_equal(wd.view("<u4"), cd.view("<u4")) and np.array_equal(wc, cc)
-            assert np.array_equal(wr, sr) and np.array_equal(wd.view("<u4"), sd.view("<u4")) and np.array_equal(wc, sc)
+            for knob, (sr, sd, sc) in variants:
+                assert np.array_equal(wr, sr) and np.array_equal(wd.view("<u4"), sd.view("<u4")) and np.array_equal(wc, sc), knob
             for i in range(3):
                 assert np.array_equal(c1[i][0][0], wr[i]) and np.array_equal(c1[i][1][0].view("<u4"), wd[i].view("<u4"))
         assert idx.device_stats()["fallbacks"] == 0
