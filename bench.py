@@ -50,14 +50,14 @@ def load_peaks():
 
 def load_traffic(world):
     """DRAM bytes per launch of the headline scan kernel from the committed `ncu --set full` capture of this very workload
-    (profiles/r1_scan_f32cos_full_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum).  Only meaningful at N = 1, where the
-    per-GPU shard is the captured 10 M-row slab."""
+    (profiles/r2_scan_f32cos_full_raw.csv, taken by profiles/r2_ncu_capture.sh: dram__bytes_read.sum + dram__bytes_write.sum).
+    Only meaningful at N = 1, where the per-GPU shard is the captured 10 M-row slab."""
     if world != 1:
         return None, "per-GPU shard differs from the captured launch"
     try:
         import csv
 
-        with open(os.path.join(ROOT, "profiles", "r1_scan_f32cos_full_raw.csv")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_scan_f32cos_full_raw.csv")) as f:
             rows = list(csv.reader(f))
         hdr, units, vals = rows[0], rows[1], rows[2]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
@@ -66,7 +66,7 @@ def load_traffic(world):
             i = hdr.index(name)
             total += float(vals[i]) * scale[units[i]]
         return total, ("static: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of this kernel on "
-                       "this workload (profiles/r1_scan_f32cos_full_raw.csv), not measured in this run")
+                       "this workload (profiles/r2_scan_f32cos_full_raw.csv), not measured in this run")
     except Exception as e:  # the capture is evidence, not a dependency
         return None, f"capture not readable: {e}"
 
