@@ -1,5 +1,5 @@
 """Differential fuzz on the GPU: for random shapes, every fast path must return exactly what the plain exact scan returns
-(tensor-core f32 / int8 batches, lane-per-query Hamming, small-merge fast path, HNSW device walk vs lockstep driver)."""
+(tensor-core f32 / int8 batches, lane-per-query Hamming, small-merge fast path, HNSW device walks — one CTA per query and one warp per query — vs lockstep driver)."""
 import os, signal, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +7,8 @@ import sqlite_vec_hnsw_b200 as vg
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 signal.alarm(int(budget) + 120)
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1234)
-KNOBS = ("VECGPU_TC", "VECGPU_HAM_BATCH", "VECGPU_MERGE_SMALL", "VECGPU_TC_MIN_WORK", "VECGPU_HNSW_DEVICE", "VECGPU_TC_TERMS", "VECGPU_TCI_SAMPLE")
+KNOBS = ("VECGPU_TC", "VECGPU_HAM_BATCH", "VECGPU_MERGE_SMALL", "VECGPU_TC_MIN_WORK", "VECGPU_HNSW_DEVICE", "VECGPU_TC_TERMS", "VECGPU_TCI_SAMPLE",
+         "VECGPU_HNSW_CTA_MAX_NQ")
 def env(**kw):
     for k in KNOBS: os.environ.pop(k, None)
     for k, v in kw.items(): os.environ[k] = str(v)
@@ -57,7 +58,9 @@ while time.time() - t0 < budget:
             env(VECGPU_HNSW_DEVICE=1); i1 = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=3); i1.rebuild(batch=bsz)
             e1 = i1.export_edges(); r1 = i1.search(q, k, ef_search=ef)
             env(VECGPU_HNSW_DEVICE=0); r2 = i1.search(q, k, ef_search=ef)       # lockstep walk of the device-built graph
-            ok = all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(r1, r2))
+            ok = all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(r1, r2))   # r1: 40 queries -> one CTA per query
+            env(VECGPU_HNSW_DEVICE=1, VECGPU_HNSW_CTA_MAX_NQ=0); r3 = i1.search(q, k, ef_search=ef)   # one warp per query
+            ok = ok and all(np.array_equal(x.view("u1"), y.view("u1")) for x, y in zip(r1, r3))
             os.environ["VECGPU_HNSW_DEVICE"] = "1"; os.environ["VECGPU_HNSW_LINK"] = "host"
             i2 = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=3); i2.rebuild(batch=bsz)   # device walk, host linking
             os.environ.pop("VECGPU_HNSW_LINK")
