@@ -147,3 +147,30 @@ def test_cta_per_query_walk_equals_the_warp_walk(vg, orc, gpu, elem, dims, monke
                 assert np.array_equal(c1[i][0][0], wr[i]) and np.array_equal(c1[i][1][0].view("<u4"), wd[i].view("<u4"))
         assert idx.device_stats()["fallbacks"] == 0
         idx.close()
+
+
+@pytest.mark.parametrize("elem,dims,metric,M", [(2, 256, 3, 16), (F32, 96, 2, 32), (I8, 64, 1, 40), (F32, 8, L2, 5)])
+def test_cta_per_query_walk_other_metrics_and_degrees(vg, orc, gpu, elem, dims, metric, M, monkeypatch):
+    """The one-CTA-per-query walk on bit / Hamming, cosine and L1 columns and with adjacency lists longer than one 32-entry
+    batch (M = 32, 40: max_m0 = 64, 80 -> several merges per expansion, look-ahead without the second row buffer when more
+    than 32 neighbours are new) and very short ones (M = 5): identical to the one-warp walk, single queries included."""
+    n, efc = 12_000, 80
+    kind = 1 if elem == F32 else 0
+    v = orc.synth_rows(elem, 16, 1, n, dims, kind)
+    q = orc.synth_rows(elem, 17, 1, 24, dims, kind)
+    with vg.Slab(elem, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, metric, M=M, ef_construction=efc, seed=5)
+        idx.rebuild()
+        for ef, k in ((1, 1), (40, 10), (300, 20), (512, 100)):
+            monkeypatch.setenv("VECGPU_HNSW_CTA_MAX_NQ", "0")
+            wr, wd, wc = idx.search(q, k, ef_search=ef)
+            monkeypatch.setenv("VECGPU_HNSW_CTA_MAX_NQ", "64")
+            cr, cd, cc = idx.search(q, k, ef_search=ef)
+            one = [idx.search(q[i], k, ef_search=ef) for i in range(2)]
+            monkeypatch.delenv("VECGPU_HNSW_CTA_MAX_NQ")
+            assert np.array_equal(wr, cr) and np.array_equal(wd.view("<u4"), cd.view("<u4")) and np.array_equal(wc, cc), (ef, k)
+            for i in range(2):
+                assert np.array_equal(one[i][0][0], wr[i]) and np.array_equal(one[i][1][0].view("<u4"), wd[i].view("<u4"))
+        assert idx.device_stats()["fallbacks"] == 0
+        idx.close()
