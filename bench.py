@@ -458,7 +458,7 @@ def run_ours(args):
                                                  "(M=16, keep-closest pruning), not the batching's; batch 1 on the GPU reproduces that graph edge for edge",
             "expansion_batch_histogram": idx.batch_histogram(),
             "note": "host wall clock around vecgpu_hnsw_build / vecgpu_hnsw_search (host buffers in and out)",
-            "kernel": "hnsw_search_kernel (whole layered walk on the device, one warp per query) for batches; hnsw_search_cta_kernel for <= 64 queries",
+            "kernel": "hnsw_search_kernel (whole layered walk on the device, one warp per query) for batches; hnsw_search_cta_kernel for calls of up to 7 queries per SM",
         }
         idx.close()
         sl.close()

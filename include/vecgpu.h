@@ -238,9 +238,9 @@ void vecgpu_tc_stats(uint64_t* queries, uint64_t* fallbacks);
  * next to a slab that holds the STORED node vectors (normalised for cosine columns, int8 when
  * index_quantization=int8: src/hnsw/insert.rs:300-322); `metric` is the INTERNAL metric (src/hnsw/mod.rs:129-137).
  * Searches (queries, and the search half of every insert of a rebuild batch) run wholly on the device, one warp per
- * query walking all layers (search_layer, src/hnsw/search.rs:340-543); calls with at most 64 queries — SQL issues ONE
- * per MATCH — take a latency form instead, one CTA per query (same results, ~0.6 ms instead of ~4.7 ms per query at
- * ef = 200 on 1 M x 384).  With VECGPU_HNSW_DEVICE=0 in the environment
+ * query walking all layers (search_layer, src/hnsw/search.rs:340-543); calls of up to 7 queries per SM (1036 on a B200) — SQL
+ * issues ONE per MATCH — take a latency form instead, one CTA per query (same results; ef = 200 on 1 M x 384: ~0.6 ms
+ * instead of ~4.7 ms for one query, 1.3 ms instead of 4.4 ms for 256).  With VECGPU_HNSW_DEVICE=0 in the environment
  * the lockstep driver is used instead: B inserts or queries advance together and each expansion round scores all
  * their unvisited neighbours in one launch.  Both give identical results. */
 typedef struct vecgpu_hnsw vecgpu_hnsw;

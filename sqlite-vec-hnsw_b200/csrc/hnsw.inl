@@ -541,9 +541,11 @@ static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) 
         grid = std::min(grid, p.nq);
         wpb = (p.nq + grid - 1) / grid;
     }
-    // Few queries (the SQL case is ONE per MATCH): one CTA per query scores all fresh neighbours of an expansion at once and
+    // Few queries (the SQL case is ONE per MATCH; up to ~1000 in a call): one CTA per query scores all fresh neighbours of an expansion at once and
     // keeps the visited set in shared memory (hnsw_search_cta_kernel).  Only for walks whose beam fits its tables.
-    const uint32_t cta_max = env_u32("VECGPU_HNSW_CTA_MAX_NQ", 64);
+    // Measured crossover (tools/hnsw_crossover.py, profiles/r2_hnsw_crossover.txt): ceil(nq / SMs) rounds of ~0.62 ms against the
+    // one-warp walk's ~4.5 ms floor (its latency; it only becomes throughput-bound beyond ~4000 queries) meet at 7 rounds.
+    const uint32_t cta_max = env_u32("VECGPU_HNSW_CTA_MAX_NQ", 7u * (uint32_t)s->num_sms);
     // visited slots: a walk touches ~ef x 30 nodes; 16 K slots (at most 3/4 used) cover ef <= 256 and leave room for the second row buffer
     p.cta_vis = p.ef_wide <= 256 ? 16384u : HC_VIS;
     size_t cta_smem = (size_t)p.cta_vis * 4 + (size_t)p.cap * 16 + (size_t)((h->max_m0 + 31u) & ~31u) * 12 + (size_t)s->row_stride * (1 + HC_ROWS) + 64;
