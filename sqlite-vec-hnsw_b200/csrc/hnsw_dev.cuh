@@ -59,7 +59,8 @@ struct HSearchParams {
     uint32_t spec_rows;          // CTA kernel: 1 = ... all the way into a second row buffer in shared memory (0: only into L2)
     uint32_t cta_vis;            // CTA kernel: visited slots in shared memory (power of two)
     uint32_t batch_admit;        // CTA kernel: 1 = admit the neighbours of an expansion in one merge (0: one sorted insert each)
-    unsigned long long* prof;    // developer hook (VECGPU_HNSW_TIMING): [8] clock cycles of the CTA kernel's 4 phases, merged / one-by-one admission batches, staged / all expansions; or NULL
+    unsigned long long* prof;    // developer hook (VECGPU_HNSW_TIMING): [20] counters of the instrumented CTA kernel — cycles of its 4 phases,
+                                 // merged / one-by-one admission batches, staged / all expansions, admission split, helper timeline; or NULL
     uint32_t max_steps;
     uint32_t q_smem;             // 1: each warp stages its query in shared memory (units * 16 bytes per warp)
 };
