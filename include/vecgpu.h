@@ -112,7 +112,10 @@ int vecgpu_knn(vecgpu_slab* slab, const void* queries, uint32_t nq, uint32_t k, 
  * (src/hnsw/search.rs:501-513, and the entry-point distance :385-389) for nq
  * queries with CSR candidate lists: candidates of query q are
  * cand_rowids[cand_offsets[q] .. cand_offsets[q+1]).  out_dists has
- * cand_offsets[nq] entries; a rowid that is absent or skipped yields NaN. */
+ * cand_offsets[nq] entries; a rowid that is absent or skipped yields NaN.
+ * A call of at most 256 pairs whose input fits 16 KB (one expansion: a query and its <= 64 neighbours) is a single
+ * kernel launch that reads the arguments from, and stores the distances to, pinned host memory (~15 us + the caller's
+ * own overhead); larger calls upload, resolve, score and download. */
 int vecgpu_score(vecgpu_slab* slab, const void* queries, uint32_t nq, const int64_t* cand_rowids,
                  const uint32_t* cand_offsets, int metric, float* out_dists);
 

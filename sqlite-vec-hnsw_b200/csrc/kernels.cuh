@@ -1497,6 +1497,88 @@ __global__ void resolve_kernel(const int64_t* cand_rowids, uint64_t n_pairs, con
     }
 }
 
+// K5s: ONE launch for a small scoring call (one search_layer expansion: a query and its <= 64 neighbour rowids).  The input
+// block — [rowids np x 8][offsets (nq + 1) x 4, padded to 16][queries nq x stride] — sits in pinned host memory and is read
+// by the kernel directly (zero-copy), the distances are stored straight into pinned host memory: no copy commands, no
+// separate rowid -> position pass.  Every block stages the whole block of input in shared memory (<= 16 KB).
+struct ScoreSmallParams {
+    const uint8_t* in;         // pinned host (or device) input block
+    uint32_t in_bytes;         // multiple of 16
+    uint32_t np, nq, q_off;    // pairs, queries, byte offset of the queries in `in`
+    const int64_t* rowids;     // slab rowids (nullptr: dense)
+    uint64_t n_rows;
+    int64_t first_rowid;
+    const uint8_t* skip;       // or nullptr
+    const uint8_t* b_base;
+    uint32_t stride, units, qc_kind;
+    float* out;                // [np], pinned host (or device)
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) score_small_kernel(const ScoreSmallParams p) {
+    constexpr int LPR = T::LPR;
+    constexpr int GPB = 256 / LPR;
+    extern __shared__ __align__(16) uint8_t ss_smem[];
+    for (uint32_t u = threadIdx.x; u < p.in_bytes / 16; u += 256) ((uint4*)ss_smem)[u] = ((const uint4*)p.in)[u];
+    __syncthreads();
+    const int64_t* cand = (const int64_t*)ss_smem;
+    const uint32_t* offsets = (const uint32_t*)(ss_smem + (size_t)p.np * 8);
+    const int lane = threadIdx.x & 31, g = lane % LPR;
+    const uint32_t pair = blockIdx.x * GPB + threadIdx.x / LPR;
+    const bool in = pair < p.np;
+    uint32_t qi = 0;
+    int64_t pos = -1;
+    if (in) {
+        uint32_t lo = 0, hi = p.nq;  // query of the pair: last q with offsets[q] <= pair
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (offsets[mid] <= pair) lo = mid;
+            else hi = mid;
+        }
+        qi = lo;
+        const int64_t r = cand[pair];
+        if (p.rowids == nullptr) {
+            if (r >= p.first_rowid && (uint64_t)(r - p.first_rowid) < p.n_rows) pos = r - p.first_rowid;
+        } else {
+            uint64_t a = 0, b = p.n_rows;
+            while (a < b) {
+                const uint64_t mid = (a + b) >> 1;
+                if (p.rowids[mid] < r) a = mid + 1;
+                else b = mid;
+            }
+            if (a < p.n_rows && p.rowids[a] == r) pos = (int64_t)a;
+        }
+        if (pos >= 0 && p.skip && p.skip[pos]) pos = -1;
+    }
+    const uint4* a = (const uint4*)(ss_smem + p.q_off + (size_t)qi * p.stride);
+    const uint4* b = (const uint4*)(p.b_base + (uint64_t)(pos < 0 ? 0 : pos) * p.stride);
+    typename T::Acc acc;
+    T::init(acc);
+    float qc = 0.f;
+    if (T::HAS_QC) qc = query_const(a, (in && pos >= 0) ? p.units : 0, g, p.qc_kind);
+    if (in && pos >= 0) {
+#pragma unroll 1
+        for (uint32_t u0 = g; u0 < p.units; u0 += LPR * 4) {  // four row pieces in flight per lane
+            uint4 xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t u = u0 + (uint32_t)j * LPR;
+                if (u < p.units) xv[j] = __ldg(b + u);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t u = u0 + (uint32_t)j * LPR;
+                if (u < p.units) {
+                    const uint4 qv[1] = {a[u]};
+                    T::step(acc, xv[j], qv);
+                }
+            }
+        }
+    }
+    const float d = T::finish(acc, 0, &qc);
+    if (in && g == 0) p.out[pair] = pos >= 0 ? d : __int_as_float(0x7FC00000);
+}
+
 // ---------------------------------------------------------------------------
 // K7 producers — src/vector.rs:444-608, bit-for-bit (IEEE ops, no contraction)
 // ---------------------------------------------------------------------------

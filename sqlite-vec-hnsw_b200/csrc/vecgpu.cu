@@ -1830,6 +1830,27 @@ static int launch_pairs(int elem, int metric, const PairParams& p, int num_sms, 
     return launch_pairs_t<BitHamming<1>>(p, num_sms, st);
 }
 
+template <class T>
+static int launch_score_small_t(const ScoreSmallParams& p, cudaStream_t st) {
+    constexpr uint32_t gpb = 256 / T::LPR;
+    score_small_kernel<T><<<(p.np + gpb - 1) / gpb, 256, p.in_bytes, st>>>(p);
+    LAUNCHED();
+    return 0;
+}
+static int launch_score_small(int elem, int metric, const ScoreSmallParams& p, cudaStream_t st) {
+    if (elem == VECGPU_F32) {
+        if (metric == VECGPU_L2) return launch_score_small_t<F32L2<1>>(p, st);
+        if (metric == VECGPU_L1) return launch_score_small_t<F32L1<1>>(p, st);
+        return launch_score_small_t<F32Cos<1>>(p, st);
+    }
+    if (elem == VECGPU_I8) {
+        if (metric == VECGPU_L2) return launch_score_small_t<I8Dot<1, false>>(p, st);
+        if (metric == VECGPU_L1) return launch_score_small_t<I8L1<1>>(p, st);
+        return launch_score_small_t<I8Dot<1, true>>(p, st);
+    }
+    return launch_score_small_t<BitHamming<1>>(p, st);
+}
+
 extern "C" int vecgpu_score(vecgpu_slab* s, const void* queries, uint32_t nq, const int64_t* cand_rowids,
                             const uint32_t* cand_offsets, int metric, float* out_dists) {
     VG_TRY
@@ -1847,6 +1868,45 @@ extern "C" int vecgpu_score(vecgpu_slab* s, const void* queries, uint32_t nq, co
     std::lock_guard<std::mutex> lk(s->mu);
     rc = use_device(s->device);
     if (rc) return rc;
+    {
+        // Small calls — one expansion of search_layer is a query and <= 64 rowids — run as ONE launch that reads its input
+        // from pinned host memory and stores the distances there (score_small_kernel): ~3x less fixed cost than the
+        // upload / resolve / score / download sequence below.
+        const size_t offs_bytes = (((size_t)(nq + 1) * 4) + 15) & ~(size_t)15, q_off = (size_t)np * 8 + offs_bytes;
+        const size_t in_bytes = q_off + (size_t)nq * s->row_stride, out_off = (in_bytes + 255) & ~(size_t)255;
+        if (np <= 256 && in_bytes <= 16384) {
+            if (env_u32("VECGPU_SCORE_SMALL", 1)) {
+                if ((rc = pin_reserve(s, 1, out_off + (size_t)np * 4))) return rc;
+                uint8_t* h = (uint8_t*)s->h_pin[1];
+                memset(h, 0, in_bytes);
+                memcpy(h, cand_rowids, np * 8);
+                memcpy(h + np * 8, cand_offsets, (size_t)(nq + 1) * 4);
+                const uint32_t rbytes = vecgpu_row_bytes(s->elem, s->dims);
+                for (uint32_t q = 0; q < nq; ++q) memcpy(h + q_off + (size_t)q * s->row_stride, (const uint8_t*)queries + (size_t)q * rbytes, rbytes);
+                if ((rc = slab_sync_rowids(s))) return rc;
+                if ((rc = slab_sync_skip(s))) return rc;
+                ScoreSmallParams sp{};
+                sp.in = h;
+                sp.in_bytes = (uint32_t)((in_bytes + 15) & ~(size_t)15);
+                sp.np = (uint32_t)np;
+                sp.nq = nq;
+                sp.q_off = (uint32_t)q_off;
+                sp.rowids = s->dense ? nullptr : s->d_rowids;
+                sp.n_rows = s->rows;
+                sp.first_rowid = s->first_rowid;
+                sp.skip = s->n_skip ? s->d_skip : nullptr;
+                sp.b_base = s->d_vec;
+                sp.stride = s->row_stride;
+                sp.units = s->row_stride / 16;
+                sp.qc_kind = metric_qc_kind(s->elem);
+                sp.out = (float*)(h + out_off);
+                if ((rc = launch_score_small(s->elem, metric, sp, s->stream))) return rc;
+                CU(cudaStreamSynchronize(s->stream));
+                memcpy(out_dists, h + out_off, np * 4);
+                return 0;
+            }
+        }
+    }
     rc = stage_queries(s, queries, nq);
     if (rc) return rc;
     // candidates + offsets in one pinned upload: [rowids np*8][offsets (nq+1)*4]

@@ -280,6 +280,42 @@ def test_score_matches_oracle(vg, orc, gpu, elem, metric):
             assert np.float32(out[j]).view("<u4") == np.float32(want).view("<u4")
 
 
+@pytest.mark.parametrize("elem,metric", PAIRS, ids=PAIR_IDS)
+def test_score_small_call_equals_the_general_path(vg, orc, gpu, elem, metric, monkeypatch):
+    """A call of <= 256 pairs whose input fits 16 KB (one expansion of search_layer) is ONE launch reading pinned host memory
+    (score_small_kernel); VECGPU_SCORE_SMALL=0 forces the upload / resolve / score / download sequence.  Same bits, on a
+    sparse slab with deleted, empty-blob and absent rowids; and against the oracle."""
+    dims = 96 if elem != BIT else 200
+    n = 3000
+    v = random_rows(elem, n, dims, seed=41 + elem)
+    q = random_rows(elem, 3, dims, seed=42)
+    rng = np.random.default_rng(43)
+    rowids = np.sort(rng.choice(np.arange(1, 5 * n), size=n, replace=False)).astype("<i8")
+    for sparse in (False, True):
+        with vg.Slab(elem, dims) as s:
+            s.load(v, rowids if sparse else None)
+            ids = rowids if sparse else np.arange(1, n + 1, dtype="<i8")
+            s.delete(int(ids[5]))
+            s.upsert(int(ids[9]), b"")
+            sizes = [32, 0, 64]
+            offsets = np.concatenate([[0], np.cumsum(sizes)]).astype("<u4")
+            cands = ids[rng.integers(0, n, size=offsets[-1])].copy()
+            cands[0], cands[1], cands[2], cands[40] = ids[5], ids[9], -7, int(ids[-1]) + 11  # deleted, skipped, absent, absent
+            small = s.score(q, cands, offsets, metric)
+            monkeypatch.setenv("VECGPU_SCORE_SMALL", "0")
+            general = s.score(q, cands, offsets, metric)
+            monkeypatch.delenv("VECGPU_SCORE_SMALL")
+            assert np.array_equal(small.view("<u4"), general.view("<u4"))
+            assert np.isnan(small[[0, 1, 2, 40]]).all()
+            pos = {int(r): i for i, r in enumerate(ids)}
+            for qi in range(3):
+                for j in range(offsets[qi], offsets[qi + 1]):
+                    if j in (0, 1, 2, 40):
+                        continue
+                    want = orc.distance(elem, q[qi], v[pos[int(cands[j])]], metric)
+                    assert np.float32(small[j]).view("<u4") == np.float32(want).view("<u4")
+
+
 def test_score_hnsw_cosine_contract(vg, orc, gpu):
     # HNSW cosine = L2 on normalised vectors, output d^2/2 (src/hnsw/mod.rs:129-146, insert.rs:300-322)
     dims = 64
