@@ -1872,7 +1872,7 @@ extern "C" int vecgpu_score(vecgpu_slab* s, const void* queries, uint32_t nq, co
         // Small calls — one expansion of search_layer is a query and <= 64 rowids — run as ONE launch that reads its input
         // from pinned host memory and stores the distances there (score_small_kernel): ~3x less fixed cost than the
         // upload / resolve / score / download sequence below.
-        const size_t offs_bytes = (((size_t)(nq + 1) * 4) + 15) & ~(size_t)15, q_off = (size_t)np * 8 + offs_bytes;
+        const size_t q_off = ((size_t)np * 8 + (size_t)(nq + 1) * 4 + 15) & ~(size_t)15;  // the queries start 16-byte aligned
         const size_t in_bytes = q_off + (size_t)nq * s->row_stride, out_off = (in_bytes + 255) & ~(size_t)255;
         if (np <= 256 && in_bytes <= 16384) {
             if (env_u32("VECGPU_SCORE_SMALL", 1)) {
