@@ -44,3 +44,21 @@ for trial in range(3):
     sl.close()
     del ballast
     torch.cuda.empty_cache()
+
+# ... and right behind the int8 tensor-core batches of cfg3, as in bench.py
+import subprocess  # noqa: E402
+s8 = vg.Slab(1, 1024)
+s8.fill_synthetic(seed=5, n=50_000_000, kind=0)
+qb8 = torch.from_numpy(oracle.synth_rows(1, 78, 1, 1024, 1024, 0).copy()).to(dev)
+sl = vg.Slab(2, dims)
+sl.fill_synthetic(seed=6, n=n, kind=0)
+measure(sl, "before the int8 batches")
+for _ in range(4):
+    s8.knn_device(qb8, 100, 0, stream=torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+print("clocks right after the batches:", subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_throttle_reasons.sw_power_cap", "--format=csv,noheader"],
+                                                       capture_output=True, text=True).stdout.strip(), flush=True)
+measure(sl, "right after 4 int8 1024-query batches")
+sl.close()
+s8.close()
+
