@@ -680,6 +680,39 @@ def test_hnsw_ref_recall_l2_1000x128(vg, orc, gpu):
         idx.close()
 
 
+def test_ref_scale_10k_x_128_query_latency(vg, orc, gpu):
+    """tests/test_scale.rs:3-114: 10 000 vectors (i*128+j)/10000, default metric cosine, HNSW enabled; query j/128, k = 10;
+    10 results, ascending distances, query latency < 100 ms.  Here: the exact scan equals the oracle, the HNSW answer is drawn
+    from the same rows with their exact distances, and both calls meet the reference's latency bar with room to spare."""
+    import time
+    n, dims = 10_000, 128
+    i = np.arange(n, dtype=np.int64)[:, None]
+    j = np.arange(dims, dtype=np.int64)[None, :]
+    v = ((i * 128 + j).astype("<f4") / np.float32(10000.0)).astype("<f4")
+    q = (np.arange(dims, dtype="<f4") / np.float32(128.0)).reshape(1, dims)
+    with vg.Slab(F32, dims) as s:
+        for lo in range(0, n, 1000):  # the reference inserts in transactions of 1000 rows
+            s.append(v[lo:lo + 1000])
+        assert s.count() == (n, n)
+        s.knn(q, 10, COSINE)
+        t0 = time.perf_counter()
+        r, d, c = s.knn(q, 10, COSINE)
+        dt = time.perf_counter() - t0
+        er, ed, ec = orc.knn(F32, dims, v, q, 10, COSINE)
+        assert c[0] == 10 and np.array_equal(r, er) and np.array_equal(bits(d), bits(ed)) and np.all(np.diff(d[0]) >= 0)
+        assert dt < 0.1
+        idx = vg.HnswIndex.for_column(s, vg.DistanceMetric.Cosine)
+        assert idx.rebuild() == n  # node count == row count (test_scale.rs:60-68)
+        idx.search(q, 10)
+        t0 = time.perf_counter()
+        hr, hd, hc = idx.search(q, 10)
+        dth = time.perf_counter() - t0
+        assert hc[0] == 10 and np.all(np.diff(hd[0]) >= 0) and dth < 0.1
+        want = np.array([orc.distance(F32, q[0], v[rid - 1], COSINE) for rid in hr[0]], dtype="<f4")
+        assert np.all(np.abs(hd[0] - want) <= 1e-5 * np.maximum(1.0, np.abs(want)))  # d^2/2 on normalised vectors vs 1 - cos
+        idx.close()
+
+
 def test_hnsw_ref_recall_cosine_100x128(vg, orc, gpu):
     # tests/test_recall_cosine.rs:15-125: ((7i+13j)%100)/100, cosine, recall >= 90 %; HNSW cosine = L2 on
     # normalised vectors, output d^2/2 (src/hnsw/mod.rs:129-146)
