@@ -265,6 +265,12 @@ void vecgpu_hnsw_destroy(vecgpu_hnsw* h);
 /* vec_rebuild_hnsw (src/sql_functions.rs:436-534 -> src/hnsw/insert.rs:279-532): rebuild over every live row of
  * the slab, at most `batch` inserts per search launch (0 = 16384; never more than a quarter of the graph built so far). */
 int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch);
+/* insert_hnsw (src/hnsw/insert.rs:279-532, called by Vec0Tab::insert when the column has an index) for rows that arrive in
+ * rowid order: indexes the rows appended to the slab (vecgpu_slab_append / _upsert of a new highest rowid) since the graph
+ * was last built or extended, by continuing the rebuild's insertion loop — a batch of 1 continues the strictly sequential
+ * build edge for edge.  *n_inserted (may be NULL) = nodes added.  An empty index is simply built.  Rows inserted OUT of
+ * rowid order move row positions: the index then fails with status 4 (like searches) until vecgpu_hnsw_build. */
+int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint64_t* n_inserted);
 /* search_hnsw (src/hnsw/search.rs:267-335): ef = max(ef_search, k); results closest first, distances in the
  * internal metric (apply convert_distance_for_output for cosine columns); unused slots rowid -1 / +inf. */
 int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef_search,
@@ -274,8 +280,9 @@ int vecgpu_hnsw_stats(vecgpu_hnsw* h, uint64_t* nodes, uint64_t* edges, int32_t*
 /* Entry point of the graph (rowid, level) for the {t}_{c}_hnsw_meta row (HnswMetadata.entry_point_rowid / entry_point_level, src/hnsw/mod.rs:97-103); rowid -1 / level -1
  * when the index is empty. */
 int vecgpu_hnsw_entry_point(vecgpu_hnsw* h, int64_t* rowid, int32_t* level);
-/* Node list for a bulk write-back into {t}_{c}_hnsw_nodes(rowid, level, vector) (src/shadow.rs:464-474): the rows the last
- * rebuild indexed, ascending rowid, with their level.  cap = 0 only counts. */
+/* Node list for a bulk write-back into {t}_{c}_hnsw_nodes(rowid, level, vector) (src/shadow.rs:464-474): the rows indexed
+ * so far (rebuild + incremental inserts) that have not been deleted since, ascending rowid, with their level.  cap = 0
+ * only counts. */
 int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* rowids, int32_t* levels, uint64_t* n_out);
 /* Device-search counters: queries (or inserts) answered by the search kernel, how many of those hit a device capacity
  * limit and were re-run by the lockstep driver, and the number of search launches. */
@@ -285,7 +292,8 @@ int vecgpu_hnsw_device_stats(vecgpu_hnsw* h, uint64_t* queries, uint64_t* fallba
  * neighbours they scored. */
 int vecgpu_hnsw_batch_histogram(vecgpu_hnsw* h, uint64_t out5[5]);
 /* Edge list for a bulk write-back into {t}_{c}_hnsw_edges (src/shadow.rs:478-487; insert_edges_batch shape,
- * src/hnsw/storage.rs:346-383).  cap = 0 only counts. */
+ * src/hnsw/storage.rs:346-383); edges from or to a row deleted since are left out, as Vec0Tab::delete removes them
+ * (src/vtab.rs:1340-1397).  cap = 0 only counts. */
 int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* from_rowids, int64_t* to_rowids, int32_t* levels,
                              float* dists, uint64_t* n_out);
 

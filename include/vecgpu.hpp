@@ -370,6 +370,13 @@ public:
         if (rc) return Error::from_status(rc);
         return Unit{};
     }
+    // insert_hnsw for rows appended to the slab in rowid order since the last rebuild / insert (src/hnsw/insert.rs:279-532)
+    Result<uint64_t> insert_appended(uint32_t batch = 0) {
+        uint64_t n = 0;
+        int rc = vecgpu_hnsw_insert_appended(h_, batch, &n);
+        if (rc) return Error::from_status(rc);
+        return n;
+    }
     // search_hnsw (src/hnsw/search.rs:267-335); the query must already be in the stored representation
     Result<std::vector<std::pair<int64_t, float>>> search(const std::vector<uint8_t>& query, uint32_t k, uint32_t ef_search = 200) {
         std::vector<int64_t> rowids(k);

@@ -848,54 +848,84 @@ static void hq_init(vecgpu_hnsw* h, HQuery& q, uint32_t a_index, int node_level,
     hq_start_layer(q);
 }
 
-// vec_rebuild_hnsw: (re)build the graph over every live row of the slab, `batch` inserts in lockstep
-extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
-    VG_TRY
-    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+// vec_rebuild_hnsw: (re)build the graph over every live row of the slab, `batch` inserts in lockstep — or, `incremental`,
+// continue the same insertion loop over the rows appended to the slab since the graph was last built or extended
+// (insert_hnsw for rows that arrive in rowid order, src/hnsw/insert.rs:279-532: the loop is the rebuild's, so a batch of one
+// continues the strictly sequential build).  Caller holds both mutexes.
+static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, uint64_t* n_inserted) {
     vecgpu_slab* s = h->slab;
-    std::lock_guard<std::mutex> lk(s->mu);
-    std::lock_guard<std::mutex> lk2(h->mu);
     int rc = use_device(s->device);
     if (rc) return rc;
     if (batch == 0) batch = 16384;  // measured on 1 M x 384: 3.7 / 2.8 / 2.5 / 2.2 s at 4096 / 8192 / 16384 / 32768, same recall
     const uint64_t n = s->rows;
     if (n >= 0xFFFFFFFFull) return fail(VECGPU_ERR_INVALID_PARAM, "too many rows");
-    h->n_nodes = 0;
-    h->entry = -1;
-    h->entry_level = -1;
-    h->scored = h->rounds = 0;
-    for (int b = 0; b < 5; ++b) h->batch_hist[b] = 0;
-    h->slab_gen = s->layout_gen;
-    h->node_level.assign(n, 0);
-    h->in_graph.assign(n, 0);
-    h->upper_base.assign(n, 0);
-    uint64_t upper_slots = 0;
-    for (uint64_t pos = 0; pos < n; ++pos) {
-        const int L = hnsw_level_for(h, pos);
-        h->node_level[pos] = (int8_t)L;
-        h->upper_base[pos] = (uint32_t)upper_slots;
-        upper_slots += (uint64_t)L;
-    }
-    h->nbr0.assign((size_t)n * h->max_m0, 0);
-    h->dist0.assign((size_t)n * h->max_m0, 0.f);
-    h->deg0.assign(n, 0);
-    h->nbrU.assign((size_t)upper_slots * h->M, 0);
-    h->distU.assign((size_t)upper_slots * h->M, 0.f);
-    h->degU.assign(upper_slots, 0);
-
     const bool use_dev = hnsw_device_enabled(h);
-    h->host_stale = false;  // the host lists were just reset
+    uint64_t pos0 = 0;
+    if (n_inserted) *n_inserted = 0;
+    if (incremental && h->entry >= 0) {
+        if (h->slab_gen != s->layout_gen)
+            return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction, reload or out-of-order insert) since this HNSW index was built: rebuild it");
+        pos0 = h->node_level.size();
+        if (pos0 > n) return fail(VECGPU_ERR_CUDA, "the slab has fewer rows than the index: rebuild it");
+        if (pos0 == n) return 0;
+        if ((rc = hnsw_ensure_host(h))) return rc;  // the lists are extended on the host, then uploaded again
+        uint64_t upper_slots = h->degU.size();
+        h->node_level.resize(n, 0);
+        h->in_graph.resize(n, 0);
+        h->upper_base.resize(n, 0);
+        for (uint64_t pos = pos0; pos < n; ++pos) {
+            const int L = hnsw_level_for(h, pos);
+            h->node_level[pos] = (int8_t)L;
+            h->upper_base[pos] = (uint32_t)upper_slots;
+            upper_slots += (uint64_t)L;
+        }
+        h->nbr0.resize((size_t)n * h->max_m0, 0);
+        h->dist0.resize((size_t)n * h->max_m0, 0.f);
+        h->deg0.resize(n, 0);
+        h->nbrU.resize((size_t)upper_slots * h->M, 0);
+        h->distU.resize((size_t)upper_slots * h->M, 0.f);
+        h->degU.resize(upper_slots, 0);
+        if (use_dev) {
+            if ((rc = hnsw_dev_upload_all(h, false))) return rc;
+        } else {
+            hnsw_dev_free_graph(h);
+        }
+    } else {
+        h->n_nodes = 0;
+        h->entry = -1;
+        h->entry_level = -1;
+        h->scored = h->rounds = 0;
+        for (int b = 0; b < 5; ++b) h->batch_hist[b] = 0;
+        h->slab_gen = s->layout_gen;
+        h->node_level.assign(n, 0);
+        h->in_graph.assign(n, 0);
+        h->upper_base.assign(n, 0);
+        uint64_t upper_slots = 0;
+        for (uint64_t pos = 0; pos < n; ++pos) {
+            const int L = hnsw_level_for(h, pos);
+            h->node_level[pos] = (int8_t)L;
+            h->upper_base[pos] = (uint32_t)upper_slots;
+            upper_slots += (uint64_t)L;
+        }
+        h->nbr0.assign((size_t)n * h->max_m0, 0);
+        h->dist0.assign((size_t)n * h->max_m0, 0.f);
+        h->deg0.assign(n, 0);
+        h->nbrU.assign((size_t)upper_slots * h->M, 0);
+        h->distU.assign((size_t)upper_slots * h->M, 0.f);
+        h->degU.assign(upper_slots, 0);
+        h->host_stale = false;  // the host lists were just reset
+        if (use_dev) {
+            if ((rc = hnsw_dev_upload_all(h, true))) return rc;  // empty lists; kept in sync batch by batch
+        } else {
+            hnsw_dev_free_graph(h);
+        }
+    }
     // device search + device linking by default; VECGPU_HNSW_LINK=host keeps the ordered edge replay on the host threads
     const char* link_env = getenv("VECGPU_HNSW_LINK");
     const bool dev_link = use_dev && !(link_env && link_env[0] == 'h') && batch <= 32768 && h->max_m0 <= 256;
     const bool timing = getenv("VECGPU_HNSW_TIMING") != nullptr;
     double t_search = 0, t_decode = 0, t_ops = 0, t_link = 0, t_flush = 0;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    if (use_dev) {
-        if ((rc = hnsw_dev_upload_all(h, true))) return rc;  // empty lists; kept in sync batch by batch
-    } else {
-        hnsw_dev_free_graph(h);
-    }
 
     struct HOp {
         uint32_t from, to;
@@ -908,7 +938,8 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     std::vector<HOp> ops;
     const int nthreads = std::max(1, omp_get_max_threads());
     std::vector<std::vector<uint32_t>> t_dirty0(nthreads), t_dirtyU(nthreads);
-    uint64_t pos = 0;
+    uint64_t pos = pos0;
+    const uint64_t nodes_before = h->n_nodes;
     while (pos < n) {
         const uint64_t want = std::min<uint64_t>(batch, std::max<uint64_t>(1, h->n_nodes / 4));
         nodes.clear();
@@ -1054,7 +1085,25 @@ extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
     if (timing)
         fprintf(stderr, "[vecgpu hnsw build] search+flush %.3f s  decode %.3f s  ops %.3f s  link %.3f s  (threads %d, %s linking)\n",
                 t_search + t_flush, t_decode, t_ops, t_link, nthreads, dev_link ? "device" : "host");
+    if (n_inserted) *n_inserted = h->n_nodes - nodes_before;
     return 0;
+}
+
+extern "C" int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch) {
+    VG_TRY
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lk(h->slab->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    return hnsw_build_locked(h, batch, false, nullptr);
+    VG_CATCH
+}
+
+extern "C" int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint64_t* n_inserted) {
+    VG_TRY
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lk(h->slab->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    return hnsw_build_locked(h, batch, true, n_inserted);
     VG_CATCH
 }
 
@@ -1204,6 +1253,7 @@ extern "C" int vecgpu_hnsw_export_nodes(vecgpu_hnsw* h, uint64_t cap, int64_t* r
         const uint64_t rows = h->node_level.size();
         for (uint64_t pos = 0; pos < rows; ++pos) {
             if (!h->in_graph[pos]) continue;
+            if (pos < s->h_skip.size() && s->h_skip[pos]) continue;  // deleted since: Vec0Tab::delete removed the node row (vtab.rs:1340-1397)
             if (n < cap) {
                 rowids[n] = h_rowid_of(s, (uint32_t)pos);
                 levels[n] = h->node_level[pos];
@@ -1257,19 +1307,23 @@ extern "C" int vecgpu_hnsw_export_edges(vecgpu_hnsw* h, uint64_t cap, int64_t* f
     }
     uint64_t n = 0;
     const uint64_t rows = h->node_level.size();
+    auto gone = [&](uint64_t pos) { return pos < s->h_skip.size() && s->h_skip[pos] != 0; };  // deleted since the build
     for (uint64_t node = 0; node < rows; ++node) {
+        if (gone(node)) continue;  // Vec0Tab::delete removed its edges in both directions (vtab.rs:1340-1397)
         for (int lv = 0; lv <= h->node_level[node]; ++lv) {
             float* dist;
             uint16_t* deg;
             uint32_t maxc;
             const uint32_t* nb = h_nbr(h, (uint32_t)node, lv, &dist, &deg, &maxc);
-            for (uint32_t i = 0; i < *deg; ++i, ++n) {
+            for (uint32_t i = 0; i < *deg; ++i) {
+                if (gone(nb[i])) continue;
                 if (n < cap) {
                     from_rowids[n] = h_rowid_of(s, (uint32_t)node);
                     to_rowids[n] = h_rowid_of(s, nb[i]);
                     levels[n] = lv;
                     dists[n] = dist[i];
                 }
+                ++n;
             }
         }
     }

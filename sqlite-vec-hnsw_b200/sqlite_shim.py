@@ -158,12 +158,29 @@ class Vec0Table:
             # the vtab rejects wrong-length vectors on insert (src/vtab.rs:1474-1498)
             raise vec0.DimensionMismatch(
                 f"Dimension mismatch: expected {self.dims}, got {len(blob)} bytes", self.dims, None)
+        appended = self.slab is not None and rowid > self._max_rowid()
         self.conn.execute(f'INSERT INTO "main"."{self.table}_data" (rowid, vec{self.column_idx:02d}) VALUES (?, ?)', (rowid, blob))
         if self.slab is not None:
             self.slab.upsert(rowid, blob or b"")
             self._fingerprint = self._current_fingerprint()
-        self._hnsw_stale = getattr(self, "_hnsw", None) is not None
+        idx = getattr(self, "_hnsw", None)
+        if idx is not None and not getattr(self, "_hnsw_stale", False) and appended:
+            # Vec0Tab::insert -> insert_hnsw (src/vtab.rs:1409, src/hnsw/insert.rs:279-532): a row that arrives in rowid order
+            # is inserted into the resident graph at once (vecgpu_hnsw_insert_appended); the shadow tables follow at the
+            # next flush_hnsw_shadow() / rebuild_hnsw()
+            if blob:
+                if self._hnsw_slab is not self.slab:
+                    idx.insert_appended(new_vectors=np.frombuffer(blob, dtype="<f4").reshape(1, -1), new_rowids=[rowid])
+                else:
+                    idx.insert_appended()
+                self._hnsw_shadow_lag = True
+        else:
+            self._hnsw_stale = idx is not None  # out of rowid order: row positions moved, the index is rebuilt on demand
         return rowid
+
+    def _max_rowid(self):
+        mx = self.conn.execute(f'SELECT MAX(rowid) FROM "main"."{self.table}_data"').fetchone()[0]
+        return 0 if mx is None else mx
 
     def update(self, rowid, blob):
         self.conn.execute(f'UPDATE "main"."{self.table}_data" SET vec{self.column_idx:02d} = ? WHERE rowid = ?', (blob, int(rowid)))
@@ -219,9 +236,22 @@ class Vec0Table:
         self._hnsw_column = column
         self._hnsw_stale = False
         self._hnsw.rebuild()
+        return self.flush_hnsw_shadow(m, efc)
+
+    def flush_hnsw_shadow(self, m=None, efc=None):
+        """Write the resident graph back into "{t}_{c}_hnsw_nodes / _hnsw_edges / _hnsw_meta" in bulk (after a rebuild, or after
+        rows were inserted incrementally).  -> number of nodes."""
+        column = self._hnsw_column
+        meta = f'"{self.table}_{column}_hnsw_meta"'
+        if m is None:
+            m, efc = self.conn.execute(f"SELECT m, ef_construction FROM {meta} WHERE id = 1").fetchone()
+        self._hnsw_shadow_lag = False
         rid, lv = self._hnsw.export_nodes()
         fr, to, elv, dist = self._hnsw.export_edges()
         entry, entry_level = self._hnsw.entry_point()
+        if len(rid) and entry not in set(rid.tolist()):  # the entry point was deleted since: the highest remaining node (vtab.rs:1380-1394)
+            top = int(np.argmax(lv))
+            entry, entry_level = int(rid[top]), int(lv[top])
         nodes, edges = f'"{self.table}_{column}_hnsw_nodes"', f'"{self.table}_{column}_hnsw_edges"'
         self.conn.execute(f"DELETE FROM {edges}")
         self.conn.execute(f"DELETE FROM {nodes}")
@@ -236,9 +266,9 @@ class Vec0Table:
 
     def hnsw_knn(self, query, k, ef_search=200, auto_rebuild=False):
         """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)].
-        Rows deleted since the rebuild are never returned.  Rows inserted or updated since the rebuild are not in the graph
-        (the reference inserts them incrementally, src/vtab.rs:1409 -> insert_hnsw; this index is rebuilt in bulk instead):
-        the call refuses to answer from a stale index unless auto_rebuild=True rebuilds it first."""
+        Rows deleted since the rebuild are never returned; rows inserted in rowid order since are in the graph already
+        (insert()).  Rows inserted out of rowid order, or updated, are not (their row positions or stored vectors changed):
+        the call then refuses to answer from the stale index unless auto_rebuild=True rebuilds it first."""
         if getattr(self, "_hnsw", None) is None:
             raise vec0.InvalidState("no HNSW index: call rebuild_hnsw() first")
         if getattr(self, "_hnsw_stale", False):

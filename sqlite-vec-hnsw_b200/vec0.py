@@ -682,6 +682,32 @@ class HnswIndex:
         _check(self._lib.vecgpu_hnsw_build(self._h, batch))
         return self.stats()["nodes"]
 
+    def insert_appended(self, batch=0, new_vectors=None, new_rowids=None):
+        """insert_hnsw (src/hnsw/insert.rs:279-532) for rows that arrive in rowid order: index the rows appended to the slab
+        since the last rebuild / insert_appended.  An index made by for_column() keeps its own slab of STORED vectors
+        (normalised and / or int8): pass the raw column vectors of the new rows (and their rowids, if the column's are not
+        1..n) and they are converted like the rest (insert.rs:300-322) and appended there first.  -> nodes added."""
+        if new_vectors is not None:
+            if not getattr(self, "_owns_slab", False):
+                raise InvalidParameter("new_vectors is for indexes made by for_column(); append to the column slab instead")
+            raw = np.ascontiguousarray(new_vectors, dtype="<f4").reshape(-1, self.slab.dims)
+            bad = np.zeros(len(raw), dtype=bool)
+            if self.normalize_vectors and self.metric == DistanceMetric.Cosine:
+                bad = ~(np.einsum("ij,ij->i", raw.astype(np.float64), raw.astype(np.float64)) > 0)  # "Cannot normalize zero vector"
+                safe = raw.copy()
+                safe[bad] = 1.0
+                raw = normalize(safe)
+            stored = quantize_int8_for_index(raw) if self.slab.vec_type == VectorType.Int8 else raw
+            first = self.slab.count()[0]
+            self.slab.append(stored, new_rowids)
+            if bad.any():
+                ids = np.arange(first + 1, first + 1 + len(raw)) if new_rowids is None else np.asarray(new_rowids)
+                for i in np.flatnonzero(bad):
+                    self.slab.upsert(int(ids[i]), b"")  # cannot be stored: a skipped row, like in the rebuild
+        n = C.c_uint64()
+        _check(self._lib.vecgpu_hnsw_insert_appended(self._h, batch, C.byref(n)))
+        return n.value
+
     def stats(self):
         n, e, r, sc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         lvl = C.c_int32()

@@ -128,6 +128,11 @@ int main() {
         auto ep = idx->entry_point().unwrap();           // -> _hnsw_meta entry_point_rowid / _level (src/hnsw/mod.rs:97-103)
         CHECK(ep.first >= 1 && ep.first <= 3 && ep.second >= 0);
         CHECK(HnswIndex::create(*slab, DistanceMetric::Cosine, 1, 400).is_err());  // M in [2,100] (src/sql_functions.rs:442-469)
+        // Vec0Tab::insert -> insert_hnsw: a row that arrives in rowid order joins the graph without a rebuild
+        CHECK(slab->upsert(4, blob_f32({0.6f, 0.8f, 0})).is_ok());
+        CHECK(idx->insert_appended().unwrap() == 1 && idx->insert_appended().unwrap() == 0);
+        auto res4 = idx->search(blob_f32({0.6f, 0.8f, 0}), 2).unwrap();
+        CHECK(res4.size() == 2 && res4[0].first == 4 && res4[1].first == 2);
         delete idx;
         delete slab;
     }

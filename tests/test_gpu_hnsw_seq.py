@@ -174,3 +174,95 @@ def test_cta_per_query_walk_other_metrics_and_degrees(vg, orc, gpu, elem, dims, 
                 assert np.array_equal(one[i][0][0], wr[i]) and np.array_equal(one[i][1][0].view("<u4"), wd[i].view("<u4"))
         assert idx.device_stats()["fallbacks"] == 0
         idx.close()
+
+
+def test_insert_appended_with_batch_one_continues_the_sequential_build(vg, orc, gpu):
+    """vecgpu_hnsw_insert_appended: rows appended to the slab after a build are indexed by continuing the rebuild's insertion
+    loop.  With batches of one, building the first 1800 rows and then inserting 700 more (in two appends) gives the strictly
+    sequential reference graph of all 2500 rows, edge for edge and distance bit for distance bit (insert.rs:279-532)."""
+    elem, dims, n, M, efc = F32, 32, 2500, 12, 60
+    v = orc.synth_rows(elem, 6, 1, n, dims, 1)
+    q = orc.synth_rows(elem, 7, 1, 12, dims, 1)
+    with vg.Slab(elem, dims) as s:
+        s.load(v[:1800])
+        idx = vg.HnswIndex(s, L2, M=M, ef_construction=efc, seed=1)
+        assert idx.insert_appended(batch=1) == 1800      # an empty index is simply built
+        assert idx.insert_appended(batch=1) == 0         # nothing new
+        s.append(v[1800:2200])
+        assert idx.insert_appended(batch=1) == 400
+        for i in range(2200, n):                         # the reference's shape: one INSERT at a time
+            s.upsert(i + 1, v[i].tobytes())
+        assert idx.insert_appended(batch=1) == n - 2200
+        want_levels = orc.HnswSeq.levels(1, n, M)
+        h = orc.HnswSeq(elem, dims, L2, v, M=M, ef_construction=efc, quirk=False)
+        h.build(want_levels)
+        fr, to, lv, ds = idx.export_edges()
+        got = _edge_map(fr - 1, to - 1, lv, ds)
+        ofr, oto, olv, ods = h.export()
+        want = _edge_map(ofr, oto, olv, ods)
+        assert got.keys() == want.keys()
+        for key in want:
+            assert got[key] == want[key], f"adjacency of node {key[0]} at level {key[1]} differs from the sequential build"
+        info = h.info()
+        assert idx.entry_point() == (info["entry"] + 1, info["entry_level"]) and idx.stats()["nodes"] == n
+        r, d, c = idx.search(q, 10, ef_search=64)
+        orr, od = h.search(q, 10, 64)
+        assert np.array_equal(r, orr + 1) and np.array_equal(d.view("<u4"), od.view("<u4"))
+        idx.close()
+        h.close()
+
+
+def test_insert_appended_batched_and_its_failure_modes(vg, orc, gpu):
+    """Default batching: 20 000 rows built, 10 000 appended and inserted — every row is a node, recall against the exact scan is
+    that of a full rebuild; deleted rows are never returned; an out-of-order insert moves row positions, after which the
+    index refuses to be extended or searched until it is rebuilt."""
+    dims, n0, n = 48, 20_000, 30_000
+    v = orc.synth_rows(F32, 6, 1, n, dims, 1)
+    q = orc.synth_rows(F32, 7, 1, 200, dims, 1)
+    rowids = np.arange(1, n + 1, dtype="<i8") * 2           # even rowids: room for an out-of-order insert
+    with vg.Slab(F32, dims) as s:
+        s.load(v[:n0], rowids[:n0])
+        idx = vg.HnswIndex(s, L2, M=16, ef_construction=100, seed=3)
+        assert idx.rebuild() == n0
+        s.append(v[n0:], rowids[n0:])
+        s.delete(int(rowids[n0 + 5]))                        # a new row deleted before it is indexed: never a node
+        assert idx.insert_appended() == n - n0 - 1
+        assert idx.stats()["nodes"] == n - 1
+        er, _, _ = s.knn(q, 10, L2)
+        r, d, c = idx.search(q, 10, ef_search=100)
+        rec_inc = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(r, er)])
+        assert not np.isin(r, [rowids[n0 + 5]]).any()
+        assert (r > rowids[n0 - 1]).any(), "appended rows are found"
+        idx2 = vg.HnswIndex(s, L2, M=16, ef_construction=100, seed=3)
+        idx2.rebuild()
+        r2, _, _ = idx2.search(q, 10, ef_search=100)
+        rec_full = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(r2, er)])
+        assert rec_inc >= rec_full - 0.03 and rec_inc >= 0.8, (rec_inc, rec_full)
+        idx2.close()
+        s.upsert(7, v[3].tobytes())                          # rowid 7 lies between 6 and 8: row positions move
+        with pytest.raises(vg.InvalidState):
+            idx.insert_appended()
+        with pytest.raises(vg.InvalidState):
+            idx.search(q[:1], 10)
+        assert idx.rebuild() == n                            # n - 1 live rows + the new one
+        idx.close()
+
+
+def test_insert_appended_on_a_cosine_int8_column(vg, orc, gpu):
+    """An index made by for_column() owns the slab of stored vectors: new rows are passed raw, normalised and quantised like the
+    rest (insert.rs:300-322); a zero vector cannot be normalised and stays out of the index."""
+    dims, n0, n = 64, 3000, 4000
+    v = orc.synth_rows(F32, 6, 1, n, dims, 1)
+    v[3500] = 0
+    q = orc.synth_rows(F32, 7, 1, 50, dims, 1)
+    with vg.Slab(F32, dims) as col:
+        col.load(v[:n0])
+        idx = vg.HnswIndex.for_column(col, vg.DistanceMetric.Cosine, M=16, ef_construction=100, index_quantization="int8")
+        assert idx.rebuild() == n0
+        col.append(v[n0:])
+        assert idx.insert_appended(new_vectors=v[n0:]) == n - n0 - 1
+        er, ed, _ = col.knn(q, 10, vg.DistanceMetric.Cosine)
+        r, d, c = idx.search(q, 10, ef_search=200)
+        rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(r, er)])
+        assert rec >= 0.9 and (r > n0).any() and not (r == 3501).any()   # the reference's bar for int8 indexes (>= 90 %)
+        idx.close()

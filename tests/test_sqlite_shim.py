@@ -198,13 +198,23 @@ def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
     # the exact scan agrees that both are gone
     exact = [r for r, _ in t.knn(v[99].tobytes(), 10)]
     assert 100 not in exact and ep not in exact
-    # an insert leaves the bulk-built index stale: refuse, or rebuild on demand
-    new = random_rows(F32, 1, dims, seed=18)[0]
-    new_id = t.insert(new.tobytes())
+    # rows that arrive in rowid order are inserted into the resident graph at once (Vec0Tab::insert -> insert_hnsw,
+    # src/vtab.rs:1409); the shadow tables follow at the next flush
+    new = random_rows(F32, 3, dims, seed=18)
+    ids = [t.insert(new[i].tobytes()) for i in range(3)]
+    assert ids == [n + 1, n + 2, n + 3]
+    for i in range(3):
+        assert t.hnsw_knn(new[i].tobytes(), 3)[0][0] == ids[i]
+    assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_nodes" WHERE rowid > ?', (n,)).fetchone()[0] == 0
+    assert t.flush_hnsw_shadow() == n - 2 + 3
+    assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_nodes" WHERE rowid > ?', (n,)).fetchone()[0] == 3
+    assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_edges" WHERE from_rowid = ?', (ids[0],)).fetchone()[0] > 0
+    # an insert OUT of rowid order (rowid 100 was deleted above) moves row positions: the index is stale — refuse, or rebuild
+    old_id = t.insert(new[0].tobytes(), rowid=100)
     with pytest.raises(vg.InvalidState):
-        t.hnsw_knn(new.tobytes(), 3)
-    assert t.hnsw_knn(new.tobytes(), 3, auto_rebuild=True)[0][0] == new_id
-    t.update(5, new.tobytes())
+        t.hnsw_knn(new[0].tobytes(), 3)
+    assert {r for r, _ in t.hnsw_knn(new[0].tobytes(), 3, auto_rebuild=True)[:2]} == {old_id, ids[0]}
+    t.update(5, new[1].tobytes())
     with pytest.raises(vg.InvalidState):
         t.hnsw_knn(new.tobytes(), 3)
     t.close()
