@@ -128,6 +128,7 @@ struct vecgpu_hnsw {
     uint32_t* d_nbrU = nullptr;
     uint16_t* d_degU = nullptr;
     size_t dn_rows = 0, dn_slots = 0;
+    size_t dcap_rows = 0, dcap_slots = 0;  // allocated capacity of the device lists (>= dn_rows / dn_slots: incremental inserts grow them)
     bool dev_valid = false;              // device copy exists and matches the host lists except for the dirty ones
     std::vector<uint8_t> dirty0, dirtyU;
     std::vector<uint32_t> dirty0_list, dirtyU_list;
@@ -396,6 +397,7 @@ static void hnsw_dev_free_graph(vecgpu_hnsw* h) {
     h->d_deg0 = h->d_degU = nullptr;
     h->d_dist0 = h->d_distU = nullptr;
     h->dn_rows = h->dn_slots = 0;
+    h->dcap_rows = h->dcap_slots = 0;
     h->dev_valid = false;
 }
 
@@ -412,8 +414,8 @@ static int hnsw_dev_upload_all(vecgpu_hnsw* h, bool empty_graph = false) {
     CU(cudaMalloc(&h->d_degU, std::max<size_t>(1, slots) * 2));
     CU(cudaMalloc(&h->d_dist0, std::max<size_t>(1, n * h->max_m0) * 4));
     CU(cudaMalloc(&h->d_distU, std::max<size_t>(1, slots * h->M) * 4));
-    h->dn_rows = n;
-    h->dn_slots = slots;
+    h->dn_rows = h->dcap_rows = n;
+    h->dn_slots = h->dcap_slots = slots;
     if (n) CU(cudaMemcpyAsync(h->d_upper_base, h->upper_base.data(), n * 4, cudaMemcpyHostToDevice, s->stream));
     if (empty_graph) {  // start of a rebuild: every list is empty, only the degrees need a defined value
         CU(cudaMemsetAsync(h->d_deg0, 0, std::max<size_t>(1, n) * 2, s->stream));
@@ -436,6 +438,48 @@ static int hnsw_dev_upload_all(vecgpu_hnsw* h, bool empty_graph = false) {
     h->dirty0_list.clear();
     h->dirtyU_list.clear();
     h->dev_valid = true;
+    return 0;
+}
+
+// Extend the device lists for rows appended to the slab (incremental inserts): capacity grows geometrically, the existing
+// lists stay where they are (or move device to device), the new nodes start with empty lists.  No host round trip of the graph.
+static int hnsw_dev_grow(vecgpu_hnsw* h, size_t n_old, size_t slots_old, size_t n, size_t slots) {
+    vecgpu_slab* s = h->slab;
+    auto regrow = [&](void** p, size_t old_bytes, size_t new_bytes) -> int {
+        void* np = nullptr;
+        CU(cudaMalloc(&np, std::max<size_t>(16, new_bytes)));
+        if (*p && old_bytes) CU(cudaMemcpyAsync(np, *p, old_bytes, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (*p) cudaFree(*p);
+        *p = np;
+        return 0;
+    };
+    int rc;
+    if (n > h->dcap_rows) {
+        const size_t cap = std::max(n, h->dcap_rows + h->dcap_rows / 2);
+        if ((rc = regrow((void**)&h->d_nbr0, n_old * h->max_m0 * 4, cap * h->max_m0 * 4))) return rc;
+        if ((rc = regrow((void**)&h->d_dist0, n_old * h->max_m0 * 4, cap * h->max_m0 * 4))) return rc;
+        if ((rc = regrow((void**)&h->d_deg0, n_old * 2, cap * 2))) return rc;
+        if ((rc = regrow((void**)&h->d_upper_base, n_old * 4, cap * 4))) return rc;
+        h->dcap_rows = cap;
+    }
+    if (slots > h->dcap_slots) {
+        const size_t cap = std::max(slots, h->dcap_slots + h->dcap_slots / 2);
+        if ((rc = regrow((void**)&h->d_nbrU, slots_old * h->M * 4, cap * h->M * 4))) return rc;
+        if ((rc = regrow((void**)&h->d_distU, slots_old * h->M * 4, cap * h->M * 4))) return rc;
+        if ((rc = regrow((void**)&h->d_degU, slots_old * 2, cap * 2))) return rc;
+        h->dcap_slots = cap;
+    }
+    if (n > n_old) {
+        CU(cudaMemcpyAsync(h->d_upper_base + n_old, h->upper_base.data() + n_old, (n - n_old) * 4, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemsetAsync(h->d_deg0 + n_old, 0, (n - n_old) * 2, s->stream));
+    }
+    if (slots > slots_old) CU(cudaMemsetAsync(h->d_degU + slots_old, 0, (slots - slots_old) * 2, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    h->dn_rows = n;
+    h->dn_slots = slots;
+    h->dirty0.resize(n, 0);
+    h->dirtyU.resize(slots, 0);
     return 0;
 }
 
@@ -554,7 +598,8 @@ static int hnsw_dev_launch_t(vecgpu_hnsw* h, HSearchParams& p, size_t per_warp) 
         p.spec_rows = 1;
         cta_smem += (size_t)s->row_stride * HC_ROWS;
     }
-    if (p.nq <= cta_max && p.node_level == nullptr && p.q_smem && cta_smem <= 220 * 1024 && p.ef_wide <= 512) {
+    // (inserts too: a rebuild's first batches and incremental inserts are a handful of walks)
+    if (p.nq <= cta_max && p.q_smem && cta_smem <= 220 * 1024 && p.ef_wide <= 512) {
         static int cfg_dev_cta = -1;
         int dev2 = 0;
         CU(cudaGetDevice(&dev2));
@@ -868,8 +913,14 @@ static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, u
         pos0 = h->node_level.size();
         if (pos0 > n) return fail(VECGPU_ERR_CUDA, "the slab has fewer rows than the index: rebuild it");
         if (pos0 == n) return 0;
-        if ((rc = hnsw_ensure_host(h))) return rc;  // the lists are extended on the host, then uploaded again
-        uint64_t upper_slots = h->degU.size();
+        const bool grow_on_device = use_dev && h->dev_valid;
+        if (grow_on_device) {
+            if ((rc = hnsw_dev_flush_dirty(h))) return rc;  // the device copy is the current one from here on
+        } else if ((rc = hnsw_ensure_host(h))) {            // the lists are extended on the host, then uploaded
+            return rc;
+        }
+        const uint64_t slots_old = h->degU.size();
+        uint64_t upper_slots = slots_old;
         h->node_level.resize(n, 0);
         h->in_graph.resize(n, 0);
         h->upper_base.resize(n, 0);
@@ -885,7 +936,9 @@ static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, u
         h->nbrU.resize((size_t)upper_slots * h->M, 0);
         h->distU.resize((size_t)upper_slots * h->M, 0.f);
         h->degU.resize(upper_slots, 0);
-        if (use_dev) {
+        if (grow_on_device) {
+            if ((rc = hnsw_dev_grow(h, pos0, slots_old, n, upper_slots))) return rc;
+        } else if (use_dev) {
             if ((rc = hnsw_dev_upload_all(h, false))) return rc;
         } else {
             hnsw_dev_free_graph(h);
