@@ -271,6 +271,12 @@ int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch);
  * build edge for edge.  *n_inserted (may be NULL) = nodes added.  An empty index is simply built.  Rows inserted OUT of
  * rowid order move row positions: the index then fails with status 4 (like searches) until vecgpu_hnsw_build. */
 int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint64_t* n_inserted);
+/* Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): the node of `rowid` and every edge from or to it are
+ * deleted, then the row — whose vector in the slab the caller has just replaced with vecgpu_slab_upsert — is inserted
+ * again (insert_hnsw).  A row that is now deleted or empty only leaves the graph.  If the node was the entry point, the
+ * highest remaining node takes over for the re-insertion.  The lists are edited on the host and uploaded again: the cost
+ * is one round trip of the graph, not a rebuild. */
+int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid);
 /* search_hnsw (src/hnsw/search.rs:267-335): ef = max(ef_search, k); results closest first, distances in the
  * internal metric (apply convert_distance_for_output for cosine columns); unused slots rowid -1 / +inf. */
 int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef_search,

@@ -377,6 +377,12 @@ public:
         if (rc) return Error::from_status(rc);
         return n;
     }
+    // Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): node and edges deleted, row inserted again
+    Result<Unit> reinsert(int64_t rowid) {
+        int rc = vecgpu_hnsw_reinsert(h_, rowid);
+        if (rc) return Error::from_status(rc);
+        return Unit{};
+    }
     // search_hnsw (src/hnsw/search.rs:267-335); the query must already be in the stored representation
     Result<std::vector<std::pair<int64_t, float>>> search(const std::vector<uint8_t>& query, uint32_t k, uint32_t ef_search = 200) {
         std::vector<int64_t> rowids(k);

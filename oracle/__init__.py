@@ -103,6 +103,7 @@ def _bind(path):
         L.orc_hnsw_new.argtypes = [C.c_int, C.c_uint32, C.c_int, p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
         L.orc_hnsw_free.argtypes = [p]
         L.orc_hnsw_insert.argtypes = [p, C.c_uint32, C.c_int]
+        L.orc_hnsw_reinsert.argtypes = [p, C.c_uint32, C.c_int, C.c_int]
         L.orc_hnsw_build.argtypes = [p, p, p]
         L.orc_hnsw_search.restype = C.c_uint32
         L.orc_hnsw_search.argtypes = [p, p, C.c_uint32, C.c_uint32, p, p]
@@ -328,6 +329,11 @@ class HnswSeq:
         out = np.empty(n, dtype="i1")
         lib().orc_hnsw_levels(seed, n, M, _ptr(out))
         return out
+
+    def reinsert(self, node, level, insert_again=True):
+        """Vec0Tab::update (src/vtab.rs:1860-1895): delete the node and its edges in both directions, then insert it again (the
+        caller has replaced its vector in the array this object was made from)."""
+        lib().orc_hnsw_reinsert(self._h, int(node), int(level), 1 if insert_again else 0)
 
     def build(self, levels, skip=None):
         lv = np.ascontiguousarray(levels, dtype="i1")

@@ -227,7 +227,8 @@ hnsw_t* orc_hnsw_new(int elem, uint32_t dims, int metric, const void* vectors, u
     h->quirk = quirk;
     h->n = n;
     h->vec = vectors;
-    h->level = calloc(n ? n : 1, 1);
+    h->level = malloc(n ? n : 1);
+    memset(h->level, 0xFF, n ? n : 1); /* -1: not a node (yet) */
     h->l0 = calloc(n ? n : 1, sizeof(adj_t));
     h->up = calloc(n ? n : 1, sizeof(adj_t*));
     h->seen = calloc(n ? n : 1, sizeof(uint32_t));
@@ -296,6 +297,43 @@ void orc_hnsw_insert(hnsw_t* h, uint32_t node, int level) {
     free(out);
     free(res);
     free(cand);
+}
+
+/* Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): DELETE the node row and every edge from or to it, then
+ * insert_hnsw the row again (its vector — read through h->vec — has been replaced by the caller).  The level is the caller's
+ * (the product keeps the level of the row position).  When the node was the entry point the search for the re-insertion
+ * starts from the highest remaining node (first such position), which is what the meta row would be repaired to. */
+void orc_hnsw_reinsert(hnsw_t* h, uint32_t node, int level, int insert_again) {
+    for (uint64_t v = 0; v < h->n; ++v) {
+        for (int lv = 0; lv < MAX_LEVELS; ++lv) {
+            adj_t* a = adj_of(h, (uint32_t)v, lv, 0);
+            if (!a) break;
+            if (v == node) {
+                a->deg = 0;
+                continue;
+            }
+            uint32_t w = 0;
+            for (uint32_t i = 0; i < a->deg; ++i)
+                if (a->nb[i] != node) {
+                    a->nb[w] = a->nb[i];
+                    a->d[w] = a->d[i];
+                    ++w;
+                }
+            a->deg = w;
+        }
+    }
+    h->level[node] = -1; /* not a node any more */
+    --h->n_nodes;
+    if (h->entry == (int64_t)node) {
+        h->entry = -1;
+        h->entry_level = -1;
+        for (uint64_t v = 0; v < h->n; ++v)
+            if (h->level[v] > h->entry_level) {
+                h->entry = (int64_t)v;
+                h->entry_level = h->level[v];
+            }
+    }
+    if (insert_again) orc_hnsw_insert(h, node, level);
 }
 
 /* vec_rebuild_hnsw shape: insert rows 0..n-1 in order with the given levels (skip[i] != 0: row not indexed) */

@@ -897,7 +897,8 @@ static void hq_init(vecgpu_hnsw* h, HQuery& q, uint32_t a_index, int node_level,
 // continue the same insertion loop over the rows appended to the slab since the graph was last built or extended
 // (insert_hnsw for rows that arrive in rowid order, src/hnsw/insert.rs:279-532: the loop is the rebuild's, so a batch of one
 // continues the strictly sequential build).  Caller holds both mutexes.
-static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, uint64_t* n_inserted) {
+static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, uint64_t* n_inserted,
+                             const std::vector<uint32_t>* only_nodes = nullptr) {
     vecgpu_slab* s = h->slab;
     int rc = use_device(s->device);
     if (rc) return rc;
@@ -912,7 +913,7 @@ static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, u
             return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction, reload or out-of-order insert) since this HNSW index was built: rebuild it");
         pos0 = h->node_level.size();
         if (pos0 > n) return fail(VECGPU_ERR_CUDA, "the slab has fewer rows than the index: rebuild it");
-        if (pos0 == n) return 0;
+        if (pos0 == n && !only_nodes) return 0;
         const bool grow_on_device = use_dev && h->dev_valid;
         if (grow_on_device) {
             if ((rc = hnsw_dev_flush_dirty(h))) return rc;  // the device copy is the current one from here on
@@ -991,11 +992,19 @@ static int hnsw_build_locked(vecgpu_hnsw* h, uint32_t batch, bool incremental, u
     std::vector<HOp> ops;
     const int nthreads = std::max(1, omp_get_max_threads());
     std::vector<std::vector<uint32_t>> t_dirty0(nthreads), t_dirtyU(nthreads);
-    uint64_t pos = pos0;
+    uint64_t pos = only_nodes ? n : pos0;  // only_nodes: (re)insert exactly these row positions, as one batch
+    bool explicit_batch = only_nodes != nullptr;
     const uint64_t nodes_before = h->n_nodes;
-    while (pos < n) {
+    while (explicit_batch || pos < n) {
         const uint64_t want = std::min<uint64_t>(batch, std::max<uint64_t>(1, h->n_nodes / 4));
         nodes.clear();
+        if (explicit_batch) {
+            explicit_batch = false;
+            for (uint32_t p : *only_nodes) {
+                nodes.push_back(p);
+                h->in_graph[p] = 1;
+            }
+        }
         while (pos < n && nodes.size() < want) {
             if (s->h_skip.empty() || !s->h_skip[pos]) {
                 nodes.push_back((uint32_t)pos);
@@ -1157,6 +1166,72 @@ extern "C" int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint6
     std::lock_guard<std::mutex> lk(h->slab->mu);
     std::lock_guard<std::mutex> lk2(h->mu);
     return hnsw_build_locked(h, batch, true, n_inserted);
+    VG_CATCH
+}
+
+// Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): the node and every edge from or to it are deleted, then the
+// row — whose vector in the slab has just been replaced by vecgpu_slab_upsert — is inserted again (insert_hnsw).  The node
+// keeps its row position and therefore its level.  If the row is now deleted or empty it only leaves the graph.  The entry
+// point, when it is the node itself, passes to the highest remaining node (the first such position) for the re-insertion.
+extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
+    VG_TRY
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    vecgpu_slab* s = h->slab;
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    if (h->entry < 0) return fail(VECGPU_ERR_INVALID_PARAM, "the index is empty: build it first");
+    if (h->slab_gen != s->layout_gen)
+        return fail(VECGPU_ERR_CUDA, "the slab's rows moved (compaction, reload or out-of-order insert) since this HNSW index was built: rebuild it");
+    const int64_t p64 = slab_find(s, rowid, nullptr);
+    if (p64 < 0) return fail(VECGPU_ERR_INVALID_PARAM, "rowid %lld is not in the slab", (long long)rowid);
+    const uint64_t rows = h->node_level.size();
+    if ((uint64_t)p64 >= rows) return fail(VECGPU_ERR_INVALID_PARAM, "rowid %lld was appended after the index was built: use vecgpu_hnsw_insert_appended", (long long)rowid);
+    const uint32_t pos = (uint32_t)p64;
+    if ((rc = hnsw_ensure_host(h))) return rc;  // the lists are edited on the host and uploaded again
+    if (h->in_graph[pos]) {
+        const int64_t nrows = (int64_t)rows;
+#pragma omp parallel for schedule(static)
+        for (int64_t v = 0; v < nrows; ++v) {
+            for (int lv = 0; lv <= h->node_level[v]; ++lv) {
+                float* dist;
+                uint16_t* deg;
+                uint32_t maxc;
+                uint32_t* nb = h_nbr(h, (uint32_t)v, lv, &dist, &deg, &maxc);
+                if ((uint32_t)v == pos) {
+                    *deg = 0;
+                    continue;
+                }
+                uint32_t w = 0;
+                for (uint32_t i = 0; i < *deg; ++i)
+                    if (nb[i] != pos) {
+                        nb[w] = nb[i];
+                        dist[w] = dist[i];
+                        ++w;
+                    }
+                *deg = (uint16_t)w;
+            }
+        }
+        h->in_graph[pos] = 0;
+        h->n_nodes -= 1;
+        if ((uint32_t)h->entry == pos) {
+            h->entry = -1;
+            h->entry_level = -1;
+            for (uint64_t v = 0; v < rows; ++v)
+                if (h->in_graph[v] && !(v < s->h_skip.size() && s->h_skip[v]) && h->node_level[v] > h->entry_level) {
+                    h->entry = (int64_t)v;
+                    h->entry_level = h->node_level[v];
+                }
+        }
+    }
+    h->host_stale = false;
+    if (hnsw_device_enabled(h)) {
+        if ((rc = hnsw_dev_upload_all(h, false))) return rc;
+    }
+    if (pos < s->h_skip.size() && s->h_skip[pos]) return 0;  // deleted or emptied: it only leaves the graph
+    std::vector<uint32_t> one{pos};
+    return hnsw_build_locked(h, 1, true, nullptr, &one);
     VG_CATCH
 }
 

@@ -187,7 +187,14 @@ class Vec0Table:
         if self.slab is not None:
             self.slab.upsert(int(rowid), blob or b"")
             self._fingerprint = self._current_fingerprint()
-        self._hnsw_stale = getattr(self, "_hnsw", None) is not None
+        idx = getattr(self, "_hnsw", None)
+        if idx is not None and not getattr(self, "_hnsw_stale", False):
+            # Vec0Tab::update (src/vtab.rs:1860-1895): delete the node and its edges, insert the row again
+            if self._hnsw_slab is not self.slab:
+                idx.reinsert(int(rowid), None if not blob else np.frombuffer(blob, dtype="<f4"))
+            else:
+                idx.reinsert(int(rowid))
+            self._hnsw_shadow_lag = True
 
     def delete(self, rowid):
         rowid = int(rowid)
@@ -267,7 +274,7 @@ class Vec0Table:
     def hnsw_knn(self, query, k, ef_search=200, auto_rebuild=False):
         """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)].
         Rows deleted since the rebuild are never returned; rows inserted in rowid order since are in the graph already
-        (insert()).  Rows inserted out of rowid order, or updated, are not (their row positions or stored vectors changed):
+        (insert()) and updated rows have been re-inserted (update()).  A row inserted out of rowid order moves row positions:
         the call then refuses to answer from the stale index unless auto_rebuild=True rebuilds it first."""
         if getattr(self, "_hnsw", None) is None:
             raise vec0.InvalidState("no HNSW index: call rebuild_hnsw() first")

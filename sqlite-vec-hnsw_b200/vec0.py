@@ -708,6 +708,24 @@ class HnswIndex:
         _check(self._lib.vecgpu_hnsw_insert_appended(self._h, batch, C.byref(n)))
         return n.value
 
+    def reinsert(self, rowid, new_vector=None):
+        """Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): the row's node and its edges in both directions are
+        deleted and the row is inserted again with the vector it has in the slab now.  An index made by for_column() takes
+        the new raw column vector (None / empty: the row leaves the index) and stores its converted form first."""
+        rowid = int(rowid)
+        if getattr(self, "_owns_slab", False):
+            if new_vector is None or len(new_vector) == 0:
+                self.slab.upsert(rowid, b"")
+            else:
+                raw = np.ascontiguousarray(new_vector, dtype="<f4").reshape(1, self.slab.dims)
+                ok = True
+                if self.normalize_vectors and self.metric == DistanceMetric.Cosine:
+                    ok = float(np.dot(raw[0].astype(np.float64), raw[0].astype(np.float64))) > 0
+                    raw = normalize(raw) if ok else raw
+                stored = quantize_int8_for_index(raw) if self.slab.vec_type == VectorType.Int8 else raw
+                self.slab.upsert(rowid, stored.tobytes() if ok else b"")
+        _check(self._lib.vecgpu_hnsw_reinsert(self._h, rowid))
+
     def stats(self):
         n, e, r, sc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         lvl = C.c_int32()

@@ -133,6 +133,11 @@ int main() {
         CHECK(idx->insert_appended().unwrap() == 1 && idx->insert_appended().unwrap() == 0);
         auto res4 = idx->search(blob_f32({0.6f, 0.8f, 0}), 2).unwrap();
         CHECK(res4.size() == 2 && res4[0].first == 4 && res4[1].first == 2);
+        // Vec0Tab::update: the row gets a new vector, its node is deleted and inserted again
+        CHECK(slab->upsert(3, blob_f32({0, 1, 0})).is_ok() && idx->reinsert(3).is_ok());
+        auto res3 = idx->search(blob_f32({0, 1, 0}), 2).unwrap();
+        CHECK(res3.size() == 2 && res3[0].first == 3 && res3[0].second < 1e-6f && res3[1].first == 4);
+        CHECK(idx->reinsert(77).is_err());
         delete idx;
         delete slab;
     }

@@ -266,3 +266,53 @@ def test_insert_appended_on_a_cosine_int8_column(vg, orc, gpu):
         rec = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(r, er)])
         assert rec >= 0.9 and (r > n0).any() and not (r == 3501).any()   # the reference's bar for int8 indexes (>= 90 %)
         idx.close()
+
+
+def test_reinsert_equals_the_sequential_reference_update(vg, orc, gpu):
+    """vecgpu_hnsw_reinsert = Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): delete the node and its edges in
+    both directions, insert the row again with its new vector.  After a batch-of-one build and a series of updates — ordinary
+    nodes, the entry point itself, a row that becomes empty — the graph equals the sequential restatement's after the same
+    operations, edge for edge and distance bit for distance bit, and searches agree."""
+    elem, dims, n, M, efc = F32, 24, 1500, 8, 50
+    v = orc.synth_rows(elem, 6, 1, n, dims, 1).copy()
+    new = orc.synth_rows(elem, 9, 1, 8, dims, 1)
+    q = np.concatenate([orc.synth_rows(elem, 7, 1, 8, dims, 1), new])
+    levels = orc.HnswSeq.levels(1, n, M)
+    with vg.Slab(elem, dims) as s:
+        s.load(v)
+        idx = vg.HnswIndex(s, L2, M=M, ef_construction=efc, seed=1)
+        idx.rebuild(batch=1)
+        h = orc.HnswSeq(elem, dims, L2, v, M=M, ef_construction=efc, quirk=False)   # borrows v: edits below are seen
+        h.build(levels)
+        ep = idx.entry_point()[0]
+        targets = [17, 900, ep, 3, 1499, ep]   # the entry point twice (it changes hands the first time)
+        for j, rid in enumerate(targets):
+            if j == 5:
+                rid = idx.entry_point()[0]
+            v[rid - 1] = new[j]
+            h._v[rid - 1] = new[j]
+            s.upsert(rid, new[j].tobytes())
+            idx.reinsert(rid)
+            h.reinsert(rid - 1, levels[rid - 1])
+        s.upsert(40, b"")                          # the row becomes empty: it only leaves the graph
+        idx.reinsert(40)
+        h.reinsert(39, levels[39], insert_again=False)
+        fr, to, lv, ds = idx.export_edges()
+        got = _edge_map(fr - 1, to - 1, lv, ds)
+        ofr, oto, olv, ods = h.export()
+        want = _edge_map(ofr, oto, olv, ods)
+        assert got.keys() == want.keys()
+        for key in want:
+            assert got[key] == want[key], f"adjacency of node {key[0]} at level {key[1]} differs from the sequential update"
+        info = h.info()
+        assert idx.entry_point() == (info["entry"] + 1, info["entry_level"]) and idx.stats()["nodes"] == n - 1
+        r, d, c = idx.search(q, 5, ef_search=64)
+        orr, od = h.search(q, 5, 64)
+        assert np.array_equal(r, orr + 1) and np.array_equal(d.view("<u4"), od.view("<u4"))
+        assert 40 not in r
+        for j in (0, 1, 3, 4):                     # the updated rows are found by their new vectors
+            assert r[8 + j, 0] == targets[j] and d[8 + j, 0] == 0
+        with pytest.raises(vg.InvalidParameter):
+            idx.reinsert(n + 5)                    # not in the slab
+        idx.close()
+        h.close()

@@ -173,7 +173,8 @@ def test_rebuild_hnsw_writes_the_reference_shadow_tables(vg, orc, gpu, tmp_path,
 @pytest.mark.gpu
 def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
     """Vec0Tab::delete (src/vtab.rs:1340-1397) removes the node, its edges in both directions and fixes the meta row;
-    the resident index never returns a deleted rowid; inserts / updates make it stale until it is rebuilt."""
+    the resident index never returns a deleted rowid; rows inserted in rowid order and updated rows are (re)inserted into the
+    resident graph at once; a row inserted out of rowid order makes it stale until it is rebuilt."""
     sh = _shim()
     conn = sqlite3.connect(str(tmp_path / "hooks.db"))
     sh.create_shadow_tables(conn, "docs", 1, [])
@@ -214,9 +215,15 @@ def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
     with pytest.raises(vg.InvalidState):
         t.hnsw_knn(new[0].tobytes(), 3)
     assert {r for r, _ in t.hnsw_knn(new[0].tobytes(), 3, auto_rebuild=True)[:2]} == {old_id, ids[0]}
+    # Vec0Tab::update (src/vtab.rs:1860-1895): the node is deleted and inserted again with the new vector
+    t.update(5, new[2].tobytes())
+    got5 = t.hnsw_knn(new[2].tobytes(), 3)
+    assert {got5[0][0], got5[1][0]} == {5, ids[2]} and got5[0][1] < 1e-6 and got5[1][1] < 1e-6
+    t.update(6, b"")                                 # emptied: leaves the index
+    assert 6 not in [r for r, _ in t.hnsw_knn(v[5].tobytes(), 10)]
     t.update(5, new[1].tobytes())
-    with pytest.raises(vg.InvalidState):
-        t.hnsw_knn(new.tobytes(), 3)
+    got5 = t.hnsw_knn(new[1].tobytes(), 3)
+    assert {got5[0][0], got5[1][0]} == {5, ids[1]} and got5[1][1] < 1e-6
     t.close()
 
 
