@@ -1173,6 +1173,7 @@ extern "C" int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint6
 // row — whose vector in the slab has just been replaced by vecgpu_slab_upsert — is inserted again (insert_hnsw).  The node
 // keeps its row position and therefore its level.  If the row is now deleted or empty it only leaves the graph.  The entry
 // point, when it is the node itself, passes to the highest remaining node (the first such position) for the re-insertion.
+// With the graph resident the edges are removed by hnsw_unlink_kernel; in lockstep mode (VECGPU_HNSW_DEVICE=0) on the host lists.
 extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
     VG_TRY
     if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
@@ -1189,8 +1190,28 @@ extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
     const uint64_t rows = h->node_level.size();
     if ((uint64_t)p64 >= rows) return fail(VECGPU_ERR_INVALID_PARAM, "rowid %lld was appended after the index was built: use vecgpu_hnsw_insert_appended", (long long)rowid);
     const uint32_t pos = (uint32_t)p64;
-    if ((rc = hnsw_ensure_host(h))) return rc;  // the lists are edited on the host and uploaded again
-    if (h->in_graph[pos]) {
+    const bool on_device = hnsw_device_enabled(h) && h->dev_valid;
+    if (on_device) {
+        if (h->in_graph[pos]) {
+            // the edges are removed where the lists live: one thread per list, no round trip of the graph
+            if ((rc = hnsw_dev_flush_dirty(h))) return rc;
+            const uint32_t L = (uint32_t)h->node_level[pos];
+            hnsw_unlink_kernel<<<(uint32_t)std::min<uint64_t>((rows + 255) / 256, (uint64_t)s->num_sms * 16), 256, 0, s->stream>>>(
+                h->d_nbr0, h->d_dist0, h->d_deg0, rows, h->max_m0, pos, pos, 1);
+            LAUNCHED();
+            const uint64_t slots = h->degU.size();
+            if (slots) {
+                hnsw_unlink_kernel<<<(uint32_t)std::min<uint64_t>((slots + 255) / 256, (uint64_t)s->num_sms * 16), 256, 0, s->stream>>>(
+                    h->d_nbrU, h->d_distU, h->d_degU, slots, h->M, pos, h->upper_base[pos], L);
+                LAUNCHED();
+            }
+            CU(cudaStreamSynchronize(s->stream));
+            h->host_stale = true;  // the device copy is the current one
+        }
+    } else if ((rc = hnsw_ensure_host(h))) {  // (lockstep mode) the lists are edited on the host
+        return rc;
+    }
+    if (h->in_graph[pos] && !on_device) {
         const int64_t nrows = (int64_t)rows;
 #pragma omp parallel for schedule(static)
         for (int64_t v = 0; v < nrows; ++v) {
@@ -1213,6 +1234,8 @@ extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
                 *deg = (uint16_t)w;
             }
         }
+    }
+    if (h->in_graph[pos]) {
         h->in_graph[pos] = 0;
         h->n_nodes -= 1;
         if ((uint32_t)h->entry == pos) {
@@ -1225,9 +1248,9 @@ extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
                 }
         }
     }
-    h->host_stale = false;
-    if (hnsw_device_enabled(h)) {
-        if ((rc = hnsw_dev_upload_all(h, false))) return rc;
+    if (!on_device) {
+        h->host_stale = false;
+        if (hnsw_device_enabled(h) && (rc = hnsw_dev_upload_all(h, false))) return rc;
     }
     if (pos < s->h_skip.size() && s->h_skip[pos]) return 0;  // deleted or emptied: it only leaves the graph
     std::vector<uint32_t> one{pos};

@@ -932,6 +932,33 @@ __global__ void __launch_bounds__(HC_THREADS) hnsw_search_cta_kernel(const HSear
     }
 }
 
+// ---- Vec0Tab::update / delete on the resident graph (src/vtab.rs:1340-1397, 1860-1895): every edge to `node` is removed
+// (one thread per adjacency list, the rest of the list keeps its order) and its own lists are emptied.
+__global__ void __launch_bounds__(256) hnsw_unlink_kernel(uint32_t* nbr, float* dist, uint16_t* deg, uint64_t n_lists, uint32_t width,
+                                                          uint32_t node, uint64_t own_first, uint64_t own_count) {
+    for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_lists; l += (uint64_t)gridDim.x * blockDim.x) {
+        if (l >= own_first && l < own_first + own_count) {  // the node's own lists
+            deg[l] = 0;
+            continue;
+        }
+        uint32_t* nb = nbr + l * width;
+        float* ds = dist + l * width;
+        const uint32_t d = deg[l];
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < d; ++i) {
+            const uint32_t v = nb[i];
+            if (v != node) {
+                if (w != i) {
+                    nb[w] = v;
+                    ds[w] = ds[i];
+                }
+                ++w;
+            }
+        }
+        if (w != d) deg[l] = (uint16_t)w;
+    }
+}
+
 // ---- linking on the device (insert.rs:408-498 for a whole batch) ---------------------------------------------------
 // The search kernel left, per (insert, layer), the sorted closest results in out_keys.  Forward edges: the new node's own
 // list is exactly its first min(cnt, maxc) results, in order.  Reverse edges: every (neighbour, layer) list receives the

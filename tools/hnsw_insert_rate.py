@@ -40,6 +40,13 @@ for bsz in (100, 1000, 10_000):
     el = time.perf_counter() - t1
     pos += bsz
     print(f"{bsz} rows per call: slab append {(t1 - t0) * 1e3:.1f} ms, graph insert {el * 1e3:.1f} ms = {bsz / el:.0f} vec/s  {idx.device_stats()}", flush=True)
+t0 = time.perf_counter()
+for i in range(20):                      # Vec0Tab::update: the row gets a new vector, its node is deleted and inserted again
+    rid = 1000 + 37 * i
+    s.upsert(rid, new[12_000 + i].tobytes())
+    idx.reinsert(rid)
+el = time.perf_counter() - t0
+print(f"update + reinsert: 20 rows in {el:.3f} s = {el / 20 * 1e3:.1f} ms each", flush=True)
 q = new[:200]
 r, d, c = idx.search(q, 1, ef_search=64)
 print(f"the first 200 inserted rows find themselves: {(r[:, 0] == n + 1 + np.arange(200)).mean():.3f}; nodes {idx.stats()['nodes']}", flush=True)
