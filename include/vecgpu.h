@@ -273,7 +273,8 @@ int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch);
 int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint64_t* n_inserted);
 /* Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): the node of `rowid` and every edge from or to it are
  * deleted, then the row — whose vector in the slab the caller has just replaced with vecgpu_slab_upsert — is inserted
- * again (insert_hnsw).  A row that is now deleted or empty only leaves the graph.  If the node was the entry point, the
+ * again (insert_hnsw).  A row that is now deleted or empty only leaves the graph — which makes this call the HNSW side of
+ * Vec0Tab::delete too (src/vtab.rs:1340-1397), after vecgpu_slab_delete.  If the node was the entry point, the
  * highest remaining node takes over for the re-insertion.  The edges are removed where the lists live (one thread per
  * adjacency list): ~0.9 ms per update on a 1 M-row graph, removal and re-insertion together. */
 int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid);

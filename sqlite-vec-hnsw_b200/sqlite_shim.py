@@ -218,6 +218,8 @@ class Vec0Table:
             self._fingerprint = self._current_fingerprint()
         if getattr(self, "_hnsw", None) is not None and self._hnsw_slab is not self.slab:
             self._hnsw_slab.delete(rowid)  # the stored-representation slab carries its own tombstones
+        if getattr(self, "_hnsw", None) is not None and not getattr(self, "_hnsw_stale", False):
+            self._hnsw.reinsert(rowid)     # the row is deleted: its node and edges leave the resident graph too (vtab.rs:1340-1397)
 
     # ---- vec_rebuild_hnsw (src/sql_functions.rs:436-534) with the graph built on the GPU and written back in bulk
     def rebuild_hnsw(self, column, new_m=None, new_ef_construction=None):

@@ -196,6 +196,10 @@ def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
     assert conn.execute('SELECT MAX(level) FROM "docs_emb_hnsw_nodes"').fetchone()[0] == epl2
     got = [r for r, _ in t.hnsw_knn(v[99].tobytes(), 10, ef_search=80)]
     assert 100 not in got and ep not in got and len(got) == 10
+    # the resident graph lost the two nodes as well, and its entry point is a live node again
+    assert t._hnsw.stats()["nodes"] == n - 2 and t._hnsw.entry_point()[0] not in (ep, 100)
+    fr, to, _, _ = t._hnsw.export_edges()
+    assert not np.isin(fr, [ep, 100]).any() and not np.isin(to, [ep, 100]).any()
     # the exact scan agrees that both are gone
     exact = [r for r, _ in t.knn(v[99].tobytes(), 10)]
     assert 100 not in exact and ep not in exact
