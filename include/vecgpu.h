@@ -278,6 +278,14 @@ int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint64_t* n_inse
  * highest remaining node takes over for the re-insertion.  The edges are removed where the lists live (one thread per
  * adjacency list): ~0.9 ms per update on a 1 M-row graph, removal and re-insertion together. */
 int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid);
+/* insert_hnsw (src/hnsw/insert.rs:279-532) for a row inserted OUT of rowid order (Vec0Tab::insert with an explicit or re-used
+ * rowid, src/vtab.rs:1409-1682, insert_hnsw at :1667): vecgpu_slab_upsert has just placed `rowid` between existing rows, which moved every later
+ * row one position up.  The resident graph is renumbered where it lives (one thread per adjacency list; the per-node arrays
+ * shift by one row, device to device), the row gets the level of the next insertion (the level sequence follows insertion
+ * order, as in the reference) and is inserted like any other row — the graph equals the sequential build's in insertion
+ * order, edge for edge.  Exactly one out-of-order upsert may lie between two calls, with no un-indexed appended rows;
+ * otherwise status 4 and the index needs vecgpu_hnsw_build.  Needs the resident graph (not VECGPU_HNSW_DEVICE=0). */
+int vecgpu_hnsw_insert_at(vecgpu_hnsw* h, int64_t rowid);
 /* search_hnsw (src/hnsw/search.rs:267-335): ef = max(ef_search, k); results closest first, distances in the
  * internal metric (apply convert_distance_for_output for cosine columns); unused slots rowid -1 / +inf. */
 int vecgpu_hnsw_search(vecgpu_hnsw* h, const void* queries, uint32_t nq, uint32_t k, uint32_t ef_search,

@@ -383,6 +383,12 @@ public:
         if (rc) return Error::from_status(rc);
         return Unit{};
     }
+    // insert_hnsw for a row the slab has just received OUT of rowid order (row positions moved by one): renumbered in place
+    Result<Unit> insert_at(int64_t rowid) {
+        int rc = vecgpu_hnsw_insert_at(h_, rowid);
+        if (rc) return Error::from_status(rc);
+        return Unit{};
+    }
     // search_hnsw (src/hnsw/search.rs:267-335); the query must already be in the stored representation
     Result<std::vector<std::pair<int64_t, float>>> search(const std::vector<uint8_t>& query, uint32_t k, uint32_t ef_search = 200) {
         std::vector<int64_t> rowids(k);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "vecgpu_hnsw_build": (C.c_int, [C.c_void_p, C.c_uint32]),
     "vecgpu_hnsw_insert_appended": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
     "vecgpu_hnsw_reinsert": (C.c_int, [C.c_void_p, C.c_int64]),
+    "vecgpu_hnsw_insert_at": (C.c_int, [C.c_void_p, C.c_int64]),
     "vecgpu_hnsw_search": (C.c_int, [C.c_void_p, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _p, _p]),
     "vecgpu_hnsw_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -144,6 +144,8 @@ struct vecgpu_hnsw {
     float* d_dist0 = nullptr;
     float* d_distU = nullptr;
     bool host_stale = false;
+    void* d_spare[4] = {nullptr, nullptr, nullptr, nullptr};  // vecgpu_hnsw_insert_at: second set of the level-0 arrays (nbr0, dist0, deg0, upper_base)
+    size_t spare_rows = 0;
     uint8_t* d_link = nullptr;
     size_t link_cap = 0;
 };
@@ -393,6 +395,11 @@ static void hnsw_dev_free_graph(vecgpu_hnsw* h) {
     cudaFree(h->d_degU);
     cudaFree(h->d_dist0);
     cudaFree(h->d_distU);
+    for (void*& sp : h->d_spare) {
+        cudaFree(sp);
+        sp = nullptr;
+    }
+    h->spare_rows = 0;
     h->d_nbr0 = h->d_upper_base = h->d_nbrU = nullptr;
     h->d_deg0 = h->d_degU = nullptr;
     h->d_dist0 = h->d_distU = nullptr;
@@ -1174,12 +1181,8 @@ extern "C" int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint6
 // keeps its row position and therefore its level.  If the row is now deleted or empty it only leaves the graph.  The entry
 // point, when it is the node itself, passes to the highest remaining node (the first such position) for the re-insertion.
 // With the graph resident the edges are removed by hnsw_unlink_kernel; in lockstep mode (VECGPU_HNSW_DEVICE=0) on the host lists.
-extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
-    VG_TRY
-    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+static int hnsw_reinsert_locked(vecgpu_hnsw* h, int64_t rowid) {
     vecgpu_slab* s = h->slab;
-    std::lock_guard<std::mutex> lk(s->mu);
-    std::lock_guard<std::mutex> lk2(h->mu);
     int rc = use_device(s->device);
     if (rc) return rc;
     if (h->entry < 0) return fail(VECGPU_ERR_INVALID_PARAM, "the index is empty: build it first");
@@ -1255,6 +1258,119 @@ extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
     if (pos < s->h_skip.size() && s->h_skip[pos]) return 0;  // deleted or emptied: it only leaves the graph
     std::vector<uint32_t> one{pos};
     return hnsw_build_locked(h, 1, true, nullptr, &one);
+}
+
+extern "C" int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid) {
+    VG_TRY
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    std::lock_guard<std::mutex> lk(h->slab->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    return hnsw_reinsert_locked(h, rowid);
+    VG_CATCH
+}
+
+// Vec0Tab::insert of a row whose rowid is NOT the highest (an explicit rowid, or a re-used one): vecgpu_slab_upsert has just
+// placed it between existing rows, which moved every later row one position up.  Node ids are row positions: the graph is
+// renumbered in place (neighbour ids >= the new position + 1, the per-node arrays shifted by one row), the new row gets the
+// level it would have had as an appended row (level_for(old row count)), its upper lists go behind the existing ones, and it
+// is inserted like any other row (insert_hnsw).  Exactly ONE such insert may lie between two calls.
+extern "C" int vecgpu_hnsw_insert_at(vecgpu_hnsw* h, int64_t rowid) {
+    VG_TRY
+    if (!h) return fail(VECGPU_ERR_INVALID_PARAM, "hnsw is NULL");
+    vecgpu_slab* s = h->slab;
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk2(h->mu);
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    if (h->entry < 0) return fail(VECGPU_ERR_INVALID_PARAM, "the index is empty: build it first");
+    const uint64_t n_old = h->node_level.size();
+    if (s->layout_gen == h->slab_gen && s->rows == n_old) {
+        // a re-used rowid whose tombstoned row still sits in the slab: no row moved, the node is simply inserted again
+        const int64_t q64 = slab_find(s, rowid, nullptr);
+        if (q64 >= 0 && !h->in_graph[(size_t)q64]) return hnsw_reinsert_locked(h, rowid);
+    }
+    if (s->layout_gen != h->slab_gen + 1 || s->rows != n_old + 1)
+        return fail(VECGPU_ERR_CUDA, "more than one change of row positions (or appended rows not yet indexed) since the index was last brought up to date: rebuild it");
+    const int64_t p64 = slab_find(s, rowid, nullptr);
+    if (p64 < 0) return fail(VECGPU_ERR_INVALID_PARAM, "rowid %lld is not in the slab", (long long)rowid);
+    const uint32_t p = (uint32_t)p64;
+    const bool use_dev = hnsw_device_enabled(h);
+    if (!use_dev || !h->dev_valid) return fail(VECGPU_ERR_CUDA, "the graph is not resident on the device (lockstep mode or after a capacity overflow): rebuild it");
+    if ((rc = hnsw_dev_flush_dirty(h))) return rc;
+    const uint64_t slots_old = h->degU.size();
+    const int L = hnsw_level_for(h, n_old);  // the level the row would have got as row number n_old (appended)
+    // ---- shift the level-0 arrays by one row from p into the spare set, renumbering the neighbour ids on the way; the
+    //      two sets swap roles (no allocation per insert once both exist)
+    const bool timing = getenv("VECGPU_HNSW_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    const uint64_t n = n_old + 1;
+    const size_t item_bytes[4] = {(size_t)h->max_m0 * 4, (size_t)h->max_m0 * 4, 2, 4};
+    if (h->spare_rows < n) {
+        const size_t cap = std::max<size_t>(n + n / 8, h->dcap_rows);
+        for (int a = 0; a < 4; ++a) {
+            if (h->d_spare[a]) CU(cudaFree(h->d_spare[a]));
+            h->d_spare[a] = nullptr;
+        }
+        h->spare_rows = 0;
+        for (int a = 0; a < 4; ++a) CU(cudaMalloc(&h->d_spare[a], std::max<size_t>(16, cap * item_bytes[a])));
+        h->spare_rows = cap;
+    }
+    {
+        const uint64_t items = n_old * h->max_m0;
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((items + h->max_m0 + 255) / 256, (uint64_t)s->num_sms * 32);
+        const uint32_t blocks1 = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)s->num_sms * 32);
+        hnsw_shift_rows_kernel<uint32_t, true><<<blocks, 256, 0, s->stream>>>(h->d_nbr0, (uint32_t*)h->d_spare[0], items, h->max_m0, p);
+        LAUNCHED();
+        hnsw_shift_rows_kernel<uint32_t, false><<<blocks, 256, 0, s->stream>>>((const uint32_t*)h->d_dist0, (uint32_t*)h->d_spare[1], items, h->max_m0, p);
+        LAUNCHED();
+        hnsw_shift_rows_kernel<uint16_t, false><<<blocks1, 256, 0, s->stream>>>(h->d_deg0, (uint16_t*)h->d_spare[2], n_old, 1, p);
+        LAUNCHED();
+        hnsw_shift_rows_kernel<uint32_t, false><<<blocks1, 256, 0, s->stream>>>(h->d_upper_base, (uint32_t*)h->d_spare[3], n_old, 1, p);
+        LAUNCHED();
+        if (slots_old) {
+            hnsw_renumber_kernel<<<(uint32_t)std::min<uint64_t>((slots_old + 255) / 256, (uint64_t)s->num_sms * 16), 256, 0, s->stream>>>(
+                h->d_nbrU, h->d_degU, slots_old, h->M, p);
+            LAUNCHED();
+        }
+        std::swap(*(void**)&h->d_nbr0, h->d_spare[0]);
+        std::swap(*(void**)&h->d_dist0, h->d_spare[1]);
+        std::swap(*(void**)&h->d_deg0, h->d_spare[2]);
+        std::swap(*(void**)&h->d_upper_base, h->d_spare[3]);
+        std::swap(h->dcap_rows, h->spare_rows);
+        h->dn_rows = n;
+        const uint32_t ub = (uint32_t)slots_old;  // the new node's upper lists (if any) go behind the existing ones
+        CU(cudaMemcpyAsync(h->d_upper_base + p, &ub, 4, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    const double t_shift = now();
+    // ---- host mirrors of the per-node state (the host LISTS are stale from here on: the device copy is the current one)
+    h->node_level.insert(h->node_level.begin() + p, (int8_t)L);
+    h->in_graph.insert(h->in_graph.begin() + p, 0);
+    h->upper_base.insert(h->upper_base.begin() + p, (uint32_t)slots_old);
+    h->nbr0.resize((size_t)n * h->max_m0, 0);
+    h->dist0.resize((size_t)n * h->max_m0, 0.f);
+    h->deg0.resize(n, 0);
+    h->dirty0.assign(n, 0);
+    h->host_stale = true;
+    if ((uint64_t)h->entry >= p) h->entry += 1;
+    // ---- the new node's upper lists go behind the existing ones
+    if (L > 0) {
+        const uint64_t slots = slots_old + (uint64_t)L;
+        h->nbrU.resize((size_t)slots * h->M, 0);
+        h->distU.resize((size_t)slots * h->M, 0.f);
+        h->degU.resize(slots, 0);
+        if ((rc = hnsw_dev_grow(h, n, slots_old, n, slots))) return rc;
+    }
+    h->slab_gen = s->layout_gen;
+    if (p < s->h_skip.size() && s->h_skip[p]) return 0;  // an empty blob: a row, but not a node
+    std::vector<uint32_t> one{p};
+    const double t_host = now();
+    rc = hnsw_build_locked(h, 1, true, nullptr, &one);
+    if (timing)
+        fprintf(stderr, "[vecgpu hnsw insert_at] shift+renumber %.3f ms  host mirrors %.3f ms  insert %.3f ms\n", (t_shift - t_begin) * 1e3,
+                (t_host - t_shift) * 1e3, (now() - t_host) * 1e3);
+    return rc;
     VG_CATCH
 }
 

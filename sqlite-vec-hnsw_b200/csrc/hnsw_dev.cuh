@@ -959,6 +959,37 @@ __global__ void __launch_bounds__(256) hnsw_unlink_kernel(uint32_t* nbr, float* 
     }
 }
 
+// ---- a row inserted OUT of rowid order moved every later row one position up: node ids are row positions, so every
+// neighbour id >= first_moved goes up by one and the per-node arrays shift by one row from there.  The level-0 arrays are
+// rewritten into a spare allocation of the same size (the two swap roles call after call: no allocation per insert), the
+// renumbering fused into the copy of the ids; coalesced, one pass: 2 x (read + write) of the level-0 lists per insert.
+// Ids behind a list's degree are renumbered too — they are never read.
+template <typename T, bool RENUMBER>
+__global__ void __launch_bounds__(256) hnsw_shift_rows_kernel(const T* __restrict__ in, T* __restrict__ out, uint64_t n_items,
+                                                              uint32_t width, uint32_t first_moved) {
+    const uint64_t hole = (uint64_t)first_moved * width;  // first item of the new (empty) row
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_items + width; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i >= hole && i < hole + width) {
+            out[i] = 0;
+            continue;
+        }
+        T v = in[i < hole ? i : i - width];
+        if (RENUMBER && v >= (T)first_moved) v += 1;
+        out[i] = v;
+    }
+}
+
+// the upper lists are few (one node in M has any): renumbered in place, one thread per list
+__global__ void __launch_bounds__(256) hnsw_renumber_kernel(uint32_t* nbr, const uint16_t* deg, uint64_t n_lists, uint32_t width,
+                                                            uint32_t first_moved) {
+    for (uint64_t l = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; l < n_lists; l += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t* nb = nbr + l * width;
+        const uint32_t d = deg[l];
+        for (uint32_t i = 0; i < d; ++i)
+            if (nb[i] >= first_moved) nb[i] += 1;
+    }
+}
+
 // ---- linking on the device (insert.rs:408-498 for a whole batch) ---------------------------------------------------
 // The search kernel left, per (insert, layer), the sorted closest results in out_keys.  Forward edges: the new node's own
 // list is exactly its first min(cnt, maxc) results, in order.  Reverse edges: every (neighbour, layer) list receives the

@@ -174,8 +174,19 @@ class Vec0Table:
                 else:
                     idx.insert_appended()
                 self._hnsw_shadow_lag = True
+        elif idx is not None and not getattr(self, "_hnsw_stale", False) and self.slab is not None:
+            # an explicit rowid below the highest one: the row went between existing rows and every later row moved one
+            # position up — the resident graph is renumbered on the device and the row inserted (vecgpu_hnsw_insert_at)
+            try:
+                if self._hnsw_slab is not self.slab:
+                    idx.insert_at(rowid, None if not blob else np.frombuffer(blob, dtype="<f4"))
+                else:
+                    idx.insert_at(rowid)
+                self._hnsw_shadow_lag = True
+            except vec0.VecError:
+                self._hnsw_stale = True  # (lockstep mode, or rows the index never saw): rebuilt on demand
         else:
-            self._hnsw_stale = idx is not None  # out of rowid order: row positions moved, the index is rebuilt on demand
+            self._hnsw_stale = idx is not None
         return rowid
 
     def _max_rowid(self):

@@ -726,6 +726,25 @@ class HnswIndex:
                 self.slab.upsert(rowid, stored.tobytes() if ok else b"")
         _check(self._lib.vecgpu_hnsw_reinsert(self._h, rowid))
 
+    def insert_at(self, rowid, new_vector=None):
+        """insert_hnsw for a row inserted OUT of rowid order (Vec0Tab::insert with an explicit rowid, src/vtab.rs:1409-1682): the
+        slab has just received `rowid` between existing rows (every later row moved one position up); the resident graph is
+        renumbered on the device and the row is inserted like any other.  One such row per call.  An index made by
+        for_column() takes the raw column vector and stores its converted form first."""
+        rowid = int(rowid)
+        if getattr(self, "_owns_slab", False):
+            if new_vector is None or len(new_vector) == 0:
+                self.slab.upsert(rowid, b"")
+            else:
+                raw = np.ascontiguousarray(new_vector, dtype="<f4").reshape(1, self.slab.dims)
+                ok = True
+                if self.normalize_vectors and self.metric == DistanceMetric.Cosine:
+                    ok = float(np.dot(raw[0].astype(np.float64), raw[0].astype(np.float64))) > 0
+                    raw = normalize(raw) if ok else raw
+                stored = quantize_int8_for_index(raw) if self.slab.vec_type == VectorType.Int8 else raw
+                self.slab.upsert(rowid, stored.tobytes() if ok else b"")
+        _check(self._lib.vecgpu_hnsw_insert_at(self._h, rowid))
+
     def stats(self):
         n, e, r, sc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         lvl = C.c_int32()

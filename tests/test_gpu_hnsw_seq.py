@@ -316,3 +316,72 @@ def test_reinsert_equals_the_sequential_reference_update(vg, orc, gpu):
             idx.reinsert(n + 5)                    # not in the slab
         idx.close()
         h.close()
+
+
+def test_insert_at_equals_the_sequential_build_in_insertion_order(vg, orc, gpu):
+    """vecgpu_hnsw_insert_at = Vec0Tab::insert with an explicit rowid below the highest one (src/vtab.rs:1409-1682 ->
+    insert_hnsw, src/hnsw/insert.rs:279-532).  The slab keeps rows in rowid order, so the new row lands between existing rows
+    and every later row (= node id) moves up by one; the resident graph is renumbered on the device and the row inserted.
+    After a batch-of-one build over even rowids and a series of odd-rowid inserts — first row, last gap, middle, next to the
+    entry point, an empty blob — interleaved with appended rows, the graph equals the sequential restatement's built over
+    the same vectors in INSERTION order, edge for edge and distance bit for distance bit (node ids compared as rowids)."""
+    elem, dims, n0, M, efc = F32, 24, 1500, 8, 50
+    extra = 40
+    v = orc.synth_rows(elem, 6, 1, n0 + extra, dims, 1)
+    q = np.concatenate([orc.synth_rows(elem, 7, 1, 12, dims, 1), v[n0:n0 + 8]])
+    rowids0 = np.arange(1, n0 + 1, dtype="<i8") * 2
+    with vg.Slab(elem, dims) as s:
+        s.load(v[:n0], rowids0)
+        idx = vg.HnswIndex(s, L2, M=M, ef_construction=efc, seed=1)
+        idx.rebuild(batch=1)
+        ep = idx.entry_point()[0]
+        order = list(rowids0)                     # rowid of the k-th inserted row
+        rng = np.random.default_rng(3)
+        odd = [1, 2 * n0 - 1, 1501, ep - 1, ep + 1] + [int(x) for x in rng.choice(np.arange(3, 2 * n0 - 2, 2), 27, replace=False)]
+        odd = [x for x in dict.fromkeys(odd) if 0 < x < 2 * n0][:extra - 8]
+        spare = [x for x in range(3, 2 * n0, 2) if x not in odd][:3]   # odd rowids left free
+        k = n0
+        for j, rid in enumerate(odd):
+            s.upsert(rid, v[k].tobytes())
+            idx.insert_at(rid)
+            order.append(rid)
+            k += 1
+            if j % 8 == 7:                         # an ordinary appended row in between: the level sequence goes on
+                top = 2 * n0 + 2 * (j // 8 + 1)
+                s.upsert(top, v[k].tobytes())
+                assert idx.insert_appended(batch=1) == 1
+                order.append(top)
+                k += 1
+        n = k
+        order = np.array(order, dtype="<i8")
+        assert idx.stats()["nodes"] == n
+        s.upsert(spare[0], b"")                  # an empty blob out of order: a row, not a node
+        idx.insert_at(spare[0])
+        assert idx.stats()["nodes"] == n
+        h = orc.HnswSeq(elem, dims, L2, v[:n], M=M, ef_construction=efc, quirk=False)
+        h.build(orc.HnswSeq.levels(1, n, M))
+        fr, to, lv, ds = idx.export_edges()
+        pos_of = {int(r): i for i, r in enumerate(order)}
+        got = _edge_map(np.array([pos_of[int(x)] for x in fr]), np.array([pos_of[int(x)] for x in to]), lv, ds)
+        ofr, oto, olv, ods = h.export()
+        want = _edge_map(ofr, oto, olv, ods)
+        assert got.keys() == want.keys()
+        for key in want:
+            assert got[key] == want[key], f"adjacency of insertion {key[0]} at level {key[1]} differs from the sequential build"
+        info = h.info()
+        assert idx.entry_point() == (int(order[info["entry"]]), info["entry_level"])
+        r, d, c = idx.search(q, 5, ef_search=64)
+        orr, od = h.search(q, 5, 64)
+        assert np.array_equal(r, order[orr]) and np.array_equal(d.view("<u4"), od.view("<u4"))
+        # the rows inserted out of order sit where the exact scan finds them, and the walk (M = 8: not every one) finds them too
+        er, ed, _ = s.knn(q[12:], 1, L2)
+        assert np.array_equal(er[:, 0], order[n0:n0 + 8]) and not ed.any()
+        assert (r[12:, 0] == er[:, 0]).sum() >= 5
+        # two out-of-order rows without a call in between: the index cannot follow, and says so
+        s.upsert(spare[1], v[0].tobytes())
+        s.upsert(spare[2], v[1].tobytes())
+        with pytest.raises(vg.InvalidState):
+            idx.insert_at(spare[2])
+        assert idx.rebuild() == n + 2
+        idx.close()
+        h.close()

@@ -214,11 +214,10 @@ def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
     assert t.flush_hnsw_shadow() == n - 2 + 3
     assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_nodes" WHERE rowid > ?', (n,)).fetchone()[0] == 3
     assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_edges" WHERE from_rowid = ?', (ids[0],)).fetchone()[0] > 0
-    # an insert OUT of rowid order (rowid 100 was deleted above) moves row positions: the index is stale — refuse, or rebuild
+    # a re-used rowid (100 was deleted above; its tombstoned row still sits in the slab): no row moves, the node goes straight in
     old_id = t.insert(new[0].tobytes(), rowid=100)
-    with pytest.raises(vg.InvalidState):
-        t.hnsw_knn(new[0].tobytes(), 3)
-    assert {r for r, _ in t.hnsw_knn(new[0].tobytes(), 3, auto_rebuild=True)[:2]} == {old_id, ids[0]}
+    assert {r for r, _ in t.hnsw_knn(new[0].tobytes(), 3)[:2]} == {old_id, ids[0]}
+    assert t._hnsw.stats()["nodes"] == n - 2 + 3 + 1
     # Vec0Tab::update (src/vtab.rs:1860-1895): the node is deleted and inserted again with the new vector
     t.update(5, new[2].tobytes())
     got5 = t.hnsw_knn(new[2].tobytes(), 3)
@@ -228,6 +227,37 @@ def test_hnsw_hooks_after_rebuild_delete_insert_update(vg, orc, gpu, tmp_path):
     t.update(5, new[1].tobytes())
     got5 = t.hnsw_knn(new[1].tobytes(), 3)
     assert {got5[0][0], got5[1][0]} == {5, ids[1]} and got5[1][1] < 1e-6
+    t.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("quant", [None, "int8"])
+def test_hnsw_hook_for_a_row_inserted_out_of_rowid_order(vg, orc, gpu, tmp_path, quant):
+    """Vec0Tab::insert with an explicit rowid BETWEEN existing ones (src/vtab.rs:1409-1682): the slab keeps rowid order, so every
+    later row moves up one position; the resident graph is renumbered on the device (vecgpu_hnsw_insert_at) and answers at
+    once — no rebuild — for a plain cosine column (stored = normalised) and an int8-quantised one (stored slab of its own)."""
+    sh = _shim()
+    conn = sqlite3.connect(str(tmp_path / "gap.db"))
+    sh.create_shadow_tables(conn, "docs", 1, [])
+    n, dims = 900, 32
+    v = random_rows(F32, n + 6, dims, seed=23)
+    conn.executemany('INSERT INTO "docs_data" (rowid, vec00) VALUES (?, ?)', [(10 * (i + 1), v[i].tobytes()) for i in range(n)])
+    kw = {} if quant is None else {"index_quantization": quant}
+    sh.create_hnsw_shadow_tables(conn, "docs", "emb", dims, "float32", "cosine", m=8, ef_construction=60, **kw)
+    t = sh.Vec0Table(conn, "docs", F32, dims, distance_metric=COSINE)
+    assert t.rebuild_hnsw("emb") == n
+    for j, rid in enumerate([5, 4567, 8995, 15, 4568, 10 * n + 10]):   # first, middle, last gap, ..., and one appended row
+        assert t.insert(v[n + j].tobytes(), rowid=rid) == rid
+        got = t.hnsw_knn(v[n + j].tobytes(), 3, ef_search=80)
+        assert got[0][0] == rid and got[0][1] < 1e-3, (rid, got)
+        assert t.knn(v[n + j].tobytes(), 1)[0][0] == rid
+    assert not getattr(t, "_hnsw_stale", False) and t._hnsw.stats()["nodes"] == n + 6
+    # the old rows are still found where they are now (every position behind rowid 5 moved six times)
+    for i in (0, 1, 455, 456, 457, n - 1):
+        assert t.hnsw_knn(v[i].tobytes(), 1, ef_search=80)[0][0] == 10 * (i + 1)
+    assert t.flush_hnsw_shadow() == n + 6
+    assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_nodes" WHERE rowid IN (5, 15, 4567, 4568, 8995)').fetchone()[0] == 5
+    assert conn.execute('SELECT COUNT(*) FROM "docs_emb_hnsw_edges" WHERE from_rowid = 4567').fetchone()[0] > 0
     t.close()
 
 

@@ -52,3 +52,31 @@ r, d, c = idx.search(q, 1, ef_search=64)
 print(f"the first 200 inserted rows find themselves: {(r[:, 0] == n + 1 + np.arange(200)).mean():.3f}; nodes {idx.stats()['nodes']}", flush=True)
 idx.close()
 s.close()
+
+# ---- rows inserted OUT of rowid order (vecgpu_slab_upsert between existing rows + vecgpu_hnsw_insert_at): every later row and
+#      node id moves up by one, on the device.  Needs rowids with gaps, so this table is loaded with even rowids.
+v = oracle.synth_rows(0, 6, 1, n, dims, 1)
+s = vg.Slab(0, dims)
+s.load(v, np.arange(1, n + 1, dtype="<i8") * 2)
+del v
+idx = vg.HnswIndex(s, 0, M=16, ef_construction=200, seed=1)
+idx.rebuild()
+s.upsert(2 * n + 2, new[0].tobytes())     # grows the allocations once (not timed)
+idx.insert_appended(batch=1)
+rng = np.random.default_rng(1)
+rids = (rng.choice(n - 2, 40, replace=False).astype(np.int64) + 1) * 2 + 1
+for lo, hi, label in ((0, 20, "anywhere in the table"),):
+    t_slab = t_idx = 0.0
+    for i in range(lo, hi):
+        t0 = time.perf_counter()
+        s.upsert(int(rids[i]), new[100 + i].tobytes())
+        t1 = time.perf_counter()
+        idx.insert_at(int(rids[i]))
+        t2 = time.perf_counter()
+        t_slab += t1 - t0
+        t_idx += t2 - t1
+    print(f"out-of-order insert ({label}): {hi - lo} rows, slab upsert {t_slab / (hi - lo) * 1e3:.2f} ms + graph insert_at {t_idx / (hi - lo) * 1e3:.2f} ms each", flush=True)
+r, d, c = idx.search(new[100:120], 1, ef_search=64)
+print(f"the 20 rows inserted out of order find themselves: {(r[:, 0] == rids[:20]).mean():.3f}; nodes {idx.stats()['nodes']}", flush=True)
+idx.close()
+s.close()
