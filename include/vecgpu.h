@@ -269,7 +269,8 @@ int vecgpu_hnsw_build(vecgpu_hnsw* h, uint32_t batch);
  * rowid order: indexes the rows appended to the slab (vecgpu_slab_append / _upsert of a new highest rowid) since the graph
  * was last built or extended, by continuing the rebuild's insertion loop — a batch of 1 continues the strictly sequential
  * build edge for edge.  *n_inserted (may be NULL) = nodes added.  An empty index is simply built.  Rows inserted OUT of
- * rowid order move row positions: the index then fails with status 4 (like searches) until vecgpu_hnsw_build. */
+ * rowid order move row positions: call vecgpu_hnsw_insert_at after each such upsert, or the index fails with status 4
+ * (like searches) until vecgpu_hnsw_build. */
 int vecgpu_hnsw_insert_appended(vecgpu_hnsw* h, uint32_t batch, uint64_t* n_inserted);
 /* Vec0Tab::update of an indexed column (src/vtab.rs:1860-1895): the node of `rowid` and every edge from or to it are
  * deleted, then the row — whose vector in the slab the caller has just replaced with vecgpu_slab_upsert — is inserted

@@ -287,8 +287,9 @@ class Vec0Table:
     def hnsw_knn(self, query, k, ef_search=200, auto_rebuild=False):
         """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)].
         Rows deleted since the rebuild are never returned; rows inserted in rowid order since are in the graph already
-        (insert()) and updated rows have been re-inserted (update()).  A row inserted out of rowid order moves row positions:
-        the call then refuses to answer from the stale index unless auto_rebuild=True rebuilds it first."""
+        (insert()) and updated rows have been re-inserted (update()).  A row inserted out of rowid order is inserted as well
+        (the resident graph is renumbered on the device).  Only if that failed (lockstep mode) the index is stale: the call
+        then refuses to answer unless auto_rebuild=True rebuilds it first."""
         if getattr(self, "_hnsw", None) is None:
             raise vec0.InvalidState("no HNSW index: call rebuild_hnsw() first")
         if getattr(self, "_hnsw_stale", False):
