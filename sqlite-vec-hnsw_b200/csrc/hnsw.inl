@@ -1284,15 +1284,12 @@ extern "C" int vecgpu_hnsw_insert_at(vecgpu_hnsw* h, int64_t rowid) {
     if (rc) return rc;
     if (h->entry < 0) return fail(VECGPU_ERR_INVALID_PARAM, "the index is empty: build it first");
     const uint64_t n_old = h->node_level.size();
-    if (s->layout_gen == h->slab_gen && s->rows == n_old) {
-        // a re-used rowid whose tombstoned row still sits in the slab: no row moved, the node is simply inserted again
-        const int64_t q64 = slab_find(s, rowid, nullptr);
-        if (q64 >= 0 && !h->in_graph[(size_t)q64]) return hnsw_reinsert_locked(h, rowid);
-    }
-    if (s->layout_gen != h->slab_gen + 1 || s->rows != n_old + 1)
-        return fail(VECGPU_ERR_CUDA, "more than one change of row positions (or appended rows not yet indexed) since the index was last brought up to date: rebuild it");
     const int64_t p64 = slab_find(s, rowid, nullptr);
     if (p64 < 0) return fail(VECGPU_ERR_INVALID_PARAM, "rowid %lld is not in the slab", (long long)rowid);
+    // a re-used rowid whose tombstoned row still sits in the slab: no row moved, the node is simply inserted again
+    if (s->layout_gen == h->slab_gen && s->rows == n_old && !h->in_graph[(size_t)p64]) return hnsw_reinsert_locked(h, rowid);
+    if (s->layout_gen != h->slab_gen + 1 || s->rows != n_old + 1)
+        return fail(VECGPU_ERR_CUDA, "more than one change of row positions (or appended rows not yet indexed) since the index was last brought up to date: rebuild it");
     const uint32_t p = (uint32_t)p64;
     const bool use_dev = hnsw_device_enabled(h);
     if (!use_dev || !h->dev_valid) return fail(VECGPU_ERR_CUDA, "the graph is not resident on the device (lockstep mode or after a capacity overflow): rebuild it");

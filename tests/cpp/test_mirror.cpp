@@ -138,6 +138,14 @@ int main() {
         auto res3 = idx->search(blob_f32({0, 1, 0}), 2).unwrap();
         CHECK(res3.size() == 2 && res3[0].first == 3 && res3[0].second < 1e-6f && res3[1].first == 4);
         CHECK(idx->reinsert(77).is_err());
+        // Vec0Tab::insert with an explicit rowid BETWEEN existing ones: row positions move, the resident graph is renumbered
+        CHECK(slab->upsert(10, blob_f32({0.8f, 0, 0.6f})).is_ok() && idx->insert_appended().unwrap() == 1);
+        CHECK(slab->upsert(7, blob_f32({0, 0.6f, 0.8f})).is_ok() && idx->insert_at(7).is_ok());
+        auto res7 = idx->search(blob_f32({0, 0.6f, 0.8f}), 1).unwrap();
+        CHECK(res7.size() == 1 && res7[0].first == 7 && res7[0].second < 1e-6f);
+        auto res10 = idx->search(blob_f32({0.8f, 0, 0.6f}), 1).unwrap();
+        CHECK(res10.size() == 1 && res10[0].first == 10);
+        CHECK(idx->insert_at(8).is_err());  // not in the slab
         delete idx;
         delete slab;
     }

@@ -378,6 +378,8 @@ def test_insert_at_equals_the_sequential_build_in_insertion_order(vg, orc, gpu):
         assert np.array_equal(er[:, 0], order[n0:n0 + 8]) and not ed.any()
         assert (r[12:, 0] == er[:, 0]).sum() >= 5
         # two out-of-order rows without a call in between: the index cannot follow, and says so
+        with pytest.raises(vg.InvalidParameter):
+            idx.insert_at(spare[1])                # not in the slab
         s.upsert(spare[1], v[0].tobytes())
         s.upsert(spare[2], v[1].tobytes())
         with pytest.raises(vg.InvalidState):
