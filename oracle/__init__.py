@@ -330,6 +330,10 @@ class HnswSeq:
         lib().orc_hnsw_levels(seed, n, M, _ptr(out))
         return out
 
+    def insert(self, node, level):
+        """insert_hnsw (src/hnsw/insert.rs:279-532) of one row of the array this object was made from."""
+        lib().orc_hnsw_insert(self._h, int(node), int(level))
+
     def reinsert(self, node, level, insert_again=True):
         """Vec0Tab::update (src/vtab.rs:1860-1895): delete the node and its edges in both directions, then insert it again (the
         caller has replaced its vector in the array this object was made from)."""

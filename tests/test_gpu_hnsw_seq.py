@@ -387,3 +387,96 @@ def test_insert_at_equals_the_sequential_build_in_insertion_order(vg, orc, gpu):
         assert idx.rebuild() == n + 2
         idx.close()
         h.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_random_write_traffic_equals_the_sequential_reference(vg, orc, gpu, seed):
+    """Differential test of every write hook on the resident graph, interleaved at random: rows appended (insert_appended), rows
+    inserted between existing rowids (insert_at), rows updated (reinsert), rows deleted (delete + reinsert) and deleted rowids
+    used again (insert_at on the tombstoned row).  The sequential restatement performs the same operations in the same order
+    (insert_hnsw / the delete-and-insert of Vec0Tab::update / Vec0Tab::delete); its node ids are insertion numbers, the
+    product's are row positions that keep moving — the graphs must agree edge for edge, distance bit for distance bit, after
+    every 50 operations, and so must the walks."""
+    rng = np.random.default_rng(seed)
+    elem, dims, n0, M, efc, n_ops = F32, 16, 600, 6, 40, 200
+    total = n0 + n_ops
+    vecs = orc.synth_rows(elem, 20 + seed, 1, total, dims, 1).copy()
+    fresh = orc.synth_rows(elem, 40 + seed, 1, n_ops, dims, 1)
+    q = orc.synth_rows(elem, 7, 1, 16, dims, 1)
+    levels = orc.HnswSeq.levels(seed, total, M)
+    h = orc.HnswSeq(elem, dims, L2, vecs, M=M, ef_construction=efc, quirk=False)
+    rowid_of = [10 * (i + 1) for i in range(n0)]          # insertion number -> rowid
+    node_of = {r: i for i, r in enumerate(rowid_of)}       # rowid -> insertion number
+    live, dead = set(rowid_of), []
+    with vg.Slab(elem, dims) as s:
+        s.load(vecs[:n0], np.array(rowid_of, dtype="<i8"))
+        idx = vg.HnswIndex(s, L2, M=M, ef_construction=efc, seed=seed)
+        idx.rebuild(batch=1)
+        for i in range(n0):
+            h.insert(i, levels[i])
+
+        def check():
+            fr, to, lv, ds = idx.export_edges()
+            got = _edge_map(np.array([node_of[int(x)] for x in fr]), np.array([node_of[int(x)] for x in to]), lv, ds)
+            ofr, oto, olv, ods = h.export()
+            want = _edge_map(ofr, oto, olv, ods)
+            assert got.keys() == want.keys()
+            for key in want:
+                assert got[key] == want[key], f"adjacency of insertion {key[0]} (rowid {rowid_of[key[0]]}) at level {key[1]} differs"
+            info = h.info()
+            assert idx.entry_point() == (rowid_of[info["entry"]], info["entry_level"]) and idx.stats()["nodes"] == info["nodes"] == len(live)
+            r, d, c = idx.search(q, 5, ef_search=48)
+            orr, od = h.search(q, 5, 48)
+            assert np.array_equal(r, np.array(rowid_of, dtype="<i8")[orr]) and np.array_equal(d.view("<u4"), od.view("<u4"))
+
+        check()
+        counts = dict(append=0, between=0, update=0, delete=0, reuse=0)
+        for op in range(n_ops):
+            entry = idx.entry_point()[0]
+            kind = rng.choice(["append", "between", "update", "delete", "reuse"], p=[0.25, 0.3, 0.2, 0.15, 0.1])
+            if kind == "reuse" and not dead:
+                kind = "between"
+            if kind in ("append", "between"):
+                k = len(rowid_of)
+                top = max(rowid_of)
+                if kind == "append":
+                    rid = top + 10
+                else:
+                    rid = int(rng.integers(1, top))
+                    while rid in node_of:
+                        rid = int(rng.integers(1, top))
+                s.upsert(rid, vecs[k].tobytes())
+                if kind == "append":
+                    assert idx.insert_appended(batch=1) == 1
+                else:
+                    idx.insert_at(rid)
+                rowid_of.append(rid)
+                node_of[rid] = k
+                live.add(rid)
+                h.insert(k, levels[k])
+            elif kind == "update":
+                rid = int(rng.choice(sorted(live - {entry})))
+                h._v[node_of[rid]] = fresh[op]
+                s.upsert(rid, fresh[op].tobytes())
+                idx.reinsert(rid)
+                h.reinsert(node_of[rid], levels[node_of[rid]])
+            elif kind == "delete":
+                rid = int(rng.choice(sorted(live - {entry})))
+                s.delete(rid)
+                idx.reinsert(rid)
+                h.reinsert(node_of[rid], levels[node_of[rid]], insert_again=False)
+                live.discard(rid)
+                dead.append(rid)
+            else:
+                rid = dead.pop(int(rng.integers(len(dead))))
+                h._v[node_of[rid]] = fresh[op]
+                s.upsert(rid, fresh[op].tobytes())
+                idx.insert_at(rid)                 # the tombstoned row is still in the slab: nothing moves
+                h.insert(node_of[rid], levels[node_of[rid]])
+                live.add(rid)
+            counts[kind] += 1
+            if op % 50 == 49:
+                check()
+        assert all(counts.values()), counts
+        idx.close()
+    h.close()
