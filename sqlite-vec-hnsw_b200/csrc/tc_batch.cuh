@@ -634,6 +634,13 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const uint8_t* base, uin
     if ((threadIdx.x & 31) == 0 && max_bits) atomicMax(max_bits, __float_as_uint(mx));
 }
 
+// an out-of-order insert moved the rows from `first_moved` on up by one position: the listed positions follow
+__global__ void renumber_positions_kernel(uint32_t* list, uint32_t max_items, uint32_t first_moved) {
+    const uint32_t n = min(list[0], max_items);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (list[1 + i] >= first_moved) list[1 + i] += 1;
+}
+
 // Per query: gather the kept approximate scores of all its CTAs, sort, derive the certified candidate set.
 struct TcCollectParams {
     TcParams t;

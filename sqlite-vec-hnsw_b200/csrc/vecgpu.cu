@@ -627,10 +627,31 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
             CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_skip + ins, tail, cudaMemcpyDeviceToDevice, s->stream));
             CU(cudaMemcpyAsync(s->d_skip + ins + 1, s->d_ws[WS_TMP], tail, cudaMemcpyDeviceToDevice, s->stream));
         }
+        // the cached |row|^2 are position-indexed too: they move with the rows (and the few positions on the always-re-ranked
+        // list are renumbered) instead of being discarded — the next batched query would recompute all of them
+        if (s->norms_valid && s->elem != VECGPU_BIT && s->rows + 1 > s->cap_norms) {
+            const uint64_t cap = std::max<uint64_t>(s->rows + 1, s->cap);
+            float* nn = nullptr;
+            CU(cudaMalloc((void**)&nn, cap * sizeof(float)));
+            CU(cudaMemcpyAsync(nn, s->d_norms, s->cap_norms * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            cudaFree(s->d_norms);
+            s->d_norms = nn;
+            s->cap_norms = cap;
+        }
+        if (s->norms_valid && s->elem != VECGPU_BIT) {
+            CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_norms + ins, tail * 4, cudaMemcpyDeviceToDevice, s->stream));
+            CU(cudaMemcpyAsync(s->d_norms + ins + 1, s->d_ws[WS_TMP], tail * 4, cudaMemcpyDeviceToDevice, s->stream));
+            if (s->elem == VECGPU_F32 && s->d_unsafe) {
+                renumber_positions_kernel<<<1, 256, 0, s->stream>>>(s->d_unsafe, TC_MAX_UNSAFE, (uint32_t)ins);
+                LAUNCHED();
+            }
+        } else {
+            s->norms_valid = false;
+        }
         CU(cudaStreamSynchronize(s->stream));
     }
     ++s->layout_gen;
-    s->norms_valid = false;  // cached norms are position-indexed
     s->h_rowids.insert(s->h_rowids.begin() + (ptrdiff_t)ins, rowid);
     if (has_skip) s->h_skip.insert(s->h_skip.begin() + (ptrdiff_t)ins, 0);
     s->rows += 1;
@@ -1307,9 +1328,19 @@ static int slab_ensure_norms(vecgpu_slab* s, cudaStream_t st) {
 // row that was unusable stays on the always-re-ranked list: both remain valid (conservative) bounds.
 static int slab_update_norms(vecgpu_slab* s, uint64_t pos, uint64_t n) {
     if (!s->norms_valid || n == 0) return 0;
-    if (pos + n > s->cap_norms || s->elem == VECGPU_BIT) {
+    if (s->elem == VECGPU_BIT) {
         s->norms_valid = false;
         return 0;
+    }
+    if (pos + n > s->cap_norms) {  // rows appended past the cache's capacity: it grows with the slab, the cached values move along
+        const uint64_t cap = std::max<uint64_t>(pos + n, s->cap);
+        float* nn = nullptr;
+        CU(cudaMalloc((void**)&nn, cap * sizeof(float)));
+        CU(cudaMemcpyAsync(nn, s->d_norms, s->cap_norms * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_norms);
+        s->d_norms = nn;
+        s->cap_norms = cap;
     }
     const uint8_t* base = s->d_vec + pos * s->row_stride;
     const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 63) / 64, (uint64_t)s->num_sms * 8));

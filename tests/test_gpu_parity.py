@@ -1261,10 +1261,30 @@ def test_norm_cache_is_updated_by_upserts_not_discarded(vg, orc, gpu, elem, metr
         s.upsert(new_id, q[2].tobytes())
         vv = np.concatenate([vv[:5001], q[2:3], vv[5001:]])
         rr = np.concatenate([rr[:5001], [new_id], rr[5001:]])
+        l0 = vg.launch_count()
         r, d, c = s.knn(q, k, metric)
+        l1 = vg.launch_count()
         er, ed, ec = orc.knn(elem, dims, vv, q, k, metric, rowids=rr)
         assert np.array_equal(r, er) and same_bits(d, ed)
         assert r[0, 0] == rr[1234] and r[1, 0] == rr[-1] and r[2, 0] == new_id
+        # none of the three writes discarded the cache: the same call again launches exactly as many kernels (no norm pass)
+        r2, d2, _ = s.knn(q, k, metric)
+        assert vg.launch_count() - l1 == l1 - l0 and np.array_equal(r2, r) and same_bits(d2, d)
+        # a zero row (cosine: on the always-re-ranked list) keeps its place on that list when rows before it move
+        if metric == COSINE:
+            s.upsert(int(rr[9000]), np.zeros(dims, dtype="<f4").tobytes())
+            vv[9000] = 0
+            base = rr.copy()
+            for j in range(3):                       # every insert moves the positions behind it up by one
+                nid = int(base[100 + 10 * j] + 1)
+                s.upsert(nid, q[3 + j].tobytes())
+                vv = np.concatenate([vv, q[3 + j:4 + j]])
+                rr = np.concatenate([rr, [nid]])
+            order = np.argsort(rr, kind="stable")
+            vv, rr = vv[order], rr[order]
+            r, d, c = s.knn(q, k, metric)
+            er, ed, ec = orc.knn(elem, dims, vv, q, k, metric, rowids=rr)
+            assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
 
 
 def test_out_of_order_inserts_with_tombstones(vg, orc, gpu):
