@@ -616,17 +616,25 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
     s->skip_synced = std::min<uint64_t>(s->skip_synced, has_skip ? s->rows : 0);
     if (rc) return rc;
     if (tail) {
-        const size_t vb = (size_t)tail * s->row_stride;
-        rc = ws_reserve(s, WS_TMP, std::max(vb, (size_t)tail * 8));
+        // [ins, rows) moves up by one item, from the end backwards, in chunks through a bounded scratch buffer (the whole tail
+        // at once would need a second copy of up to the whole slab next to it)
+        const size_t chunk = (size_t)std::max(1u, env_u32("VECGPU_SHIFT_CHUNK_MB", 256)) << 20;
+        rc = ws_reserve(s, WS_TMP, std::min(chunk, std::max((size_t)tail * s->row_stride, (size_t)tail * 8)));
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_vec + ins * s->row_stride, vb, cudaMemcpyDeviceToDevice, s->stream));
-        CU(cudaMemcpyAsync(s->d_vec + (ins + 1) * s->row_stride, s->d_ws[WS_TMP], vb, cudaMemcpyDeviceToDevice, s->stream));
-        CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_rowids + ins, tail * 8, cudaMemcpyDeviceToDevice, s->stream));
-        CU(cudaMemcpyAsync(s->d_rowids + ins + 1, s->d_ws[WS_TMP], tail * 8, cudaMemcpyDeviceToDevice, s->stream));
-        if (has_skip) {
-            CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_skip + ins, tail, cudaMemcpyDeviceToDevice, s->stream));
-            CU(cudaMemcpyAsync(s->d_skip + ins + 1, s->d_ws[WS_TMP], tail, cudaMemcpyDeviceToDevice, s->stream));
-        }
+        auto shift_up = [&](uint8_t* base, size_t item) -> int {
+            const size_t bytes = (size_t)tail * item;
+            uint8_t* first = base + ins * item;
+            for (size_t done = 0; done < bytes;) {
+                const size_t m = std::min(chunk, bytes - done), off = bytes - done - m;
+                CU(cudaMemcpyAsync(s->d_ws[WS_TMP], first + off, m, cudaMemcpyDeviceToDevice, s->stream));
+                CU(cudaMemcpyAsync(first + off + item, s->d_ws[WS_TMP], m, cudaMemcpyDeviceToDevice, s->stream));
+                done += m;
+            }
+            return 0;
+        };
+        if ((rc = shift_up(s->d_vec, s->row_stride))) return rc;
+        if ((rc = shift_up((uint8_t*)s->d_rowids, 8))) return rc;
+        if (has_skip && (rc = shift_up(s->d_skip, 1))) return rc;
         // the cached |row|^2 are position-indexed too: they move with the rows (and the few positions on the always-re-ranked
         // list are renumbered) instead of being discarded — the next batched query would recompute all of them
         if (s->norms_valid && s->elem != VECGPU_BIT && s->rows + 1 > s->cap_norms) {
@@ -640,8 +648,7 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
             s->cap_norms = cap;
         }
         if (s->norms_valid && s->elem != VECGPU_BIT) {
-            CU(cudaMemcpyAsync(s->d_ws[WS_TMP], s->d_norms + ins, tail * 4, cudaMemcpyDeviceToDevice, s->stream));
-            CU(cudaMemcpyAsync(s->d_norms + ins + 1, s->d_ws[WS_TMP], tail * 4, cudaMemcpyDeviceToDevice, s->stream));
+            if ((rc = shift_up((uint8_t*)s->d_norms, 4))) return rc;
             if (s->elem == VECGPU_F32 && s->d_unsafe) {
                 renumber_positions_kernel<<<1, 256, 0, s->stream>>>(s->d_unsafe, TC_MAX_UNSAFE, (uint32_t)ins);
                 LAUNCHED();

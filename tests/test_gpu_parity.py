@@ -1287,6 +1287,38 @@ def test_norm_cache_is_updated_by_upserts_not_discarded(vg, orc, gpu, elem, metr
             assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
 
 
+def test_out_of_order_insert_moves_the_tail_in_chunks(vg, orc, gpu, monkeypatch):
+    """The tail of the slab moves up by one row through a bounded scratch buffer, from the end backwards (256 MB chunks; 1 MB
+    here so that an 11 MB slab needs a dozen): vectors, rowids, tombstones and cached norms all arrive where they belong."""
+    monkeypatch.setenv("VECGPU_SHIFT_CHUNK_MB", "1")
+    n, dims, nq, k = 30_000, 96, 32, 10
+    v = random_rows(F32, n, dims, seed=51)
+    q = random_rows(F32, nq, dims, seed=52)
+    rr = np.arange(10, 10 + 3 * n, 3, dtype="<i8")
+    with vg.Slab(F32, dims) as s:
+        s.load(v, rr)
+        s.delete(int(rr[777]))
+        s.delete(int(rr[n - 2]))
+        s.knn(q, k, L2)                                   # the norm cache exists
+        live = np.ones(n, dtype=bool)
+        live[[777, n - 2]] = False
+        vv, ids = v[live], rr[live]
+        for j, at in enumerate([0, 1, 12_345, n // 2, n - 3, n - 1]):
+            nid = int(rr[at] + 1)
+            s.upsert(nid, q[j].tobytes())
+            vv, ids = np.concatenate([vv, q[j:j + 1]]), np.concatenate([ids, [nid]])
+        order = np.argsort(ids, kind="stable")
+        vv, ids = vv[order], ids[order]
+        r, d, c = s.knn(q, k, L2)                         # batched: tensor-core path with the moved norms
+        er, ed, ec = orc.knn(F32, dims, vv, q, k, L2, rowids=ids)
+        assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec)
+        r1, d1, _ = s.knn(q[:1], k, L2)                   # single query: the streaming scan
+        assert np.array_equal(r1, er[:1]) and same_bits(d1, ed[:1])
+        for i in (0, 1, 2, 5000, 12_345, 12_346, n // 2 + 3, len(ids) - 1):
+            assert s.get(int(ids[i])) == vv[i].tobytes()
+        assert s.count() == (n + 6, n + 4)
+
+
 def test_out_of_order_inserts_with_tombstones(vg, orc, gpu):
     dims = 12
     rng = np.random.default_rng(9)
