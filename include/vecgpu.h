@@ -285,7 +285,8 @@ int vecgpu_hnsw_reinsert(vecgpu_hnsw* h, int64_t rowid);
  * shift by one row, device to device), the row gets the level of the next insertion (the level sequence follows insertion
  * order, as in the reference) and is inserted like any other row — the graph equals the sequential build's in insertion
  * order, edge for edge.  Exactly one out-of-order upsert may lie between two calls, with no un-indexed appended rows;
- * otherwise status 4 and the index needs vecgpu_hnsw_build.  Needs the resident graph (not VECGPU_HNSW_DEVICE=0). */
+ * otherwise status 4 and the index needs vecgpu_hnsw_build.  (In lockstep mode, VECGPU_HNSW_DEVICE=0, the host lists are
+ * renumbered instead.) */
 int vecgpu_hnsw_insert_at(vecgpu_hnsw* h, int64_t rowid);
 /* search_hnsw (src/hnsw/search.rs:267-335): ef = max(ef_search, k); results closest first, distances in the
  * internal metric (apply convert_distance_for_output for cosine columns); unused slots rowid -1 / +inf. */

@@ -1292,10 +1292,37 @@ extern "C" int vecgpu_hnsw_insert_at(vecgpu_hnsw* h, int64_t rowid) {
         return fail(VECGPU_ERR_CUDA, "more than one change of row positions (or appended rows not yet indexed) since the index was last brought up to date: rebuild it");
     const uint32_t p = (uint32_t)p64;
     const bool use_dev = hnsw_device_enabled(h);
-    if (!use_dev || !h->dev_valid) return fail(VECGPU_ERR_CUDA, "the graph is not resident on the device (lockstep mode or after a capacity overflow): rebuild it");
-    if ((rc = hnsw_dev_flush_dirty(h))) return rc;
     const uint64_t slots_old = h->degU.size();
     const int L = hnsw_level_for(h, n_old);  // the level the row would have got as row number n_old (appended)
+    if (!use_dev || !h->dev_valid) {
+        // ---- the graph is not resident (lockstep mode, or a capacity overflow sent the last batch to the host): the same
+        //      renumbering and shift on the host lists; the insertion below uploads them again where a device copy is kept
+        if ((rc = hnsw_ensure_host(h))) return rc;
+        for (uint64_t v = 0; v < n_old; ++v)
+            for (uint32_t i = 0; i < h->deg0[v]; ++i)
+                if (h->nbr0[v * h->max_m0 + i] >= p) h->nbr0[v * h->max_m0 + i] += 1;
+        for (uint64_t sl = 0; sl < slots_old; ++sl)
+            for (uint32_t i = 0; i < h->degU[sl]; ++i)
+                if (h->nbrU[sl * h->M + i] >= p) h->nbrU[sl * h->M + i] += 1;
+        h->nbr0.insert(h->nbr0.begin() + (size_t)p * h->max_m0, h->max_m0, 0u);
+        h->dist0.insert(h->dist0.begin() + (size_t)p * h->max_m0, h->max_m0, 0.f);
+        h->deg0.insert(h->deg0.begin() + p, (uint16_t)0);
+        h->node_level.insert(h->node_level.begin() + p, (int8_t)L);
+        h->in_graph.insert(h->in_graph.begin() + p, 0);
+        h->upper_base.insert(h->upper_base.begin() + p, (uint32_t)slots_old);
+        if (L > 0) {
+            h->nbrU.resize((size_t)(slots_old + L) * h->M, 0);
+            h->distU.resize((size_t)(slots_old + L) * h->M, 0.f);
+            h->degU.resize(slots_old + L, 0);
+        }
+        if ((uint64_t)h->entry >= p) h->entry += 1;
+        h->dev_valid = false;
+        h->slab_gen = s->layout_gen;
+        if (p < s->h_skip.size() && s->h_skip[p]) return 0;  // an empty blob: a row, but not a node
+        std::vector<uint32_t> one_host{p};
+        return hnsw_build_locked(h, 1, true, nullptr, &one_host);
+    }
+    if ((rc = hnsw_dev_flush_dirty(h))) return rc;
     // ---- shift the level-0 arrays by one row from p into the spare set, renumbering the neighbour ids on the way; the
     //      two sets swap roles (no allocation per insert once both exist)
     const bool timing = getenv("VECGPU_HNSW_TIMING") != nullptr;

@@ -184,7 +184,7 @@ class Vec0Table:
                     idx.insert_at(rowid)
                 self._hnsw_shadow_lag = True
             except vec0.VecError:
-                self._hnsw_stale = True  # (lockstep mode, or rows the index never saw): rebuilt on demand
+                self._hnsw_stale = True  # (rows the index never saw, e.g. after writers that bypassed the hooks): rebuilt on demand
         else:
             self._hnsw_stale = idx is not None
         return rowid
@@ -288,7 +288,7 @@ class Vec0Table:
         """search_hnsw over the resident index (src/hnsw/search.rs:267-335): -> [(rowid, distance in the column's metric)].
         Rows deleted since the rebuild are never returned; rows inserted in rowid order since are in the graph already
         (insert()) and updated rows have been re-inserted (update()).  A row inserted out of rowid order is inserted as well
-        (the resident graph is renumbered on the device).  Only if that failed (lockstep mode) the index is stale: the call
+        (the resident graph is renumbered on the device).  Only if that failed the index is stale: the call
         then refuses to answer unless auto_rebuild=True rebuilds it first."""
         if getattr(self, "_hnsw", None) is None:
             raise vec0.InvalidState("no HNSW index: call rebuild_hnsw() first")

@@ -318,13 +318,17 @@ def test_reinsert_equals_the_sequential_reference_update(vg, orc, gpu):
         h.close()
 
 
-def test_insert_at_equals_the_sequential_build_in_insertion_order(vg, orc, gpu):
+@pytest.mark.parametrize("resident", [True, False])
+def test_insert_at_equals_the_sequential_build_in_insertion_order(vg, orc, gpu, monkeypatch, resident):
     """vecgpu_hnsw_insert_at = Vec0Tab::insert with an explicit rowid below the highest one (src/vtab.rs:1409-1682 ->
     insert_hnsw, src/hnsw/insert.rs:279-532).  The slab keeps rows in rowid order, so the new row lands between existing rows
     and every later row (= node id) moves up by one; the resident graph is renumbered on the device and the row inserted.
     After a batch-of-one build over even rowids and a series of odd-rowid inserts — first row, last gap, middle, next to the
     entry point, an empty blob — interleaved with appended rows, the graph equals the sequential restatement's built over
-    the same vectors in INSERTION order, edge for edge and distance bit for distance bit (node ids compared as rowids)."""
+    the same vectors in INSERTION order, edge for edge and distance bit for distance bit (node ids compared as rowids).
+    resident=False: lockstep mode (VECGPU_HNSW_DEVICE=0), where the same renumbering happens on the host lists."""
+    if not resident:
+        monkeypatch.setenv("VECGPU_HNSW_DEVICE", "0")
     elem, dims, n0, M, efc = F32, 24, 1500, 8, 50
     extra = 40
     v = orc.synth_rows(elem, 6, 1, n0 + extra, dims, 1)
