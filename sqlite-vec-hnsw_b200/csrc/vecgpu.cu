@@ -632,11 +632,7 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
             }
             return 0;
         };
-        if ((rc = shift_up(s->d_vec, s->row_stride))) return rc;
-        if ((rc = shift_up((uint8_t*)s->d_rowids, 8))) return rc;
-        if (has_skip && (rc = shift_up(s->d_skip, 1))) return rc;
-        // the cached |row|^2 are position-indexed too: they move with the rows (and the few positions on the always-re-ranked
-        // list are renumbered) instead of being discarded — the next batched query would recompute all of them
+        // (allocations first: nothing has moved yet if one fails)
         if (s->norms_valid && s->elem != VECGPU_BIT && s->rows + 1 > s->cap_norms) {
             const uint64_t cap = std::max<uint64_t>(s->rows + 1, s->cap);
             float* nn = nullptr;
@@ -647,6 +643,11 @@ extern "C" int vecgpu_slab_upsert(vecgpu_slab* s, int64_t rowid, const void* vec
             s->d_norms = nn;
             s->cap_norms = cap;
         }
+        if ((rc = shift_up(s->d_vec, s->row_stride))) return rc;
+        if ((rc = shift_up((uint8_t*)s->d_rowids, 8))) return rc;
+        if (has_skip && (rc = shift_up(s->d_skip, 1))) return rc;
+        // the cached |row|^2 are position-indexed too: they move with the rows (and the few positions on the always-re-ranked
+        // list are renumbered) instead of being discarded — the next batched query would recompute all of them
         if (s->norms_valid && s->elem != VECGPU_BIT) {
             if ((rc = shift_up((uint8_t*)s->d_norms, 4))) return rc;
             if (s->elem == VECGPU_F32 && s->d_unsafe) {
