@@ -1438,3 +1438,25 @@ def test_two_stream_pipelining_of_single_query_scans(vg, orc, gpu):
         assert np.array_equal(big[0].cpu().numpy(), er[:32]) and np.array_equal(bits(big[1].cpu().numpy()), bits(ed[:32]))
         for j in range(8):
             assert np.array_equal(late[j][0].cpu().numpy()[0], er[32 + j])
+
+
+@pytest.mark.parametrize("elem,metric,dims", [(F32, L2, 384), (F32, COSINE, 96), (I8, L2, 128), (BIT, HAMMING, 256)])
+def test_small_table_with_a_long_result_list_scans_with_fewer_ctas(vg, orc, gpu, monkeypatch, elem, metric, dims):
+    """A single query with 28 <= k <= 110 on a small table: the scan runs with fewer CTAs so that the fused final merge sorts
+    fewer keys (vecgpu.cu, tools/small_table_gx.py).  Whatever the CTA count — the automatic choice, one CTA, one per SM —
+    the answer is the oracle's, rowids and distance bits (ties included: duplicated rows)."""
+    for n in (300, 10_000, 120_000):
+        v = random_rows(elem, n, dims, seed=61)
+        v[n // 2:n // 2 + 40] = v[:40]                    # exact duplicates: equal distances, rowid order decides
+        q = random_rows(elem, 2, dims, seed=62)
+        with vg.Slab(elem, dims) as s:
+            s.load(v)
+            for k in (27, 28, 50, 100, 110, 111):
+                er, ed, ec = orc.knn(elem, dims, v, q[:1], k, metric)
+                for cap in (None, "1", "148"):
+                    if cap is None:
+                        monkeypatch.delenv("VECGPU_SCAN_GX", raising=False)
+                    else:
+                        monkeypatch.setenv("VECGPU_SCAN_GX", cap)
+                    r, d, c = s.knn(q[:1], k, metric)
+                    assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec), (n, k, cap)
