@@ -6,7 +6,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle
 import sqlite_vec_hnsw_b200 as vg
-for n, dims, metric, k in ((10_000, 384, 0, 10), (50_000, 384, 0, 10), (10_000, 384, 0, 100), (10_000, 384, 0, 32), (10_000, 384, 0, 64), (100_000, 384, 0, 100), (1_000_000, 384, 0, 100), (2_000, 128, 0, 50)):
+CASES = ((10_000, 384, 0, 10), (50_000, 384, 0, 10), (10_000, 384, 0, 100), (10_000, 384, 0, 32), (10_000, 384, 0, 64), (100_000, 384, 0, 100),
+         (1_000_000, 384, 0, 100), (2_000, 128, 0, 50))
+if len(sys.argv) > 1 and sys.argv[1] == "long":   # result lists beyond the fused merge's reach at one CTA per SM (148 k > 16384)
+    CASES = ((10_000, 384, 0, 200), (10_000, 384, 0, 500), (10_000, 384, 0, 1000), (100_000, 384, 0, 200), (100_000, 384, 0, 1000), (1_000_000, 384, 0, 500))
+for n, dims, metric, k in CASES:
     with vg.Slab(0, dims) as s:
         s.fill_synthetic(seed=1, n=n, kind=1)
         q = oracle.synth_rows(0, 2, 1, 1, dims, 1)
