@@ -1157,16 +1157,17 @@ static int knn_exact(vecgpu_slab* s, const uint8_t* d_q, uint32_t nq, uint32_t k
         uint32_t gx = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)s->num_sms);
         if (const uint32_t cap_gx = env_u32("VECGPU_SCAN_GX", 0)) {
             gx = std::max(1u, std::min(gx, cap_gx));
-        } else if (nq == 1 && k >= 28 && (uint64_t)gx * k <= 16384) {
-            // A small table with a long result list: the fused final merge sorts next_pow2(gx * k) keys in ONE CTA, which costs
-            // more than the scan itself (10 k x f32[384], k = 100: 236 us with 148 CTAs, 81 us with 16 — tools/small_table_gx.py).
-            // Fewer CTAs stream more rows each (~42 GB/s per CTA) but leave fewer partial lists; the fit below (us) picks the
-            // count.  Tables of any size where streaming dominates keep one CTA per SM.
-            const double bytes = (double)s->rows * s->row_stride;
-            auto est = [&](uint32_t g) { return bytes / ((double)g * 42e3) + 0.0115 * (double)std::max(2u, next_pow2(g * k)); };
+        } else if (nq <= c.QB && k >= 28 && (uint64_t)gx * k <= 16384) {
+            // A small table with a long result list, one query pass: the fused final merge sorts next_pow2(gx * k) keys in ONE
+            // CTA, once per query of the pass, which costs more than the scan itself (10 k x f32[384], k = 100: 236 us with 148
+            // CTAs, 81 us with 16; four queries: 1101 vs 299 us — tools/small_table_gx.py).  Fewer CTAs stream more rows each
+            // (~42 GB/s per CTA, ~0.43 more per extra query of the pass) but leave fewer partial lists; the fit below (us)
+            // picks the count.  Tables of any size where streaming dominates keep one CTA per SM.
+            const double bytes = (double)s->rows * s->row_stride * (1.0 + 0.43 * (nq - 1));
+            auto est = [&](uint32_t g) { return bytes / ((double)g * 42e3) + 0.0115 * nq * (double)std::max(2u, next_pow2(g * k)); };
             uint32_t best = gx;
             double t_best = est(gx);
-            for (uint32_t keys = 1024; keys <= 8192; keys <<= 1) {
+            for (uint32_t keys = nq == 1 ? 1024 : 2048; keys <= 8192; keys <<= 1) {
                 const uint32_t g = std::min(gx, std::max(1u, keys / k));
                 if (est(g) < t_best) {
                     t_best = est(g);

@@ -1448,15 +1448,16 @@ def test_small_table_with_a_long_result_list_scans_with_fewer_ctas(vg, orc, gpu,
     for n in (300, 10_000, 120_000):
         v = random_rows(elem, n, dims, seed=61)
         v[n // 2:n // 2 + 40] = v[:40]                    # exact duplicates: equal distances, rowid order decides
-        q = random_rows(elem, 2, dims, seed=62)
+        q = random_rows(elem, 3, dims, seed=62)
         with vg.Slab(elem, dims) as s:
             s.load(v)
             for k in (27, 28, 50, 100, 110, 111):
-                er, ed, ec = orc.knn(elem, dims, v, q[:1], k, metric)
-                for cap in (None, "1", "148"):
-                    if cap is None:
-                        monkeypatch.delenv("VECGPU_SCAN_GX", raising=False)
-                    else:
-                        monkeypatch.setenv("VECGPU_SCAN_GX", cap)
-                    r, d, c = s.knn(q[:1], k, metric)
-                    assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec), (n, k, cap)
+                for nq in (1, 3):                          # a small batch shares one pass of the scan: same choice, per query
+                    er, ed, ec = orc.knn(elem, dims, v, q[:nq], k, metric)
+                    for cap in (None, "1", "148"):
+                        if cap is None:
+                            monkeypatch.delenv("VECGPU_SCAN_GX", raising=False)
+                        else:
+                            monkeypatch.setenv("VECGPU_SCAN_GX", cap)
+                        r, d, c = s.knn(q[:nq], k, metric)
+                        assert np.array_equal(r, er) and same_bits(d, ed) and np.array_equal(c, ec), (n, k, nq, cap)

@@ -8,12 +8,13 @@ import oracle
 import sqlite_vec_hnsw_b200 as vg
 CASES = ((10_000, 384, 0, 10), (50_000, 384, 0, 10), (10_000, 384, 0, 100), (10_000, 384, 0, 32), (10_000, 384, 0, 64), (100_000, 384, 0, 100),
          (1_000_000, 384, 0, 100), (2_000, 128, 0, 50))
+NQ = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # queries per call (a small batch shares one pass of the scan)
 if len(sys.argv) > 1 and sys.argv[1] == "long":   # result lists beyond the fused merge's reach at one CTA per SM (148 k > 16384)
     CASES = ((10_000, 384, 0, 200), (10_000, 384, 0, 500), (10_000, 384, 0, 1000), (100_000, 384, 0, 200), (100_000, 384, 0, 1000), (1_000_000, 384, 0, 500))
 for n, dims, metric, k in CASES:
     with vg.Slab(0, dims) as s:
         s.fill_synthetic(seed=1, n=n, kind=1)
-        q = oracle.synth_rows(0, 2, 1, 1, dims, 1)
+        q = oracle.synth_rows(0, 2, 1, NQ, dims, 1)
         line = []
         ref = None
         for cap in (0, 8, 16, 24, 32, 48, 64, 96, 148):
@@ -26,5 +27,5 @@ for n, dims, metric, k in CASES:
             if ref is None: ref = r
             assert all(np.array_equal(a.view("u1"), b.view("u1")) for a, b in zip(r, ref))
             line.append(f"{cap or 'auto'}: {us:.1f}")
-        print(f"{n} x f32[{dims}] metric {metric} k={k}  us per query by CTA cap  " + "  ".join(line), flush=True)
+        print(f"{n} x f32[{dims}] metric {metric} k={k} nq={NQ}  us per call by CTA cap  " + "  ".join(line), flush=True)
 os.environ.pop("VECGPU_SCAN_GX", None)
